@@ -1,0 +1,10 @@
+"""Import alias: ``import rcd_b200`` loads the package that lives in the directory
+``realtime-collision-detection_b200/`` (a hyphenated name cannot be imported directly)."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))),
+                      "realtime-collision-detection_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+del _f
