@@ -1,0 +1,204 @@
+/*
+ * rcd.h -- C-ABI of the B200-native collision core (librcd_b200.so).
+ *
+ * The reference (jectpro7/realtime-collision-detection) is pure Python and has no FFI; its hot
+ * path sits behind plain in-process classes.  This header is the boundary a maintainer binds
+ * with ctypes: every entry point names the reference interface it replaces
+ * (file:line relative to the reference tree).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns int: RCD_OK (0) or a negative RCD_E* code; never throws, never
+ *     long-jumps; rcd_last_error() gives a message for the last failure on that handle.
+ *   - the library never frees or keeps caller memory; inputs are copied during the call (host
+ *     pointers) or enqueued on the handle's stream (device pointers, src = RCD_SRC_DEVICE).
+ *   - one CUDA stream per handle; a handle is used from one thread at a time (the reference is
+ *     single-threaded asyncio: src/collision/warning_system.py:680-714).
+ *   - object state is fp32 SoA (48 B/object).  Decisions (pair sets, thresholds, alert classes)
+ *     are taken exactly as the reference's float64 arithmetic would take them on these fp32
+ *     values: the fp32 kernels only pre-filter, every pair near a threshold is re-evaluated in
+ *     fp64 on the device ("exactness").
+ *   - there is no CPU fallback: without a CUDA device rcd_create fails with RCD_ENODEVICE.
+ */
+#ifndef RCD_H_
+#define RCD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCD_VERSION 100 /* 0.1.0 */
+
+enum {
+    RCD_OK = 0,
+    RCD_EINVAL = -1,    /* bad argument */
+    RCD_ENODEVICE = -2, /* no usable CUDA device */
+    RCD_ENOMEM = -3,    /* host or device allocation failed */
+    RCD_ECUDA = -4,     /* a CUDA call failed (see rcd_last_error) */
+    RCD_ECAPACITY = -5, /* more objects than max_objects */
+    RCD_ESTATE = -6     /* call order (e.g. download before step) */
+};
+
+/* frame modes for rcd_step */
+enum {
+    /* CollisionDetector.detect_collisions for every object
+     * (src/collision/collision_detection.py:110-191, stages :208-389) */
+    RCD_MODE_DETECT = 0,
+    /* CollisionPredictionModel.predict_collisions for every object (:572-865); per-object
+     * trajectory pattern from rcd_set_patterns (pattern 3 = history < 2 -> detect path, :590-592) */
+    RCD_MODE_PREDICT = 1,
+    /* compute-node detector: SpatialIndex.query_nearby + CollisionDetector.detect_collisions
+     * (src/compute/compute_node.py:98-119, :229-321) */
+    RCD_MODE_COMPUTE_NODE = 2
+};
+
+/* OR-ed into the mode of rcd_step: keep the pairs and totals of the previous rcd_step of this frame
+ * and append to them.  The reference's perf harness runs detect and predict for every vehicle in
+ * one frame (src/test/performance_test.py:794-813); that is rcd_step(DETECT) followed by
+ * rcd_step(PREDICT | RCD_STEP_APPEND) on the same index. */
+#define RCD_STEP_APPEND 0x100
+
+enum { RCD_SRC_HOST = 0, RCD_SRC_DEVICE = 1 };
+
+/* trajectory pattern codes (collision_detection.py:698-703; 3 = fewer than 2 history samples) */
+enum { RCD_PAT_STATIONARY = 0, RCD_PAT_CONSTANT_VELOCITY = 1, RCD_PAT_ACCELERATING = 2, RCD_PAT_NO_HISTORY = 3 };
+
+typedef struct rcd_handle_s *rcd_handle;
+
+typedef struct {
+    int32_t device;       /* CUDA device ordinal */
+    uint32_t flags;       /* RCD_FLAG_* */
+    uint64_t max_objects; /* capacity of the handle (owned + halo objects) */
+    uint64_t max_pairs;   /* capacity of the emitted-pair buffer; counts stay exact beyond it */
+    /* grid bounds.  If world_min[0] > world_max[0] the bounds are taken from the data each
+     * frame (one extra device->host sync per frame); objects outside the bounds are clamped
+     * into the border cells, which stays exact ("grid"). */
+    float world_min[3];
+    float world_max[3];
+} rcd_config;
+
+#define RCD_FLAG_PROFILE 1u /* record CUDA events around every stage (rcd_stage_ms) */
+
+/* One emitted, directed pair (i -> j): the fields of the reference's CollisionRisk
+ * (collision_detection.py:156-166, :831-842) plus the stage-2 values and the alert class
+ * (src/collision/warning_system.py:259-311).  48 bytes. */
+typedef struct {
+    uint32_t i, j;      /* caller ids of the querying object and of the other object */
+    float ttc;          /* time_to_collision: k*0.1 (detect) or k*0.1 + t_m (predict); B: formula ttc */
+    float distance;     /* distance at the first sample inside the safe distance; B: future distance */
+    float rel_speed;    /* |v_i - v_j| */
+    float risk;         /* risk_level in [0, 1] */
+    float cx, cy, cz;   /* collision_position (midpoint) */
+    float t_closest;    /* detect: time_to_closest (stage 2); predict: winning offset time t_m */
+    float d_closest;    /* detect: closest_distance (stage 2); otherwise 0 */
+    int8_t priority;    /* alert class: -1 below RISK_LEVEL_LOW, else 0..3; B: -1 */
+    uint8_t offset;     /* predict: winning offset index m (0..19); otherwise 255 */
+    uint8_t predicted;  /* CollisionRisk.is_predicted */
+    uint8_t reserved;
+} rcd_pair;
+
+/* frame totals (exact even when the pair buffer overflowed) */
+typedef struct {
+    uint64_t n_objects;    /* objects in the frame (owned + halo) */
+    uint64_t n_owned;      /* objects queried */
+    uint64_t n_candidates; /* directed broad-phase pairs (stage 1); B counts self like query_nearby */
+    uint64_t n_potential;  /* stage-2 survivors (stats["potential_collisions"], :177) */
+    uint64_t n_pairs;      /* emitted risks */
+    uint64_t n_high_risk;  /* risk > 0.7 (stats["high_risk_collisions"], :178) */
+    uint64_t n_written;    /* pairs actually stored (<= max_pairs) */
+    uint64_t n_alerts[4];  /* alerts by priority 0..3 (risk >= 0.3) */
+    uint64_t n_exact;      /* pairs that took the fp64 re-evaluation path (diagnostic) */
+} rcd_counts_t;
+
+#define RCD_NUM_STAGES 8
+/* stage indices for rcd_stage_ms */
+enum {
+    RCD_STAGE_UPLOAD = 0,  /* host->device copies of the SoA state */
+    RCD_STAGE_KEYS = 1,    /* cell keys + digit histograms */
+    RCD_STAGE_SORT = 2,    /* radix sort passes */
+    RCD_STAGE_REORDER = 3, /* gather into cell order + cell ranges */
+    RCD_STAGE_PAIRS = 4,   /* pair enumeration + narrow phase + classification */
+    RCD_STAGE_FINALIZE = 5,
+    RCD_STAGE_DOWNLOAD = 6,
+    RCD_STAGE_TOTAL = 7
+};
+
+int rcd_version(void);
+const char *rcd_last_error(rcd_handle h); /* h may be NULL: last error of rcd_create */
+
+int rcd_create(const rcd_config *cfg, rcd_handle *out);
+int rcd_destroy(rcd_handle h);
+
+/* Replace the frame's object state.  Replaces N x CollisionDetector.update_vehicle +
+ * SpatialIndex.insert_vehicle (collision_detection.py:74-85, spatial_index.py:162-200) and
+ * compute_node.SpatialIndex.insert (compute_node.py:55-72).  All arrays have n entries; id may be
+ * NULL (ids 0..n-1); type is a small integer per distinct type string (only equality is used,
+ * collision_detection.py:498-513).  az/ay/ax/heading/size/type may be NULL (zeros). */
+int rcd_upload(rcd_handle h, uint64_t n, const float *px, const float *py, const float *pz,
+               const float *vx, const float *vy, const float *vz, const float *ax, const float *ay,
+               const float *az, const float *size, const float *heading, const uint8_t *type,
+               const uint32_t *id, int32_t src);
+
+/* Per-object flags: predict mode = trajectory pattern code (RCD_PAT_*); compute-node mode =
+ * 1 if the VehicleState has >= 2 history samples (compute_node.py:202-203), else 0.
+ * NULL resets to the default (RCD_PAT_ACCELERATING / has history). */
+int rcd_set_patterns(rcd_handle h, uint64_t n, const uint8_t *pattern, int32_t src);
+
+/* Objects [0, n_owned) are queried; objects [n_owned, n) are halo copies owned by another
+ * shard: they are neighbours only (spatial slabs).  Default: all owned. */
+int rcd_set_owned(rcd_handle h, uint64_t n_owned);
+
+/* Run one frame for every owned object, asynchronously on the handle's stream.
+ * search_radius / time_window: the arguments of detect_collisions (collision_detection.py:110-111);
+ * predict mode always uses 100.0 / 1.0 like the reference (:802, :821) and ignores them except
+ * for pattern-3 objects, which use the defaults 100.0 / 10.0 (:592).  Compute-node mode uses
+ * search_radius as NodeConfig.search_radius (compute_node.py:620-622). */
+int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window);
+
+/* The object state was modified in place (device-resident frames): rebuild the index on the next
+ * rcd_step even though rcd_upload was not called. */
+int rcd_invalidate(rcd_handle h);
+
+/* Wait for the frame and return its totals. */
+int rcd_counts(rcd_handle h, rcd_counts_t *out);
+
+/* Copy the emitted pairs to host memory, sorted by (i, j, predicted); *n_out = pairs copied (<= cap). */
+int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out);
+
+/* Per-object broad-phase candidate counts of the last frame, in upload order (n entries). */
+int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n);
+
+/* Radius queries against the uploaded objects.  Replaces SpatialIndex.get_nearby_vehicles
+ * (spatial_index.py:229-271) and compute_node.SpatialIndex.query_nearby (compute_node.py:98-119):
+ * all ids with distance <= radius, the querying object included (quirk Q8).  Results are
+ * returned CSR-style: offsets[nq + 1], ids (ascending upload order per query) up to cap. */
+int rcd_query_radius(rcd_handle h, uint64_t nq, const float *qx, const float *qy, const float *qz,
+                     float radius, uint64_t *offsets, uint32_t *ids, uint64_t cap);
+
+/* Trajectory-pattern classifier (collision_detection.py:623-711) for n objects with up to
+ * `stride` (x, y, z, t) float64 samples each, already in timestamp order; count[i] samples are
+ * valid.  Writes RCD_PAT_* codes to pattern_out (host). */
+int rcd_classify_patterns(rcd_handle h, uint64_t n, uint32_t stride, const double *samples,
+                          const uint32_t *count, uint8_t *pattern_out);
+
+/* Spatial-slab support: pack every owned object whose x lies within `halo` of
+ * peer p's slab [slab_lo[p], slab_hi[p]) -- p != self -- into 52-byte records
+ * (11 floats, meta u32 = type | pattern << 8, id u32), grouped by peer.  out_records is a DEVICE
+ * buffer of cap records; counts[n_peers] is written to host memory (synchronises). */
+int rcd_halo_pack(rcd_handle h, int32_t n_peers, int32_t self, const float *slab_lo,
+                  const float *slab_hi, float halo, void *out_records, uint64_t cap,
+                  uint64_t *counts);
+/* Append n_records packed halo records (DEVICE buffer) after the owned objects. */
+int rcd_halo_append(rcd_handle h, const void *records, uint64_t n_records);
+
+/* Milliseconds of each stage of the last frame (needs RCD_FLAG_PROFILE); synchronises. */
+int rcd_stage_ms(rcd_handle h, float *ms /* RCD_NUM_STAGES */);
+/* Kernel launches issued by the last rcd_step (for bench.py's gpu_launches). */
+int rcd_launch_count(rcd_handle h, uint64_t *n);
+int rcd_sync(rcd_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCD_H_ */

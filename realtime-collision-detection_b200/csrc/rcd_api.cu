@@ -1,0 +1,665 @@
+// C-ABI of the collision core (include/rcd.h): handle, device buffers, frame orchestration.
+// One stream per handle; every frame is a fixed sequence of kernel launches on that stream.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rcd_common.cuh"
+#include "rcd_index.cuh"
+#include "rcd_pairs.cuh"
+
+using namespace rcd;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr u32 CELLS_CAP_MAX = 1u << 24;
+constexpr u32 CELLS_CAP_MIN = 1u << 16;
+
+struct Stage {
+    cudaEvent_t begin = nullptr, end = nullptr;
+    bool used = false;
+};
+
+}  // namespace
+
+struct rcd_handle_s {
+    int device = 0;
+    u32 flags = 0;
+    cudaStream_t stream = nullptr;
+    u64 cap = 0, max_pairs = 0;
+    u64 n = 0, n_owned = 0;
+
+    float *in_f[11] = {};
+    uint8_t *in_type = nullptr, *in_pattern = nullptr;
+    u32 *in_id = nullptr;
+
+    u32 *keys[2] = {}, *vals[2] = {};
+    u32 *hist = nullptr, *tile_status = nullptr, *tile_counter = nullptr;
+    size_t tile_status_words = 0;
+    int sorted_buf = 0;
+
+    float4 *P0 = nullptr, *P1 = nullptr, *P2 = nullptr;
+    u32 *sorted_slot = nullptr;
+    u32 *cell_start = nullptr, *cell_end = nullptr;
+    u32 cells_cap = 0;
+
+    bool world_static = false;
+    float wmin[3] = {}, wmax[3] = {};
+    int *bbox_dev = nullptr;
+    int *bbox_host = nullptr;  // pinned
+    GridParams grid = {};
+    bool index_valid = false;
+    float index_cell_req = 0.0f;
+
+    rcd_pair *out = nullptr;
+    Counters *counters = nullptr;
+    Counters *counters_host = nullptr;  // pinned
+    u32 *cand_count = nullptr;
+    bool frame_done = false;
+    int last_mode = -1;
+
+    Stage stages[RCD_NUM_STAGES];
+    u64 launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(rcd_handle h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                          \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            return fail((h), e__ == cudaErrorMemoryAllocation ? RCD_ENOMEM : RCD_ECUDA,            \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                      \
+        }                                                                                          \
+    } while (0)
+
+#define KERNEL_CHECK(h)                                                                            \
+    do {                                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) return fail((h), RCD_ECUDA, std::string("launch: ") + cudaGetErrorString(e__)); \
+        ++(h)->launches;                                                                           \
+    } while (0)
+
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t count) {
+    return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
+}
+
+void stage_begin(rcd_handle h, int s) {
+    if (h->flags & RCD_FLAG_PROFILE) {
+        cudaEventRecord(h->stages[s].begin, h->stream);
+        h->stages[s].used = true;
+    }
+}
+void stage_end(rcd_handle h, int s) {
+    if (h->flags & RCD_FLAG_PROFILE) cudaEventRecord(h->stages[s].end, h->stream);
+}
+
+InputState input_state(rcd_handle h) {
+    InputState in;
+    in.px = h->in_f[0]; in.py = h->in_f[1]; in.pz = h->in_f[2];
+    in.vx = h->in_f[3]; in.vy = h->in_f[4]; in.vz = h->in_f[5];
+    in.ax = h->in_f[6]; in.ay = h->in_f[7]; in.az = h->in_f[8];
+    in.size = h->in_f[9]; in.heading = h->in_f[10];
+    in.type = h->in_type; in.pattern = h->in_pattern; in.id = h->in_id;
+    return in;
+}
+
+// Grid for a requested minimum cell edge.  cell >= cell_req * (1 + 1e-4) + 0.02 keeps two objects
+// within cell_req of each other in adjacent cells despite fp32 rounding of (x - origin) / cell.
+GridParams make_grid(const float *wmin, const float *wmax, float cell_req, u32 cells_cap) {
+    GridParams g;
+    double cell = (double)cell_req * 1.0001 + 0.02;
+    if (!(cell > 1e-3)) cell = 1e-3;
+    double ext[3];
+    for (int d = 0; d < 3; ++d) {
+        double e = (double)wmax[d] - (double)wmin[d];
+        ext[d] = (e > 0 && std::isfinite(e)) ? e : 0.0;
+    }
+    for (;;) {
+        double nx = std::floor(ext[0] / cell) + 1, ny = std::floor(ext[1] / cell) + 1, nz = std::floor(ext[2] / cell) + 1;
+        if (nx * ny * nz <= (double)cells_cap) {
+            g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
+            break;
+        }
+        cell *= 1.25;
+    }
+    g.ox = wmin[0]; g.oy = wmin[1]; g.oz = wmin[2];
+    g.cell = (float)cell;
+    g.inv_cell = (float)(1.0 / cell);
+    g.ncells = (u32)g.nx * (u32)g.ny * (u32)g.nz;
+    return g;
+}
+
+int key_passes(u32 ncells) {
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)ncells) ++bits;
+    return std::max(1, (bits + RADIX_BITS - 1) / RADIX_BITS);
+}
+
+// Build the cell-ordered index for the current objects (keys -> sort -> reorder + ranges).
+int build_index(rcd_handle h, float cell_req) {
+    const u32 n = (u32)h->n;
+    if (h->index_valid && h->index_cell_req == cell_req) return RCD_OK;
+    h->index_valid = false;
+    if (n == 0) {
+        float z[3] = {0, 0, 0};
+        h->grid = make_grid(z, z, cell_req, h->cells_cap);
+        h->index_valid = true;
+        h->index_cell_req = cell_req;
+        return RCD_OK;
+    }
+    if (!h->world_static) {
+        h->bbox_host[0] = h->bbox_host[1] = h->bbox_host[2] = 0x7fffffff;
+        h->bbox_host[3] = h->bbox_host[4] = h->bbox_host[5] = (int)0x80000000;
+        CUDA_TRY(h, cudaMemcpyAsync(h->bbox_dev, h->bbox_host, 6 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        int blocks = (int)std::min<u64>((n + 255) / 256, 148 * 8);
+        k_bbox<<<blocks, 256, 0, h->stream>>>(h->in_f[0], h->in_f[1], h->in_f[2], n, h->bbox_dev);
+        KERNEL_CHECK(h);
+        CUDA_TRY(h, cudaMemcpyAsync(h->bbox_host, h->bbox_dev, 6 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        for (int d = 0; d < 3; ++d) {
+            h->wmin[d] = ordered_float(h->bbox_host[d]);
+            h->wmax[d] = ordered_float(h->bbox_host[3 + d]);
+            if (!(h->wmin[d] <= h->wmax[d])) h->wmin[d] = h->wmax[d] = 0.0f;  // no finite coordinate
+        }
+    }
+    h->grid = make_grid(h->wmin, h->wmax, cell_req, h->cells_cap);
+    const GridParams g = h->grid;
+    const int passes = key_passes(g.ncells);
+    const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
+
+    stage_begin(h, RCD_STAGE_KEYS);
+    CUDA_TRY(h, cudaMemsetAsync(h->hist, 0, MAX_PASSES * RADIX * sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->tile_status, 0, (size_t)passes * tiles * RADIX * sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->tile_counter, 0, MAX_PASSES * sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->cell_start, 0, (size_t)g.ncells * sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->cell_end, 0, (size_t)g.ncells * sizeof(u32), h->stream));
+    {
+        u32 groups = std::max<u32>(n / 4, 1);
+        int blocks = (int)std::min<u64>((groups + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
+        k_cell_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(h->in_f[0], h->in_f[1], h->in_f[2], n, g, passes,
+                                                            h->keys[0], h->vals[0], h->hist);
+        KERNEL_CHECK(h);
+        k_scan_hist<<<1, RADIX, 0, h->stream>>>(h->hist, passes);
+        KERNEL_CHECK(h);
+    }
+    stage_end(h, RCD_STAGE_KEYS);
+
+    stage_begin(h, RCD_STAGE_SORT);
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        k_onesweep_pass<<<tiles, SORT_THREADS, 0, h->stream>>>(
+            h->keys[cur], h->vals[cur], h->keys[cur ^ 1], h->vals[cur ^ 1], n, p * RADIX_BITS,
+            h->hist + p * RADIX, h->tile_status + (size_t)p * tiles * RADIX, h->tile_counter + p);
+        KERNEL_CHECK(h);
+        cur ^= 1;
+    }
+    h->sorted_buf = cur;
+    stage_end(h, RCD_STAGE_SORT);
+
+    stage_begin(h, RCD_STAGE_REORDER);
+    k_reorder<<<(n + REORDER_THREADS - 1) / REORDER_THREADS, REORDER_THREADS, 0, h->stream>>>(
+        h->keys[cur], h->vals[cur], n, (u32)h->n_owned, input_state(h), h->P0, h->P1, h->P2, h->sorted_slot,
+        h->cell_start, h->cell_end);
+    KERNEL_CHECK(h);
+    stage_end(h, RCD_STAGE_REORDER);
+    h->index_valid = true;
+    h->index_cell_req = cell_req;
+    return RCD_OK;
+}
+
+int copy_in(rcd_handle h, void *dst, const void *src, size_t bytes, int32_t srckind) {
+    CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, srckind == RCD_SRC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                h->stream));
+    return RCD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rcd_version(void) { return RCD_VERSION; }
+
+const char *rcd_last_error(rcd_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rcd_create(const rcd_config *cfg, rcd_handle *out) {
+    if (!cfg || !out) return fail(nullptr, RCD_EINVAL, "rcd_create: null argument");
+    *out = nullptr;
+    if (cfg->max_objects == 0 || cfg->max_objects >= (1ull << 30))
+        return fail(nullptr, RCD_EINVAL, "rcd_create: max_objects must be in [1, 2^30)");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        (void)cudaGetLastError();
+        return fail(nullptr, RCD_ENODEVICE, "rcd_create: no usable CUDA device (this library has no CPU fallback)");
+    }
+    rcd_handle h = new (std::nothrow) rcd_handle_s();
+    if (!h) return fail(nullptr, RCD_ENOMEM, "rcd_create: out of host memory");
+    h->device = cfg->device;
+    h->flags = cfg->flags;
+    h->cap = cfg->max_objects;
+    h->max_pairs = std::max<u64>(cfg->max_pairs, 1);
+    h->world_static = cfg->world_min[0] <= cfg->world_max[0];
+    for (int d = 0; d < 3; ++d) { h->wmin[d] = cfg->world_min[d]; h->wmax[d] = cfg->world_max[d]; }
+    h->cells_cap = (u32)std::min<u64>(std::max<u64>(4 * h->cap, CELLS_CAP_MIN), CELLS_CAP_MAX);
+
+#define CREATE_TRY(call)                                                                   \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            int rc__ = fail(nullptr, e__ == cudaErrorMemoryAllocation ? RCD_ENOMEM : RCD_ECUDA, \
+                            std::string(#call) + ": " + cudaGetErrorString(e__));         \
+            rcd_destroy(h);                                                                \
+            return rc__;                                                                   \
+        }                                                                                  \
+    } while (0)
+
+    CREATE_TRY(cudaSetDevice(h->device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    const size_t cap = (size_t)h->cap;
+    for (int k = 0; k < 11; ++k) {
+        CREATE_TRY(dev_alloc(&h->in_f[k], cap));
+        CREATE_TRY(cudaMemsetAsync(h->in_f[k], 0, cap * sizeof(float), h->stream));
+    }
+    CREATE_TRY(dev_alloc(&h->in_type, cap));
+    CREATE_TRY(dev_alloc(&h->in_pattern, cap));
+    CREATE_TRY(dev_alloc(&h->in_id, cap));
+    for (int k = 0; k < 2; ++k) {
+        CREATE_TRY(dev_alloc(&h->keys[k], cap + 4));
+        CREATE_TRY(dev_alloc(&h->vals[k], cap + 4));
+    }
+    CREATE_TRY(dev_alloc(&h->hist, MAX_PASSES * RADIX));
+    h->tile_status_words = (size_t)MAX_PASSES * ((cap + SORT_TILE - 1) / SORT_TILE) * RADIX;
+    CREATE_TRY(dev_alloc(&h->tile_status, h->tile_status_words));
+    CREATE_TRY(dev_alloc(&h->tile_counter, MAX_PASSES));
+    CREATE_TRY(dev_alloc(&h->P0, cap));
+    CREATE_TRY(dev_alloc(&h->P1, cap));
+    CREATE_TRY(dev_alloc(&h->P2, cap));
+    CREATE_TRY(dev_alloc(&h->sorted_slot, cap));
+    CREATE_TRY(dev_alloc(&h->cell_start, h->cells_cap));
+    CREATE_TRY(dev_alloc(&h->cell_end, h->cells_cap));
+    CREATE_TRY(dev_alloc(&h->bbox_dev, 6));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->bbox_host), 6 * sizeof(int)));
+    CREATE_TRY(dev_alloc(&h->out, (size_t)h->max_pairs));
+    CREATE_TRY(dev_alloc(&h->counters, 1));
+    CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->counters_host), sizeof(Counters)));
+    CREATE_TRY(dev_alloc(&h->cand_count, cap));
+    for (int s = 0; s < RCD_NUM_STAGES; ++s) {
+        CREATE_TRY(cudaEventCreate(&h->stages[s].begin));
+        CREATE_TRY(cudaEventCreate(&h->stages[s].end));
+    }
+    CREATE_TRY(cudaStreamSynchronize(h->stream));
+#undef CREATE_TRY
+    *out = h;
+    return RCD_OK;
+}
+
+int rcd_destroy(rcd_handle h) {
+    if (!h) return RCD_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int k = 0; k < 11; ++k) cudaFree(h->in_f[k]);
+    cudaFree(h->in_type); cudaFree(h->in_pattern); cudaFree(h->in_id);
+    for (int k = 0; k < 2; ++k) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
+    cudaFree(h->hist); cudaFree(h->tile_status); cudaFree(h->tile_counter);
+    cudaFree(h->P0); cudaFree(h->P1); cudaFree(h->P2); cudaFree(h->sorted_slot);
+    cudaFree(h->cell_start); cudaFree(h->cell_end); cudaFree(h->bbox_dev);
+    if (h->bbox_host) cudaFreeHost(h->bbox_host);
+    cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count);
+    if (h->counters_host) cudaFreeHost(h->counters_host);
+    for (int s = 0; s < RCD_NUM_STAGES; ++s) {
+        if (h->stages[s].begin) cudaEventDestroy(h->stages[s].begin);
+        if (h->stages[s].end) cudaEventDestroy(h->stages[s].end);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    (void)cudaGetLastError();
+    delete h;
+    return RCD_OK;
+}
+
+int rcd_upload(rcd_handle h, uint64_t n, const float *px, const float *py, const float *pz, const float *vx,
+               const float *vy, const float *vz, const float *ax, const float *ay, const float *az,
+               const float *size, const float *heading, const uint8_t *type, const uint32_t *id, int32_t src) {
+    if (!h) return RCD_EINVAL;
+    if (n > h->cap) return fail(h, RCD_ECAPACITY, "rcd_upload: n exceeds max_objects");
+    if (n && (!px || !py || !pz || !vx || !vy || !vz)) return fail(h, RCD_EINVAL, "rcd_upload: position/velocity arrays are required");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (int s = 0; s < RCD_NUM_STAGES; ++s) h->stages[s].used = false;
+    stage_begin(h, RCD_STAGE_UPLOAD);
+    const float *f[11] = {px, py, pz, vx, vy, vz, ax, ay, az, size, heading};
+    const size_t bytes = (size_t)n * sizeof(float);
+    for (int k = 0; k < 11 && n; ++k) {
+        if (f[k]) {
+            int rc = copy_in(h, h->in_f[k], f[k], bytes, src);
+            if (rc) return rc;
+        } else {
+            CUDA_TRY(h, cudaMemsetAsync(h->in_f[k], 0, bytes, h->stream));
+        }
+    }
+    if (n) {
+        if (type) { int rc = copy_in(h, h->in_type, type, (size_t)n, src); if (rc) return rc; }
+        else CUDA_TRY(h, cudaMemsetAsync(h->in_type, 0, (size_t)n, h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(h->in_pattern, RCD_PAT_ACCELERATING, (size_t)n, h->stream));
+        if (id) { int rc = copy_in(h, h->in_id, id, (size_t)n * sizeof(u32), src); if (rc) return rc; }
+        else {
+            k_iota<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->in_id, (u32)n);
+            KERNEL_CHECK(h);
+        }
+    }
+    stage_end(h, RCD_STAGE_UPLOAD);
+    h->n = n;
+    h->n_owned = n;
+    h->index_valid = false;
+    h->frame_done = false;
+    return RCD_OK;
+}
+
+int rcd_set_patterns(rcd_handle h, uint64_t n, const uint8_t *pattern, int32_t src) {
+    if (!h) return RCD_EINVAL;
+    if (n > h->n) return fail(h, RCD_EINVAL, "rcd_set_patterns: n exceeds the uploaded object count");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (n) {
+        if (pattern) { int rc = copy_in(h, h->in_pattern, pattern, (size_t)n, src); if (rc) return rc; }
+        else CUDA_TRY(h, cudaMemsetAsync(h->in_pattern, RCD_PAT_ACCELERATING, (size_t)n, h->stream));
+    }
+    h->index_valid = false;  // the pattern is packed into the cell-ordered state
+    h->frame_done = false;
+    return RCD_OK;
+}
+
+int rcd_set_owned(rcd_handle h, uint64_t n_owned) {
+    if (!h) return RCD_EINVAL;
+    if (n_owned > h->n) return fail(h, RCD_EINVAL, "rcd_set_owned: n_owned exceeds the object count");
+    h->n_owned = n_owned;
+    h->index_valid = false;
+    h->frame_done = false;
+    return RCD_OK;
+}
+
+int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window) {
+    if (!h) return RCD_EINVAL;
+    const bool append = (mode & RCD_STEP_APPEND) != 0;
+    mode &= ~RCD_STEP_APPEND;
+    if (mode < RCD_MODE_DETECT || mode > RCD_MODE_COMPUTE_NODE) return fail(h, RCD_EINVAL, "rcd_step: unknown mode");
+    if (append && !h->frame_done) return fail(h, RCD_ESTATE, "rcd_step: RCD_STEP_APPEND needs a previous step of this frame");
+    if (!(search_radius > 0.0f) || !std::isfinite(search_radius)) return fail(h, RCD_EINVAL, "rcd_step: search_radius must be positive");
+    if (mode == RCD_MODE_DETECT && !(time_window >= 0.0f)) return fail(h, RCD_EINVAL, "rcd_step: time_window must be >= 0");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!append) h->launches = 0;
+    h->frame_done = false;
+    stage_begin(h, RCD_STAGE_TOTAL);
+    const float cell_req = (mode == RCD_MODE_PREDICT) ? PREDICT_RADIUS : search_radius;
+    int rc = build_index(h, cell_req);
+    if (rc) return rc;
+
+    stage_begin(h, RCD_STAGE_PAIRS);
+    if (!append) CUDA_TRY(h, cudaMemsetAsync(h->counters, 0, sizeof(Counters), h->stream));
+    if (h->n) CUDA_TRY(h, cudaMemsetAsync(h->cand_count, 0, (size_t)h->n * sizeof(u32), h->stream));
+    if (h->n && h->n_owned) {
+        PairParams P;
+        P.n = (u32)h->n;
+        P.g = h->grid;
+        P.P0 = h->P0; P.P1 = h->P1; P.P2 = h->P2;
+        P.keys = h->keys[h->sorted_buf];
+        P.sorted_slot = h->sorted_slot;
+        P.in_id = h->in_id;
+        P.cell_start = h->cell_start; P.cell_end = h->cell_end;
+        P.R = search_radius;
+        P.T = time_window;
+        P.steps = (int)((double)time_window / 0.1);  // int(time_window / time_step), collision_detection.py:322
+        P.pt = 5.0f;         // CollisionDetector(prediction_time=5.0, risk_threshold=0.5), compute_node.py:218
+        P.threshold = 0.5f;
+        P.out = h->out;
+        P.out_cap = h->max_pairs;
+        P.counters = h->counters;
+        P.cand_count = h->cand_count;
+        const unsigned tiles = (unsigned)((h->n + TQ - 1) / TQ);
+        if (mode == RCD_MODE_DETECT) k_pairs<RCD_MODE_DETECT><<<tiles, TQ, 0, h->stream>>>(P);
+        else if (mode == RCD_MODE_PREDICT) k_pairs<RCD_MODE_PREDICT><<<tiles, TQ, 0, h->stream>>>(P);
+        else k_pairs<RCD_MODE_COMPUTE_NODE><<<tiles, TQ, 0, h->stream>>>(P);
+        KERNEL_CHECK(h);
+    }
+    stage_end(h, RCD_STAGE_PAIRS);
+    stage_end(h, RCD_STAGE_TOTAL);
+    h->frame_done = true;
+    h->last_mode = mode;
+    return RCD_OK;
+}
+
+int rcd_invalidate(rcd_handle h) {
+    if (!h) return RCD_EINVAL;
+    h->index_valid = false;
+    h->frame_done = false;
+    return RCD_OK;
+}
+
+int rcd_counts(rcd_handle h, rcd_counts_t *out) {
+    if (!h || !out) return RCD_EINVAL;
+    if (!h->frame_done) return fail(h, RCD_ESTATE, "rcd_counts: no frame has been stepped");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->counters_host, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const Counters &c = *h->counters_host;
+    out->n_objects = h->n;
+    out->n_owned = h->n_owned;
+    out->n_candidates = c.n_candidates;
+    out->n_potential = c.n_potential;
+    out->n_pairs = c.n_pairs;
+    out->n_high_risk = c.n_high_risk;
+    out->n_written = std::min<u64>(c.n_pairs, h->max_pairs);
+    for (int k = 0; k < 4; ++k) out->n_alerts[k] = c.n_alerts[k];
+    out->n_exact = c.n_exact;
+    return RCD_OK;
+}
+
+int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
+    if (!h || !n_out || (cap && !out)) return RCD_EINVAL;
+    rcd_counts_t c;
+    int rc = rcd_counts(h, &c);
+    if (rc) return rc;
+    stage_begin(h, RCD_STAGE_DOWNLOAD);
+    u64 m = std::min<u64>(c.n_written, cap);
+    if (m) {
+        CUDA_TRY(h, cudaMemcpyAsync(out, h->out, (size_t)m * sizeof(rcd_pair), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        std::sort(out, out + m, [](const rcd_pair &a, const rcd_pair &b) {
+            return a.i != b.i ? a.i < b.i : (a.j != b.j ? a.j < b.j : a.predicted < b.predicted);
+        });
+    }
+    stage_end(h, RCD_STAGE_DOWNLOAD);
+    *n_out = m;
+    return RCD_OK;
+}
+
+int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n) {
+    if (!h || (n && !out)) return RCD_EINVAL;
+    if (!h->frame_done) return fail(h, RCD_ESTATE, "rcd_download_candidate_counts: no frame has been stepped");
+    if (n > h->n) return fail(h, RCD_EINVAL, "rcd_download_candidate_counts: n exceeds the object count");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (n) CUDA_TRY(h, cudaMemcpyAsync(out, h->cand_count, (size_t)n * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return RCD_OK;
+}
+
+int rcd_query_radius(rcd_handle h, uint64_t nq, const float *qx, const float *qy, const float *qz, float radius,
+                     uint64_t *offsets, uint32_t *ids, uint64_t cap) {
+    if (!h || !offsets || (nq && (!qx || !qy || !qz)) || (cap && !ids)) return RCD_EINVAL;
+    if (!(radius >= 0.0f) || !std::isfinite(radius)) return fail(h, RCD_EINVAL, "rcd_query_radius: bad radius");
+    for (u64 q = 0; q <= nq; ++q) offsets[q] = 0;
+    if (nq == 0 || h->n == 0) return RCD_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    // reuse the index of the last frame if there is one, else build one with the default cell
+    int rc = build_index(h, h->index_valid ? h->index_cell_req : std::max(radius, 1.0f));
+    if (rc) return rc;
+    float *dq = nullptr;
+    uint2 *dhits = nullptr;
+    CUDA_TRY(h, dev_alloc(&dq, 3 * (size_t)nq));
+    cudaError_t e = dev_alloc(&dhits, (size_t)std::max<u64>(cap, 1));
+    if (e != cudaSuccess) { cudaFree(dq); return fail(h, RCD_ENOMEM, "rcd_query_radius: device allocation failed"); }
+    auto cleanup = [&]() { cudaFree(dq); cudaFree(dhits); };
+    cudaMemcpyAsync(dq, qx, nq * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(dq + nq, qy, nq * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    cudaMemcpyAsync(dq + 2 * nq, qz, nq * sizeof(float), cudaMemcpyHostToDevice, h->stream);
+    cudaMemsetAsync(&h->counters->n_query_hits, 0, sizeof(unsigned long long), h->stream);
+    const unsigned blocks = (unsigned)((nq * 32 + 127) / 128);
+    k_query_radius<<<blocks, 128, 0, h->stream>>>((u32)nq, dq, dq + nq, dq + 2 * nq, radius, h->grid, (u32)h->n, h->P0,
+                                                   h->keys[h->sorted_buf], h->sorted_slot, dhits, cap, h->counters);
+    e = cudaGetLastError();
+    unsigned long long total = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&total, &h->counters->n_query_hits, sizeof(total), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(h, RCD_ECUDA, std::string("rcd_query_radius: ") + cudaGetErrorString(e)); }
+    ++h->launches;
+    if (total > cap) {
+        offsets[nq] = total;  // tells the caller how much room a retry needs
+        cleanup();
+        return fail(h, RCD_ECAPACITY, "rcd_query_radius: result buffer too small");
+    }
+    std::vector<uint2> hits((size_t)total);
+    std::vector<u32> idmap;
+    if (total) e = cudaMemcpy(hits.data(), dhits, (size_t)total * sizeof(uint2), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+        idmap.resize((size_t)h->n);
+        e = cudaMemcpy(idmap.data(), h->in_id, (size_t)h->n * sizeof(u32), cudaMemcpyDeviceToHost);
+    }
+    cleanup();
+    if (e != cudaSuccess) return fail(h, RCD_ECUDA, std::string("rcd_query_radius: ") + cudaGetErrorString(e));
+    std::sort(hits.begin(), hits.end(), [](const uint2 &a, const uint2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    for (const uint2 &hq : hits) offsets[hq.x + 1]++;
+    for (u64 q = 0; q < nq; ++q) offsets[q + 1] += offsets[q];
+    for (size_t k = 0; k < hits.size(); ++k) ids[k] = idmap[hits[k].y];
+    return RCD_OK;
+}
+
+int rcd_classify_patterns(rcd_handle h, uint64_t n, uint32_t stride, const double *samples, const uint32_t *count,
+                          uint8_t *pattern_out) {
+    if (!h || (n && (!samples || !count || !pattern_out)) || stride == 0) return RCD_EINVAL;
+    if (n == 0) return RCD_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    double *ds = nullptr;
+    u32 *dc = nullptr;
+    uint8_t *dout = nullptr;
+    const size_t ns = (size_t)n * stride * 4;
+    cudaError_t e = dev_alloc(&ds, ns);
+    if (e == cudaSuccess) e = dev_alloc(&dc, (size_t)n);
+    if (e == cudaSuccess) e = dev_alloc(&dout, (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ds, samples, ns * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dc, count, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_classify_patterns<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>((u32)n, stride, ds, dc, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pattern_out, dout, (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(ds); cudaFree(dc); cudaFree(dout);
+    if (e != cudaSuccess) return fail(h, e == cudaErrorMemoryAllocation ? RCD_ENOMEM : RCD_ECUDA,
+                                      std::string("rcd_classify_patterns: ") + cudaGetErrorString(e));
+    ++h->launches;
+    return RCD_OK;
+}
+
+int rcd_halo_pack(rcd_handle h, int32_t n_peers, int32_t self, const float *slab_lo, const float *slab_hi, float halo,
+                  void *out_records, uint64_t cap, uint64_t *counts) {
+    if (!h || !slab_lo || !slab_hi || !counts || n_peers < 1 || n_peers > MAX_PEERS || self < 0 || self >= n_peers)
+        return fail(h, RCD_EINVAL, "rcd_halo_pack: bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    for (int p = 0; p < n_peers; ++p) counts[p] = 0;
+    if (h->n_owned == 0) return RCD_OK;
+    SlabParams sp;
+    sp.n_peers = n_peers; sp.self = self; sp.halo = halo;
+    for (int p = 0; p < n_peers; ++p) { sp.lo[p] = slab_lo[p]; sp.hi[p] = slab_hi[p]; }
+    unsigned long long *dcnt = nullptr;
+    CUDA_TRY(h, dev_alloc(&dcnt, 2 * (size_t)MAX_PEERS));
+    unsigned long long host_cnt[MAX_PEERS] = {}, host_base[MAX_PEERS] = {};
+    const unsigned blocks = (unsigned)((h->n_owned + 255) / 256);
+    cudaError_t e = cudaMemsetAsync(dcnt, 0, 2 * MAX_PEERS * sizeof(unsigned long long), h->stream);
+    if (e == cudaSuccess) {
+        k_halo_pack<<<blocks, 256, 0, h->stream>>>((u32)h->n_owned, input_state(h), sp, 0, dcnt, dcnt + MAX_PEERS, nullptr, 0);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_cnt, dcnt, n_peers * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    u64 total = 0;
+    if (e == cudaSuccess) {
+        for (int p = 0; p < n_peers; ++p) { host_base[p] = total; total += host_cnt[p]; counts[p] = host_cnt[p]; }
+        if (total > cap || (total && !out_records)) {
+            cudaFree(dcnt);
+            return fail(h, RCD_ECAPACITY, "rcd_halo_pack: record buffer too small");
+        }
+    }
+    if (e == cudaSuccess && total) {
+        e = cudaMemsetAsync(dcnt, 0, MAX_PEERS * sizeof(unsigned long long), h->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dcnt + MAX_PEERS, host_base, n_peers * sizeof(unsigned long long), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) {
+            k_halo_pack<<<blocks, 256, 0, h->stream>>>((u32)h->n_owned, input_state(h), sp, 1, dcnt, dcnt + MAX_PEERS,
+                                                      static_cast<u32 *>(out_records), cap);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(dcnt);
+    if (e != cudaSuccess) return fail(h, RCD_ECUDA, std::string("rcd_halo_pack: ") + cudaGetErrorString(e));
+    h->launches += total ? 2 : 1;
+    return RCD_OK;
+}
+
+int rcd_halo_append(rcd_handle h, const void *records, uint64_t n_records) {
+    if (!h || (n_records && !records)) return RCD_EINVAL;
+    if (h->n + n_records > h->cap) return fail(h, RCD_ECAPACITY, "rcd_halo_append: exceeds max_objects");
+    if (n_records == 0) return RCD_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    MutableState st;
+    for (int k = 0; k < 11; ++k) st.f[k] = h->in_f[k];
+    st.type = h->in_type; st.pattern = h->in_pattern; st.id = h->in_id;
+    k_halo_append<<<(unsigned)((n_records + 255) / 256), 256, 0, h->stream>>>(static_cast<const u32 *>(records),
+                                                                             (u32)n_records, (u32)h->n, st);
+    KERNEL_CHECK(h);
+    h->n += n_records;
+    h->index_valid = false;
+    h->frame_done = false;
+    return RCD_OK;
+}
+
+int rcd_stage_ms(rcd_handle h, float *ms) {
+    if (!h || !ms) return RCD_EINVAL;
+    if (!(h->flags & RCD_FLAG_PROFILE)) return fail(h, RCD_ESTATE, "rcd_stage_ms: handle was created without RCD_FLAG_PROFILE");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int s = 0; s < RCD_NUM_STAGES; ++s) {
+        ms[s] = 0.0f;
+        if (h->stages[s].used) {
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, h->stages[s].begin, h->stages[s].end) == cudaSuccess) ms[s] = t;
+            else (void)cudaGetLastError();
+        }
+    }
+    return RCD_OK;
+}
+
+int rcd_launch_count(rcd_handle h, uint64_t *n) {
+    if (!h || !n) return RCD_EINVAL;
+    *n = h->launches;
+    return RCD_OK;
+}
+
+int rcd_sync(rcd_handle h) {
+    if (!h) return RCD_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return RCD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,307 @@
+// Spatial index build: cell keys -> hand-written onesweep radix sort -> cell-ordered packed
+// state + cell ranges.  Replaces the per-vehicle dict/set churn of SpatialIndex.insert_vehicle
+// (src/collision/spatial_index.py:162-227) and compute_node.SpatialIndex.insert
+// (src/compute/compute_node.py:55-96) with one whole-frame rebuild, which is also what the
+// reference's perf harness times (src/test/performance_test.py:794-800: clear + N x insert).
+#pragma once
+#include "rcd_common.cuh"
+
+namespace rcd {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int MAX_PASSES = 4;
+
+// SoA input state as uploaded (device pointers)
+struct InputState {
+    const float *px, *py, *pz, *vx, *vy, *vz, *ax, *ay, *az, *size, *heading;
+    const uint8_t *type;
+    const uint8_t *pattern;
+    const u32 *id;  // may be null -> identity
+};
+
+// -------------------------------------------------------------------------------------------------
+// K1: cell keys + identity permutation + digit histograms of every pass (one read of x,y,z).
+// Algorithmic bytes: 12 N read + 8 N written.
+// -------------------------------------------------------------------------------------------------
+constexpr int KEYS_THREADS = 256;
+
+__global__ void __launch_bounds__(KEYS_THREADS)
+k_cell_keys(const float *__restrict__ px, const float *__restrict__ py, const float *__restrict__ pz,
+            u32 n, GridParams g, int passes, u32 *__restrict__ keys, u32 *__restrict__ vals,
+            u32 *__restrict__ hist /* [MAX_PASSES][RADIX] */) {
+    __shared__ u32 s_hist[MAX_PASSES][RADIX];
+    for (int k = threadIdx.x; k < MAX_PASSES * RADIX; k += KEYS_THREADS) (&s_hist[0][0])[k] = 0;
+    __syncthreads();
+
+    const u32 n4 = n >> 2;  // groups of 4 objects: 128-bit loads / stores (arrays are 256 B aligned)
+    const u32 stride = gridDim.x * KEYS_THREADS;
+    for (u32 q = blockIdx.x * KEYS_THREADS + threadIdx.x; q < n4; q += stride) {
+        float4 x = __ldcs(reinterpret_cast<const float4 *>(px) + q);
+        float4 y = __ldcs(reinterpret_cast<const float4 *>(py) + q);
+        float4 z = __ldcs(reinterpret_cast<const float4 *>(pz) + q);
+        uint4 k4;
+        k4.x = cell_key(g, x.x, y.x, z.x);
+        k4.y = cell_key(g, x.y, y.y, z.y);
+        k4.z = cell_key(g, x.z, y.z, z.z);
+        k4.w = cell_key(g, x.w, y.w, z.w);
+        reinterpret_cast<uint4 *>(keys)[q] = k4;
+        reinterpret_cast<uint4 *>(vals)[q] = make_uint4(4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3);
+        for (int p = 0; p < passes; ++p) {
+            atomicAdd(&s_hist[p][(k4.x >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+            atomicAdd(&s_hist[p][(k4.y >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+            atomicAdd(&s_hist[p][(k4.z >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+            atomicAdd(&s_hist[p][(k4.w >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+        }
+    }
+    // tail (< 4 objects)
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) {
+        u32 i = (n4 << 2) + threadIdx.x;
+        u32 k = cell_key(g, px[i], py[i], pz[i]);
+        keys[i] = k;
+        vals[i] = i;
+        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(k >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < passes * RADIX; k += KEYS_THREADS) {
+        u32 c = (&s_hist[0][0])[k];
+        if (c) atomicAdd(&hist[k], c);
+    }
+}
+
+// K2: exclusive scan of each pass's 256-bin histogram (one block, one warp per 32 bins).
+__global__ void __launch_bounds__(RADIX) k_scan_hist(u32 *__restrict__ hist, int passes) {
+    __shared__ u32 s_warp[RADIX / 32];
+    for (int p = 0; p < passes; ++p) {
+        u32 v = hist[p * RADIX + threadIdx.x];
+        u32 incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane_id() >= (u32)o) incl += t;
+        }
+        if (lane_id() == 31) s_warp[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        u32 base = 0;
+        for (u32 w = 0; w < (threadIdx.x >> 5); ++w) base += s_warp[w];
+        hist[p * RADIX + threadIdx.x] = base + incl - v;
+        __syncthreads();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K3: one onesweep pass (LSD, 8-bit digit): a single read and a single write of keys + values
+// per pass.  Tiles take tickets from an atomic counter, so a tile only ever waits on tiles that
+// are already running (decoupled look-back, forward progress guaranteed inside one launch).
+// Ranking is stable: warp-striped loads, per-warp digit counters updated with match.any.
+// Algorithmic bytes per pass: 8 N read + 8 N written.
+// -------------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 8;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 2048 keys
+constexpr u32 STATUS_AGGREGATE = 1u << 30;
+constexpr u32 STATUS_PREFIX = 2u << 30;
+constexpr u32 STATUS_VALUE_MASK = (1u << 30) - 1u;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
+                u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 n, int shift,
+                const u32 *__restrict__ digit_base /* [RADIX] exclusive, this pass */,
+                volatile u32 *tile_status /* [tiles][RADIX], zeroed */, u32 *tile_counter) {
+    __shared__ u32 s_warp_hist[SORT_WARPS][RADIX];
+    __shared__ u32 s_digit_excl[RADIX];
+    __shared__ u32 s_global_base[RADIX];
+    __shared__ u32 s_scan[SORT_WARPS];
+    __shared__ u32 s_keys[SORT_TILE];
+    __shared__ u32 s_vals[SORT_TILE];
+    __shared__ u32 s_tile;
+
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int k = tid; k < SORT_WARPS * RADIX; k += SORT_THREADS) (&s_warp_hist[0][0])[k] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 tile_base = tile * SORT_TILE;
+    const u32 tile_count = min((u32)SORT_TILE, n - tile_base);
+
+    // ---- load (warp-striped: item k of lane l is element warp*ITEMS*32 + k*32 + l) and rank ----
+    u32 key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+    const u32 warp_base = warp * (SORT_ITEMS * 32);
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        u32 local = warp_base + k * 32 + lane;
+        bool valid = local < tile_count;
+        key[k] = valid ? __ldcs(keys_in + tile_base + local) : 0xffffffffu;
+        val[k] = valid ? __ldcs(vals_in + tile_base + local) : 0u;
+    }
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        u32 local = warp_base + k * 32 + lane;
+        bool valid = local < tile_count;
+        u32 digit = (key[k] >> shift) & (RADIX - 1);
+        // invalid lanes form their own group (digit 256) and do not touch the counters
+        u32 group = __match_any_sync(FULL_MASK, valid ? digit : (u32)RADIX);
+        u32 leader = __ffs(group) - 1;
+        u32 before = 0;
+        if (valid && lane == leader) {
+            before = s_warp_hist[warp][digit];
+            s_warp_hist[warp][digit] = before + __popc(group);
+        }
+        before = __shfl_sync(FULL_MASK, before, leader);
+        rank[k] = before + __popc(group & lt);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per digit (thread d): exclusive scan over warps, tile total ---------------------------
+    u32 total = 0;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+        u32 c = s_warp_hist[w][tid];
+        s_warp_hist[w][tid] = total;
+        total += c;
+    }
+    // publish this tile's digit count as early as possible
+    if (tile == 0) {
+        tile_status[tid] = STATUS_PREFIX | total;
+    } else {
+        tile_status[(size_t)tile * RADIX + tid] = STATUS_AGGREGATE | total;
+    }
+    // exclusive scan of the 256 digit totals -> start of each digit inside the sorted tile
+    {
+        u32 incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= (u32)o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        u32 base = 0;
+        for (u32 w = 0; w < warp; ++w) base += s_scan[w];
+        s_digit_excl[tid] = base + incl - total;
+    }
+    // ---- decoupled look-back for digit `tid` ----------------------------------------------------
+    u32 excl = 0;
+    if (tile > 0) {
+        int t = (int)tile - 1;
+        while (true) {
+            u32 st = tile_status[(size_t)t * RADIX + tid];
+            u32 flag = st & ~STATUS_VALUE_MASK;
+            if (flag == 0) continue;  // predecessor has a ticket, so it is running: spin
+            excl += st & STATUS_VALUE_MASK;
+            if (flag == STATUS_PREFIX) break;
+            --t;
+        }
+        tile_status[(size_t)tile * RADIX + tid] = STATUS_PREFIX | (excl + total);
+    }
+    s_global_base[tid] = digit_base[tid] + excl - s_digit_excl[tid];
+    __syncthreads();
+
+    // ---- scatter into shared memory in sorted order, then write runs to global ----------------
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        u32 local = warp_base + k * 32 + lane;
+        if (local < tile_count) {
+            u32 digit = (key[k] >> shift) & (RADIX - 1);
+            u32 pos = s_digit_excl[digit] + s_warp_hist[warp][digit] + rank[k];
+            s_keys[pos] = key[k];
+            s_vals[pos] = val[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        u32 idx = k * SORT_THREADS + tid;
+        if (idx < tile_count) {
+            u32 kk = s_keys[idx];
+            u32 digit = (kk >> shift) & (RADIX - 1);
+            u32 out = s_global_base[digit] + idx;
+            keys_out[out] = kk;
+            vals_out[out] = s_vals[idx];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// K4: gather the SoA state into cell order (three float4 planes) and mark the cell ranges.
+// Algorithmic bytes: 8 N (key + perm) + 46 N gathered + 56 N written (+ 8 B per occupied cell).
+// -------------------------------------------------------------------------------------------------
+constexpr int REORDER_THREADS = 256;
+
+__global__ void __launch_bounds__(REORDER_THREADS)
+k_reorder(const u32 *__restrict__ keys, const u32 *__restrict__ perm, u32 n, u32 n_owned, InputState in,
+          float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2,
+          u32 *__restrict__ sorted_id, u32 *__restrict__ cell_start, u32 *__restrict__ cell_end) {
+    u32 s = blockIdx.x * REORDER_THREADS + threadIdx.x;
+    if (s >= n) return;
+    u32 key = keys[s];
+    u32 src = perm[s];
+    u32 prev = (s > 0) ? keys[s - 1] : 0xffffffffu;
+    u32 next = (s + 1 < n) ? keys[s + 1] : 0xffffffffu;
+    if (s == 0 || key != prev) cell_start[key] = s;
+    if (s + 1 == n || key != next) cell_end[key] = s + 1;
+
+    float4 a, b, c;
+    a.x = in.px[src]; a.y = in.py[src]; a.z = in.pz[src];
+    a.w = in.size ? in.size[src] : 0.0f;
+    b.x = in.vx[src]; b.y = in.vy[src]; b.z = in.vz[src];
+    b.w = in.heading ? in.heading[src] : 0.0f;
+    c.x = in.ax ? in.ax[src] : 0.0f;
+    c.y = in.ay ? in.ay[src] : 0.0f;
+    c.z = in.az ? in.az[src] : 0.0f;
+    u32 meta = (in.type ? (u32)in.type[src] : 0u) | ((in.pattern ? (u32)(in.pattern[src] & 3u) : 2u) << 8) |
+               (src < n_owned ? META_OWNED : 0u);
+    c.w = __uint_as_float(meta);
+    P0[s] = a;
+    P1[s] = b;
+    P2[s] = c;
+    sorted_id[s] = src;
+}
+
+// bounding box of the positions (auto grid): ordered-int atomics
+__device__ __forceinline__ int float_ordered(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float ordered_float(int i) {
+    int j = i >= 0 ? i : i ^ 0x7fffffff;
+#ifdef __CUDA_ARCH__
+    return __int_as_float(j);
+#else
+    float f;
+    memcpy(&f, &j, 4);
+    return f;
+#endif
+}
+
+__global__ void __launch_bounds__(256)
+k_bbox(const float *__restrict__ px, const float *__restrict__ py, const float *__restrict__ pz, u32 n,
+       int *__restrict__ bbox /* min x,y,z, max x,y,z (ordered ints) */) {
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float p[3] = {px[i], py[i], pz[i]};
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            if (p[d] == p[d] && fabsf(p[d]) < 1.0e30f) {  // ignore non-finite coordinates
+                lo[d] = fminf(lo[d], p[d]);
+                hi[d] = fmaxf(hi[d], p[d]);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(FULL_MASK, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(FULL_MASK, hi[d], o));
+        }
+        if (lane_id() == 0) {
+            atomicMin(&bbox[d], float_ordered(lo[d]));
+            atomicMax(&bbox[3 + d], float_ordered(hi[d]));
+        }
+    }
+}
+
+}  // namespace rcd

@@ -1,0 +1,108 @@
+"""ctypes binding of librcd_b200.so (include/rcd.h).  Fails loudly: there is no CPU fallback.
+
+The library is built in-tree by ``realtime-collision-detection_b200/build.py`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB_PATH = os.path.join(_PKG, "librcd_b200.so")
+
+RCD_OK, RCD_EINVAL, RCD_ENODEVICE, RCD_ENOMEM, RCD_ECUDA, RCD_ECAPACITY, RCD_ESTATE = 0, -1, -2, -3, -4, -5, -6
+MODE_DETECT, MODE_PREDICT, MODE_COMPUTE_NODE = 0, 1, 2
+STEP_APPEND = 0x100
+SRC_HOST, SRC_DEVICE = 0, 1
+PAT_STATIONARY, PAT_CONSTANT_VELOCITY, PAT_ACCELERATING, PAT_NO_HISTORY = 0, 1, 2, 3
+FLAG_PROFILE = 1
+NUM_STAGES = 8
+STAGE_NAMES = ("upload", "keys", "sort", "reorder", "pairs", "finalize", "download", "total")
+HALO_RECORD_WORDS = 13
+
+# every symbol include/rcd.h declares (tests/test_abi.py checks the export table against this
+# list and against the header itself)
+SYMBOLS = (
+    "rcd_version", "rcd_last_error", "rcd_create", "rcd_destroy", "rcd_upload", "rcd_set_patterns",
+    "rcd_set_owned", "rcd_step", "rcd_invalidate", "rcd_counts", "rcd_download",
+    "rcd_download_candidate_counts", "rcd_query_radius", "rcd_classify_patterns", "rcd_halo_pack",
+    "rcd_halo_append", "rcd_stage_ms", "rcd_launch_count", "rcd_sync",
+)
+
+
+class RcdConfig(ctypes.Structure):
+    _fields_ = [("device", ctypes.c_int32), ("flags", ctypes.c_uint32), ("max_objects", ctypes.c_uint64),
+                ("max_pairs", ctypes.c_uint64), ("world_min", ctypes.c_float * 3),
+                ("world_max", ctypes.c_float * 3)]
+
+
+class RcdCounts(ctypes.Structure):
+    _fields_ = [("n_objects", ctypes.c_uint64), ("n_owned", ctypes.c_uint64), ("n_candidates", ctypes.c_uint64),
+                ("n_potential", ctypes.c_uint64), ("n_pairs", ctypes.c_uint64), ("n_high_risk", ctypes.c_uint64),
+                ("n_written", ctypes.c_uint64), ("n_alerts", ctypes.c_uint64 * 4), ("n_exact", ctypes.c_uint64)]
+
+
+# numpy mirror of rcd_pair (48 bytes)
+PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("ttc", "<f4"), ("distance", "<f4"), ("rel_speed", "<f4"),
+                       ("risk", "<f4"), ("cx", "<f4"), ("cy", "<f4"), ("cz", "<f4"), ("t_closest", "<f4"),
+                       ("d_closest", "<f4"), ("priority", "i1"), ("offset", "u1"), ("predicted", "u1"),
+                       ("reserved", "u1")])
+assert PAIR_DTYPE.itemsize == 48
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"librcd_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the CUDA library; raise if it was not built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python realtime-collision-detection_b200/build.py` "
+            "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, u32, i32, f32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int32, ctypes.c_float
+    L.rcd_version.restype = ctypes.c_int
+    L.rcd_version.argtypes = []
+    L.rcd_last_error.restype = ctypes.c_char_p
+    L.rcd_last_error.argtypes = [vp]
+    L.rcd_create.argtypes = [ctypes.POINTER(RcdConfig), ctypes.POINTER(vp)]
+    L.rcd_destroy.argtypes = [vp]
+    L.rcd_upload.argtypes = [vp, u64] + [vp] * 13 + [i32]
+    L.rcd_set_patterns.argtypes = [vp, u64, vp, i32]
+    L.rcd_set_owned.argtypes = [vp, u64]
+    L.rcd_step.argtypes = [vp, i32, f32, f32]
+    L.rcd_invalidate.argtypes = [vp]
+    L.rcd_counts.argtypes = [vp, ctypes.POINTER(RcdCounts)]
+    L.rcd_download.argtypes = [vp, vp, u64, ctypes.POINTER(u64)]
+    L.rcd_download_candidate_counts.argtypes = [vp, vp, u64]
+    L.rcd_query_radius.argtypes = [vp, u64, vp, vp, vp, f32, vp, vp, u64]
+    L.rcd_classify_patterns.argtypes = [vp, u64, u32, vp, vp, vp]
+    L.rcd_halo_pack.argtypes = [vp, i32, i32, vp, vp, f32, vp, u64, vp]
+    L.rcd_halo_append.argtypes = [vp, vp, u64]
+    L.rcd_stage_ms.argtypes = [vp, vp]
+    L.rcd_launch_count.argtypes = [vp, ctypes.POINTER(u64)]
+    L.rcd_sync.argtypes = [vp]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("rcd_last_error", "rcd_version"):
+            fn.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int, handle=None) -> None:
+    if rc != RCD_OK:
+        msg = load().rcd_last_error(handle)
+        raise NativeError(rc, msg.decode("utf-8", "replace") if msg else "")

@@ -1,0 +1,195 @@
+"""Whole-frame engine over the C-ABI: the additive batch API the drop-in classes are built on.
+
+One ``FrameEngine`` owns one ``rcd_handle`` (one GPU, one stream).  Frames are dicts of fp32 SoA
+numpy arrays (see ``workloads.py``) or raw device pointers.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+FRAME_FIELDS = ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "size", "heading")
+
+
+def _as(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _vp(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class FrameEngine:
+    """Batch interface: upload a frame, run detect / predict / compute-node for every object."""
+
+    def __init__(self, max_objects: int, max_pairs: Optional[int] = None, device: int = 0,
+                 world_bounds: Optional[Tuple[Sequence[float], Sequence[float]]] = None, profile: bool = False):
+        self._lib = N.load()
+        self._h = ctypes.c_void_p()
+        cfg = N.RcdConfig()
+        cfg.device = int(device)
+        cfg.flags = N.FLAG_PROFILE if profile else 0
+        cfg.max_objects = int(max(1, max_objects))
+        cfg.max_pairs = int(max_pairs if max_pairs is not None else max(4096, 16 * max_objects))
+        if world_bounds is None:
+            cfg.world_min[:] = [1.0, 1.0, 1.0]
+            cfg.world_max[:] = [0.0, 0.0, 0.0]
+        else:
+            cfg.world_min[:] = [float(v) for v in world_bounds[0]]
+            cfg.world_max[:] = [float(v) for v in world_bounds[1]]
+        self.max_objects = int(cfg.max_objects)
+        self.max_pairs = int(cfg.max_pairs)
+        self.device = int(device)
+        self.n = 0
+        N.check(self._lib.rcd_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.rcd_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- state ------------------------------------------------------------------------------
+    def upload(self, frame: Dict[str, np.ndarray], ids: Optional[np.ndarray] = None) -> None:
+        """N x update_vehicle (collision_detection.py:74-85) as one SoA copy."""
+        arrs = [_as(frame[k], np.float32) for k in FRAME_FIELDS]
+        n = int(arrs[0].shape[0])
+        typ = _as(frame["type"], np.uint8) if "type" in frame else None
+        idv = _as(ids, np.uint32) if ids is not None else None
+        self._keep = (arrs, typ, idv)  # keep the host buffers alive until the copies are done
+        N.check(self._lib.rcd_upload(self._h, n, *[_vp(a) for a in arrs], _vp(typ), _vp(idv), N.SRC_HOST), self._h)
+        self.n = n
+
+    def upload_device(self, n: int, ptrs: Sequence[int], type_ptr: int = 0, id_ptr: int = 0) -> None:
+        """Same, from 11 device pointers (float32, n entries each) in FRAME_FIELDS order."""
+        args = [ctypes.c_void_p(int(p)) if p else None for p in ptrs]
+        N.check(self._lib.rcd_upload(self._h, int(n), *args, ctypes.c_void_p(type_ptr) if type_ptr else None,
+                                     ctypes.c_void_p(id_ptr) if id_ptr else None, N.SRC_DEVICE), self._h)
+        self.n = int(n)
+
+    def set_patterns(self, pattern: Optional[np.ndarray]) -> None:
+        if pattern is None:
+            N.check(self._lib.rcd_set_patterns(self._h, self.n, None, N.SRC_HOST), self._h)
+            return
+        p = _as(pattern, np.uint8)
+        self._keep_pat = p
+        N.check(self._lib.rcd_set_patterns(self._h, int(p.shape[0]), _vp(p), N.SRC_HOST), self._h)
+
+    def set_owned(self, n_owned: int) -> None:
+        N.check(self._lib.rcd_set_owned(self._h, int(n_owned)), self._h)
+
+    def invalidate(self) -> None:
+        N.check(self._lib.rcd_invalidate(self._h), self._h)
+
+    # -- frames -----------------------------------------------------------------------------
+    def step(self, mode: int, search_radius: float = 100.0, time_window: float = 10.0, append: bool = False) -> None:
+        m = int(mode) | (N.STEP_APPEND if append else 0)
+        N.check(self._lib.rcd_step(self._h, m, float(search_radius), float(time_window)), self._h)
+
+    def counts(self) -> Dict[str, int]:
+        c = N.RcdCounts()
+        N.check(self._lib.rcd_counts(self._h, ctypes.byref(c)), self._h)
+        return {"n_objects": c.n_objects, "n_owned": c.n_owned, "n_candidates": c.n_candidates,
+                "n_potential": c.n_potential, "n_pairs": c.n_pairs, "n_high_risk": c.n_high_risk,
+                "n_written": c.n_written, "n_alerts": [int(v) for v in c.n_alerts], "n_exact": c.n_exact}
+
+    def download(self, cap: Optional[int] = None) -> np.ndarray:
+        cap = int(self.max_pairs if cap is None else cap)
+        c = self.counts()
+        m = min(cap, int(c["n_written"]))
+        out = np.zeros(m, N.PAIR_DTYPE)
+        got = ctypes.c_uint64(0)
+        N.check(self._lib.rcd_download(self._h, _vp(out), m, ctypes.byref(got)), self._h)
+        return out[: got.value]
+
+    def candidate_counts(self) -> np.ndarray:
+        out = np.zeros(int(self.counts()["n_objects"]), np.uint32)
+        N.check(self._lib.rcd_download_candidate_counts(self._h, _vp(out), out.shape[0]), self._h)
+        return out
+
+    def detect(self, search_radius: float = 100.0, time_window: float = 10.0) -> np.ndarray:
+        self.step(N.MODE_DETECT, search_radius, time_window)
+        return self.download()
+
+    def predict(self) -> np.ndarray:
+        self.step(N.MODE_PREDICT)
+        return self.download()
+
+    def compute_node(self, search_radius: float = 100.0) -> np.ndarray:
+        self.step(N.MODE_COMPUTE_NODE, search_radius)
+        return self.download()
+
+    # -- queries ----------------------------------------------------------------------------
+    def query_radius(self, queries, radius: float):
+        """get_nearby_vehicles / query_nearby for a batch of points -> list of id arrays."""
+        q = _as(queries, np.float32).reshape(-1, 3)
+        nq = q.shape[0]
+        qx, qy, qz = (np.ascontiguousarray(q[:, k]) for k in range(3))
+        offs = np.zeros(nq + 1, np.uint64)
+        cap = max(1024, 64 * nq)
+        for _ in range(3):
+            ids = np.zeros(cap, np.uint32)
+            rc = self._lib.rcd_query_radius(self._h, nq, _vp(qx), _vp(qy), _vp(qz), float(radius), _vp(offs),
+                                            _vp(ids), cap)
+            if rc == N.RCD_ECAPACITY:
+                cap = int(offs[nq]) + 16
+                continue
+            N.check(rc, self._h)
+            break
+        else:  # pragma: no cover
+            raise N.NativeError(N.RCD_ECAPACITY, "query_radius: result buffer kept overflowing")
+        return [ids[int(offs[k]): int(offs[k + 1])].copy() for k in range(nq)]
+
+    def classify_patterns(self, samples: np.ndarray, count: np.ndarray) -> np.ndarray:
+        """samples: float64 [n, stride, 4] (x, y, z, t) in timestamp order; count: valid samples."""
+        s = _as(samples, np.float64)
+        n, stride = int(s.shape[0]), int(s.shape[1])
+        c = _as(count, np.uint32)
+        out = np.zeros(n, np.uint8)
+        N.check(self._lib.rcd_classify_patterns(self._h, n, stride, _vp(s), _vp(c), _vp(out)), self._h)
+        return out
+
+    # -- slabs ------------------------------------------------------------------------------
+    def halo_pack(self, slab_lo, slab_hi, self_rank: int, halo: float, out_ptr: int, cap: int) -> np.ndarray:
+        lo = _as(slab_lo, np.float32)
+        hi = _as(slab_hi, np.float32)
+        counts = np.zeros(lo.shape[0], np.uint64)
+        N.check(self._lib.rcd_halo_pack(self._h, int(lo.shape[0]), int(self_rank), _vp(lo), _vp(hi), float(halo),
+                                        ctypes.c_void_p(int(out_ptr)) if out_ptr else None, int(cap), _vp(counts)),
+                self._h)
+        return counts.astype(np.int64)
+
+    def halo_append(self, rec_ptr: int, n_records: int) -> None:
+        N.check(self._lib.rcd_halo_append(self._h, ctypes.c_void_p(int(rec_ptr)) if rec_ptr else None,
+                                          int(n_records)), self._h)
+        self.n += int(n_records)
+
+    # -- instrumentation -----------------------------------------------------------------------
+    def stage_ms(self) -> Dict[str, float]:
+        ms = np.zeros(N.NUM_STAGES, np.float32)
+        N.check(self._lib.rcd_stage_ms(self._h, _vp(ms)), self._h)
+        return {name: float(ms[k]) for k, name in enumerate(N.STAGE_NAMES)}
+
+    def launch_count(self) -> int:
+        v = ctypes.c_uint64(0)
+        N.check(self._lib.rcd_launch_count(self._h, ctypes.byref(v)), self._h)
+        return int(v.value)
+
+    def sync(self) -> None:
+        N.check(self._lib.rcd_sync(self._h), self._h)

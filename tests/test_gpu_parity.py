@@ -1,0 +1,294 @@
+"""GPU parity: the CUDA path through the C-ABI against (a) the golden vectors produced by the
+reference's own bytecode and (b) the CPU oracle on fresh seeded frames.  Pair sets bit-exact,
+values within tolerance (tests/gpu_helpers.py)."""
+import numpy as np
+import pytest
+
+from tests.gpu_helpers import compare_counts, compare_pairs
+from tests.helpers import assert_pairs_equal, f64_frame, load_golden
+
+pytestmark = pytest.mark.gpu
+
+DETECT = ["detect_dense3d.npz", "detect_2d_noaccel.npz", "detect_r60_t4.npz", "detect_city1k.npz"]
+PREDICT = ["predict_dense3d.npz", "predict_2d_allcv.npz", "predict_city300.npz"]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from rcd_b200.host.engine import FrameEngine
+    e = FrameEngine(max_objects=1_100_000, max_pairs=4_000_000, profile=True)
+    yield e
+    e.close()
+
+
+def _oracle():
+    from oracle import oracle as O
+    return O
+
+
+def _risks_from_golden(tab, with_offset=False):
+    from oracle.oracle import RISK_DTYPE
+    r = np.zeros(len(tab), RISK_DTYPE)
+    for k, c in enumerate(("i", "j", "ttc", "distance", "rel_speed", "risk", "cx", "cy", "cz")):
+        r[c] = tab[:, k]
+    return r
+
+
+@pytest.mark.parametrize("name", DETECT)
+def test_detect_golden(eng, name):
+    z, frame = load_golden(name)
+    eng.upload(frame)
+    got = eng.detect(float(z["R"]), float(z["T"]))
+    want = z["risks"]
+    assert_pairs_equal(np.stack([got["i"], got["j"]], 1), want[:, :2], "detect pair set vs reference golden")
+    ora = _oracle().frame_A(f64_frame(frame), "detect", R=float(z["R"]), T=float(z["T"]))
+    compare_pairs(got, ora["risks"], "detect")
+    c = eng.counts()
+    assert c["n_candidates"] == len(z["candidates"])
+    assert np.array_equal(eng.candidate_counts(), np.bincount(z["candidates"][:, 0], minlength=len(frame["px"])))
+    assert c["n_potential"] == int(z["stat_potential"]) and c["n_high_risk"] == int(z["stat_high"])
+    # stage-2 values ride along with every emitted pair
+    pots = {(int(p[0]), int(p[1])): (p[2], p[3]) for p in z["potentials"]}
+    for r in got:
+        tc, cd = pots[(int(r["i"]), int(r["j"]))]
+        assert abs(r["t_closest"] - tc) <= 1e-6 * abs(tc) + 1e-7 and abs(r["d_closest"] - cd) <= 1e-6 * cd + 1e-7
+
+
+@pytest.mark.parametrize("name", PREDICT)
+def test_predict_golden(eng, name):
+    z, frame = load_golden(name)
+    eng.upload(frame)
+    eng.set_patterns(z["pattern"])
+    got = eng.predict()
+    assert_pairs_equal(np.stack([got["i"], got["j"]], 1), z["risks"][:, :2], "predict pair set vs reference golden")
+    assert np.array_equal(got["predicted"].astype(bool), z["is_predicted"])
+    ora = _oracle().frame_A(f64_frame(frame), "predict", pattern_codes=z["pattern"])
+    compare_pairs(got, ora["risks"], "predict")
+    compare_counts(eng.counts(), eng.candidate_counts(), ora, "predict")
+
+
+def test_compute_node_golden(eng):
+    z, frame = load_golden("implB_dense.npz")
+    eng.upload(frame)
+    eng.set_patterns(z["has_history"].astype(np.uint8))
+    got = eng.compute_node(100.0)
+    assert_pairs_equal(np.stack([got["i"], got["j"]], 1), z["risks"][:, :2], "compute-node pair set vs golden")
+    ora = _oracle().frame_B(f64_frame(frame), z["has_history"])
+    compare_pairs(got, ora["risks"], "compute_node")
+    compare_counts(eng.counts(), eng.candidate_counts(), ora, "compute_node")
+
+
+@pytest.mark.parametrize("seed,n,box,drones,static_bounds", [
+    (11, 3000, 900.0, 0.3, False), (12, 6000, 1500.0, 0.0, True), (13, 2049, 500.0, 0.5, False),
+    (14, 20000, 4000.0, 0.3, True), (15, 4097, 700.0, 0.2, False)])
+def test_detect_and_predict_vs_oracle(seed, n, box, drones, static_bounds):
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    O = _oracle()
+    frame = W.uniform_frame(n, seed, map_size=box, drone_fraction=drones)
+    pat = W.random_patterns(n, seed + 100)
+    bounds = ((0, 0, 0), (box, box, 100.0)) if static_bounds else None
+    with FrameEngine(n, 64 * n, world_bounds=bounds) as e:
+        e.upload(frame)
+        got = e.detect()
+        ora = O.frame_A(f64_frame(frame), "detect")
+        compare_pairs(got, ora["risks"], "detect")
+        compare_counts(e.counts(), e.candidate_counts(), ora, "detect")
+        e.set_patterns(pat)
+        got = e.predict()
+        ora = O.frame_A(f64_frame(frame), "predict", pattern_codes=pat)
+        compare_pairs(got, ora["risks"], "predict")
+        compare_counts(e.counts(), e.candidate_counts(), ora, "predict")
+
+
+def test_append_mode_is_detect_plus_predict(eng):
+    from rcd_b200.host import _native as N
+    from rcd_b200.host import workloads as W
+    frame = W.uniform_frame(5000, 21, map_size=1200.0, drone_fraction=0.3)
+    eng.upload(frame)
+    eng.set_patterns(np.full(5000, 1, np.uint8))
+    d = eng.detect()
+    cd = eng.counts()
+    p = eng.predict()
+    cp = eng.counts()
+    eng.step(N.MODE_DETECT)
+    eng.step(N.MODE_PREDICT, append=True)
+    both = eng.download()
+    cb = eng.counts()
+    assert len(both) == len(d) + len(p) > 0
+    assert cb["n_candidates"] == cd["n_candidates"] + cp["n_candidates"]
+    assert np.array_equal(np.sort(both[both["predicted"] == 0], order=["i", "j"]), d)
+    assert np.array_equal(np.sort(both[both["predicted"] == 1], order=["i", "j"]), p)
+
+
+@pytest.mark.parametrize("R,T", [(10.0, 10.0), (250.0, 3.0), (100.0, 0.05), (37.5, 20.0)])
+def test_detect_nondefault_radius_and_window(eng, R, T):
+    from rcd_b200.host import workloads as W
+    frame = W.uniform_frame(4000, 31, map_size=1000.0, drone_fraction=0.3)
+    eng.upload(frame)
+    got = eng.detect(R, T)
+    ora = _oracle().frame_A(f64_frame(frame), "detect", R=R, T=T)
+    compare_pairs(got, ora["risks"], "detect")
+    compare_counts(eng.counts(), eng.candidate_counts(), ora, "detect")
+
+
+def test_edge_cases(eng):
+    from rcd_b200.host import workloads as W
+    O = _oracle()
+    # empty frame and single object
+    for n in (0, 1):
+        eng.upload(W.uniform_frame(n, 1))
+        assert len(eng.detect()) == 0 and len(eng.predict()) == 0
+        c = eng.counts()
+        assert c["n_candidates"] == 0 and c["n_pairs"] == 0 and c["n_objects"] == n
+    # coincident objects, negative coordinates, everything in one cell, stationary vehicles
+    f = W.uniform_frame(300, 41, map_size=40.0, drone_fraction=0.3)
+    for k in ("px", "py"):
+        f[k] = (f[k] - 20.0).astype(np.float32)
+    f["px"][:10] = f["px"][0]; f["py"][:10] = f["py"][0]; f["pz"][:10] = f["pz"][0]
+    for k in ("vx", "vy", "vz", "ax", "ay", "az"):
+        f[k][100:160] = 0.0
+    pat = W.random_patterns(300, 42)
+    eng.upload(f)
+    got = eng.detect()
+    ora = O.frame_A(f64_frame(f), "detect")
+    compare_pairs(got, ora["risks"], "detect")
+    compare_counts(eng.counts(), eng.candidate_counts(), ora, "detect")
+    eng.set_patterns(pat)
+    got = eng.predict()
+    ora = O.frame_A(f64_frame(f), "predict", pattern_codes=pat)
+    compare_pairs(got, ora["risks"], "predict")
+    compare_counts(eng.counts(), eng.candidate_counts(), ora, "predict")
+
+
+def test_objects_outside_static_bounds_are_clamped_not_lost():
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    frame = W.uniform_frame(5000, 51, map_size=1500.0, drone_fraction=0.3)
+    # the grid only covers the middle of the map: everything else lands in border cells
+    with FrameEngine(5000, 500000, world_bounds=((500, 500, 20), (1000, 1000, 60))) as e:
+        e.upload(frame)
+        got = e.detect()
+        ora = _oracle().frame_A(f64_frame(frame), "detect")
+        compare_pairs(got, ora["risks"], "detect")
+        compare_counts(e.counts(), e.candidate_counts(), ora, "detect")
+
+
+def test_pair_buffer_overflow_keeps_counts_exact():
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    frame = W.uniform_frame(3000, 61, map_size=300.0, drone_fraction=0.3)
+    ora = _oracle().frame_A(f64_frame(frame), "detect")
+    assert ora["counts"][2] > 64
+    with FrameEngine(3000, 64) as e:
+        e.upload(frame)
+        got = e.detect()
+        c = e.counts()
+        assert len(got) == 64 and c["n_written"] == 64 and c["n_pairs"] == int(ora["counts"][2])
+
+
+def test_caller_ids_are_reported(eng):
+    from rcd_b200.host import workloads as W
+    frame = W.uniform_frame(2000, 71, map_size=400.0)
+    ids = (np.arange(2000, dtype=np.uint32) * 7 + 1000)
+    eng.upload(frame, ids=ids)
+    got = eng.detect()
+    ora = _oracle().frame_A(f64_frame(frame), "detect")["risks"]
+    assert len(got) == len(ora) > 0
+    assert_pairs_equal(np.stack([got["i"], got["j"]], 1), np.stack([ids[ora["i"]], ids[ora["j"]]], 1), "ids")
+
+
+def test_radius_queries(eng):
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "scalars.npz"))
+    frame = {k[len("near_frame_"):]: z[k] for k in z.files if k.startswith("near_frame_")}
+    eng.upload(frame)
+    res = eng.query_radius(z["near_q"], float(z["near_radius"]))
+    off = z["near_off"]
+    for k, ids in enumerate(res):
+        assert np.array_equal(ids, z["near_ids"][off[k]:off[k + 1]]), f"query {k}"
+    # after a frame was built with a different cell size, and with a radius larger than the cell
+    eng.detect(30.0, 10.0)
+    q = np.random.default_rng(5).uniform(-100, 800, (200, 3)).astype(np.float32)
+    q[:, 2] *= 0.1
+    for radius in (5.0, 120.0):
+        res = eng.query_radius(q, radius)
+        want = _oracle().query_radius(f64_frame(frame), q.astype(np.float64), radius)
+        for a, b in zip(res, want):
+            assert np.array_equal(a, b)
+
+
+def test_pattern_classifier(eng):
+    import os
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "scalars.npz"))
+    off = z["hist_off"]
+    n = len(off) - 1
+    stride = int(np.max(np.diff(off)))
+    samples = np.zeros((n, max(stride, 1), 4))
+    count = np.diff(off).astype(np.uint32)
+    for k in range(n):
+        h = z["hist"][off[k]:off[k + 1]]
+        h = h[np.argsort(h[:, 3], kind="stable")]  # the reference sorts by timestamp (stable)
+        samples[k, :len(h)] = h
+    got = eng.classify_patterns(samples, count)
+    assert np.array_equal(got, z["hist_class"].astype(np.uint8))
+
+
+def test_two_slabs_with_halo_equal_one_domain():
+    """Spatial slabs emulated on one GPU: each slab owns its objects, receives the
+    packed halo of the other, and the union of the owners' results is the single-domain result."""
+    import torch
+    from rcd_b200.host import _native as N
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n, box = 8000, 2000.0
+    frame = W.uniform_frame(n, 81, map_size=box, drone_fraction=0.3)
+    ids = np.arange(n, dtype=np.uint32)
+    cut = float(np.median(frame["px"]))
+    lo, hi = np.array([-1e9, cut], np.float32), np.array([cut, 1e9], np.float32)
+    halo = 100.0 + 30.0 * 9.5 + 0.5 * 1.5 * 9.5 ** 2 + 1.0
+    pat = np.full(n, 2, np.uint8)
+    ora = _oracle().frame_A(f64_frame(frame), "predict", pattern_codes=pat)["risks"]
+    engines, bufs, counts, owned = [], [], [], []
+    for r in range(2):
+        m = (frame["px"] >= lo[r]) & (frame["px"] < hi[r])
+        owned.append(m)
+        e = FrameEngine(n, 64 * n)
+        e.upload(W.take(frame, m), ids=ids[m])
+        buf = torch.empty((n, N.HALO_RECORD_WORDS), dtype=torch.int32, device="cuda")
+        counts.append(e.halo_pack(lo, hi, r, halo, buf.data_ptr(), n))
+        engines.append(e); bufs.append(buf)
+    torch.cuda.synchronize()
+    got = []
+    for r in range(2):
+        src = 1 - r
+        assert counts[src][src] == 0 and counts[src][r] > 0
+        engines[r].halo_append(bufs[src].data_ptr(), int(counts[src][r]))
+        got.append(engines[r].predict())
+        assert engines[r].counts()["n_owned"] == int(owned[r].sum())
+    both = np.sort(np.concatenate(got), order=["i", "j"])
+    compare_pairs(both, ora, "predict")
+    for e in engines:
+        e.close()
+
+
+def test_full_size_100k_counts_and_pairs():
+    """configs[2] at full size: 100k uniform 2-D vehicles; oracle runs in about a second."""
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    frame = W.make_workload("cfg3_100k_uniform2d")
+    O = _oracle()
+    with FrameEngine(100_000, 2_000_000, world_bounds=((0, 0, 0), (10000, 10000, 0))) as e:
+        e.upload(frame)
+        got = e.detect()
+        ora = O.frame_A(f64_frame(frame), "detect", want_potentials=False)
+        compare_pairs(got, ora["risks"], "detect")
+        compare_counts(e.counts(), e.candidate_counts(), ora, "detect")
+        pat = np.ones(100_000, np.uint8)
+        e.set_patterns(pat)
+        got = e.predict()
+        ora = O.frame_A(f64_frame(frame), "predict", pattern_codes=pat, want_potentials=False)
+        compare_pairs(got, ora["risks"], "predict")
+        compare_counts(e.counts(), e.candidate_counts(), ora, "predict")
