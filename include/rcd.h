@@ -79,6 +79,11 @@ typedef struct {
 } rcd_config;
 
 #define RCD_FLAG_PROFILE 1u /* record CUDA events around every stage (rcd_stage_ms) */
+/* Predict mode: also count the (i, j, offset) radius hits of collision_detection.py:801-803 in
+ * n_candidates / the per-object counts.  The reference keeps no such statistic on the predict
+ * path; it is a diagnostic (and the parity tests use it) and costs one more distance test per
+ * offset.  Without the flag predict frames report candidates only for pattern-3 objects. */
+#define RCD_FLAG_COUNT_PREDICT_CANDIDATES 2u
 
 /* One emitted, directed pair (i -> j): the fields of the reference's CollisionRisk
  * (collision_detection.py:156-166, :831-842) plus the stage-2 values and the alert class
@@ -102,7 +107,8 @@ typedef struct {
 typedef struct {
     uint64_t n_objects;    /* objects in the frame (owned + halo) */
     uint64_t n_owned;      /* objects queried */
-    uint64_t n_candidates; /* directed broad-phase pairs (stage 1); B counts self like query_nearby */
+    uint64_t n_candidates; /* directed broad-phase pairs (stage 1); compute-node mode counts self like
+                              query_nearby; predict mode: see RCD_FLAG_COUNT_PREDICT_CANDIDATES */
     uint64_t n_potential;  /* stage-2 survivors (stats["potential_collisions"], :177) */
     uint64_t n_pairs;      /* emitted risks */
     uint64_t n_high_risk;  /* risk > 0.7 (stats["high_risk_collisions"], :178) */
@@ -192,8 +198,13 @@ int rcd_halo_pack(rcd_handle h, int32_t n_peers, int32_t self, const float *slab
 /* Append n_records packed halo records (DEVICE buffer) after the owned objects. */
 int rcd_halo_append(rcd_handle h, const void *records, uint64_t n_records);
 
-/* Milliseconds of each stage of the last frame (needs RCD_FLAG_PROFILE); synchronises. */
-int rcd_stage_ms(rcd_handle h, float *ms /* RCD_NUM_STAGES */);
+/* Milliseconds of each stage of the last rcd_step that ran in `mode` (needs RCD_FLAG_PROFILE);
+ * synchronises.  Index stages (keys, sort, reorder) are reported under the mode that built it;
+ * upload / download are reported under every mode. */
+int rcd_stage_ms(rcd_handle h, int32_t mode, float *ms /* RCD_NUM_STAGES */);
+/* The handle's CUDA stream (a cudaStream_t), so the caller can order its own work -- halo
+ * exchange with NCCL, timing events -- with the frame without extra synchronisation. */
+int rcd_get_stream(rcd_handle h, void **stream);
 /* Kernel launches issued by the last rcd_step (for bench.py's gpu_launches). */
 int rcd_launch_count(rcd_handle h, uint64_t *n);
 int rcd_sync(rcd_handle h);

@@ -64,7 +64,8 @@ struct rcd_handle_s {
     bool frame_done = false;
     int last_mode = -1;
 
-    Stage stages[RCD_NUM_STAGES];
+    Stage stages[3][RCD_NUM_STAGES];  // per frame mode
+    int stage_mode = 0;
     u64 launches = 0;
     std::string err;
 };
@@ -99,12 +100,12 @@ cudaError_t dev_alloc(T **p, size_t count) {
 
 void stage_begin(rcd_handle h, int s) {
     if (h->flags & RCD_FLAG_PROFILE) {
-        cudaEventRecord(h->stages[s].begin, h->stream);
-        h->stages[s].used = true;
+        cudaEventRecord(h->stages[h->stage_mode][s].begin, h->stream);
+        h->stages[h->stage_mode][s].used = true;
     }
 }
 void stage_end(rcd_handle h, int s) {
-    if (h->flags & RCD_FLAG_PROFILE) cudaEventRecord(h->stages[s].end, h->stream);
+    if (h->flags & RCD_FLAG_PROFILE) cudaEventRecord(h->stages[h->stage_mode][s].end, h->stream);
 }
 
 InputState input_state(rcd_handle h) {
@@ -296,10 +297,11 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->counters, 1));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->counters_host), sizeof(Counters)));
     CREATE_TRY(dev_alloc(&h->cand_count, cap));
-    for (int s = 0; s < RCD_NUM_STAGES; ++s) {
-        CREATE_TRY(cudaEventCreate(&h->stages[s].begin));
-        CREATE_TRY(cudaEventCreate(&h->stages[s].end));
-    }
+    for (int m = 0; m < 3; ++m)
+        for (int s = 0; s < RCD_NUM_STAGES; ++s) {
+            CREATE_TRY(cudaEventCreate(&h->stages[m][s].begin));
+            CREATE_TRY(cudaEventCreate(&h->stages[m][s].end));
+        }
     CREATE_TRY(cudaStreamSynchronize(h->stream));
 #undef CREATE_TRY
     *out = h;
@@ -319,10 +321,11 @@ int rcd_destroy(rcd_handle h) {
     if (h->bbox_host) cudaFreeHost(h->bbox_host);
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count);
     if (h->counters_host) cudaFreeHost(h->counters_host);
-    for (int s = 0; s < RCD_NUM_STAGES; ++s) {
-        if (h->stages[s].begin) cudaEventDestroy(h->stages[s].begin);
-        if (h->stages[s].end) cudaEventDestroy(h->stages[s].end);
-    }
+    for (int m = 0; m < 3; ++m)
+        for (int s = 0; s < RCD_NUM_STAGES; ++s) {
+            if (h->stages[m][s].begin) cudaEventDestroy(h->stages[m][s].begin);
+            if (h->stages[m][s].end) cudaEventDestroy(h->stages[m][s].end);
+        }
     if (h->stream) cudaStreamDestroy(h->stream);
     (void)cudaGetLastError();
     delete h;
@@ -336,7 +339,9 @@ int rcd_upload(rcd_handle h, uint64_t n, const float *px, const float *py, const
     if (n > h->cap) return fail(h, RCD_ECAPACITY, "rcd_upload: n exceeds max_objects");
     if (n && (!px || !py || !pz || !vx || !vy || !vz)) return fail(h, RCD_EINVAL, "rcd_upload: position/velocity arrays are required");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    for (int s = 0; s < RCD_NUM_STAGES; ++s) h->stages[s].used = false;
+    for (int m = 0; m < 3; ++m)
+        for (int s = 0; s < RCD_NUM_STAGES; ++s) h->stages[m][s].used = false;
+    h->stage_mode = 0;
     stage_begin(h, RCD_STAGE_UPLOAD);
     const float *f[11] = {px, py, pz, vx, vy, vz, ax, ay, az, size, heading};
     const size_t bytes = (size_t)n * sizeof(float);
@@ -399,6 +404,8 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (!append) h->launches = 0;
     h->frame_done = false;
+    h->stage_mode = mode;
+    for (int s = RCD_STAGE_KEYS; s <= RCD_STAGE_PAIRS; ++s) h->stages[mode][s].used = false;
     stage_begin(h, RCD_STAGE_TOTAL);
     const float cell_req = (mode == RCD_MODE_PREDICT) ? PREDICT_RADIUS : search_radius;
     int rc = build_index(h, cell_req);
@@ -426,9 +433,11 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         P.counters = h->counters;
         P.cand_count = h->cand_count;
         const unsigned tiles = (unsigned)((h->n + TQ - 1) / TQ);
-        if (mode == RCD_MODE_DETECT) k_pairs<RCD_MODE_DETECT><<<tiles, TQ, 0, h->stream>>>(P);
-        else if (mode == RCD_MODE_PREDICT) k_pairs<RCD_MODE_PREDICT><<<tiles, TQ, 0, h->stream>>>(P);
-        else k_pairs<RCD_MODE_COMPUTE_NODE><<<tiles, TQ, 0, h->stream>>>(P);
+        P.count_candidates = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) ? 1 : 0;
+        if (mode == RCD_MODE_DETECT) k_pairs<RCD_MODE_DETECT, true><<<tiles, TQ, 0, h->stream>>>(P);
+        else if (mode == RCD_MODE_PREDICT && P.count_candidates) k_pairs<RCD_MODE_PREDICT, true><<<tiles, TQ, 0, h->stream>>>(P);
+        else if (mode == RCD_MODE_PREDICT) k_pairs<RCD_MODE_PREDICT, false><<<tiles, TQ, 0, h->stream>>>(P);
+        else k_pairs<RCD_MODE_COMPUTE_NODE, true><<<tiles, TQ, 0, h->stream>>>(P);
         KERNEL_CHECK(h);
     }
     stage_end(h, RCD_STAGE_PAIRS);
@@ -469,6 +478,7 @@ int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
     rcd_counts_t c;
     int rc = rcd_counts(h, &c);
     if (rc) return rc;
+    h->stage_mode = 0;
     stage_begin(h, RCD_STAGE_DOWNLOAD);
     u64 m = std::min<u64>(c.n_written, cap);
     if (m) {
@@ -633,16 +643,23 @@ int rcd_halo_append(rcd_handle h, const void *records, uint64_t n_records) {
     return RCD_OK;
 }
 
-int rcd_stage_ms(rcd_handle h, float *ms) {
-    if (!h || !ms) return RCD_EINVAL;
+int rcd_get_stream(rcd_handle h, void **stream) {
+    if (!h || !stream) return RCD_EINVAL;
+    *stream = static_cast<void *>(h->stream);
+    return RCD_OK;
+}
+
+int rcd_stage_ms(rcd_handle h, int32_t mode, float *ms) {
+    if (!h || !ms || mode < 0 || mode > 2) return RCD_EINVAL;
     if (!(h->flags & RCD_FLAG_PROFILE)) return fail(h, RCD_ESTATE, "rcd_stage_ms: handle was created without RCD_FLAG_PROFILE");
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (int s = 0; s < RCD_NUM_STAGES; ++s) {
         ms[s] = 0.0f;
-        if (h->stages[s].used) {
+        const Stage &st = (s == RCD_STAGE_UPLOAD || s == RCD_STAGE_DOWNLOAD) ? h->stages[0][s] : h->stages[mode][s];
+        if (st.used) {
             float t = 0.0f;
-            if (cudaEventElapsedTime(&t, h->stages[s].begin, h->stages[s].end) == cudaSuccess) ms[s] = t;
+            if (cudaEventElapsedTime(&t, st.begin, st.end) == cudaSuccess) ms[s] = t;
             else (void)cudaGetLastError();
         }
     }

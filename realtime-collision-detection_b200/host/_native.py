@@ -19,6 +19,7 @@ STEP_APPEND = 0x100
 SRC_HOST, SRC_DEVICE = 0, 1
 PAT_STATIONARY, PAT_CONSTANT_VELOCITY, PAT_ACCELERATING, PAT_NO_HISTORY = 0, 1, 2, 3
 FLAG_PROFILE = 1
+FLAG_COUNT_PREDICT_CANDIDATES = 2
 NUM_STAGES = 8
 STAGE_NAMES = ("upload", "keys", "sort", "reorder", "pairs", "finalize", "download", "total")
 HALO_RECORD_WORDS = 13
@@ -29,7 +30,7 @@ SYMBOLS = (
     "rcd_version", "rcd_last_error", "rcd_create", "rcd_destroy", "rcd_upload", "rcd_set_patterns",
     "rcd_set_owned", "rcd_step", "rcd_invalidate", "rcd_counts", "rcd_download",
     "rcd_download_candidate_counts", "rcd_query_radius", "rcd_classify_patterns", "rcd_halo_pack",
-    "rcd_halo_append", "rcd_stage_ms", "rcd_launch_count", "rcd_sync",
+    "rcd_halo_append", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_sync",
 )
 
 
@@ -91,7 +92,8 @@ def load() -> ctypes.CDLL:
     L.rcd_classify_patterns.argtypes = [vp, u64, u32, vp, vp, vp]
     L.rcd_halo_pack.argtypes = [vp, i32, i32, vp, vp, f32, vp, u64, vp]
     L.rcd_halo_append.argtypes = [vp, vp, u64]
-    L.rcd_stage_ms.argtypes = [vp, vp]
+    L.rcd_stage_ms.argtypes = [vp, i32, vp]
+    L.rcd_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
     L.rcd_launch_count.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_sync.argtypes = [vp]
     for name in SYMBOLS:

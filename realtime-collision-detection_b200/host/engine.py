@@ -27,12 +27,14 @@ class FrameEngine:
     """Batch interface: upload a frame, run detect / predict / compute-node for every object."""
 
     def __init__(self, max_objects: int, max_pairs: Optional[int] = None, device: int = 0,
-                 world_bounds: Optional[Tuple[Sequence[float], Sequence[float]]] = None, profile: bool = False):
+                 world_bounds: Optional[Tuple[Sequence[float], Sequence[float]]] = None, profile: bool = False,
+                 count_predict_candidates: bool = False):
         self._lib = N.load()
         self._h = ctypes.c_void_p()
         cfg = N.RcdConfig()
         cfg.device = int(device)
-        cfg.flags = N.FLAG_PROFILE if profile else 0
+        cfg.flags = (N.FLAG_PROFILE if profile else 0) | (
+            N.FLAG_COUNT_PREDICT_CANDIDATES if count_predict_candidates else 0)
         cfg.max_objects = int(max(1, max_objects))
         cfg.max_pairs = int(max_pairs if max_pairs is not None else max(4096, 16 * max_objects))
         if world_bounds is None:
@@ -181,10 +183,16 @@ class FrameEngine:
         self.n += int(n_records)
 
     # -- instrumentation -----------------------------------------------------------------------
-    def stage_ms(self) -> Dict[str, float]:
+    def stage_ms(self, mode: int = N.MODE_DETECT) -> Dict[str, float]:
         ms = np.zeros(N.NUM_STAGES, np.float32)
-        N.check(self._lib.rcd_stage_ms(self._h, _vp(ms)), self._h)
+        N.check(self._lib.rcd_stage_ms(self._h, int(mode), _vp(ms)), self._h)
         return {name: float(ms[k]) for k, name in enumerate(N.STAGE_NAMES)}
+
+    def cuda_stream(self) -> int:
+        """The handle's cudaStream_t as an integer (wrap with torch.cuda.ExternalStream)."""
+        s = ctypes.c_void_p()
+        N.check(self._lib.rcd_get_stream(self._h, ctypes.byref(s)), self._h)
+        return int(s.value or 0)
 
     def launch_count(self) -> int:
         v = ctypes.c_uint64(0)

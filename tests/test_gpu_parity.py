@@ -16,7 +16,7 @@ PREDICT = ["predict_dense3d.npz", "predict_2d_allcv.npz", "predict_city300.npz"]
 @pytest.fixture(scope="module")
 def eng():
     from rcd_b200.host.engine import FrameEngine
-    e = FrameEngine(max_objects=1_100_000, max_pairs=4_000_000, profile=True)
+    e = FrameEngine(max_objects=1_100_000, max_pairs=4_000_000, profile=True, count_predict_candidates=True)
     yield e
     e.close()
 
@@ -88,7 +88,8 @@ def test_detect_and_predict_vs_oracle(seed, n, box, drones, static_bounds):
     frame = W.uniform_frame(n, seed, map_size=box, drone_fraction=drones)
     pat = W.random_patterns(n, seed + 100)
     bounds = ((0, 0, 0), (box, box, 100.0)) if static_bounds else None
-    with FrameEngine(n, 64 * n, world_bounds=bounds) as e:
+    count = bool(seed % 2)  # exercise both predict kernels (with / without candidate counting)
+    with FrameEngine(n, 64 * n, world_bounds=bounds, count_predict_candidates=count) as e:
         e.upload(frame)
         got = e.detect()
         ora = O.frame_A(f64_frame(frame), "detect")
@@ -98,7 +99,7 @@ def test_detect_and_predict_vs_oracle(seed, n, box, drones, static_bounds):
         got = e.predict()
         ora = O.frame_A(f64_frame(frame), "predict", pattern_codes=pat)
         compare_pairs(got, ora["risks"], "predict")
-        compare_counts(e.counts(), e.candidate_counts(), ora, "predict")
+        compare_counts(e.counts(), e.candidate_counts(), ora, "predict", candidates=count)
 
 
 def test_append_mode_is_detect_plus_predict(eng):
@@ -291,4 +292,4 @@ def test_full_size_100k_counts_and_pairs():
         got = e.predict()
         ora = O.frame_A(f64_frame(frame), "predict", pattern_codes=pat, want_potentials=False)
         compare_pairs(got, ora["risks"], "predict")
-        compare_counts(e.counts(), e.candidate_counts(), ora, "predict")
+        compare_counts(e.counts(), e.candidate_counts(), ora, "predict", candidates=False)
