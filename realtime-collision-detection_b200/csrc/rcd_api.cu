@@ -61,6 +61,11 @@ struct rcd_handle_s {
     Counters *counters = nullptr;
     Counters *counters_host = nullptr;  // pinned
     u32 *cand_count = nullptr;
+    u32 *pair_tile_counter = nullptr;
+    QEntry *q2 = nullptr, *q3 = nullptr;
+    u32 qcap = 0;
+    int stage_blocks = 0;
+    int pair_blocks[4] = {0, 0, 0, 0};  // resident blocks per SM x SMs, per kernel variant
     bool frame_done = false;
     int last_mode = -1;
 
@@ -118,11 +123,12 @@ InputState input_state(rcd_handle h) {
     return in;
 }
 
-// Grid for a requested minimum cell edge.  cell >= cell_req * (1 + 1e-4) + 0.02 keeps two objects
-// within cell_req of each other in adjacent cells despite fp32 rounding of (x - origin) / cell.
+// Grid for a requested minimum cell edge.  cell = cell_req * 1.002 + 0.02 keeps two objects within
+// cell_req of each other in adjacent cells despite the fp32 rounding of (x - origin) / cell (up to
+// ~1e-4 cells at 100 km coordinates; the stencil radius adds 1e-3 cells of slack, rcd_pairs.cuh).
 GridParams make_grid(const float *wmin, const float *wmax, float cell_req, u32 cells_cap) {
     GridParams g;
-    double cell = (double)cell_req * 1.0001 + 0.02;
+    double cell = (double)cell_req * 1.002 + 0.02;
     if (!(cell > 1e-3)) cell = 1e-3;
     double ext[3];
     for (int d = 0; d < 3; ++d) {
@@ -297,6 +303,10 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->counters, 1));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->counters_host), sizeof(Counters)));
     CREATE_TRY(dev_alloc(&h->cand_count, cap));
+    CREATE_TRY(dev_alloc(&h->pair_tile_counter, 1));
+    h->qcap = (u32)std::min<u64>(2 * h->max_pairs + 65536, 1ull << 30);
+    CREATE_TRY(dev_alloc(&h->q2, (size_t)h->qcap));
+    CREATE_TRY(dev_alloc(&h->q3, (size_t)h->qcap));
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) {
             CREATE_TRY(cudaEventCreate(&h->stages[m][s].begin));
@@ -319,7 +329,8 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->P0); cudaFree(h->P1); cudaFree(h->P2); cudaFree(h->sorted_slot);
     cudaFree(h->cell_start); cudaFree(h->cell_end); cudaFree(h->bbox_dev);
     if (h->bbox_host) cudaFreeHost(h->bbox_host);
-    cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count);
+    cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
+    cudaFree(h->q2); cudaFree(h->q3);
     if (h->counters_host) cudaFreeHost(h->counters_host);
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) {
@@ -432,12 +443,42 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         P.out_cap = h->max_pairs;
         P.counters = h->counters;
         P.cand_count = h->cand_count;
-        const unsigned tiles = (unsigned)((h->n + TQ - 1) / TQ);
-        P.count_candidates = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) ? 1 : 0;
-        if (mode == RCD_MODE_DETECT) k_pairs<RCD_MODE_DETECT, true><<<tiles, TQ, 0, h->stream>>>(P);
-        else if (mode == RCD_MODE_PREDICT && P.count_candidates) k_pairs<RCD_MODE_PREDICT, true><<<tiles, TQ, 0, h->stream>>>(P);
-        else if (mode == RCD_MODE_PREDICT) k_pairs<RCD_MODE_PREDICT, false><<<tiles, TQ, 0, h->stream>>>(P);
-        else k_pairs<RCD_MODE_COMPUTE_NODE, true><<<tiles, TQ, 0, h->stream>>>(P);
+        P.ntiles = (u32)((h->n + TQ - 1) / TQ);
+        P.tile_counter = h->pair_tile_counter;
+        P.q2 = h->q2; P.q3 = h->q3; P.qcap = h->qcap;
+        CUDA_TRY(h, cudaMemsetAsync(h->pair_tile_counter, 0, sizeof(u32), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_q2, 0, 2 * sizeof(unsigned long long), h->stream));
+        const bool count = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) != 0;
+        // persistent launch: as many blocks as can be resident, warps pull tiles from a counter
+        const int variant = mode == RCD_MODE_DETECT ? 0 : (mode == RCD_MODE_COMPUTE_NODE ? 3 : (count ? 2 : 1));
+        if (h->pair_blocks[variant] == 0) {
+            int per_sm = 0, sms = 0;
+            const void *fn = variant == 0 ? (const void *)k_pairs<RCD_MODE_DETECT, true>
+                           : variant == 1 ? (const void *)k_pairs<RCD_MODE_PREDICT, false>
+                           : variant == 2 ? (const void *)k_pairs<RCD_MODE_PREDICT, true>
+                                          : (const void *)k_pairs<RCD_MODE_COMPUTE_NODE, true>;
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PAIR_THREADS, 0));
+            CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            h->pair_blocks[variant] = std::max(1, per_sm) * std::max(1, sms);
+        }
+        const unsigned blocks = (unsigned)std::min<u64>((P.ntiles + PAIR_WARPS - 1) / PAIR_WARPS, (u64)h->pair_blocks[variant]);
+        if (variant == 0) k_pairs<RCD_MODE_DETECT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+        else if (variant == 1) k_pairs<RCD_MODE_PREDICT, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+        else if (variant == 2) k_pairs<RCD_MODE_PREDICT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+        else k_pairs<RCD_MODE_COMPUTE_NODE, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+        KERNEL_CHECK(h);
+        // the later stages read their queue lengths on the device: fixed grids, no host round trip
+        if (h->stage_blocks == 0) {
+            int sms = 0;
+            CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            h->stage_blocks = std::max(1, sms) * 8;
+        }
+        const unsigned sb = (unsigned)std::min<u64>((u64)h->stage_blocks, (h->n + STAGE_THREADS - 1) / STAGE_THREADS + 1);
+        if (variant == 1) { k_sample<false><<<sb, STAGE_THREADS, 0, h->stream>>>(P); KERNEL_CHECK(h); }
+        if (variant == 2) { k_sample<true><<<sb, STAGE_THREADS, 0, h->stream>>>(P); KERNEL_CHECK(h); }
+        if (variant == 0) k_exact<RCD_MODE_DETECT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        else if (variant == 3) k_exact<RCD_MODE_COMPUTE_NODE><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        else k_exact<RCD_MODE_PREDICT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         KERNEL_CHECK(h);
     }
     stage_end(h, RCD_STAGE_PAIRS);

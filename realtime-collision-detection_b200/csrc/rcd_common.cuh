@@ -66,6 +66,8 @@ struct Counters {
     unsigned long long n_alerts[4];
     unsigned long long n_exact;
     unsigned long long n_query_hits;  // rcd_query_radius
+    // lengths of the global queues between k_pairs / k_sample / k_exact (reset before every step)
+    unsigned long long n_q2, n_q3;
 };
 
 // ---- warp / block helpers -----------------------------------------------------------------------

@@ -1,16 +1,27 @@
-// Pair enumeration + narrow phase + classification, one fused kernel per frame mode.
+// Pair enumeration + narrow phase + classification.
 //
-// A tile is TQ consecutive objects in cell order (one thread per querying object).  The tile
-// finds the cell rows that can hold neighbours of any of its queries, flattens their contiguous
-// spans and streams them through shared memory in double-buffered chunks (cp.async).  Work is
-// split in two phases so that the expensive part runs with full warps:
-//   filter : every query tests every staged neighbour with one broadcast LDS.128 and a squared
-//            distance; survivors are compacted with __ballot_sync into a per-warp queue of
-//            (query, neighbour) pairs in shared memory;
-//   heavy  : whenever 32 pairs are queued, each lane takes one pair and runs the narrow phase
-//            (temporal filter / 20 predicted offsets x 10 samples) in fp32 as a conservative
-//            pre-filter; pairs that survive are decided in fp64 (rcd_exact.cuh), emitted through
-//            one 64-bit atomic cursor and classified (alert priority) on the spot.
+// Three small kernels per frame, connected by compact queues in global memory, so that every
+// stage runs with full warps and each kernel's hot loop stays I-cache resident:
+//
+//   k_pairs  : persistent.  A tile is 32 consecutive objects in cell order, handled by ONE warp
+//              (one lane per querying object); warps take tiles from an atomic counter, so dense
+//              regions spread over all SMs.  The warp finds the cell rows that can hold neighbours
+//              of its queries, flattens their contiguous spans and streams them through its own
+//              slice of shared memory in double-buffered chunks (cp.async); there is no block-wide
+//              barrier, everything is warp-synchronous.
+//                S1 filter : lane = query; every staged neighbour is tested with one broadcast
+//                            LDS.128 and a squared distance; survivors are compacted with
+//                            __ballot_sync into a shared-memory queue of (query, neighbour) pairs.
+//                S2 narrow : lane = pair, 32 queued pairs at a time.  detect: temporal filter +
+//                            closest approach.  predict: closest approach of the relative
+//                            trajectory rejects most pairs outright; the rest are compacted again
+//                            and the offsets inside the reachable time window are scanned.
+//              Survivors go to global queues (warp-aggregated atomics).
+//   k_sample : (predict) lane = pair; per surviving offset: radius test + the 10 samples.
+//   k_exact  : lane = pair; the decision is taken in fp64 in the reference's operation order
+//              (rcd_exact.cuh), merged over offsets, emitted through one 64-bit atomic cursor and
+//              classified (alert priority).
+// The fp32 stages only ever *reject*, with guard bands that dominate the rounding error.
 //
 // Replaces the reference's per-vehicle Python loops:
 //   detect : CollisionDetector.detect_collisions      src/collision/collision_detection.py:110-191
@@ -25,15 +36,22 @@
 
 namespace rcd {
 
-constexpr int TQ = 128;           // queries (threads) per tile
-constexpr int NW = TQ / 32;       // warps per tile
-constexpr int CH = 256;           // neighbours staged per chunk
-constexpr int MAX_ROWS = TQ;      // cell rows handled per batch (one thread computes one row span)
+constexpr int TQ = 32;            // queries per tile = one warp
+constexpr int PAIR_WARPS = 4;     // warps (independent tiles) per block
+constexpr int PAIR_THREADS = PAIR_WARPS * 32;
+constexpr int CH = 64;            // neighbours staged per chunk (2 per lane)
 constexpr int ROW_SCAN_MAX = 32;  // rows up to this many cells wide are scanned cell by cell
-constexpr int QCAP = 64;          // per-warp pair queue (<= 31 carried + 32 pushed)
+constexpr int QCAP1 = 160;        // Q1 capacity (<= 31 carried + 4 x 32 pushed)
+constexpr int QCAP1B = 64;        // Q1b capacity (<= 31 carried + 32 pushed)
+
+// one queued pair between kernels: positions in cell order + offset mask (predict)
+struct QEntry {
+    u32 si, sj, mask;
+};
 
 struct PairParams {
     u32 n;
+    u32 ntiles;
     GridParams g;
     const float4 *P0, *P1, *P2;
     const u32 *keys;         // sorted cell keys
@@ -43,32 +61,32 @@ struct PairParams {
     float R, T;              // search radius / time window (detect)
     int steps;               // int(T / 0.1)
     float pt, threshold;     // compute-node: prediction_time, risk_threshold
-    int count_candidates;    // predict: also count the (i, j, m) radius hits (diagnostic, slower)
     rcd_pair *out;
     unsigned long long out_cap;
     Counters *counters;
+    u32 *tile_counter;
     u32 *cand_count;         // per upload slot
+    QEntry *q2, *q3;         // global queues: -> k_sample, -> k_exact
+    u32 qcap;                // capacity of each
 };
 
 // relative guard band of the fp32 radius test (fp32 error of d2 is < 1e-6 relative)
 constexpr float BAND_R2 = 2.0e-5f;
 
-// shared-memory state of one tile
+// shared-memory state of one warp
 struct StageBuf {
     float4 p0[CH], p1[CH], p2[CH];
     u32 pos[CH];  // position in cell order of the staged object
 };
-struct TileShared {
+struct WarpShared {
     StageBuf buf[2];
     float4 q0[TQ], q1[TQ], q2[TQ];  // the tile's own (querying) objects
-    unsigned short queue[NW][QCAP];
-    u32 cand[TQ];                   // candidates found in the heavy phase (per query)
-    u32 row_lo[MAX_ROWS];
-    u32 row_prefix[MAX_ROWS + 1];
-    int red_i[NW][6];
-    float red_f[NW];
-    u32 scan[NW];
-    u32 n_pot, n_exact;
+    unsigned short q1e[QCAP1];      // Q1: ql << 8 | jj
+    u32 q1b_pos[QCAP1B];            // Q1b (predict): neighbour position in cell order
+    unsigned char q1b_ql[QCAP1B];   //                query lane
+    u32 cand[TQ];                   // candidates resolved outside the filter (per query)
+    u32 row_lo[TQ];
+    u32 row_prefix[TQ + 1];
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -78,6 +96,9 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// sqrt(x) rounded up a little: only ever used for conservative bounds
+__device__ __forceinline__ float sqrt_ub(float x) { return x * rsqrtf(fmaxf(x, 1.0e-30f)) * (1.0f + 4.0e-6f); }
 
 __device__ __forceinline__ void emit_pair(const PairParams &P, u32 slot_i, u32 slot_j, double ttc, double dist,
                                           double rs, double risk, double mx, double my, double mz, double tcl,
@@ -104,88 +125,85 @@ __device__ __forceinline__ void emit_pair(const PairParams &P, u32 slot_i, u32 s
     }
 }
 
-
-// ---- cold paths: fp64 re-evaluation, kept out of line so the fp32 loops stay lean in registers ----
+// ---- fp64 decisions (rare) ---------------------------------------------------------------------------
 __device__ __noinline__ bool exact_within_radius(float ax, float ay, float az, float bx, float by, float bz, float R) {
     return within_radius_d(ax, ay, az, bx, by, bz, (double)R);
 }
 
-__device__ __noinline__ void exact_detect(const PairParams &P, TileShared &sh, const StageBuf &buf, u32 ql, u32 jj,
-                                          u32 si, float T, int steps) {
-    atomicAdd(&sh.n_exact, 1u);
-    ObjD A = widen(sh.q0[ql], sh.q1[ql], sh.q2[ql]), B = widen(buf.p0[jj], buf.p1[jj], buf.p2[jj]);
+// detect: stages 2-4 in fp64 for the pair (si, sj); returns 1 if the pair passed stage 2
+__device__ __noinline__ u32 exact_detect(const PairParams &P, u32 si, u32 sj, float T, int steps) {
+    ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
     DetectResultD r = detect_pair_d(A, B, (double)T, steps);
-    if (r.potential) atomicAdd(&sh.n_pot, 1u);
     if (r.hit)
-        emit_pair(P, P.sorted_slot[si], P.sorted_slot[buf.pos[jj]], r.ttc, r.dist, r.rs, r.risk, r.mx, r.my, r.mz,
-                  r.tc, r.cd, r.priority, 255, false);
+        emit_pair(P, P.sorted_slot[si], P.sorted_slot[sj], r.ttc, r.dist, r.rs, r.risk, r.mx, r.my, r.mz, r.tc, r.cd,
+                  r.priority, 255, false);
+    return r.potential ? 1u : 0u;
 }
 
-struct PredictBest {
-    double risk;
-    double ttc, dist, rs, mx, my, mz;
-    int m;
-};
-
-__device__ __noinline__ bool exact_predict_radius(TileShared &sh, const StageBuf &buf, u32 ql, u32 jj, u32 pattern,
-                                                  int m) {
-    atomicAdd(&sh.n_exact, 1u);
-    ObjD A = widen(sh.q0[ql], sh.q1[ql], sh.q2[ql]);
-    const float4 b0 = buf.p0[jj];
+__device__ __noinline__ bool exact_predict_radius(const PairParams &P, u32 si, u32 sj, u32 pattern, int m) {
+    ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]);
+    const float4 b0 = P.P0[sj];
     double cx, cy, cz;
     predict_centre_d(A, pattern, 0.5 * (double)m, cx, cy, cz);
     return within_radius_d(cx, cy, cz, b0.x, b0.y, b0.z, (double)PREDICT_RADIUS);
 }
 
-__device__ __noinline__ void exact_predict(TileShared &sh, const StageBuf &buf, u32 ql, u32 jj, u32 pattern, int m,
-                                           PredictBest *best) {
-    atomicAdd(&sh.n_exact, 1u);
-    ObjD A = widen(sh.q0[ql], sh.q1[ql], sh.q2[ql]), B = widen(buf.p0[jj], buf.p1[jj], buf.p2[jj]);
-    PredictResultD r = predict_pair_d(A, B, pattern, m);
-    if (r.hit && r.risk > best->risk) {  // strict >, offsets ascending (:862)
-        best->risk = r.risk; best->ttc = r.ttc; best->dist = r.dist; best->rs = r.rs;
-        best->mx = r.mx; best->my = r.my; best->mz = r.mz; best->m = m;
+// predict: every offset in `mask` in fp64, max-risk merge (strict >, offsets ascending, :848-865)
+__device__ __noinline__ void exact_predict(const PairParams &P, u32 si, u32 sj, u32 pattern, u32 mask) {
+    ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
+    double best_risk = -1.0;
+    PredictResultD best;
+    int best_m = -1;
+    while (mask) {
+        int m = __ffs(mask) - 1;
+        mask &= mask - 1;
+        PredictResultD r = predict_pair_d(A, B, pattern, m);
+        if (r.hit && r.risk > best_risk) { best_risk = r.risk; best = r; best_m = m; }
     }
+    if (best_m >= 0)
+        emit_pair(P, P.sorted_slot[si], P.sorted_slot[sj], best.ttc, best.dist, best.rs, best.risk, best.mx, best.my,
+                  best.mz, 0.5 * (double)best_m, 0.0, priority_d(best.risk, best.ttc), best_m, true);
 }
 
-__device__ __noinline__ void emit_predict(const PairParams &P, const StageBuf &buf, u32 si, u32 jj,
-                                          const PredictBest *b) {
-    emit_pair(P, P.sorted_slot[si], P.sorted_slot[buf.pos[jj]], b->ttc, b->dist, b->rs, b->risk, b->mx, b->my, b->mz,
-              0.5 * (double)b->m, 0.0, priority_d(b->risk, b->ttc), b->m, true);
-}
-
-__device__ __noinline__ void exact_compute_node(const PairParams &P, TileShared &sh, const StageBuf &buf, u32 ql,
-                                                u32 jj, u32 si) {
-    atomicAdd(&sh.n_exact, 1u);
-    ObjD A = widen(sh.q0[ql], sh.q1[ql], sh.q2[ql]), B = widen(buf.p0[jj], buf.p1[jj], buf.p2[jj]);
+__device__ __noinline__ void exact_compute_node(const PairParams &P, u32 si, u32 sj) {
+    ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
     ComputeNodeResultD r = compute_node_pair_d(A, B, (double)P.pt, (double)P.threshold);
     if (r.hit)
-        emit_pair(P, P.sorted_slot[si], P.sorted_slot[buf.pos[jj]], r.ttc, r.fut, r.rs, r.risk, r.mx, r.my, r.mz, 0.0,
-                  0.0, -1, 255, false);
+        emit_pair(P, P.sorted_slot[si], P.sorted_slot[sj], r.ttc, r.fut, r.rs, r.risk, r.mx, r.my, r.mz, 0.0, 0.0, -1,
+                  255, false);
 }
 
-// ---- detect: stages 1-4 for one queued pair ----------------------------------------------------
-// a* = querying object, b* = neighbour, si / sj = their positions in cell order
-__device__ __forceinline__ void heavy_detect(const PairParams &P, TileShared &sh, const StageBuf &buf, u32 ql, u32 jj,
-                                             const float4 &a0, const float4 &a1, const float4 &a2, const float4 &b0,
-                                             const float4 &b1, const float4 &b2, u32 si, float R, float T,
-                                             int steps) {
+// the exact stage for one queue entry (also the inline fallback when a global queue is full)
+template <int MODE>
+__device__ __forceinline__ u32 exact_entry(const PairParams &P, u32 si, u32 sj, u32 mask) {
+    if (MODE == RCD_MODE_DETECT) return exact_detect(P, si, sj, P.T, P.steps);
+    if (MODE == RCD_MODE_COMPUTE_NODE) { exact_compute_node(P, si, sj); return 0; }
+    if (mask == 0) return exact_detect(P, si, sj, 10.0f, 100);  // pattern 3: detect defaults (:592)
+    exact_predict(P, si, sj, meta_pattern(__float_as_uint(P.P2[si].w)), mask);
+    return 0;
+}
+
+// ---- S2, detect: temporal filter + closest approach in fp32 (collision_detection.py:244-292) ------
+// returns true when the pair must be decided in fp64
+__device__ __forceinline__ bool narrow_detect(WarpShared &ws, u32 ql, const float4 &a0, const float4 &a1,
+                                              const float4 &a2, const float4 &b0, const float4 &b1, const float4 &b2,
+                                              float R, float T, u32 &n_exact) {
     const float R2 = R * R;
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;  // rel_position = other - self
     float d2 = dx * dx + dy * dy + dz * dz;
     if (d2 >= R2 * (1.0f - BAND_R2)) {  // the filter could not decide the radius test (spatial_index.py:268)
-        atomicAdd(&sh.n_exact, 1u);
-        if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, R)) return;
-        atomicAdd(&sh.cand[ql], 1u);
+        ++n_exact;
+        if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, R)) return false;
+        atomicAdd(&ws.cand[ql], 1u);
     }
     float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;  // rel_velocity = self - other
     float rs2 = rvx * rvx + rvy * rvy + rvz * rvz;
-    if (rs2 < 0.0099f) return;  // rel_speed < 0.1 with margin (0.1^2 = 0.01)
+    if (rs2 < 0.0099f) return false;  // rel_speed < 0.1 with margin (0.1^2 = 0.01)
     float dot = dx * rvx + dy * rvy + dz * rvz;
     float edot = 4.0e-6f * sqrtf(d2 * rs2) + 1.0e-20f;
     // dot > 0: either (dot > 0 and cur > 5) or time_to_closest < 0 rejects the pair (:273, :280)
-    if (dot > edot) return;
-    if (-dot > T * rs2 * (1.0f + 1.0e-5f) + edot) return;  // time_to_closest > time_window
+    if (dot > edot) return false;
+    if (-dot > T * rs2 * (1.0f + 1.0e-5f) + edot) return false;  // time_to_closest > time_window
     float tc = fmaxf(-dot, 0.0f) / rs2;
     float rax = a2.x - b2.x, ray = a2.y - b2.y, raz = a2.z - b2.z;
     float h = 0.5f * tc * tc;
@@ -195,106 +213,176 @@ __device__ __forceinline__ void heavy_detect(const PairParams &P, TileShared &sh
     float tcerr = edot / rs2 + 4.0e-6f * tc;
     float band = 2.0e-3f + 2.0f * (sqrtf(rs2) + sqrtf(rax * rax + ray * ray + raz * raz) * tc) * tcerr;
     float thr = safe + band;
-    if (cd2 > thr * thr) return;
-    // ---- survivor: decide everything in fp64, in the reference's operation order -------------
-    exact_detect(P, sh, buf, ql, jj, si, T, steps);
+    return cd2 <= thr * thr;
 }
 
-// ---- predict: 20 offsets x (radius test, <= 10 samples), max-risk merge ------------------------
-template <bool COUNT_CAND>
-__device__ __forceinline__ void heavy_predict(const PairParams &P, TileShared &sh, const StageBuf &buf, u32 ql, u32 jj,
-                                              const float4 &a0, const float4 &a1, const float4 &a2, const float4 &b0,
-                                              const float4 &b1, const float4 &b2, u32 si, u32 pattern) {
-    const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
+// coefficients of one predict pair: g(t) = centre_i(t) - predicted_j(t) = -d + cv t + ca t^2/2 (:814),
+// e(t) = centre_i(t) - p_j = -d + uv t + ua t^2/2 (:801-803); the samples move with rv, ra (:326-327)
+struct PredictCoef {
+    float dx, dy, dz;
+    float uvx, uvy, uvz, uax, uay, uaz;
+    float cvx, cvy, cvz, cax, cay, caz;
+    float safe_b2, hr, hr2;
+};
+__device__ __forceinline__ PredictCoef predict_coef(const float4 &a0, const float4 &a1, const float4 &a2,
+                                                    const float4 &b0, const float4 &b1, const float4 &b2,
+                                                    u32 pattern) {
+    PredictCoef c;
     const float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f;
     const float fa = (pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f;
-    // centre_i(t) = p_i + uv t + ua t^2/2 (pattern: stationary / constant_velocity / accelerating, :728-761)
-    const float uvx = a1.x * fv, uvy = a1.y * fv, uvz = a1.z * fv;
-    const float uax = a2.x * fa, uay = a2.y * fa, uaz = a2.z * fa;
-    float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;
-    float d2 = dx * dx + dy * dy + dz * dz;
-    // g(t) = centre_i(t) - predicted_j(t) = -d + cv t + ca t^2/2   (:814)
-    float cvx = uvx - b1.x, cvy = uvy - b1.y, cvz = uvz - b1.z;
-    float cax = uax - b2.x, cay = uay - b2.y, caz = uaz - b2.z;
-    // the 10 samples advance both vehicles with their own v, a (:326-327, quirk Q6)
+    c.uvx = a1.x * fv; c.uvy = a1.y * fv; c.uvz = a1.z * fv;
+    c.uax = a2.x * fa; c.uay = a2.y * fa; c.uaz = a2.z * fa;
+    c.dx = b0.x - a0.x; c.dy = b0.y - a0.y; c.dz = b0.z - a0.z;
+    c.cvx = c.uvx - b1.x; c.cvy = c.uvy - b1.y; c.cvz = c.uvz - b1.z;
+    c.cax = c.uax - b2.x; c.cay = c.uay - b2.y; c.caz = c.uaz - b2.z;
     float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;
     float rax = a2.x - b2.x, ray = a2.y - b2.y, raz = a2.z - b2.z;
-    float rvn = sqrtf(rvx * rvx + rvy * rvy + rvz * rvz);
-    float ran = sqrtf(rax * rax + ray * ray + raz * raz);
+    float rvn = sqrt_ub(rvx * rvx + rvy * rvy + rvz * rvz);
+    float ran = sqrt_ub(rax * rax + ray * ray + raz * raz);
+    float d2 = c.dx * c.dx + c.dy * c.dy + c.dz * c.dz;
     float safe = (a0.w + b0.w) * 0.5f + 5.0f;
-    float safe_b = safe + 2.0e-3f + 1.0e-6f * sqrtf(d2);
-    float safe_b2 = safe_b * safe_b;
-    // the samples move the pair by at most |rv|*0.9 + |ra|*0.405 from the offset state
-    float hr = safe_b + rvn * 0.9f + ran * 0.405f;
-    float hr2 = hr * hr;
-    if (!COUNT_CAND) {
-        // whole-pair rejection: |g(t)| >= |-d + cv t| - |ca| t^2/2 on [0, 9.5]
-        float cv2 = cvx * cvx + cvy * cvy + cvz * cvz;
-        float ts = (cv2 > 1.0e-12f) ? fminf(fmaxf((dx * cvx + dy * cvy + dz * cvz) / cv2, 0.0f), 9.5f) : 0.0f;
-        float lx = cvx * ts - dx, ly = cvy * ts - dy, lz = cvz * ts - dz;
-        float lim = hr + sqrtf(cax * cax + cay * cay + caz * caz) * 45.125f + 1.0e-3f * sqrtf(d2) + 1.0e-2f;
-        if (lx * lx + ly * ly + lz * lz > lim * lim) return;
-    }
-    PredictBest best;
-    best.risk = -1.0;
-    best.m = -1;
-    u32 ncand = 0;
+    float safe_b = safe + 2.0e-3f + 1.0e-6f * sqrt_ub(d2);
+    c.safe_b2 = safe_b * safe_b;
+    // the 10 samples move the pair by at most |rv|*0.9 + |ra|*0.405 from the offset state
+    c.hr = safe_b + rvn * 0.9f + ran * 0.405f;
+    c.hr2 = c.hr * c.hr;
+    return c;
+}
+__device__ __forceinline__ float g2_at(const PredictCoef &c, float t) {
+    float h = 0.5f * t * t;
+    float gx = c.cvx * t + c.cax * h - c.dx, gy = c.cvy * t + c.cay * h - c.dy, gz = c.cvz * t + c.caz * h - c.dz;
+    return gx * gx + gy * gy + gz * gz;
+}
+
+// ---- S2a, predict: can the relative trajectory come close at all? -------------------------------------
+// |g(t)| >= |-d + cv t| - |ca| t^2/2 on [0, 9.5]; the linear part is minimal at ts = d.cv / |cv|^2.
+// Returns false when no offset can be hit; otherwise [m_lo, m_hi] bounds the offsets worth testing.
+__device__ __forceinline__ bool predict_window(const PredictCoef &c, int &m_lo, int &m_hi) {
+    const float d2 = c.dx * c.dx + c.dy * c.dy + c.dz * c.dz;
+    const float cv2 = c.cvx * c.cvx + c.cvy * c.cvy + c.cvz * c.cvz;
+    const float can = sqrt_ub(c.cax * c.cax + c.cay * c.cay + c.caz * c.caz);
+    const float L = (c.hr + 45.125f * can) * (1.0f + 1.0e-4f) + 1.0e-2f + 1.0e-5f * sqrt_ub(d2);
+    const float L2 = L * L;
+    m_lo = 0;
+    m_hi = PREDICT_OFFSETS - 1;
+    if (!(cv2 > 1.0e-8f)) return d2 <= L2;  // (almost) no relative drift: every offset looks the same
+    const float inv = 1.0f / cv2;
+    const float ts = (c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz) * inv;
+    // closest point of the linear part on [0, 9.5]
+    const float tc = fminf(fmaxf(ts, 0.0f), 9.5f);
+    const float lx = c.cvx * tc - c.dx, ly = c.cvy * tc - c.dy, lz = c.cvz * tc - c.dz;
+    const float dmin2 = lx * lx + ly * ly + lz * lz;
+    if (dmin2 > L2) return false;
+    // |-d + cv t|^2 = dg2 + cv2 (t - ts)^2 with dg2 the global minimum: t must lie within w of ts
+    const float dg2 = fmaxf(d2 - (c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz) * ts, 0.0f);
+    // the cancellation in dg2 (a few ulp of d2) moves w by up to ~2e-3 sqrt(d2 / cv2): covered twice over
+    const float w = sqrt_ub(fmaxf(L2 - dg2, 0.0f) * inv) + 1.0e-3f + 4.0e-3f * sqrt_ub(d2 * inv);
+    const float t_lo = ts - w, t_hi = ts + w;
+    if (t_hi < 0.0f || t_lo > 9.5f) return false;
+    m_lo = max((int)floorf(2.0f * t_lo), 0);
+    m_hi = min((int)ceilf(2.0f * t_hi), PREDICT_OFFSETS - 1);
+    return true;
+}
+
+// ---- S2b, predict: scan the offsets of the window; bit m set <=> offset m may be hit -----------------
+template <bool COUNT_CAND>
+__device__ __forceinline__ u32 predict_scan(WarpShared &ws, const PairParams &P, const PredictCoef &c, u32 ql, u32 si,
+                                            u32 sj, u32 pattern, int m_lo, int m_hi, u32 &n_exact) {
+    u32 mask = 0;
+    if (COUNT_CAND) {
+        // diagnostic variant: every offset takes the radius test so that candidates can be counted
+        const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
+        u32 ncand = 0;
 #pragma unroll 1
-    for (int m = 0; m < PREDICT_OFFSETS; ++m) {
-        float t = 0.5f * (float)m;
-        float h = 0.5f * t * t;
-        float gx = cvx * t + cax * h - dx, gy = cvy * t + cay * h - dy, gz = cvz * t + caz * h - dz;
-        float g2 = gx * gx + gy * gy + gz * gz;
-        if (!COUNT_CAND && g2 > hr2) continue;
-        // e = centre_i(t) - p_j: others are looked up at their CURRENT positions (:801-803)
-        float ex = uvx * t + uax * h - dx, ey = uvy * t + uay * h - dy, ez = uvz * t + uaz * h - dz;
-        float c2 = ex * ex + ey * ey + ez * ez;
-        if (c2 > R2 * (1.0f + BAND_R2)) continue;
-        if (c2 >= R2 * (1.0f - BAND_R2)) {
-            if (!exact_predict_radius(sh, buf, ql, jj, pattern, m)) continue;
+        for (int m = 0; m < PREDICT_OFFSETS; ++m) {
+            float t = 0.5f * (float)m, h = 0.5f * t * t;
+            float ex = c.uvx * t + c.uax * h - c.dx, ey = c.uvy * t + c.uay * h - c.dy, ez = c.uvz * t + c.uaz * h - c.dz;
+            float c2 = ex * ex + ey * ey + ez * ez;
+            if (c2 > R2 * (1.0f + BAND_R2)) continue;
+            if (c2 >= R2 * (1.0f - BAND_R2)) {
+                ++n_exact;
+                if (!exact_predict_radius(P, si, sj, pattern, m)) continue;
+            }
+            ++ncand;
+            if (m >= m_lo && m <= m_hi && g2_at(c, t) <= c.hr2) mask |= 1u << m;
         }
-        ++ncand;
-        if (COUNT_CAND && g2 > hr2) continue;
+        if (ncand) atomicAdd(&ws.cand[ql], ncand);
+        return mask;
+    }
+#pragma unroll 1
+    for (int m = m_lo; m <= m_hi; ++m)
+        if (g2_at(c, 0.5f * (float)m) <= c.hr2) mask |= 1u << m;
+    return mask;
+}
+
+// ---- k_sample body: radius test + the 10 samples in fp32 for every offset in `mask` -----------------
+template <bool COUNT_CAND>
+__device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 sj, u32 mask, u32 &n_exact) {
+    const float4 a0 = P.P0[si], a1 = P.P1[si], a2 = P.P2[si];
+    const float4 b0 = P.P0[sj], b1 = P.P1[sj], b2 = P.P2[sj];
+    const u32 pattern = meta_pattern(__float_as_uint(a2.w));
+    const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pattern);
+    const float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;
+    const float rax = a2.x - b2.x, ray = a2.y - b2.y, raz = a2.z - b2.z;
+    const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
+    u32 out = 0;
+    while (mask) {
+        const int m = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float t = 0.5f * (float)m, h = 0.5f * t * t;
+        if (!COUNT_CAND) {  // with COUNT_CAND the radius test was already taken in k_pairs
+            float ex = c.uvx * t + c.uax * h - c.dx, ey = c.uvy * t + c.uay * h - c.dy, ez = c.uvz * t + c.uaz * h - c.dz;
+            float c2 = ex * ex + ey * ey + ez * ez;
+            if (c2 > R2 * (1.0f + BAND_R2)) continue;
+            if (c2 >= R2 * (1.0f - BAND_R2)) {
+                ++n_exact;
+                if (!exact_predict_radius(P, si, sj, pattern, m)) continue;
+            }
+        }
+        const float gx = c.cvx * t + c.cax * h - c.dx, gy = c.cvy * t + c.cay * h - c.dy, gz = c.cvz * t + c.caz * h - c.dz;
         bool maybe = false;
 #pragma unroll
         for (int k = 0; k < PREDICT_STEPS; ++k) {
-            float tau = 0.1f * (float)k;
-            float hh = 0.5f * tau * tau;
+            const float tau = 0.1f * (float)k, hh = 0.5f * tau * tau;
             float rx = gx + rvx * tau + rax * hh, ry = gy + rvy * tau + ray * hh, rz = gz + rvz * tau + raz * hh;
-            maybe |= (rx * rx + ry * ry + rz * rz <= safe_b2);
+            maybe |= (rx * rx + ry * ry + rz * rz <= c.safe_b2);
         }
-        if (!maybe) continue;
-        exact_predict(sh, buf, ql, jj, pattern, m, &best);
+        if (maybe) out |= 1u << m;
     }
-    if (COUNT_CAND && ncand) atomicAdd(&sh.cand[ql], ncand);
-    if (best.m >= 0) emit_predict(P, buf, si, jj, &best);
+    return out;
 }
 
-// ---- compute-node pair function ------------------------------------------------------------------
-__device__ __forceinline__ void heavy_compute_node(const PairParams &P, TileShared &sh, const StageBuf &buf, u32 ql,
-                                                   u32 jj, const float4 &a0, const float4 &a1, const float4 &a2,
-                                                   const float4 &b0, const float4 &b1, const float4 &b2, u32 si,
-                                                   u32 sj) {
+// ---- S2, compute-node pair function in fp32 (compute_node.py:258-292) --------------------------------
+__device__ __forceinline__ bool narrow_compute_node(WarpShared &ws, const PairParams &P, u32 ql, const float4 &a0,
+                                                    const float4 &a1, const float4 &a2, const float4 &b0,
+                                                    const float4 &b1, const float4 &b2, bool self, u32 &n_exact) {
     const float R2 = P.R * P.R;
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;
     float d2 = dx * dx + dy * dy + dz * dz;
     if (d2 >= R2 * (1.0f - BAND_R2)) {
-        atomicAdd(&sh.n_exact, 1u);
-        if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, P.R)) return;
-        atomicAdd(&sh.cand[ql], 1u);  // query_nearby returns the querying vehicle too (quirk Q8)
+        ++n_exact;
+        if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, P.R)) return false;
+        atomicAdd(&ws.cand[ql], 1u);  // query_nearby returns the querying vehicle too (quirk Q8)
     }
-    if (sj == si) return;                          // compute_node.py:251-252
-    if (d2 > 2500.0f * (1.0f + BAND_R2)) return;   // current_distance > 50
+    if (self) return false;                              // compute_node.py:251-252
+    if (d2 > 2500.0f * (1.0f + BAND_R2)) return false;   // current_distance > 50
     if (meta_pattern(__float_as_uint(a2.w)) == 0u || meta_pattern(__float_as_uint(b2.w)) == 0u)
-        return;                                    // predict_position needs >= 2 samples (:202-203)
+        return false;                                    // predict_position needs >= 2 samples (:202-203)
     float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;
     float fx = dx - rvx * P.pt, fy = dy - rvy * P.pt, fz = dz - rvz * P.pt;  // future_j - future_i
     float fut2 = fx * fx + fy * fy + fz * fz;
     float rs2 = rvx * rvx + rvy * rvy + rvz * rvz;
-    if (fut2 > d2 * (1.0f + 1.0e-4f) + 1.0e-6f && d2 > 16.0f * (1.0f + 1.0e-4f)) return;  // moving apart
+    if (fut2 > d2 * (1.0f + 1.0e-4f) + 1.0e-6f && d2 > 16.0f * (1.0f + 1.0e-4f)) return false;  // moving apart
     float fut = fmaxf(sqrtf(fut2), 0.1f);
-    if (0.4f * sqrtf(rs2) < P.threshold * fut * (1.0f - 1.0e-4f)) return;  // risk < threshold
-    exact_compute_node(P, sh, buf, ql, jj, si);
+    return !(0.4f * sqrtf(rs2) < P.threshold * fut * (1.0f - 1.0e-4f));  // risk >= threshold (maybe)
+}
+
+// queue-full fallback of the predict path: finish the pair in place (correct, slower, out of line)
+template <bool COUNT_CAND>
+__device__ __noinline__ void finish_predict_pair(const PairParams &P, u32 si, u32 sj, u32 mask) {
+    u32 dummy = 0;
+    const u32 m2 = sample_predict<COUNT_CAND>(P, si, sj, mask, dummy);
+    if (m2) exact_predict(P, si, sj, meta_pattern(__float_as_uint(P.P2[si].w)), m2);
 }
 
 // lower bound in the sorted key array
@@ -307,231 +395,337 @@ __device__ __forceinline__ u32 lower_bound_keys(const u32 *__restrict__ keys, u3
     return lo;
 }
 
-template <int MODE, bool COUNT_CAND>
-__device__ __forceinline__ void heavy_dispatch(const PairParams &P, TileShared &sh, const StageBuf &buf, u32 entry,
-                                               u32 tile_base) {
-    const u32 ql = entry >> 8, jj = entry & 0xffu;
-    const float4 a0 = sh.q0[ql], a1 = sh.q1[ql], a2 = sh.q2[ql];
-    const float4 b0 = buf.p0[jj], b1 = buf.p1[jj], b2 = buf.p2[jj];
-    const u32 si = tile_base + ql, sj = buf.pos[jj];
-    if (MODE == RCD_MODE_DETECT) {
-        heavy_detect(P, sh, buf, ql, jj, a0, a1, a2, b0, b1, b2, si, P.R, P.T, P.steps);
-    } else if (MODE == RCD_MODE_PREDICT) {
-        const u32 pattern = meta_pattern(__float_as_uint(a2.w));
-        if (pattern == RCD_PAT_NO_HISTORY)  // history < 2 -> detect_collisions(id) with defaults (:590-592)
-            heavy_detect(P, sh, buf, ql, jj, a0, a1, a2, b0, b1, b2, si, PREDICT_RADIUS, 10.0f, 100);
-        else
-            heavy_predict<COUNT_CAND>(P, sh, buf, ql, jj, a0, a1, a2, b0, b1, b2, si, pattern);
-    } else {
-        heavy_compute_node(P, sh, buf, ql, jj, a0, a1, a2, b0, b1, b2, si, sj);
-    }
+// warp-aggregated append to a global queue; returns false for the lanes whose entry did not fit
+__device__ __forceinline__ bool global_push(QEntry *q, u32 cap, unsigned long long *count, bool flag, u32 si, u32 sj,
+                                            u32 mask) {
+    const u32 ballot = __ballot_sync(FULL_MASK, flag);
+    if (ballot == 0) return true;
+    unsigned long long base = 0;
+    const u32 leader = __ffs(ballot) - 1;
+    if ((threadIdx.x & 31u) == leader) base = atomicAdd(count, (unsigned long long)__popc(ballot));
+    base = __shfl_sync(FULL_MASK, base, leader);
+    if (!flag) return true;
+    const unsigned long long at = base + __popc(ballot & lanemask_lt());
+    if (at >= cap) return false;
+    QEntry e;
+    e.si = si; e.sj = sj; e.mask = mask;
+    q[at] = e;
+    return true;
 }
 
 template <int MODE, bool COUNT_CAND>
-__global__ void __launch_bounds__(TQ, 4) k_pairs(PairParams P) {
-    __shared__ TileShared sh;
-
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 tile_base = blockIdx.x * TQ;
-    const u32 s = tile_base + tid;
-    const bool valid = s < P.n;
+__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pairs(PairParams P) {
+    __shared__ WarpShared shared[PAIR_WARPS];
+    WarpShared &ws = shared[threadIdx.x >> 5];
+    const u32 lane = threadIdx.x & 31u;
     const GridParams g = P.g;
+    u32 n_exact = 0, n_pot = 0;  // per-lane statistics, flushed once at the end
 
-    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0;
-    int cx = 0, cy = 0, cz = 0;
-    u32 meta = 0;
-    if (valid) {
-        p0 = P.P0[s];
-        p1 = P.P1[s];
-        p2 = P.P2[s];
-        meta = __float_as_uint(p2.w);
-        u32 key = P.keys[s];
-        cx = (int)(key % (u32)g.nx);
-        u32 row = key / (u32)g.nx;
-        cy = (int)(row % (u32)g.ny);
-        cz = (int)(row / (u32)g.ny);
-    }
-    sh.q0[tid] = p0;
-    sh.q1[tid] = p1;
-    sh.q2[tid] = p2;
-    sh.cand[tid] = 0;
-    if (tid == 0) { sh.n_pot = 0; sh.n_exact = 0; }
-    const bool owned = valid && (meta & META_OWNED);
-    const u32 pattern = meta_pattern(meta);
-    // queries that take the radius-R test in the filter (detect-like); the others are predict queries
-    const bool radius_query = (MODE != RCD_MODE_PREDICT) || pattern == RCD_PAT_NO_HISTORY;
-    const float Rq = (MODE == RCD_MODE_PREDICT) ? PREDICT_RADIUS : P.R;
-    const float R2_hi = Rq * Rq * (1.0f + BAND_R2), R2_lo = Rq * Rq * (1.0f - BAND_R2);
+    for (;;) {
+        u32 tile = 0;
+        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(FULL_MASK, tile, 0);
+        if (tile >= P.ntiles) break;
 
-    // reach of this query: how far a neighbour can be and still matter
-    float reach;
-    if (!radius_query) {
-        float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f;
-        float fa = (pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f;
-        float travel = sqrtf(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z) * fv * 9.5f +
-                       sqrtf(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z) * fa * 45.125f;
-        reach = (PREDICT_RADIUS + travel) * (1.0f + 1.0e-5f) + 1.0e-2f;
-    } else {
-        reach = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
-    }
-    if (!(reach < 1.0e30f)) reach = 1.0e30f;  // non-finite velocity: scan everything
-    // filter threshold on the squared distance
-    const float pass2 = radius_query ? R2_hi : reach * reach;
-    u32 ncand = 0;  // candidates decided by the filter itself
-
-    // a tile that crosses a cell-row boundary is processed as two groups (first row / the rest)
-    // so that each group's cell box stays tight
-    const u32 first_row = P.keys[tile_base] / (u32)g.nx;
-    const int my_group = (valid && ((u32)(cy + cz * g.ny) != first_row)) ? 1 : 0;
-    const int ngroups = __syncthreads_or(my_group) ? 2 : 1;  // also publishes sh.q*, sh.cand
-
-    for (int grp = 0; grp < ngroups; ++grp) {
-        const bool active = owned && my_group == grp;
-        // ---- block reduction: cell box and maximum reach of the active queries ----------------
-        int r0 = active ? cx : 0x7fffffff, r1 = active ? cx : -1;
-        int r2 = active ? cy : 0x7fffffff, r3 = active ? cy : -1;
-        int r4 = active ? cz : 0x7fffffff, r5 = active ? cz : -1;
-        float rh = active ? reach : 0.0f;
-        r0 = warp_min(r0); r1 = warp_max(r1); r2 = warp_min(r2); r3 = warp_max(r3);
-        r4 = warp_min(r4); r5 = warp_max(r5); rh = warp_maxf(rh);
-        __syncthreads();  // previous group's readers of red_* are done
-        if (lane == 0) {
-            sh.red_i[warp][0] = r0; sh.red_i[warp][1] = r1; sh.red_i[warp][2] = r2;
-            sh.red_i[warp][3] = r3; sh.red_i[warp][4] = r4; sh.red_i[warp][5] = r5;
-            sh.red_f[warp] = rh;
+        const u32 tile_base = tile * TQ;
+        const u32 s = tile_base + lane;
+        const bool valid = s < P.n;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0;
+        int cx = 0, cy = 0, cz = 0;
+        u32 meta = 0;
+        if (valid) {
+            p0 = P.P0[s];
+            p1 = P.P1[s];
+            p2 = P.P2[s];
+            meta = __float_as_uint(p2.w);
+            u32 key = P.keys[s];
+            cx = (int)(key % (u32)g.nx);
+            u32 row = key / (u32)g.nx;
+            cy = (int)(row % (u32)g.ny);
+            cz = (int)(row / (u32)g.ny);
         }
-        __syncthreads();
-        int cxmin = 0x7fffffff, cxmax = -1, cymin = 0x7fffffff, cymax = -1, czmin = 0x7fffffff, czmax = -1;
-        float hmax = 0.0f;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            cxmin = min(cxmin, sh.red_i[w][0]); cxmax = max(cxmax, sh.red_i[w][1]);
-            cymin = min(cymin, sh.red_i[w][2]); cymax = max(cymax, sh.red_i[w][3]);
-            czmin = min(czmin, sh.red_i[w][4]); czmax = max(czmax, sh.red_i[w][5]);
-            hmax = fmaxf(hmax, sh.red_f[w]);
+        __syncwarp();  // the previous tile's readers of ws.q* are done
+        ws.q0[lane] = p0;
+        ws.q1[lane] = p1;
+        ws.q2[lane] = p2;
+        ws.cand[lane] = 0;
+        const bool owned = valid && (meta & META_OWNED);
+        const u32 pattern = meta_pattern(meta);
+        // queries that take the radius-R test in the filter (detect-like); the others are predict queries
+        const bool radius_query = (MODE != RCD_MODE_PREDICT) || pattern == RCD_PAT_NO_HISTORY;
+        const float Rq = (MODE == RCD_MODE_PREDICT) ? PREDICT_RADIUS : P.R;
+        const float R2_hi = Rq * Rq * (1.0f + BAND_R2), R2_lo = Rq * Rq * (1.0f - BAND_R2);
+        // reach of this query: how far a neighbour can be and still matter
+        float reach;
+        if (!radius_query) {
+            float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f;
+            float fa = (pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f;
+            float travel = sqrtf(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z) * fv * 9.5f +
+                           sqrtf(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z) * fa * 45.125f;
+            reach = (PREDICT_RADIUS + travel) * (1.0f + 1.0e-5f) + 1.0e-2f;
+        } else {
+            reach = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
         }
-        if (cxmax < 0) continue;  // no active query in this group (uniform across the block)
-        // |ci - cj| <= floor(H / cell) + 1 for clamped floor() cells (the reference's own bound,
-        // spatial_index.py:246-248)
-        float srf = floorf(hmax * g.inv_cell + 1.0e-3f) + 1.0f;
-        int sr = (srf < 1.0e6f) ? (int)srf : 1000000;
-        const int x0 = max(cxmin - sr, 0), x1 = min(cxmax + sr, g.nx - 1);
-        const int y0 = max(cymin - sr, 0), y1 = min(cymax + sr, g.ny - 1);
-        const int z0 = max(czmin - sr, 0), z1 = min(czmax + sr, g.nz - 1);
-        const int ny_span = y1 - y0 + 1;
-        const int nrows = ny_span * (z1 - z0 + 1);
+        if (!(reach < 1.0e30f)) reach = 1.0e30f;  // non-finite velocity: scan everything
+        const float pass2 = radius_query ? R2_hi : reach * reach;
+        u32 ncand = 0;   // candidates decided by the filter itself
+        u32 n1b = 0;     // warp-uniform length of Q1b (predict)
 
-        for (int rbase = 0; rbase < nrows; rbase += MAX_ROWS) {
-            // ---- span of one cell row per thread ---------------------------------------------
-            u32 lo = 0, cnt = 0;
-            if ((int)tid + rbase < nrows) {
-                int rr = rbase + (int)tid;
-                int yy = y0 + rr % ny_span, zz = z0 + rr / ny_span;
-                u32 c0 = (u32)((zz * g.ny + yy) * g.nx + x0), c1 = c0 + (u32)(x1 - x0);
-                u32 first = 0xffffffffu, last = 0;
-                if (x1 - x0 < ROW_SCAN_MAX) {
-                    for (u32 c = c0; c <= c1; ++c) {
-                        u32 st = P.cell_start[c], en = P.cell_end[c];
-                        if (en > st) { first = min(first, st); last = max(last, en); }
-                    }
-                } else {
-                    first = lower_bound_keys(P.keys, P.n, c0);
-                    last = lower_bound_keys(P.keys, P.n, c1 + 1);
+        // S2b on `take` entries from the top of Q1b: scan the window, survivors -> global Q2
+        auto run_scan = [&](u32 take) {
+            bool keep = false;
+            u32 si = 0, sj = 0, mask = 0;
+            if (lane < take) {
+                const u32 ql = ws.q1b_ql[n1b - take + lane];
+                sj = ws.q1b_pos[n1b - take + lane];
+                si = tile_base + ql;
+                const float4 a0 = ws.q0[ql], a1 = ws.q1[ql], a2 = ws.q2[ql];
+                const float4 b0 = P.P0[sj], b1 = P.P1[sj], b2 = P.P2[sj];
+                const u32 pat = meta_pattern(__float_as_uint(a2.w));
+                const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
+                int m_lo, m_hi;
+                if (predict_window(c, m_lo, m_hi) || COUNT_CAND) {
+                    mask = predict_scan<COUNT_CAND>(ws, P, c, ql, si, sj, pat, m_lo, m_hi, n_exact);
+                    keep = mask != 0;
                 }
-                if (last > first) { lo = first; cnt = last - first; }
             }
-            // exclusive scan of cnt over the block
-            u32 incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                u32 t = __shfl_up_sync(FULL_MASK, incl, o);
-                if (lane >= (u32)o) incl += t;
-            }
-            __syncthreads();  // previous batch's readers of row_* / scan are done
-            if (lane == 31) sh.scan[warp] = incl;
-            __syncthreads();
-            u32 wbase = 0;
-            for (u32 w = 0; w < warp; ++w) wbase += sh.scan[w];
-            sh.row_lo[tid] = lo;
-            sh.row_prefix[tid] = wbase + incl - cnt;
-            if (tid == TQ - 1) sh.row_prefix[MAX_ROWS] = wbase + incl;
-            __syncthreads();
-            const u32 total = sh.row_prefix[MAX_ROWS];
-            const u32 nchunks = (total + CH - 1) / CH;
+            __syncwarp();
+            n1b -= take;
+            if (!global_push(P.q2, P.qcap, &P.counters->n_q2, keep, si, sj, mask))
+                finish_predict_pair<COUNT_CAND>(P, si, sj, mask);  // queue full: finish the pair here
+        };
 
-            // stage chunk c of the flattened spans into buffer c & 1 (cp.async, 2 objects per thread)
-            auto stage = [&](u32 c) {
-                StageBuf &b = sh.buf[c & 1u];
-#pragma unroll
-                for (int e = 0; e < CH / TQ; ++e) {
-                    u32 slot = tid + e * TQ;
-                    u32 f = c * CH + slot;
-                    if (f < total) {
-                        int a = 0, z = MAX_ROWS - 1;  // last row r with prefix[r] <= f
-                        while (a < z) {
-                            int mid = (a + z + 1) >> 1;
-                            if (sh.row_prefix[mid] <= f) a = mid; else z = mid - 1;
+        // a tile that crosses a cell-row boundary is processed as two groups (first row / the rest)
+        // so that each group's cell box stays tight
+        const u32 my_row = (u32)(cy + cz * g.ny);
+        const u32 first_row = __shfl_sync(FULL_MASK, my_row, 0);
+        const int my_group = (valid && my_row != first_row) ? 1 : 0;
+        const int ngroups = __any_sync(FULL_MASK, my_group) ? 2 : 1;
+        __syncwarp();
+
+        for (int grp = 0; grp < ngroups; ++grp) {
+            const bool active = owned && my_group == grp;
+            const int cxmin = warp_min(active ? cx : 0x7fffffff), cxmax = warp_max(active ? cx : -1);
+            if (cxmax < 0) continue;  // no active query in this group (warp-uniform)
+            const int cymin = warp_min(active ? cy : 0x7fffffff), cymax = warp_max(active ? cy : -1);
+            const int czmin = warp_min(active ? cz : 0x7fffffff), czmax = warp_max(active ? cz : -1);
+            const float hmax = warp_maxf(active ? reach : 0.0f);
+            // |ci - cj| <= floor(H / cell) + 1 for clamped floor() cells (the reference's own bound,
+            // spatial_index.py:246-248); 1e-3 covers the fp32 error of the cell coordinates
+            float srf = floorf(hmax * g.inv_cell + 1.0e-3f) + 1.0f;
+            int sr = (srf < 1.0e6f) ? (int)srf : 1000000;
+            const int x0 = max(cxmin - sr, 0), x1 = min(cxmax + sr, g.nx - 1);
+            const int y0 = max(cymin - sr, 0), y1 = min(cymax + sr, g.ny - 1);
+            const int z0 = max(czmin - sr, 0), z1 = min(czmax + sr, g.nz - 1);
+            const int ny_span = y1 - y0 + 1;
+            const int nrows = ny_span * (z1 - z0 + 1);
+
+            for (int rbase = 0; rbase < nrows; rbase += TQ) {
+                // ---- span of one cell row per lane -------------------------------------------
+                u32 lo = 0, cnt = 0;
+                if ((int)lane + rbase < nrows) {
+                    int rr = rbase + (int)lane;
+                    int yy = y0 + rr % ny_span, zz = z0 + rr / ny_span;
+                    u32 c0 = (u32)((zz * g.ny + yy) * g.nx + x0), c1 = c0 + (u32)(x1 - x0);
+                    u32 first = 0xffffffffu, last = 0;
+                    if (x1 - x0 < ROW_SCAN_MAX) {
+                        for (u32 c = c0; c <= c1; ++c) {
+                            u32 st_ = P.cell_start[c], en = P.cell_end[c];
+                            if (en > st_) { first = min(first, st_); last = max(last, en); }
                         }
-                        u32 src = sh.row_lo[a] + (f - sh.row_prefix[a]);
-                        cp_async16(&b.p0[slot], P.P0 + src);
-                        cp_async16(&b.p1[slot], P.P1 + src);
-                        cp_async16(&b.p2[slot], P.P2 + src);
-                        b.pos[slot] = src;
+                    } else {
+                        first = lower_bound_keys(P.keys, P.n, c0);
+                        last = lower_bound_keys(P.keys, P.n, c1 + 1);
                     }
+                    if (last > first) { lo = first; cnt = last - first; }
                 }
-                cp_async_commit();
-            };
+                u32 incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    u32 t = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (lane >= (u32)o) incl += t;
+                }
+                __syncwarp();  // previous batch's readers of row_* are done
+                ws.row_lo[lane] = lo;
+                ws.row_prefix[lane] = incl - cnt;
+                if (lane == 31) ws.row_prefix[TQ] = incl;
+                __syncwarp();
+                const u32 total = ws.row_prefix[TQ];
+                const u32 nchunks = (total + CH - 1) / CH;
 
-            if (nchunks) stage(0);
-            for (u32 c = 0; c < nchunks; ++c) {
-                if (c + 1 < nchunks) {
-                    stage(c + 1);
-                    cp_async_wait<1>();
-                } else {
-                    cp_async_wait<0>();
-                }
-                __syncthreads();
-                const StageBuf &b = sh.buf[c & 1u];
-                const u32 m = min((u32)CH, total - c * CH);
-                // ---- filter: one query per thread against every staged neighbour ------------------
-                u32 qcount = 0;  // warp-uniform
-                for (u32 jj = 0; jj < m; ++jj) {
-                    const float4 b0 = b.p0[jj];
-                    float dx = b0.x - p0.x, dy = b0.y - p0.y, dz = b0.z - p0.z;
-                    float d2 = dx * dx + dy * dy + dz * dz;
-                    bool pass = active && d2 <= pass2;
-                    if (MODE != RCD_MODE_COMPUTE_NODE) pass = pass && (b.pos[jj] != s);  // strip self (:224-225)
-                    if (pass && radius_query && d2 < R2_lo) ++ncand;  // certainly within the radius
-                    const u32 mask = __ballot_sync(FULL_MASK, pass);
-                    if (mask) {
-                        if (pass) sh.queue[warp][qcount + __popc(mask & lanemask_lt())] = (unsigned short)((tid << 8) | jj);
-                        qcount += __popc(mask);
+                // stage chunk c of the flattened spans into buffer c & 1 (cp.async, 2 objects per lane)
+                auto stage = [&](u32 c) {
+                    StageBuf &b = ws.buf[c & 1u];
+#pragma unroll
+                    for (int e = 0; e < CH / TQ; ++e) {
+                        u32 slot = lane + e * TQ;
+                        u32 f = c * CH + slot;
+                        if (f < total) {
+                            int a = 0, z = TQ - 1;  // last row r with prefix[r] <= f
+                            while (a < z) {
+                                int mid = (a + z + 1) >> 1;
+                                if (ws.row_prefix[mid] <= f) a = mid; else z = mid - 1;
+                            }
+                            u32 src = ws.row_lo[a] + (f - ws.row_prefix[a]);
+                            cp_async16(&b.p0[slot], P.P0 + src);
+                            cp_async16(&b.p1[slot], P.P1 + src);
+                            cp_async16(&b.p2[slot], P.P2 + src);
+                            b.pos[slot] = src;
+                        }
+                    }
+                    cp_async_commit();
+                };
+
+                if (nchunks) stage(0);
+                for (u32 c = 0; c < nchunks; ++c) {
+                    if (c + 1 < nchunks) {
+                        stage(c + 1);
+                        cp_async_wait<1>();
+                    } else {
+                        cp_async_wait<0>();
+                    }
+                    __syncwarp();
+                    const StageBuf &b = ws.buf[c & 1u];
+                    const u32 m = min((u32)CH, total - c * CH);
+                    // ---- S1 filter: one query per lane against every staged neighbour --------------
+                    // Q1 is filled until it holds a full warp of pairs (or the chunk is exhausted), then
+                    // S2 runs on 32 of them: a single call site keeps the kernel small (I-cache).
+                    u32 n1 = 0;  // warp-uniform length of Q1
+                    u32 j0 = 0;
+                    for (;;) {
+                        while (j0 < m && n1 < 32) {
+                            bool pass[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float4 b0 = b.p0[min(j0 + u, (u32)CH - 1)];
+                                float dx = b0.x - p0.x, dy = b0.y - p0.y, dz = b0.z - p0.z;
+                                float d2 = dx * dx + dy * dy + dz * dz;
+                                pass[u] = active && (j0 + u < m) && d2 <= pass2;
+                                if (pass[u] && radius_query && d2 < R2_lo) ++ncand;  // certainly within the radius
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const u32 mask = __ballot_sync(FULL_MASK, pass[u]);
+                                if (pass[u]) ws.q1e[n1 + __popc(mask & lanemask_lt())] = (unsigned short)((lane << 8) | (j0 + u));
+                                n1 += __popc(mask);
+                            }
+                            j0 += 4;
+                        }
+                        if (n1 == 0) break;  // chunk exhausted and Q1 empty
                         __syncwarp();
-                        if (qcount >= 32) {
-                            heavy_dispatch<MODE, COUNT_CAND>(P, sh, b, sh.queue[warp][qcount - 32 + lane], tile_base);
-                            qcount -= 32;
-                            __syncwarp();
+                        // ---- S2 on up to 32 queued pairs ----------------------------------------------
+                        const u32 take = min(n1, 32u);
+                        const u32 entry = ws.q1e[n1 - take + min(lane, take - 1)];
+                        n1 -= take;
+                        bool keep = false;     // -> global Q3 (exact stage)
+                        bool to_scan = false;  // -> Q1b (predict window scan)
+                        u32 sj = 0;
+                        const u32 ql = entry >> 8, jj = entry & 0xffu;
+                        const u32 si = tile_base + ql;
+                        if (lane < take) {
+                            const float4 a0 = ws.q0[ql], a1 = ws.q1[ql], a2 = ws.q2[ql];
+                            const float4 b0 = b.p0[jj], b1 = b.p1[jj], b2 = b.p2[jj];
+                            sj = b.pos[jj];
+                            if (MODE == RCD_MODE_COMPUTE_NODE) {
+                                keep = narrow_compute_node(ws, P, ql, a0, a1, a2, b0, b1, b2, sj == si, n_exact);
+                            } else if (sj != si) {  // _spatial_filtering strips self (:224-225)
+                                const u32 pat = meta_pattern(__float_as_uint(a2.w));
+                                if (MODE == RCD_MODE_DETECT) {
+                                    keep = narrow_detect(ws, ql, a0, a1, a2, b0, b1, b2, P.R, P.T, n_exact);
+                                } else if (pat == RCD_PAT_NO_HISTORY) {
+                                    keep = narrow_detect(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, n_exact);
+                                } else if (COUNT_CAND) {
+                                    to_scan = true;
+                                } else {
+                                    const PredictCoef co = predict_coef(a0, a1, a2, b0, b1, b2, pat);
+                                    int m_lo, m_hi;
+                                    to_scan = predict_window(co, m_lo, m_hi);
+                                }
+                            }
                         }
+                        if (MODE == RCD_MODE_PREDICT) {
+                            const u32 bal = __ballot_sync(FULL_MASK, to_scan);
+                            if (bal) {
+                                if (to_scan) {
+                                    const u32 at = n1b + __popc(bal & lanemask_lt());
+                                    ws.q1b_pos[at] = sj;
+                                    ws.q1b_ql[at] = (unsigned char)ql;
+                                }
+                                n1b += __popc(bal);
+                                __syncwarp();
+                                if (n1b >= 32) run_scan(32);
+                            }
+                        }
+                        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, keep, si, sj, 0u))
+                            n_pot += exact_entry<MODE>(P, si, sj, 0u);  // queue full: decide here
                     }
-                }
-                if (qcount) {  // drain the tail before the buffer is recycled
-                    if (lane < qcount) heavy_dispatch<MODE, COUNT_CAND>(P, sh, b, sh.queue[warp][lane], tile_base);
                     __syncwarp();
                 }
-                __syncthreads();
             }
         }
+        // ---- end of tile ------------------------------------------------------------------------------
+        if (MODE == RCD_MODE_PREDICT) {
+            if (n1b) run_scan(n1b);  // Q1b refers to this tile's queries
+        }
+        __syncwarp();
+        ncand += ws.cand[lane];
+        // the filter counted the query itself (distance 0) for radius queries; only the
+        // compute-node index returns self (quirk Q8)
+        if (MODE != RCD_MODE_COMPUTE_NODE && owned && radius_query) ncand -= 1;
+        if (owned && P.cand_count) P.cand_count[P.sorted_slot[s]] = ncand;
+        unsigned long long csum = warp_sum((unsigned long long)(owned ? ncand : 0u));
+        if (lane == 0 && csum) atomicAdd(&P.counters->n_candidates, csum);
     }
+    unsigned long long p = warp_sum((unsigned long long)n_pot);
+    unsigned long long e = warp_sum((unsigned long long)n_exact);
+    if (lane == 0) {
+        if (p) atomicAdd(&P.counters->n_potential, p);
+        if (e) atomicAdd(&P.counters->n_exact, e);
+    }
+}
 
-    // ---- per-object candidate count + frame totals ------------------------------------------------
-    __syncthreads();
-    ncand += sh.cand[tid];
-    if (owned && P.cand_count) P.cand_count[P.sorted_slot[s]] = ncand;
-    unsigned long long c = warp_sum((unsigned long long)ncand);
-    if (lane == 0 && c) atomicAdd(&P.counters->n_candidates, c);
-    if (tid == 0) {
-        if (sh.n_pot) atomicAdd(&P.counters->n_potential, (unsigned long long)sh.n_pot);
-        if (sh.n_exact) atomicAdd(&P.counters->n_exact, (unsigned long long)sh.n_exact);
+// k_sample (predict): one queued pair per thread -> offsets that survive the fp32 samples -> Q3
+constexpr int STAGE_THREADS = 128;
+
+template <bool COUNT_CAND>
+__global__ void __launch_bounds__(STAGE_THREADS) k_sample(PairParams P) {
+    const unsigned long long n = min(P.counters->n_q2, (unsigned long long)P.qcap);
+    const unsigned long long stride = (unsigned long long)gridDim.x * STAGE_THREADS;
+    const unsigned long long rounds = (n + stride - 1) / stride;
+    u32 n_exact = 0;
+    for (unsigned long long r = 0; r < rounds; ++r) {  // uniform trip count: global_push is warp-wide
+        const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
+        bool keep = false;
+        QEntry e;
+        e.si = e.sj = e.mask = 0;
+        if (k < n) {
+            e = P.q2[k];
+            e.mask = sample_predict<COUNT_CAND>(P, e.si, e.sj, e.mask, n_exact);
+            keep = e.mask != 0;
+        }
+        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, keep, e.si, e.sj, e.mask))
+            exact_entry<RCD_MODE_PREDICT>(P, e.si, e.sj, e.mask);
+    }
+    unsigned long long ex = warp_sum((unsigned long long)n_exact);
+    if ((threadIdx.x & 31u) == 0 && ex) atomicAdd(&P.counters->n_exact, ex);
+}
+
+// k_exact: one queued pair per thread, decided in fp64
+template <int MODE>
+__global__ void __launch_bounds__(STAGE_THREADS) k_exact(PairParams P) {
+    const unsigned long long n = min(P.counters->n_q3, (unsigned long long)P.qcap);
+    const unsigned long long stride = (unsigned long long)gridDim.x * STAGE_THREADS;
+    u32 n_pot = 0, n_exact = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x; k < n; k += stride) {
+        const QEntry e = P.q3[k];
+        n_pot += exact_entry<MODE>(P, e.si, e.sj, e.mask);
+        n_exact += (MODE == RCD_MODE_PREDICT && e.mask) ? (u32)__popc(e.mask) : 1u;
+    }
+    unsigned long long p = warp_sum((unsigned long long)n_pot);
+    unsigned long long ex = warp_sum((unsigned long long)n_exact);
+    if ((threadIdx.x & 31u) == 0) {
+        if (p) atomicAdd(&P.counters->n_potential, p);
+        if (ex) atomicAdd(&P.counters->n_exact, ex);
     }
 }
 
