@@ -117,17 +117,18 @@ typedef struct {
     uint64_t n_exact;      /* pairs that took the fp64 re-evaluation path (diagnostic) */
 } rcd_counts_t;
 
-#define RCD_NUM_STAGES 8
+#define RCD_NUM_STAGES 9
 /* stage indices for rcd_stage_ms */
 enum {
     RCD_STAGE_UPLOAD = 0,  /* host->device copies of the SoA state */
-    RCD_STAGE_KEYS = 1,    /* cell keys + digit histograms */
-    RCD_STAGE_SORT = 2,    /* radix sort passes */
-    RCD_STAGE_REORDER = 3, /* gather into cell order + cell ranges */
-    RCD_STAGE_PAIRS = 4,   /* pair enumeration + narrow phase + classification */
-    RCD_STAGE_FINALIZE = 5,
-    RCD_STAGE_DOWNLOAD = 6,
-    RCD_STAGE_TOTAL = 7
+    RCD_STAGE_KEYS = 1,    /* k_cell_keys + k_scan_hist: cell keys + digit histograms */
+    RCD_STAGE_SORT = 2,    /* k_onesweep_pass x passes */
+    RCD_STAGE_REORDER = 3, /* k_reorder: gather into cell order + cell ranges */
+    RCD_STAGE_PAIRS = 4,   /* k_pairs: pair enumeration + fp32 narrow phase */
+    RCD_STAGE_SAMPLE = 5,  /* k_sample (predict): radius test + 10 samples per surviving offset */
+    RCD_STAGE_EXACT = 6,   /* k_exact: fp64 decision, merge, emit, alert class */
+    RCD_STAGE_DOWNLOAD = 7,
+    RCD_STAGE_TOTAL = 8
 };
 
 int rcd_version(void);
@@ -161,6 +162,10 @@ int rcd_set_owned(rcd_handle h, uint64_t n_owned);
  * for pattern-3 objects, which use the defaults 100.0 / 10.0 (:592).  Compute-node mode uses
  * search_radius as NodeConfig.search_radius (compute_node.py:620-622). */
 int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window);
+
+/* Keep only the first n objects (drop halo copies appended after the owned objects); the
+ * remaining objects all become owned.  n must not exceed the current object count. */
+int rcd_truncate(rcd_handle h, uint64_t n);
 
 /* The object state was modified in place (device-resident frames): rebuild the index on the next
  * rcd_step even though rcd_upload was not called. */

@@ -415,6 +415,7 @@ int orc_frame_A(int64_t n, const double *px, const double *py, const double *pz,
                 const double *vy, const double *vz, const double *ax, const double *ay,
                 const double *az, const double *size, const double *heading, const int32_t *type,
                 int32_t mode, const uint8_t *pattern, double R, double T, int32_t threads,
+                int64_t q_stride /* query only objects with i % q_stride == 0 (CPU-baseline sampling) */,
                 uint32_t *cand_count /* n or NULL */, int32_t *cand_pairs /* 2*cand_cap or NULL */,
                 int64_t cand_cap, orc_potential *pots_out, int64_t pot_cap, orc_risk *risks_out,
                 int64_t risk_cap, int64_t *counts) {
@@ -443,6 +444,7 @@ int orc_frame_A(int64_t n, const double *px, const double *py, const double *pz,
         vec_init(risks, sizeof(orc_risk));
         int64_t lo = c * chunk, hi = lo + chunk < n ? lo + chunk : n;
         for (int64_t i = lo; i < hi; ++i) {
+            if (q_stride > 1 && (i % q_stride) != 0) continue;
             int64_t r0 = risks->n, p0 = pots->n, c0 = cands->n;
             int pat = (mode == 1 && pattern) ? pattern[i] : (mode == 1 ? 2 : 3);
             if (mode == 0 || pat == 3)

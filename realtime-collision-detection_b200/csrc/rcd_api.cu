@@ -416,7 +416,7 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     if (!append) h->launches = 0;
     h->frame_done = false;
     h->stage_mode = mode;
-    for (int s = RCD_STAGE_KEYS; s <= RCD_STAGE_PAIRS; ++s) h->stages[mode][s].used = false;
+    for (int s = RCD_STAGE_KEYS; s <= RCD_STAGE_EXACT; ++s) h->stages[mode][s].used = false;
     stage_begin(h, RCD_STAGE_TOTAL);
     const float cell_req = (mode == RCD_MODE_PREDICT) ? PREDICT_RADIUS : search_radius;
     int rc = build_index(h, cell_req);
@@ -467,6 +467,7 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         else if (variant == 2) k_pairs<RCD_MODE_PREDICT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         else k_pairs<RCD_MODE_COMPUTE_NODE, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         KERNEL_CHECK(h);
+        stage_end(h, RCD_STAGE_PAIRS);
         // the later stages read their queue lengths on the device: fixed grids, no host round trip
         if (h->stage_blocks == 0) {
             int sms = 0;
@@ -474,17 +475,35 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
             h->stage_blocks = std::max(1, sms) * 8;
         }
         const unsigned sb = (unsigned)std::min<u64>((u64)h->stage_blocks, (h->n + STAGE_THREADS - 1) / STAGE_THREADS + 1);
-        if (variant == 1) { k_sample<false><<<sb, STAGE_THREADS, 0, h->stream>>>(P); KERNEL_CHECK(h); }
-        if (variant == 2) { k_sample<true><<<sb, STAGE_THREADS, 0, h->stream>>>(P); KERNEL_CHECK(h); }
+        if (variant == 1 || variant == 2) {
+            stage_begin(h, RCD_STAGE_SAMPLE);
+            if (variant == 1) k_sample<false><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+            else k_sample<true><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+            KERNEL_CHECK(h);
+            stage_end(h, RCD_STAGE_SAMPLE);
+        }
+        stage_begin(h, RCD_STAGE_EXACT);
         if (variant == 0) k_exact<RCD_MODE_DETECT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         else if (variant == 3) k_exact<RCD_MODE_COMPUTE_NODE><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         else k_exact<RCD_MODE_PREDICT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         KERNEL_CHECK(h);
+        stage_end(h, RCD_STAGE_EXACT);
+    } else {
+        stage_end(h, RCD_STAGE_PAIRS);
     }
-    stage_end(h, RCD_STAGE_PAIRS);
     stage_end(h, RCD_STAGE_TOTAL);
     h->frame_done = true;
     h->last_mode = mode;
+    return RCD_OK;
+}
+
+int rcd_truncate(rcd_handle h, uint64_t n) {
+    if (!h) return RCD_EINVAL;
+    if (n > h->n) return fail(h, RCD_EINVAL, "rcd_truncate: n exceeds the object count");
+    h->n = n;
+    h->n_owned = n;
+    h->index_valid = false;
+    h->frame_done = false;
     return RCD_OK;
 }
 

@@ -20,15 +20,15 @@ SRC_HOST, SRC_DEVICE = 0, 1
 PAT_STATIONARY, PAT_CONSTANT_VELOCITY, PAT_ACCELERATING, PAT_NO_HISTORY = 0, 1, 2, 3
 FLAG_PROFILE = 1
 FLAG_COUNT_PREDICT_CANDIDATES = 2
-NUM_STAGES = 8
-STAGE_NAMES = ("upload", "keys", "sort", "reorder", "pairs", "finalize", "download", "total")
+NUM_STAGES = 9
+STAGE_NAMES = ("upload", "keys", "sort", "reorder", "pairs", "sample", "exact", "download", "total")
 HALO_RECORD_WORDS = 13
 
 # every symbol include/rcd.h declares (tests/test_abi.py checks the export table against this
 # list and against the header itself)
 SYMBOLS = (
     "rcd_version", "rcd_last_error", "rcd_create", "rcd_destroy", "rcd_upload", "rcd_set_patterns",
-    "rcd_set_owned", "rcd_step", "rcd_invalidate", "rcd_counts", "rcd_download",
+    "rcd_set_owned", "rcd_step", "rcd_truncate", "rcd_invalidate", "rcd_counts", "rcd_download",
     "rcd_download_candidate_counts", "rcd_query_radius", "rcd_classify_patterns", "rcd_halo_pack",
     "rcd_halo_append", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_sync",
 )
@@ -84,6 +84,7 @@ def load() -> ctypes.CDLL:
     L.rcd_set_patterns.argtypes = [vp, u64, vp, i32]
     L.rcd_set_owned.argtypes = [vp, u64]
     L.rcd_step.argtypes = [vp, i32, f32, f32]
+    L.rcd_truncate.argtypes = [vp, u64]
     L.rcd_invalidate.argtypes = [vp]
     L.rcd_counts.argtypes = [vp, ctypes.POINTER(RcdCounts)]
     L.rcd_download.argtypes = [vp, vp, u64, ctypes.POINTER(u64)]

@@ -78,12 +78,30 @@ class FrameEngine:
         N.check(self._lib.rcd_upload(self._h, n, *[_vp(a) for a in arrs], _vp(typ), _vp(idv), N.SRC_HOST), self._h)
         self.n = n
 
-    def upload_device(self, n: int, ptrs: Sequence[int], type_ptr: int = 0, id_ptr: int = 0) -> None:
-        """Same, from 11 device pointers (float32, n entries each) in FRAME_FIELDS order."""
+    def upload_ptrs(self, n: int, ptrs: Sequence[int], type_ptr: int = 0, id_ptr: int = 0,
+                    src: int = N.SRC_DEVICE) -> None:
+        """Same, from 11 raw pointers (float32, n entries each, FRAME_FIELDS order) in device memory
+        (src=SRC_DEVICE) or host memory (src=SRC_HOST; pinned memory makes the copies asynchronous)."""
         args = [ctypes.c_void_p(int(p)) if p else None for p in ptrs]
         N.check(self._lib.rcd_upload(self._h, int(n), *args, ctypes.c_void_p(type_ptr) if type_ptr else None,
-                                     ctypes.c_void_p(id_ptr) if id_ptr else None, N.SRC_DEVICE), self._h)
+                                     ctypes.c_void_p(id_ptr) if id_ptr else None, int(src)), self._h)
         self.n = int(n)
+
+    def upload_device(self, n: int, ptrs: Sequence[int], type_ptr: int = 0, id_ptr: int = 0) -> None:
+        self.upload_ptrs(n, ptrs, type_ptr, id_ptr, N.SRC_DEVICE)
+
+    def upload_host_ptrs(self, n: int, ptrs: Sequence[int], type_ptr: int = 0, id_ptr: int = 0) -> None:
+        self.upload_ptrs(n, ptrs, type_ptr, id_ptr, N.SRC_HOST)
+
+    def set_patterns_ptr(self, n: int, ptr: int, src: int) -> None:
+        N.check(self._lib.rcd_set_patterns(self._h, int(n), ctypes.c_void_p(int(ptr)) if ptr else None, int(src)),
+                self._h)
+
+    def set_patterns_device(self, n: int, ptr: int) -> None:
+        self.set_patterns_ptr(n, ptr, N.SRC_DEVICE)
+
+    def set_patterns_host_ptr(self, n: int, ptr: int) -> None:
+        self.set_patterns_ptr(n, ptr, N.SRC_HOST)
 
     def set_patterns(self, pattern: Optional[np.ndarray]) -> None:
         if pattern is None:
@@ -95,6 +113,11 @@ class FrameEngine:
 
     def set_owned(self, n_owned: int) -> None:
         N.check(self._lib.rcd_set_owned(self._h, int(n_owned)), self._h)
+
+    def truncate(self, n: int) -> None:
+        """Drop everything after the first n objects (the halo copies of the previous frame)."""
+        N.check(self._lib.rcd_truncate(self._h, int(n)), self._h)
+        self.n = int(n)
 
     def invalidate(self) -> None:
         N.check(self._lib.rcd_invalidate(self._h), self._h)
