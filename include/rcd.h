@@ -163,6 +163,10 @@ int rcd_set_owned(rcd_handle h, uint64_t n_owned);
  * search_radius as NodeConfig.search_radius (compute_node.py:620-622). */
 int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window);
 
+/* Compute-node mode parameters: CollisionDetector(prediction_time=5.0, risk_threshold=0.5)
+ * (src/compute/compute_node.py:218-227).  Defaults are the reference's. */
+int rcd_set_compute_node_params(rcd_handle h, float prediction_time, float risk_threshold);
+
 /* Keep only the first n objects (drop halo copies appended after the owned objects); the
  * remaining objects all become owned.  n must not exceed the current object count. */
 int rcd_truncate(rcd_handle h, uint64_t n);
@@ -176,6 +180,10 @@ int rcd_counts(rcd_handle h, rcd_counts_t *out);
 
 /* Copy the emitted pairs to host memory, sorted by (i, j, predicted); *n_out = pairs copied (<= cap). */
 int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out);
+
+/* Same without the ordering (emission order is not deterministic): for consumers that group or
+ * sort on their own, or only stream the pairs onwards. */
+int rcd_download_unsorted(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out);
 
 /* Per-object broad-phase candidate counts of the last frame, in upload order (n entries). */
 int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n);

@@ -71,6 +71,7 @@ struct rcd_handle_s {
 
     Stage stages[3][RCD_NUM_STAGES];  // per frame mode
     int stage_mode = 0;
+    float cn_prediction_time = 5.0f, cn_risk_threshold = 0.5f;
     u64 launches = 0;
     std::string err;
 };
@@ -437,8 +438,8 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         P.R = search_radius;
         P.T = time_window;
         P.steps = (int)((double)time_window / 0.1);  // int(time_window / time_step), collision_detection.py:322
-        P.pt = 5.0f;         // CollisionDetector(prediction_time=5.0, risk_threshold=0.5), compute_node.py:218
-        P.threshold = 0.5f;
+        P.pt = h->cn_prediction_time;  // CollisionDetector(prediction_time=5.0, risk_threshold=0.5), compute_node.py:218
+        P.threshold = h->cn_risk_threshold;
         P.out = h->out;
         P.out_cap = h->max_pairs;
         P.counters = h->counters;
@@ -497,6 +498,16 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     return RCD_OK;
 }
 
+int rcd_set_compute_node_params(rcd_handle h, float prediction_time, float risk_threshold) {
+    if (!h) return RCD_EINVAL;
+    if (!(prediction_time >= 0.0f) || !std::isfinite(prediction_time) || !std::isfinite(risk_threshold))
+        return fail(h, RCD_EINVAL, "rcd_set_compute_node_params: bad parameter");
+    h->cn_prediction_time = prediction_time;
+    h->cn_risk_threshold = risk_threshold;
+    h->frame_done = false;
+    return RCD_OK;
+}
+
 int rcd_truncate(rcd_handle h, uint64_t n) {
     if (!h) return RCD_EINVAL;
     if (n > h->n) return fail(h, RCD_EINVAL, "rcd_truncate: n exceeds the object count");
@@ -533,7 +544,7 @@ int rcd_counts(rcd_handle h, rcd_counts_t *out) {
     return RCD_OK;
 }
 
-int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
+static int download_impl(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out, bool sorted) {
     if (!h || !n_out || (cap && !out)) return RCD_EINVAL;
     rcd_counts_t c;
     int rc = rcd_counts(h, &c);
@@ -544,13 +555,29 @@ int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
     if (m) {
         CUDA_TRY(h, cudaMemcpyAsync(out, h->out, (size_t)m * sizeof(rcd_pair), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-        std::sort(out, out + m, [](const rcd_pair &a, const rcd_pair &b) {
-            return a.i != b.i ? a.i < b.i : (a.j != b.j ? a.j < b.j : a.predicted < b.predicted);
-        });
+        if (sorted) {
+            // sort 16-byte (key, index) records instead of the 48-byte pairs, then permute once
+            struct KeyIdx { u64 key; u32 idx; u32 sub; };
+            std::vector<KeyIdx> keys((size_t)m);
+            for (u64 k = 0; k < m; ++k) keys[k] = {((u64)out[k].i << 32) | out[k].j, (u32)k, out[k].predicted};
+            std::sort(keys.begin(), keys.end(), [](const KeyIdx &a, const KeyIdx &b) {
+                return a.key != b.key ? a.key < b.key : a.sub < b.sub;
+            });
+            std::vector<rcd_pair> tmp(out, out + m);
+            for (u64 k = 0; k < m; ++k) out[k] = tmp[keys[k].idx];
+        }
     }
     stage_end(h, RCD_STAGE_DOWNLOAD);
     *n_out = m;
     return RCD_OK;
+}
+
+int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
+    return download_impl(h, out, cap, n_out, true);
+}
+
+int rcd_download_unsorted(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
+    return download_impl(h, out, cap, n_out, false);
 }
 
 int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n) {

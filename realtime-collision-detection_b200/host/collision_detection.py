@@ -1,0 +1,208 @@
+"""Drop-in for src/collision/collision_detection.py: ``CollisionDetector`` and
+``CollisionPredictionModel`` with the reference's signatures and return types.
+
+Per-vehicle calls are served from whole-frame GPU results: the first ``detect_collisions`` /
+``predict_collisions`` after an update runs one frame for every vehicle (csrc/rcd_pairs.cuh);
+the following calls are O(1) look-ups until a vehicle changes.  The additive batch entry points
+``detect_all`` / ``predict_all`` return every vehicle's risks at once.
+"""
+from __future__ import annotations
+
+import time
+import uuid
+from typing import Any, Dict, List, Optional, Set, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .models import CollisionRisk, Position, Vector, Vehicle
+from .spatial_index import SpatialIndex
+
+SAFE_DISTANCE_DEFAULT = 5.0
+MAX_WARNING_TIME = 10.0
+MAX_RELATIVE_SPEED = 50.0
+WEIGHT_DISTANCE, WEIGHT_TIME, WEIGHT_SPEED, WEIGHT_ANGLE, WEIGHT_TYPE = 0.3, 0.3, 0.2, 0.1, 0.1
+
+
+def _risks_from_pairs(pairs: np.ndarray, ids: List[str]) -> List[CollisionRisk]:
+    now = time.time()
+    out = []
+    for r in pairs:
+        out.append(CollisionRisk(
+            id=f"risk-{uuid.uuid4()}", vehicle_id=ids[int(r["i"])], other_vehicle_id=ids[int(r["j"])],
+            time_to_collision=float(r["ttc"]), distance=float(r["distance"]), relative_speed=float(r["rel_speed"]),
+            risk_level=float(r["risk"]),
+            collision_position=Position(float(r["cx"]), float(r["cy"]), float(r["cz"])), timestamp=now,
+            is_predicted=bool(r["predicted"]), alert_priority=int(r["priority"]),
+            time_to_closest=float(r["t_closest"]), closest_distance=float(r["d_closest"])))
+    return out
+
+
+class CollisionDetector:
+    def __init__(self, spatial_index: SpatialIndex):
+        self.spatial_index = spatial_index
+        self.vehicle_cache: Dict[str, Vehicle] = {}
+        self.collision_risks: Dict[str, Dict[str, CollisionRisk]] = {}
+        self.stats = {"total_detections": 0, "potential_collisions": 0, "high_risk_collisions": 0,
+                      "avg_detection_time_ms": 0.0, "max_detection_time_ms": 0.0}
+        self._counted: Set[Tuple] = set()
+
+    # -- updates (collision_detection.py:74-108) ----------------------------------------------
+    def update_vehicle(self, vehicle: Vehicle) -> None:
+        self.vehicle_cache[vehicle.id] = vehicle
+        idx = self.spatial_index
+        idx.vehicle_positions[vehicle.id] = vehicle.position
+        p, v, a = vehicle.position, vehicle.velocity, vehicle.acceleration
+        idx._table.set_state(vehicle.id, (p.x, p.y, p.z), (v.x, v.y, v.z), (a.x, a.y, a.z), vehicle.heading,
+                             vehicle.size, vehicle.type)
+        idx.stats["total_vehicles"] = len(idx.vehicle_positions)
+
+    def update_vehicles_batch(self, vehicles) -> None:
+        for v in vehicles:
+            self.update_vehicle(v)
+
+    def remove_vehicle(self, vehicle_id: str) -> None:
+        self.vehicle_cache.pop(vehicle_id, None)
+        self.spatial_index.remove_vehicle(vehicle_id)
+        self.collision_risks.pop(vehicle_id, None)
+        for risks in self.collision_risks.values():
+            risks.pop(vehicle_id, None)
+
+    # -- queries --------------------------------------------------------------------------------
+    def _frame(self, search_radius: float, time_window: float):
+        frames = self.spatial_index._frames
+        t0 = time.perf_counter()
+        ran_before = frames.frames_run
+        pairs, starts, counts = frames.run(N.MODE_DETECT, search_radius, time_window)
+        if frames.frames_run != ran_before:  # a new frame was computed: fold its totals into the stats
+            ms = (time.perf_counter() - t0) * 1e3
+            n = max(1, self.spatial_index._table.n)
+            self.stats["potential_collisions"] += int(counts["n_potential"])
+            self.stats["high_risk_collisions"] += int(counts["n_high_risk"])
+            self.stats["max_detection_time_ms"] = max(self.stats["max_detection_time_ms"], ms / n)
+            self._frame_ms_per_vehicle = ms / n
+        return pairs, starts, counts
+
+    def detect_collisions(self, vehicle_id: str, search_radius: float = 100.0, time_window: float = 10.0) -> List[CollisionRisk]:
+        if vehicle_id not in self.vehicle_cache:
+            return []
+        table = self.spatial_index._table
+        pairs, starts, _counts = self._frame(search_radius, time_window)
+        s = table.slot_of[vehicle_id]
+        risks = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids)
+        if risks:
+            self.collision_risks.setdefault(vehicle_id, {}).update({r.other_vehicle_id: r for r in risks})
+        self.stats["total_detections"] += 1
+        k = self.stats["total_detections"]
+        ms = getattr(self, "_frame_ms_per_vehicle", 0.0)
+        self.stats["avg_detection_time_ms"] = (self.stats["avg_detection_time_ms"] * (k - 1) + ms) / k
+        return risks
+
+    def detect_all(self, search_radius: float = 100.0, time_window: float = 10.0) -> Dict[str, List[CollisionRisk]]:
+        """Additive batch API: every vehicle's risks from one GPU frame."""
+        table = self.spatial_index._table
+        if table.n == 0:
+            return {}
+        pairs, starts, _ = self._frame(search_radius, time_window)
+        out: Dict[str, List[CollisionRisk]] = {}
+        for r in _risks_from_pairs(pairs, table.ids):
+            out.setdefault(r.vehicle_id, []).append(r)
+        return out
+
+    def get_collision_risks(self, vehicle_id: str) -> List[CollisionRisk]:
+        return list(self.collision_risks.get(vehicle_id, {}).values())
+
+    def _spatial_filtering(self, vehicle_id: str, position: Position, search_radius: float) -> Set[str]:
+        near = self.spatial_index.get_nearby_vehicles(position, search_radius)
+        near.discard(vehicle_id)
+        return near
+
+    def _predict_position(self, vehicle: Vehicle, time_delta: float) -> Position:
+        p, v, a, t = vehicle.position, vehicle.velocity, vehicle.acceleration, time_delta
+        return Position(x=p.x + v.x * t + 0.5 * a.x * t * t, y=p.y + v.y * t + 0.5 * a.y * t * t,
+                        z=p.z + v.z * t + 0.5 * a.z * t * t)
+
+    def _calculate_safe_distance(self, vehicle1: Vehicle, vehicle2: Vehicle) -> float:
+        return (vehicle1.size + vehicle2.size) / 2 + SAFE_DISTANCE_DEFAULT
+
+    def get_stats(self) -> Dict[str, Any]:
+        return self.stats
+
+
+class CollisionPredictionModel:
+    def __init__(self, collision_detector: CollisionDetector):
+        self.collision_detector = collision_detector
+        self.max_history_length = 100
+        self.prediction_horizon = 10.0
+        self.prediction_step = 0.5
+        self.trajectory_history: Dict[str, List[Tuple[Position, float]]] = {}
+        self.stats = {"total_predictions": 0, "avg_prediction_time_ms": 0.0}
+        self._hist_version = 0
+        self._pattern_key = None
+        self._patterns: Optional[np.ndarray] = None
+
+    def update_trajectory(self, vehicle_id: str, position: Position, timestamp: float) -> None:
+        h = self.trajectory_history.setdefault(vehicle_id, [])
+        h.append((position, timestamp))
+        if len(h) > self.max_history_length:
+            self.trajectory_history[vehicle_id] = h[-self.max_history_length:]
+        self._hist_version += 1
+
+    def trajectory_patterns(self) -> np.ndarray:
+        """Pattern code of every indexed vehicle (collision_detection.py:623-711), classified on the
+        GPU from the stored histories; 3 = fewer than 2 samples (-> detect path, :590-592)."""
+        table = self.collision_detector.spatial_index._table
+        key = (self._hist_version, table.version)
+        if key == self._pattern_key and self._patterns is not None:
+            return self._patterns
+        n = table.n
+        count = np.zeros(n, np.uint32)
+        stride = 1
+        for s in range(n):
+            h = self.trajectory_history.get(table.ids[s])
+            if h:
+                count[s] = len(h)
+                stride = max(stride, len(h))
+        samples = np.zeros((n, stride, 4), np.float64)
+        for s in range(n):
+            h = self.trajectory_history.get(table.ids[s])
+            if h:
+                hs = sorted(h, key=lambda e: e[1])  # stable, like the reference (:638)
+                samples[s, :len(hs)] = [(p.x, p.y, p.z, t) for p, t in hs]
+        frames = self.collision_detector.spatial_index._frames
+        frames.sync_objects()
+        self._patterns = frames.engine.classify_patterns(samples, count) if n else np.zeros(0, np.uint8)
+        self._pattern_key = key
+        return self._patterns
+
+    def _frame(self):
+        frames = self.collision_detector.spatial_index._frames
+        return frames.run(N.MODE_PREDICT, 100.0, 10.0, flags=self.trajectory_patterns())
+
+    def predict_collisions(self, vehicle_id: str) -> List[CollisionRisk]:
+        det = self.collision_detector
+        if vehicle_id not in det.vehicle_cache:
+            return []
+        table = det.spatial_index._table
+        t0 = time.perf_counter()
+        pairs, starts, _ = self._frame()
+        s = table.slot_of[vehicle_id]
+        risks = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids)
+        self.stats["total_predictions"] += 1
+        k = self.stats["total_predictions"]
+        ms = (time.perf_counter() - t0) * 1e3
+        self.stats["avg_prediction_time_ms"] = (self.stats["avg_prediction_time_ms"] * (k - 1) + ms) / k
+        return risks
+
+    def predict_all(self) -> Dict[str, List[CollisionRisk]]:
+        table = self.collision_detector.spatial_index._table
+        if table.n == 0:
+            return {}
+        pairs, _starts, _ = self._frame()
+        out: Dict[str, List[CollisionRisk]] = {}
+        for r in _risks_from_pairs(pairs, table.ids):
+            out.setdefault(r.vehicle_id, []).append(r)
+        return out
+
+    def get_stats(self) -> Dict[str, Any]:
+        return {**self.stats, "trajectory_history_count": len(self.trajectory_history)}

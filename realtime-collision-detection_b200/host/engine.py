@@ -114,6 +114,9 @@ class FrameEngine:
     def set_owned(self, n_owned: int) -> None:
         N.check(self._lib.rcd_set_owned(self._h, int(n_owned)), self._h)
 
+    def set_compute_node_params(self, prediction_time: float = 5.0, risk_threshold: float = 0.5) -> None:
+        N.check(self._lib.rcd_set_compute_node_params(self._h, float(prediction_time), float(risk_threshold)), self._h)
+
     def truncate(self, n: int) -> None:
         """Drop everything after the first n objects (the halo copies of the previous frame)."""
         N.check(self._lib.rcd_truncate(self._h, int(n)), self._h)
@@ -134,13 +137,18 @@ class FrameEngine:
                 "n_potential": c.n_potential, "n_pairs": c.n_pairs, "n_high_risk": c.n_high_risk,
                 "n_written": c.n_written, "n_alerts": [int(v) for v in c.n_alerts], "n_exact": c.n_exact}
 
-    def download(self, cap: Optional[int] = None) -> np.ndarray:
+    def download(self, cap: Optional[int] = None, sort: bool = True, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Emitted pairs as a PAIR_DTYPE array, sorted by (i, j, predicted) unless sort=False.
+        `out`: preallocated (e.g. pinned) PAIR_DTYPE buffer to copy into."""
         cap = int(self.max_pairs if cap is None else cap)
         c = self.counts()
         m = min(cap, int(c["n_written"]))
-        out = np.zeros(m, N.PAIR_DTYPE)
+        if out is None:
+            out = np.empty(m, N.PAIR_DTYPE)
+        m = min(m, out.shape[0])
         got = ctypes.c_uint64(0)
-        N.check(self._lib.rcd_download(self._h, _vp(out), m, ctypes.byref(got)), self._h)
+        fn = self._lib.rcd_download if sort else self._lib.rcd_download_unsorted
+        N.check(fn(self._h, _vp(out), m, ctypes.byref(got)), self._h)
         return out[: got.value]
 
     def candidate_counts(self) -> np.ndarray:

@@ -1,0 +1,162 @@
+"""The drop-in classes (reference signatures) on the GPU against the reference's golden vectors:
+the tests read like the reference's own use of its API (warning_system.py:638-714,
+compute_node.py:592-642)."""
+import numpy as np
+import pytest
+
+from tests.helpers import assert_close, assert_pairs_equal, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _vehicles(frame):
+    from rcd_b200.host.models import Position, Vector, Vehicle
+    out = []
+    for i in range(len(frame["px"])):
+        out.append(Vehicle(id=f"v{i}", position=Position(float(frame["px"][i]), float(frame["py"][i]), float(frame["pz"][i])),
+                           velocity=Vector(float(frame["vx"][i]), float(frame["vy"][i]), float(frame["vz"][i])),
+                           acceleration=Vector(float(frame["ax"][i]), float(frame["ay"][i]), float(frame["az"][i])),
+                           heading=float(frame["heading"][i]), size=float(frame["size"][i]),
+                           type=f"type{int(frame['type'][i])}", timestamp=0.0))
+    return out
+
+
+def _table(risks):
+    return np.array([[int(r.vehicle_id[1:]), int(r.other_vehicle_id[1:]), r.time_to_collision, r.distance,
+                      r.relative_speed, r.risk_level, r.collision_position.x, r.collision_position.y,
+                      r.collision_position.z] for r in risks], np.float64).reshape(-1, 9)
+
+
+def _compare(got, want):
+    got = got[np.lexsort((got[:, 1], got[:, 0]))]
+    assert_pairs_equal(got[:, :2], want[:, :2])
+    assert np.array_equal(np.round(got[:, 2], 5), np.round(want[:, 2], 5))
+    for c in range(3, 9):
+        assert_close(got[:, c], want[:, c], f"col {c}", 1e-6, 1e-6)
+
+
+def test_detector_per_vehicle_calls_match_golden():
+    from rcd_b200.host.collision_detection import CollisionDetector
+    from rcd_b200.host.spatial_index import SpatialIndex
+    z, frame = load_golden("detect_dense3d.npz")
+    det = CollisionDetector(SpatialIndex())
+    for v in _vehicles(frame):
+        det.update_vehicle(v)
+    assert det.detect_collisions("nobody") == []
+    risks = []
+    for vid in list(det.vehicle_cache):
+        risks += det.detect_collisions(vid)
+    _compare(_table(risks), z["risks"])
+    assert det.spatial_index._frames.frames_run == 1  # N per-vehicle calls = one GPU frame
+    st = det.get_stats()
+    assert st["total_detections"] == len(frame["px"]) and st["potential_collisions"] == int(z["stat_potential"])
+    assert st["high_risk_collisions"] == int(z["stat_high"])
+    some = int(z["risks"][0, 0])
+    assert {r.other_vehicle_id for r in det.get_collision_risks(f"v{some}")} == \
+        {f"v{int(j)}" for i, j in z["risks"][:, :2] if int(i) == some}
+    # removing a vehicle removes its pairs from the next frame
+    gone = f"v{int(z['risks'][0, 1])}"
+    det.remove_vehicle(gone)
+    after = det.detect_all()
+    assert all(r.other_vehicle_id != gone for rs in after.values() for r in rs) and gone not in after
+    # a non-default radius / window is a new frame with the reference's semantics
+    z2, frame2 = load_golden("detect_r60_t4.npz")
+    det2 = CollisionDetector(SpatialIndex())
+    det2.update_vehicles_batch(_vehicles(frame2))
+    risks2 = [r for vid in det2.vehicle_cache for r in det2.detect_collisions(vid, float(z2["R"]), float(z2["T"]))]
+    _compare(_table(risks2), z2["risks"])
+
+
+def test_spatial_index_nearby_matches_golden():
+    import os
+    from rcd_b200.host.models import Position
+    from rcd_b200.host.spatial_index import SpatialIndex
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "scalars.npz"))
+    idx = SpatialIndex()
+    n = len(z["near_frame_px"])
+    for i in range(n):
+        idx.insert_vehicle(f"v{i}", Position(float(z["near_frame_px"][i]), float(z["near_frame_py"][i]), float(z["near_frame_pz"][i])))
+    off = z["near_off"]
+    for k in (0, 7, 60, 61, 79):
+        q = z["near_q"][k]
+        got = idx.get_nearby_vehicles(Position(*[float(c) for c in q]), float(z["near_radius"]))
+        assert got == {f"v{int(i)}" for i in z["near_ids"][off[k]:off[k + 1]]}
+    batch = idx.get_nearby_vehicles_batch([tuple(map(float, q)) for q in z["near_q"]], float(z["near_radius"]))
+    assert [sorted(int(s[1:]) for s in b) for b in batch] == [z["near_ids"][off[k]:off[k + 1]].tolist() for k in range(len(off) - 1)]
+
+
+def test_prediction_model_classifies_histories_and_matches_golden():
+    from rcd_b200.host.collision_detection import CollisionDetector, CollisionPredictionModel
+    from rcd_b200.host.models import Position
+    from rcd_b200.host.spatial_index import SpatialIndex
+    z, frame = load_golden("predict_dense3d.npz")
+    det = CollisionDetector(SpatialIndex())
+    model = CollisionPredictionModel(det)
+    vehicles = _vehicles(frame)
+    for v, pat in zip(vehicles, z["pattern"]):
+        det.update_vehicle(v)
+        p = v.position
+        if pat == 3:      # fewer than two samples -> the reference falls back to detect_collisions
+            model.update_trajectory(v.id, p, 0.0)
+            continue
+        for k, t in enumerate((0.0, 1.0, 2.0, 3.0)):
+            if pat == 0:    # stationary: mean speed < 0.1
+                q = Position(p.x, p.y, p.z)
+            elif pat == 1:  # constant velocity: mean acceleration < 0.1
+                q = Position(p.x + 3.0 * t, p.y, p.z)
+            else:           # accelerating
+                q = Position(p.x + 2.0 * t + 0.5 * t * t, p.y, p.z)
+            model.update_trajectory(v.id, q, t)
+    assert np.array_equal(model.trajectory_patterns(), z["pattern"])
+    risks = [r for v in vehicles for r in model.predict_collisions(v.id)]
+    _compare(_table(risks), z["risks"])
+    assert [r.is_predicted for r in sorted(risks, key=lambda r: (int(r.vehicle_id[1:]), int(r.other_vehicle_id[1:])))] \
+        == z["is_predicted"].tolist()
+    assert det.spatial_index._frames.frames_run == 1
+    # alert classification of the same risks
+    from rcd_b200.host.warning_system import AlertManager
+    mgr = AlertManager()
+    alerts = mgr.process_collision_risks(risks)
+    assert len(alerts) == sum(r.risk_level >= 0.3 for r in risks)
+    assert all(a.priority == mgr._get_priority(a.risk_level, a.time_to_collision) for a in alerts)
+
+
+def test_compute_node_classes_match_golden():
+    from rcd_b200.host import compute_node as CN
+    from rcd_b200.host.models import LocationData, Position, Vector
+    z, frame = load_golden("implB_dense.npz")
+    n = len(frame["px"])
+    index = CN.SpatialIndex()
+    states = {}
+    for i in range(n):
+        loc = LocationData(vehicle_id=f"v{i}", timestamp=0.0,
+                           position=Position(float(frame["px"][i]), float(frame["py"][i]), float(frame["pz"][i])),
+                           velocity=Vector(float(frame["vx"][i]), float(frame["vy"][i]), float(frame["vz"][i])),
+                           heading=float(frame["heading"][i]), vehicle_type="car")
+        st = CN.VehicleState(f"v{i}")
+        st.update(loc)
+        if z["has_history"][i]:
+            st.update(loc)
+        states[f"v{i}"] = st
+        index.insert(f"v{i}", loc.position)
+    assert index.get_vehicle_count() == n
+    det = CN.CollisionDetector()
+    want = z["risks"]  # i j risk ttc rel_speed cx cy cz
+    allr = det.detect_collisions_for_all(states, 100.0)
+    got = np.array([[int(r.vehicle_id1[1:]), int(r.vehicle_id2[1:]), r.risk_level, r.relative_velocity, r.position.x,
+                     r.position.y, r.position.z] for rs in allr.values() for r in rs]).reshape(-1, 7)
+    got = got[np.lexsort((got[:, 1], got[:, 0]))]
+    assert_pairs_equal(got[:, :2], want[:, :2])
+    assert_close(got[:, 2], want[:, 2], "risk", 1e-6, 1e-7)
+    assert_close(got[:, 3], want[:, 4], "rel_speed", 1e-6, 1e-7)
+    assert_close(got[:, 4:7], want[:, 5:8], "position", 1e-6, 1e-6)
+    # the per-vehicle form with an explicit neighbour set (ComputeNode._detect_collisions_for_all)
+    for i in np.unique(want[:, 0].astype(int))[:5]:
+        near = index.query_nearby(states[f"v{i}"].get_current_location().position, 100.0)
+        assert f"v{i}" in near  # quirk Q8: the index returns the querying vehicle
+        rs = det.detect_collisions(states[f"v{i}"], {o: states[o] for o in near})
+        assert sorted(int(r.vehicle_id2[1:]) for r in rs) == sorted(int(j) for a, j in want[:, :2] if int(a) == i)
+        assert all(abs(r.time_to_collision - t) < 1e-3 for r, t in
+                   zip(sorted(rs, key=lambda r: int(r.vehicle_id2[1:])), [w[3] for w in want if int(w[0]) == i]))
+    assert index.remove("v0") and not index.remove("v0") and index.get_position("v0") is None
