@@ -68,6 +68,7 @@ struct Counters {
     unsigned long long n_query_hits;  // rcd_query_radius
     // lengths of the global queues between k_pairs / k_sample / k_exact (reset before every step)
     unsigned long long n_q2, n_q3;
+    unsigned long long n_fallback;  // resolved entries the exact stage had to redo in full (expected 0)
 };
 
 // ---- warp / block helpers -----------------------------------------------------------------------

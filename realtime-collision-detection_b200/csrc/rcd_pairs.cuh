@@ -100,29 +100,63 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // sqrt(x) rounded up a little: only ever used for conservative bounds
 __device__ __forceinline__ float sqrt_ub(float x) { return x * rsqrtf(fmaxf(x, 1.0e-30f)) * (1.0f + 4.0e-6f); }
 
-__device__ __forceinline__ void emit_pair(const PairParams &P, u32 slot_i, u32 slot_j, double ttc, double dist,
-                                          double rs, double risk, double mx, double my, double mz, double tcl,
-                                          double dcl, int prio, int offset, bool predicted) {
+// result of the exact stage for one queued pair
+struct EmitRec {
+    u32 si, sj;
+    float ttc, dist, rs, risk, cx, cy, cz, tcl, dcl;
+    int prio, offset;
+    bool hit, predicted, high;  // high: risk > 0.7 decided in fp64 (stats["high_risk_collisions"])
+    u32 potential;              // detect: the pair passed stage 2 (stats["potential_collisions"])
+};
+
+__device__ __forceinline__ EmitRec make_rec(u32 si, u32 sj, double ttc, double dist, double rs, double risk,
+                                            double mx, double my, double mz, double tcl, double dcl, int prio,
+                                            int offset, bool predicted) {
+    EmitRec r;
+    r.si = si; r.sj = sj;
+    r.ttc = (float)ttc; r.dist = (float)dist; r.rs = (float)rs; r.risk = (float)risk;
+    r.cx = (float)mx; r.cy = (float)my; r.cz = (float)mz;
+    r.tcl = (float)tcl; r.dcl = (float)dcl;
+    r.prio = prio; r.offset = offset;
+    r.hit = true; r.predicted = predicted; r.high = risk > 0.7;
+    r.potential = 0;
+    return r;
+}
+__device__ __forceinline__ EmitRec no_rec() {
+    EmitRec r;
+    r.si = r.sj = 0;
+    r.ttc = r.dist = r.rs = r.risk = r.cx = r.cy = r.cz = r.tcl = r.dcl = 0.0f;
+    r.prio = -1; r.offset = 255;
+    r.hit = false; r.predicted = false; r.high = false;
+    r.potential = 0;
+    return r;
+}
+
+// store one pair at `pos` (three 16-byte stores; rcd_pair is 48 bytes)
+__device__ __forceinline__ void store_pair(const PairParams &P, unsigned long long pos, const EmitRec &e) {
+    if (pos >= P.out_cap) return;
+    rcd_pair r;
+    r.i = P.in_id[P.sorted_slot[e.si]];
+    r.j = P.in_id[P.sorted_slot[e.sj]];
+    r.ttc = e.ttc; r.distance = e.dist; r.rel_speed = e.rs; r.risk = e.risk;
+    r.cx = e.cx; r.cy = e.cy; r.cz = e.cz;
+    r.t_closest = e.tcl; r.d_closest = e.dcl;
+    r.priority = (int8_t)e.prio;
+    r.offset = (uint8_t)e.offset;
+    r.predicted = e.predicted ? 1 : 0;
+    r.reserved = 0;
+    uint4 *dst = reinterpret_cast<uint4 *>(P.out + pos);
+    const uint4 *src = reinterpret_cast<const uint4 *>(&r);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+}
+
+// per-thread emission (queue-overflow fallbacks only; the exact stage aggregates per warp)
+__device__ __noinline__ void thread_emit(const PairParams &P, const EmitRec &e) {
+    if (!e.hit) return;
     unsigned long long pos = atomicAdd(&P.counters->n_pairs, 1ULL);
-    if (risk > 0.7) atomicAdd(&P.counters->n_high_risk, 1ULL);
-    if (prio >= 0) atomicAdd(&P.counters->n_alerts[prio], 1ULL);
-    if (pos < P.out_cap) {
-        rcd_pair r;
-        r.i = P.in_id[slot_i];
-        r.j = P.in_id[slot_j];
-        r.ttc = (float)ttc;
-        r.distance = (float)dist;
-        r.rel_speed = (float)rs;
-        r.risk = (float)risk;
-        r.cx = (float)mx; r.cy = (float)my; r.cz = (float)mz;
-        r.t_closest = (float)tcl;
-        r.d_closest = (float)dcl;
-        r.priority = (int8_t)prio;
-        r.offset = (uint8_t)offset;
-        r.predicted = predicted ? 1 : 0;
-        r.reserved = 0;
-        P.out[pos] = r;
-    }
+    if (e.high) atomicAdd(&P.counters->n_high_risk, 1ULL);
+    if (e.prio >= 0) atomicAdd(&P.counters->n_alerts[e.prio], 1ULL);
+    store_pair(P, pos, e);
 }
 
 // ---- fp64 decisions (rare) ---------------------------------------------------------------------------
@@ -130,14 +164,14 @@ __device__ __noinline__ bool exact_within_radius(float ax, float ay, float az, f
     return within_radius_d(ax, ay, az, bx, by, bz, (double)R);
 }
 
-// detect: stages 2-4 in fp64 for the pair (si, sj); returns 1 if the pair passed stage 2
-__device__ __noinline__ u32 exact_detect(const PairParams &P, u32 si, u32 sj, float T, int steps) {
+// detect: stages 2-4 in fp64 for the pair (si, sj)
+__device__ __noinline__ EmitRec exact_detect(const PairParams &P, u32 si, u32 sj, float T, int steps) {
     ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
     DetectResultD r = detect_pair_d(A, B, (double)T, steps);
-    if (r.hit)
-        emit_pair(P, P.sorted_slot[si], P.sorted_slot[sj], r.ttc, r.dist, r.rs, r.risk, r.mx, r.my, r.mz, r.tc, r.cd,
-                  r.priority, 255, false);
-    return r.potential ? 1u : 0u;
+    EmitRec e = r.hit ? make_rec(si, sj, r.ttc, r.dist, r.rs, r.risk, r.mx, r.my, r.mz, r.tc, r.cd, r.priority, 255, false)
+                      : no_rec();
+    e.potential = r.potential ? 1u : 0u;
+    return e;
 }
 
 __device__ __noinline__ bool exact_predict_radius(const PairParams &P, u32 si, u32 sj, u32 pattern, int m) {
@@ -149,7 +183,7 @@ __device__ __noinline__ bool exact_predict_radius(const PairParams &P, u32 si, u
 }
 
 // predict: every offset in `mask` in fp64, max-risk merge (strict >, offsets ascending, :848-865)
-__device__ __noinline__ void exact_predict(const PairParams &P, u32 si, u32 sj, u32 pattern, u32 mask) {
+__device__ __noinline__ EmitRec exact_predict(const PairParams &P, u32 si, u32 sj, u32 pattern, u32 mask) {
     ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
     double best_risk = -1.0;
     PredictResultD best;
@@ -160,27 +194,69 @@ __device__ __noinline__ void exact_predict(const PairParams &P, u32 si, u32 sj, 
         PredictResultD r = predict_pair_d(A, B, pattern, m);
         if (r.hit && r.risk > best_risk) { best_risk = r.risk; best = r; best_m = m; }
     }
-    if (best_m >= 0)
-        emit_pair(P, P.sorted_slot[si], P.sorted_slot[sj], best.ttc, best.dist, best.rs, best.risk, best.mx, best.my,
-                  best.mz, 0.5 * (double)best_m, 0.0, priority_d(best.risk, best.ttc), best_m, true);
+    if (best_m < 0) return no_rec();
+    return make_rec(si, sj, best.ttc, best.dist, best.rs, best.risk, best.mx, best.my, best.mz, 0.5 * (double)best_m,
+                    0.0, priority_d(best.risk, best.ttc), best_m, true);
 }
 
-__device__ __noinline__ void exact_compute_node(const PairParams &P, u32 si, u32 sj) {
+// Queue entries whose winning offset m and first hit sample k were already settled in fp32 with
+// every margin wide open carry RESOLVED | m | k << 8: one fp64 evaluation yields the emitted values.
+constexpr u32 RESOLVED = 1u << 31;
+
+// predict, full fallback: every offset, radius test included (collision_detection.py:789-865)
+__device__ __noinline__ EmitRec exact_predict_all(const PairParams &P, u32 si, u32 sj, u32 pattern) {
+    u32 mask = 0;
+    for (int m = 0; m < PREDICT_OFFSETS; ++m)
+        if (exact_predict_radius(P, si, sj, pattern, m)) mask |= 1u << m;
+    return mask ? exact_predict(P, si, sj, pattern, mask) : no_rec();
+}
+
+__device__ __noinline__ EmitRec exact_predict_resolved(const PairParams &P, u32 si, u32 sj, u32 pattern, int m, int k) {
+    ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
+    const double t = dmul(0.5, (double)m);
+    double cx, cy, cz;
+    predict_centre_d(A, pattern, t, cx, cy, cz);
+    const double qx = pos1_d(B.px, B.vx, B.ax, t), qy = pos1_d(B.py, B.vy, B.ay, t), qz = pos1_d(B.pz, B.vz, B.az, t);
+    const double safe = safe_d(A.size, B.size);
+    const double tau = dmul((double)k, 0.1);
+    const double xi = pos1_d(cx, A.vx, A.ax, tau), yi = pos1_d(cy, A.vy, A.ay, tau), zi = pos1_d(cz, A.vz, A.az, tau);
+    const double xj = pos1_d(qx, B.vx, B.ax, tau), yj = pos1_d(qy, B.vy, B.ay, tau), zj = pos1_d(qz, B.vz, B.az, tau);
+    const double d = dist3_d(xi, yi, zi, xj, yj, zj);
+    if (!(d <= safe)) {  // cannot happen while the guard bands hold; stay exact if it ever does
+        atomicAdd(&P.counters->n_fallback, 1ULL);
+        return exact_predict_all(P, si, sj, pattern);
+    }
+    const double rs = mag3_d(dsub(A.vx, B.vx), dsub(A.vy, B.vy), dsub(A.vz, B.vz));
+    const double risk = risk_level_d(A.heading, B.heading, A.type, B.type, tau, d, safe, rs);
+    const double ttc = dadd(tau, t);
+    return make_rec(si, sj, ttc, d, rs, risk, __ddiv_rn(dadd(xi, xj), 2.0), __ddiv_rn(dadd(yi, yj), 2.0),
+                    __ddiv_rn(dadd(zi, zj), 2.0), t, 0.0, priority_d(risk, ttc), m, true);
+}
+
+__device__ __noinline__ EmitRec exact_compute_node(const PairParams &P, u32 si, u32 sj) {
     ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
     ComputeNodeResultD r = compute_node_pair_d(A, B, (double)P.pt, (double)P.threshold);
-    if (r.hit)
-        emit_pair(P, P.sorted_slot[si], P.sorted_slot[sj], r.ttc, r.fut, r.rs, r.risk, r.mx, r.my, r.mz, 0.0, 0.0, -1,
-                  255, false);
+    if (!r.hit) return no_rec();
+    return make_rec(si, sj, r.ttc, r.fut, r.rs, r.risk, r.mx, r.my, r.mz, 0.0, 0.0, -1, 255, false);
 }
 
-// the exact stage for one queue entry (also the inline fallback when a global queue is full)
+// the exact stage for one queue entry
 template <int MODE>
-__device__ __forceinline__ u32 exact_entry(const PairParams &P, u32 si, u32 sj, u32 mask) {
+__device__ __forceinline__ EmitRec exact_entry(const PairParams &P, u32 si, u32 sj, u32 mask) {
     if (MODE == RCD_MODE_DETECT) return exact_detect(P, si, sj, P.T, P.steps);
-    if (MODE == RCD_MODE_COMPUTE_NODE) { exact_compute_node(P, si, sj); return 0; }
+    if (MODE == RCD_MODE_COMPUTE_NODE) return exact_compute_node(P, si, sj);
     if (mask == 0) return exact_detect(P, si, sj, 10.0f, 100);  // pattern 3: detect defaults (:592)
-    exact_predict(P, si, sj, meta_pattern(__float_as_uint(P.P2[si].w)), mask);
-    return 0;
+    const u32 pattern = meta_pattern(__float_as_uint(P.P2[si].w));
+    if (mask & RESOLVED) return exact_predict_resolved(P, si, sj, pattern, (int)(mask & 31u), (int)((mask >> 8) & 15u));
+    return exact_predict(P, si, sj, pattern, mask);
+}
+
+// queue-full fallback: decide and emit the pair in place (correct, slower, out of line)
+template <int MODE>
+__device__ __noinline__ u32 finish_entry_inline(const PairParams &P, u32 si, u32 sj, u32 mask) {
+    const EmitRec e = exact_entry<MODE>(P, si, sj, mask);
+    thread_emit(P, e);
+    return e.potential;
 }
 
 // ---- S2, detect: temporal filter + closest approach in fp32 (collision_detection.py:244-292) ------
@@ -316,6 +392,9 @@ __device__ __forceinline__ u32 predict_scan(WarpShared &ws, const PairParams &P,
 }
 
 // ---- k_sample body: radius test + the 10 samples in fp32 for every offset in `mask` -----------------
+// Returns the queue word for the exact stage: 0 (no offset can hit), RESOLVED | m | k << 8 when the
+// winner of the max-risk merge and its first hit sample are beyond doubt in fp32, else the mask of
+// the offsets the exact stage has to evaluate.
 template <bool COUNT_CAND>
 __device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 sj, u32 mask, u32 &n_exact) {
     const float4 a0 = P.P0[si], a1 = P.P1[si], a2 = P.P2[si];
@@ -325,7 +404,14 @@ __device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 s
     const float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;
     const float rax = a2.x - b2.x, ray = a2.y - b2.y, raz = a2.z - b2.z;
     const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
-    u32 out = 0;
+    const float safe = (a0.w + b0.w) * 0.5f + 5.0f;
+    const float band = sqrtf(c.safe_b2) - safe;                 // the guard band of predict_coef
+    const float safe_in = fmaxf(safe - band, 0.0f), safe_in2 = safe_in * safe_in;
+    const float inv_safe = 1.0f / safe;
+    u32 maybe_mask = 0;      // offsets with a sample inside safe + band
+    bool doubt = false;      // some decisive sample lies inside the band
+    float best = -1.0f, second = -1.0f;
+    int best_m = -1, best_k = 0;
     while (mask) {
         const int m = __ffs(mask) - 1;
         mask &= mask - 1;
@@ -340,16 +426,28 @@ __device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 s
             }
         }
         const float gx = c.cvx * t + c.cax * h - c.dx, gy = c.cvy * t + c.cay * h - c.dy, gz = c.cvz * t + c.caz * h - c.dz;
-        bool maybe = false;
+        int first = -1;
+        float r2first = 0.0f;
 #pragma unroll
-        for (int k = 0; k < PREDICT_STEPS; ++k) {
+        for (int k = PREDICT_STEPS - 1; k >= 0; --k) {  // descending: the last assignment is the first sample
             const float tau = 0.1f * (float)k, hh = 0.5f * tau * tau;
             float rx = gx + rvx * tau + rax * hh, ry = gy + rvy * tau + ray * hh, rz = gz + rvz * tau + raz * hh;
-            maybe |= (rx * rx + ry * ry + rz * rz <= c.safe_b2);
+            float r2 = rx * rx + ry * ry + rz * rz;
+            if (r2 <= c.safe_b2) { first = k; r2first = r2; }
         }
-        if (maybe) out |= 1u << m;
+        if (first < 0) continue;  // no sample within safe + band: certainly no hit at this offset
+        maybe_mask |= 1u << m;
+        if (r2first > safe_in2) { doubt = true; continue; }  // the first candidate sample is inside the band
+        // certain hit at sample `first`, and every earlier sample is certainly outside: the parts of the
+        // risk that differ between offsets (collision_detection.py:371-374) decide the merge
+        const float part = 0.3f * (1.0f - sqrtf(r2first) * inv_safe) + 0.3f * (1.0f - 0.01f * (float)first);
+        if (part > best) { second = best; best = part; best_m = m; best_k = first; }
+        else if (part > second) second = part;
     }
-    return out;
+    if (maybe_mask == 0) return 0;
+    // a runner-up within 1e-4 (fp32 error of `part` is ~1e-5) or any sample in the band: fp64 decides
+    if (doubt || best_m < 0 || best - second <= 1.0e-4f) return maybe_mask;
+    return RESOLVED | (u32)best_m | ((u32)best_k << 8);
 }
 
 // ---- S2, compute-node pair function in fp32 (compute_node.py:258-292) --------------------------------
@@ -382,7 +480,7 @@ template <bool COUNT_CAND>
 __device__ __noinline__ void finish_predict_pair(const PairParams &P, u32 si, u32 sj, u32 mask) {
     u32 dummy = 0;
     const u32 m2 = sample_predict<COUNT_CAND>(P, si, sj, mask, dummy);
-    if (m2) exact_predict(P, si, sj, meta_pattern(__float_as_uint(P.P2[si].w)), m2);
+    if (m2) finish_entry_inline<RCD_MODE_PREDICT>(P, si, sj, m2);
 }
 
 // lower bound in the sorted key array
@@ -657,7 +755,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pairs(PairParams P) {
                             }
                         }
                         if (!global_push(P.q3, P.qcap, &P.counters->n_q3, keep, si, sj, 0u))
-                            n_pot += exact_entry<MODE>(P, si, sj, 0u);  // queue full: decide here
+                            n_pot += finish_entry_inline<MODE>(P, si, sj, 0u);  // queue full: decide here
                     }
                     __syncwarp();
                 }
@@ -704,28 +802,52 @@ __global__ void __launch_bounds__(STAGE_THREADS) k_sample(PairParams P) {
             keep = e.mask != 0;
         }
         if (!global_push(P.q3, P.qcap, &P.counters->n_q3, keep, e.si, e.sj, e.mask))
-            exact_entry<RCD_MODE_PREDICT>(P, e.si, e.sj, e.mask);
+            finish_entry_inline<RCD_MODE_PREDICT>(P, e.si, e.sj, e.mask);
     }
     unsigned long long ex = warp_sum((unsigned long long)n_exact);
     if ((threadIdx.x & 31u) == 0 && ex) atomicAdd(&P.counters->n_exact, ex);
 }
 
-// k_exact: one queued pair per thread, decided in fp64
+// k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp
 template <int MODE>
 __global__ void __launch_bounds__(STAGE_THREADS) k_exact(PairParams P) {
     const unsigned long long n = min(P.counters->n_q3, (unsigned long long)P.qcap);
     const unsigned long long stride = (unsigned long long)gridDim.x * STAGE_THREADS;
-    u32 n_pot = 0, n_exact = 0;
-    for (unsigned long long k = (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x; k < n; k += stride) {
-        const QEntry e = P.q3[k];
-        n_pot += exact_entry<MODE>(P, e.si, e.sj, e.mask);
-        n_exact += (MODE == RCD_MODE_PREDICT && e.mask) ? (u32)__popc(e.mask) : 1u;
+    const unsigned long long rounds = (n + stride - 1) / stride;
+    const u32 lane = threadIdx.x & 31u;
+    u32 n_pot = 0, n_exact = 0, n_high = 0, n_prio[4] = {0, 0, 0, 0};
+    for (unsigned long long r = 0; r < rounds; ++r) {  // uniform trip count: the emission is warp-wide
+        const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
+        EmitRec e = no_rec();
+        if (k < n) {
+            const QEntry q = P.q3[k];
+            e = exact_entry<MODE>(P, q.si, q.sj, q.mask);
+            n_pot += e.potential;
+            n_exact += (MODE == RCD_MODE_PREDICT && q.mask && !(q.mask & RESOLVED)) ? (u32)__popc(q.mask) : 1u;
+        }
+        const u32 ballot = __ballot_sync(FULL_MASK, e.hit);
+        if (ballot) {
+            unsigned long long base = 0;
+            const u32 leader = __ffs(ballot) - 1;
+            if (lane == leader) base = atomicAdd(&P.counters->n_pairs, (unsigned long long)__popc(ballot));
+            base = __shfl_sync(FULL_MASK, base, leader);
+            if (e.hit) {
+                store_pair(P, base + __popc(ballot & lanemask_lt()), e);
+                n_high += e.high ? 1u : 0u;
+                if (e.prio >= 0) n_prio[e.prio] += 1u;
+            }
+        }
     }
-    unsigned long long p = warp_sum((unsigned long long)n_pot);
-    unsigned long long ex = warp_sum((unsigned long long)n_exact);
-    if ((threadIdx.x & 31u) == 0) {
-        if (p) atomicAdd(&P.counters->n_potential, p);
-        if (ex) atomicAdd(&P.counters->n_exact, ex);
+    unsigned long long v[7] = {n_pot, n_exact, n_high, n_prio[0], n_prio[1], n_prio[2], n_prio[3]};
+#pragma unroll
+    for (int q = 0; q < 7; ++q) v[q] = warp_sum(v[q]);
+    if (lane == 0) {
+        if (v[0]) atomicAdd(&P.counters->n_potential, v[0]);
+        if (v[1]) atomicAdd(&P.counters->n_exact, v[1]);
+        if (v[2]) atomicAdd(&P.counters->n_high_risk, v[2]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (v[3 + q]) atomicAdd(&P.counters->n_alerts[q], v[3 + q]);
     }
 }
 
