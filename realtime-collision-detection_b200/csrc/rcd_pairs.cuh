@@ -39,9 +39,8 @@ namespace rcd {
 constexpr int TQ = 32;            // queries per tile = one warp
 constexpr int PAIR_WARPS = 4;     // warps (independent tiles) per block
 constexpr int PAIR_THREADS = PAIR_WARPS * 32;
-constexpr int CH = 64;            // neighbours staged per chunk (2 per lane)
+constexpr int CH = 32;            // neighbours staged per chunk (1 per lane)
 constexpr int ROW_SCAN_MAX = 32;  // rows up to this many cells wide are scanned cell by cell
-constexpr int QCAP1 = 160;        // Q1 capacity (<= 31 carried + 4 x 32 pushed)
 constexpr int QCAP1B = 64;        // Q1b capacity (<= 31 carried + 32 pushed)
 
 // one queued pair between kernels: positions in cell order + offset mask (predict)
@@ -81,7 +80,7 @@ struct StageBuf {
 struct WarpShared {
     StageBuf buf[2];
     float4 q0[TQ], q1[TQ], q2[TQ];  // the tile's own (querying) objects
-    unsigned short q1e[QCAP1];      // Q1: ql << 8 | jj
+    unsigned char plist[CH][TQ];    // S1: per-lane lists of staged indices inside the lane's reach
     u32 q1b_pos[QCAP1B];            // Q1b (predict): neighbour position in cell order
     unsigned char q1b_ql[QCAP1B];   //                query lane
     u32 cand[TQ];                   // candidates resolved outside the filter (per query)
@@ -512,7 +511,7 @@ __device__ __forceinline__ bool global_push(QEntry *q, u32 cap, unsigned long lo
 }
 
 template <int MODE, bool COUNT_CAND>
-__global__ void __launch_bounds__(PAIR_THREADS, 4) k_pairs(PairParams P) {
+__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
     __shared__ WarpShared shared[PAIR_WARPS];
     WarpShared &ws = shared[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31u;
@@ -686,40 +685,51 @@ __global__ void __launch_bounds__(PAIR_THREADS, 4) k_pairs(PairParams P) {
                     const StageBuf &b = ws.buf[c & 1u];
                     const u32 m = min((u32)CH, total - c * CH);
                     // ---- S1 filter: one query per lane against every staged neighbour --------------
-                    // Q1 is filled until it holds a full warp of pairs (or the chunk is exhausted), then
-                    // S2 runs on 32 of them: a single call site keeps the kernel small (I-cache).
-                    u32 n1 = 0;  // warp-uniform length of Q1
-                    u32 j0 = 0;
-                    for (;;) {
-                        while (j0 < m && n1 < 32) {
-                            bool pass[4];
+                    // Each lane appends the neighbours inside its reach to a private list in shared memory
+                    // (no warp vote per test); the lists are then consumed 32 pairs at a time.
+                    u32 cnt = 0;
+                    for (u32 j0 = 0; j0 < m; j0 += 4) {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float4 b0 = b.p0[min(j0 + u, (u32)CH - 1)];
-                                float dx = b0.x - p0.x, dy = b0.y - p0.y, dz = b0.z - p0.z;
-                                float d2 = dx * dx + dy * dy + dz * dz;
-                                pass[u] = active && (j0 + u < m) && d2 <= pass2;
-                                if (pass[u] && radius_query && d2 < R2_lo) ++ncand;  // certainly within the radius
+                        for (int u = 0; u < 4; ++u) {
+                            const float4 b0 = b.p0[min(j0 + u, (u32)CH - 1)];
+                            float dx = b0.x - p0.x, dy = b0.y - p0.y, dz = b0.z - p0.z;
+                            float d2 = dx * dx + dy * dy + dz * dz;
+                            const bool pass = active && (j0 + u < m) && d2 <= pass2;
+                            if (pass) {
+                                ws.plist[cnt][lane] = (unsigned char)(j0 + u);
+                                ++cnt;
+                                if (radius_query && d2 < R2_lo) ++ncand;  // certainly within the radius
                             }
-#pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const u32 mask = __ballot_sync(FULL_MASK, pass[u]);
-                                if (pass[u]) ws.q1e[n1 + __popc(mask & lanemask_lt())] = (unsigned short)((lane << 8) | (j0 + u));
-                                n1 += __popc(mask);
-                            }
-                            j0 += 4;
                         }
-                        if (n1 == 0) break;  // chunk exhausted and Q1 empty
-                        __syncwarp();
-                        // ---- S2 on up to 32 queued pairs ----------------------------------------------
-                        const u32 take = min(n1, 32u);
-                        const u32 entry = ws.q1e[n1 - take + min(lane, take - 1)];
-                        n1 -= take;
+                    }
+                    // exclusive scan of the list lengths: pair f of the chunk belongs to the last lane o
+                    // with off[o] <= f
+                    u32 off = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        u32 t = __shfl_up_sync(FULL_MASK, off, o);
+                        if (lane >= (u32)o) off += t;
+                    }
+                    const u32 total_pairs = __shfl_sync(FULL_MASK, off, 31);
+                    off -= cnt;
+                    __syncwarp();
+                    for (u32 fbase = 0; fbase < total_pairs; fbase += 32) {
+                        // ---- S2 on up to 32 pairs ------------------------------------------------------
+                        const u32 f = fbase + lane;
+                        const u32 take = min(total_pairs - fbase, 32u);
+                        u32 ql = 0;
+#pragma unroll
+                        for (int step = 16; step > 0; step >>= 1) {
+                            const u32 cand = ql + step;
+                            const u32 v = __shfl_sync(FULL_MASK, off, cand & 31u);
+                            if (cand < 32u && v <= f) ql = cand;
+                        }
+                        const u32 ql_off = __shfl_sync(FULL_MASK, off, ql);
+                        const u32 jj = (lane < take) ? ws.plist[f - ql_off][ql] : 0u;
+                        const u32 si = tile_base + ql;
                         bool keep = false;     // -> global Q3 (exact stage)
                         bool to_scan = false;  // -> Q1b (predict window scan)
                         u32 sj = 0;
-                        const u32 ql = entry >> 8, jj = entry & 0xffu;
-                        const u32 si = tile_base + ql;
                         if (lane < take) {
                             const float4 a0 = ws.q0[ql], a1 = ws.q1[ql], a2 = ws.q2[ql];
                             const float4 b0 = b.p0[jj], b1 = b.p1[jj], b2 = b.p2[jj];
