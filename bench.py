@@ -373,7 +373,7 @@ def run_b200(args):
         # algorithmic bytes per launch (DESIGN.md "byte model"), rank 0's objects
         npass = max(1, -(-int(np.ceil(np.log2(max(2, eng_ncells(bounds, xlo, xhi))))) // 8))
         model = {
-            "keys": 20.0 * n_loc, "sort": (16.0 * npass) * n_loc, "reorder": 110.0 * n_loc,
+            "keys": 102.0 * n_loc, "sort": (16.0 * npass) * n_loc, "reorder": 108.0 * n_loc,
             "pairs": 56.0 * n_loc, "sample": 0.0, "exact": 0.0,
         }
         kernels = {}

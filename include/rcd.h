@@ -175,6 +175,12 @@ int rcd_truncate(rcd_handle h, uint64_t n);
  * rcd_step even though rcd_upload was not called. */
 int rcd_invalidate(rcd_handle h);
 
+/* Build the spatial index only (cell keys -> radix sort -> cell-ordered state + cell ranges) for
+ * a query radius `cell_radius`; rcd_step and rcd_query_radius do this implicitly.  Replaces the
+ * clear() + N x insert part of the reference's timed region (src/test/performance_test.py:794-800).
+ * Stage times are reported under mode RCD_MODE_DETECT. */
+int rcd_build_index(rcd_handle h, float cell_radius);
+
 /* Wait for the frame and return its totals. */
 int rcd_counts(rcd_handle h, rcd_counts_t *out);
 

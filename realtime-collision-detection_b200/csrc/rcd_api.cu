@@ -45,6 +45,7 @@ struct rcd_handle_s {
     int sorted_buf = 0;
 
     float4 *P0 = nullptr, *P1 = nullptr, *P2 = nullptr;
+    float4 *U = nullptr;  // packed 48-byte records in upload order
     u32 *sorted_slot = nullptr;
     u32 *cell_start = nullptr, *cell_end = nullptr;
     u32 cells_cap = 0;
@@ -196,10 +197,9 @@ int build_index(rcd_handle h, float cell_req) {
     CUDA_TRY(h, cudaMemsetAsync(h->cell_start, 0, (size_t)g.ncells * sizeof(u32), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->cell_end, 0, (size_t)g.ncells * sizeof(u32), h->stream));
     {
-        u32 groups = std::max<u32>(n / 4, 1);
-        int blocks = (int)std::min<u64>((groups + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
-        k_cell_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(h->in_f[0], h->in_f[1], h->in_f[2], n, g, passes,
-                                                            h->keys[0], h->vals[0], h->hist);
+        int blocks = (int)std::min<u64>(((u64)n + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
+        k_pack_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(input_state(h), n, (u32)h->n_owned, g, passes, h->keys[0],
+                                                            h->vals[0], h->hist, h->U);
         KERNEL_CHECK(h);
         k_scan_hist<<<1, RADIX, 0, h->stream>>>(h->hist, passes);
         KERNEL_CHECK(h);
@@ -220,8 +220,8 @@ int build_index(rcd_handle h, float cell_req) {
 
     stage_begin(h, RCD_STAGE_REORDER);
     k_reorder<<<(n + REORDER_THREADS - 1) / REORDER_THREADS, REORDER_THREADS, 0, h->stream>>>(
-        h->keys[cur], h->vals[cur], n, (u32)h->n_owned, input_state(h), h->P0, h->P1, h->P2, h->sorted_slot,
-        h->cell_start, h->cell_end);
+        h->keys[cur], h->vals[cur], n, h->U, h->P0, h->P1, h->P2, h->sorted_slot, h->cell_start,
+        h->cell_end);
     KERNEL_CHECK(h);
     stage_end(h, RCD_STAGE_REORDER);
     h->index_valid = true;
@@ -295,6 +295,7 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->P0, cap));
     CREATE_TRY(dev_alloc(&h->P1, cap));
     CREATE_TRY(dev_alloc(&h->P2, cap));
+    CREATE_TRY(dev_alloc(&h->U, 3 * (cap + 4)));
     CREATE_TRY(dev_alloc(&h->sorted_slot, cap));
     CREATE_TRY(dev_alloc(&h->cell_start, h->cells_cap));
     CREATE_TRY(dev_alloc(&h->cell_end, h->cells_cap));
@@ -328,6 +329,7 @@ int rcd_destroy(rcd_handle h) {
     for (int k = 0; k < 2; ++k) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
     cudaFree(h->hist); cudaFree(h->tile_status); cudaFree(h->tile_counter);
     cudaFree(h->P0); cudaFree(h->P1); cudaFree(h->P2); cudaFree(h->sorted_slot);
+    cudaFree(h->U);
     cudaFree(h->cell_start); cudaFree(h->cell_end); cudaFree(h->bbox_dev);
     if (h->bbox_host) cudaFreeHost(h->bbox_host);
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
@@ -523,6 +525,19 @@ int rcd_invalidate(rcd_handle h) {
     h->index_valid = false;
     h->frame_done = false;
     return RCD_OK;
+}
+
+int rcd_build_index(rcd_handle h, float cell_radius) {
+    if (!h) return RCD_EINVAL;
+    if (!(cell_radius > 0.0f) || !std::isfinite(cell_radius)) return fail(h, RCD_EINVAL, "rcd_build_index: bad radius");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    h->launches = 0;
+    h->stage_mode = RCD_MODE_DETECT;
+    for (int s = RCD_STAGE_KEYS; s <= RCD_STAGE_EXACT; ++s) h->stages[RCD_MODE_DETECT][s].used = false;
+    stage_begin(h, RCD_STAGE_TOTAL);
+    int rc = build_index(h, cell_radius);
+    stage_end(h, RCD_STAGE_TOTAL);
+    return rc;
 }
 
 int rcd_counts(rcd_handle h, rcd_counts_t *out) {

@@ -21,45 +21,41 @@ struct InputState {
 };
 
 // -------------------------------------------------------------------------------------------------
-// K1: cell keys + identity permutation + digit histograms of every pass (one read of x,y,z).
-// Algorithmic bytes: 12 N read + 8 N written.
+// K1: one pass over the SoA state: cell keys + identity permutation + digit histograms of every
+// sort pass, and the state packed into one dense 48-byte record per object in upload order
+// ({x,y,z,size | vx,vy,vz,heading | ax,ay,az,meta}), so that the gather after the sort reads two
+// adjacent 32-byte sectors per object instead of twelve scattered 4-byte fields.
+// Algorithmic bytes: 46 N read + 8 N + 48 N written = 102 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int KEYS_THREADS = 256;
 
+__device__ __forceinline__ u32 pack_meta(u32 type, u32 pattern, bool owned) {
+    return type | ((pattern & 3u) << 8) | (owned ? META_OWNED : 0u);
+}
+
 __global__ void __launch_bounds__(KEYS_THREADS)
-k_cell_keys(const float *__restrict__ px, const float *__restrict__ py, const float *__restrict__ pz,
-            u32 n, GridParams g, int passes, u32 *__restrict__ keys, u32 *__restrict__ vals,
-            u32 *__restrict__ hist /* [MAX_PASSES][RADIX] */) {
+k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__restrict__ keys,
+            u32 *__restrict__ vals, u32 *__restrict__ hist /* [MAX_PASSES][RADIX] */,
+            float4 *__restrict__ U /* [n][3]: one dense 48-byte record per object */) {
     __shared__ u32 s_hist[MAX_PASSES][RADIX];
     for (int k = threadIdx.x; k < MAX_PASSES * RADIX; k += KEYS_THREADS) (&s_hist[0][0])[k] = 0;
     __syncthreads();
-
-    const u32 n4 = n >> 2;  // groups of 4 objects: 128-bit loads / stores (arrays are 256 B aligned)
+    // one object per thread: every field load and the key / permutation stores are fully coalesced
+    // 128-byte warp requests, and the three 16-byte record stores of a warp tile a dense 1.5 KB span
     const u32 stride = gridDim.x * KEYS_THREADS;
-    for (u32 q = blockIdx.x * KEYS_THREADS + threadIdx.x; q < n4; q += stride) {
-        float4 x = __ldcs(reinterpret_cast<const float4 *>(px) + q);
-        float4 y = __ldcs(reinterpret_cast<const float4 *>(py) + q);
-        float4 z = __ldcs(reinterpret_cast<const float4 *>(pz) + q);
-        uint4 k4;
-        k4.x = cell_key(g, x.x, y.x, z.x);
-        k4.y = cell_key(g, x.y, y.y, z.y);
-        k4.z = cell_key(g, x.z, y.z, z.z);
-        k4.w = cell_key(g, x.w, y.w, z.w);
-        reinterpret_cast<uint4 *>(keys)[q] = k4;
-        reinterpret_cast<uint4 *>(vals)[q] = make_uint4(4 * q, 4 * q + 1, 4 * q + 2, 4 * q + 3);
-        for (int p = 0; p < passes; ++p) {
-            atomicAdd(&s_hist[p][(k4.x >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
-            atomicAdd(&s_hist[p][(k4.y >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
-            atomicAdd(&s_hist[p][(k4.z >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
-            atomicAdd(&s_hist[p][(k4.w >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
-        }
-    }
-    // tail (< 4 objects)
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3u)) {
-        u32 i = (n4 << 2) + threadIdx.x;
-        u32 k = cell_key(g, px[i], py[i], pz[i]);
+    for (u32 i = blockIdx.x * KEYS_THREADS + threadIdx.x; i < n; i += stride) {
+        const float x = __ldcs(in.px + i), y = __ldcs(in.py + i), z = __ldcs(in.pz + i);
+        const float4 r0 = make_float4(x, y, z, __ldcs(in.size + i));
+        const float4 r1 = make_float4(__ldcs(in.vx + i), __ldcs(in.vy + i), __ldcs(in.vz + i), __ldcs(in.heading + i));
+        const u32 meta = pack_meta(__ldcs(in.type + i), __ldcs(in.pattern + i), i < n_owned);
+        const float4 r2 = make_float4(__ldcs(in.ax + i), __ldcs(in.ay + i), __ldcs(in.az + i), __uint_as_float(meta));
+        const u32 k = cell_key(g, x, y, z);
         keys[i] = k;
         vals[i] = i;
+        float4 *rec = U + 3 * (size_t)i;
+        rec[0] = r0;
+        rec[1] = r1;
+        rec[2] = r2;
         for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(k >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
     }
     __syncthreads();
@@ -98,17 +94,40 @@ __global__ void __launch_bounds__(RADIX) k_scan_hist(u32 *__restrict__ hist, int
 // -------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 8;
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 2048 keys
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys
 constexpr u32 STATUS_AGGREGATE = 1u << 30;
 constexpr u32 STATUS_PREFIX = 2u << 30;
 constexpr u32 STATUS_VALUE_MASK = (1u << 30) - 1u;
+
+// look-back status words: gpu-scope relaxed accesses (the word carries its own flag, no fence needed)
+__device__ __forceinline__ u32 ld_status(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(u32 *p, u32 v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// lanes of the warp holding the same 8-bit digit: eight independent ballots pipeline far better
+// than one MATCH.ANY (whose latency the ranking chain would pay once per item)
+__device__ __forceinline__ u32 match_digit(u32 digit, bool valid) {
+    u32 peers = __ballot_sync(FULL_MASK, valid);
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; ++b) {
+        const bool bit = (digit >> b) & 1u;
+        const u32 vote = __ballot_sync(FULL_MASK, bit);
+        peers &= bit ? vote : ~vote;
+    }
+    return peers;
+}
 
 __global__ void __launch_bounds__(SORT_THREADS)
 k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                 u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 n, int shift,
                 const u32 *__restrict__ digit_base /* [RADIX] exclusive, this pass */,
-                volatile u32 *tile_status /* [tiles][RADIX], zeroed */, u32 *tile_counter) {
+                u32 *tile_status /* [tiles][RADIX], zeroed */, u32 *tile_counter) {
     __shared__ u32 s_warp_hist[SORT_WARPS][RADIX];
     __shared__ u32 s_digit_excl[RADIX];
     __shared__ u32 s_global_base[RADIX];
@@ -141,8 +160,9 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
         u32 local = warp_base + k * 32 + lane;
         bool valid = local < tile_count;
         u32 digit = (key[k] >> shift) & (RADIX - 1);
-        // invalid lanes form their own group (digit 256) and do not touch the counters
-        u32 group = __match_any_sync(FULL_MASK, valid ? digit : (u32)RADIX);
+        // invalid lanes are in nobody's group and do not touch the counters
+        u32 group = match_digit(digit, valid);
+        if (!valid) group = 1u << lane;
         u32 leader = __ffs(group) - 1;
         u32 before = 0;
         if (valid && lane == leader) {
@@ -165,9 +185,9 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
     }
     // publish this tile's digit count as early as possible
     if (tile == 0) {
-        tile_status[tid] = STATUS_PREFIX | total;
+        st_status(tile_status + tid, STATUS_PREFIX | total);
     } else {
-        tile_status[(size_t)tile * RADIX + tid] = STATUS_AGGREGATE | total;
+        st_status(tile_status + (size_t)tile * RADIX + tid, STATUS_AGGREGATE | total);
     }
     // exclusive scan of the 256 digit totals -> start of each digit inside the sorted tile
     {
@@ -188,14 +208,14 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
     if (tile > 0) {
         int t = (int)tile - 1;
         while (true) {
-            u32 st = tile_status[(size_t)t * RADIX + tid];
+            u32 st = ld_status(tile_status + (size_t)t * RADIX + tid);
             u32 flag = st & ~STATUS_VALUE_MASK;
             if (flag == 0) continue;  // predecessor has a ticket, so it is running: spin
             excl += st & STATUS_VALUE_MASK;
             if (flag == STATUS_PREFIX) break;
             --t;
         }
-        tile_status[(size_t)tile * RADIX + tid] = STATUS_PREFIX | (excl + total);
+        st_status(tile_status + (size_t)tile * RADIX + tid, STATUS_PREFIX | (excl + total));
     }
     s_global_base[tid] = digit_base[tid] + excl - s_digit_excl[tid];
     __syncthreads();
@@ -226,39 +246,30 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
 }
 
 // -------------------------------------------------------------------------------------------------
-// K4: gather the SoA state into cell order (three float4 planes) and mark the cell ranges.
-// Algorithmic bytes: 8 N (key + perm) + 46 N gathered + 56 N written (+ 8 B per occupied cell).
+// K4: gather the packed planes into cell order and mark the cell ranges.
+// Algorithmic bytes: 8 N (key + perm) + 48 N gathered + 52 N written = 108 N (+ 8 B per occupied cell);
+// a 48-byte record spans exactly two 32-byte sectors, so DRAM traffic is about 124 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int REORDER_THREADS = 256;
 
 __global__ void __launch_bounds__(REORDER_THREADS)
-k_reorder(const u32 *__restrict__ keys, const u32 *__restrict__ perm, u32 n, u32 n_owned, InputState in,
+k_reorder(const u32 *__restrict__ keys, const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
           float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2,
-          u32 *__restrict__ sorted_id, u32 *__restrict__ cell_start, u32 *__restrict__ cell_end) {
+          u32 *__restrict__ sorted_slot, u32 *__restrict__ cell_start, u32 *__restrict__ cell_end) {
     u32 s = blockIdx.x * REORDER_THREADS + threadIdx.x;
     if (s >= n) return;
-    u32 key = keys[s];
-    u32 src = perm[s];
-    u32 prev = (s > 0) ? keys[s - 1] : 0xffffffffu;
-    u32 next = (s + 1 < n) ? keys[s + 1] : 0xffffffffu;
+    const u32 key = keys[s];
+    const u32 src = perm[s];
+    const u32 prev = (s > 0) ? keys[s - 1] : 0xffffffffu;
+    const u32 next = (s + 1 < n) ? keys[s + 1] : 0xffffffffu;
     if (s == 0 || key != prev) cell_start[key] = s;
     if (s + 1 == n || key != next) cell_end[key] = s + 1;
-
-    float4 a, b, c;
-    a.x = in.px[src]; a.y = in.py[src]; a.z = in.pz[src];
-    a.w = in.size ? in.size[src] : 0.0f;
-    b.x = in.vx[src]; b.y = in.vy[src]; b.z = in.vz[src];
-    b.w = in.heading ? in.heading[src] : 0.0f;
-    c.x = in.ax ? in.ax[src] : 0.0f;
-    c.y = in.ay ? in.ay[src] : 0.0f;
-    c.z = in.az ? in.az[src] : 0.0f;
-    u32 meta = (in.type ? (u32)in.type[src] : 0u) | ((in.pattern ? (u32)(in.pattern[src] & 3u) : 2u) << 8) |
-               (src < n_owned ? META_OWNED : 0u);
-    c.w = __uint_as_float(meta);
+    const float4 *rec = U + 3 * (size_t)src;
+    const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
     P0[s] = a;
     P1[s] = b;
     P2[s] = c;
-    sorted_id[s] = src;
+    sorted_slot[s] = src;
 }
 
 // bounding box of the positions (auto grid): ordered-int atomics

@@ -130,6 +130,9 @@ class FrameEngine:
         m = int(mode) | (N.STEP_APPEND if append else 0)
         N.check(self._lib.rcd_step(self._h, m, float(search_radius), float(time_window)), self._h)
 
+    def build_index(self, cell_radius: float = 100.0) -> None:
+        N.check(self._lib.rcd_build_index(self._h, float(cell_radius)), self._h)
+
     def counts(self) -> Dict[str, int]:
         c = N.RcdCounts()
         N.check(self._lib.rcd_counts(self._h, ctypes.byref(c)), self._h)
