@@ -204,16 +204,27 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
         s_digit_excl[tid] = base + incl - total;
     }
     // ---- decoupled look-back for digit `tid` ----------------------------------------------------
+    // Up to LOOKBACK predecessors are fetched with independent loads and then consumed in order, so a
+    // long run of AGGREGATE tiles costs one memory latency per batch instead of one per tile.
     u32 excl = 0;
     if (tile > 0) {
+        constexpr int LOOKBACK = 8;
         int t = (int)tile - 1;
-        while (true) {
-            u32 st = ld_status(tile_status + (size_t)t * RADIX + tid);
-            u32 flag = st & ~STATUS_VALUE_MASK;
-            if (flag == 0) continue;  // predecessor has a ticket, so it is running: spin
-            excl += st & STATUS_VALUE_MASK;
-            if (flag == STATUS_PREFIX) break;
-            --t;
+        bool done = false;
+        while (!done) {
+            u32 st[LOOKBACK];
+#pragma unroll
+            for (int k = 0; k < LOOKBACK; ++k)
+                st[k] = (t - k >= 0) ? ld_status(tile_status + (size_t)(t - k) * RADIX + tid) : STATUS_PREFIX;
+#pragma unroll
+            for (int k = 0; k < LOOKBACK; ++k) {
+                if (done) break;
+                const u32 flag = st[k] & ~STATUS_VALUE_MASK;
+                if (flag == 0) break;  // that predecessor holds a ticket, so it is running: fetch again from it
+                excl += st[k] & STATUS_VALUE_MASK;
+                --t;
+                if (flag == STATUS_PREFIX) done = true;
+            }
         }
         st_status(tile_status + (size_t)tile * RADIX + tid, STATUS_PREFIX | (excl + total));
     }
