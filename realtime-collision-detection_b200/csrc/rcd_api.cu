@@ -306,7 +306,9 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->counters_host), sizeof(Counters)));
     CREATE_TRY(dev_alloc(&h->cand_count, cap));
     CREATE_TRY(dev_alloc(&h->pair_tile_counter, 1));
-    h->qcap = (u32)std::min<u64>(2 * h->max_pairs + 65536, 1ull << 30);
+    // the fp32 stages forward about 5 candidate entries per emitted pair on clustered frames; a full
+    // queue is not an error (the pair is then finished in place) but it is slower
+    h->qcap = (u32)std::min<u64>(6 * h->max_pairs + 65536, 1ull << 28);
     CREATE_TRY(dev_alloc(&h->q2, (size_t)h->qcap));
     CREATE_TRY(dev_alloc(&h->q3, (size_t)h->qcap));
     for (int m = 0; m < 3; ++m)

@@ -96,8 +96,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
-// sqrt(x) rounded up a little: only ever used for conservative bounds
-__device__ __forceinline__ float sqrt_ub(float x) { return x * rsqrtf(fmaxf(x, 1.0e-30f)) * (1.0f + 4.0e-6f); }
+// sqrt(x) rounded up a little: only ever used for conservative bounds (MUFU.SQRT, ~1 ulp)
+__device__ __forceinline__ float sqrt_ub(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * (1.0f + 4.0e-6f);
+}
+// 1/x to ~1 ulp (MUFU.RCP); callers cover the error with their slack terms
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 
 // result of the exact stage for one queued pair
 struct EmitRec {
@@ -341,19 +351,34 @@ __device__ __forceinline__ bool predict_window(const PredictCoef &c, int &m_lo, 
     m_lo = 0;
     m_hi = PREDICT_OFFSETS - 1;
     if (!(cv2 > 1.0e-8f)) return d2 <= L2;  // (almost) no relative drift: every offset looks the same
-    const float inv = 1.0f / cv2;
+    const float inv = rcp_fast(cv2);
     const float ts = (c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz) * inv;
     // closest point of the linear part on [0, 9.5]
     const float tc = fminf(fmaxf(ts, 0.0f), 9.5f);
     const float lx = c.cvx * tc - c.dx, ly = c.cvy * tc - c.dy, lz = c.cvz * tc - c.dz;
     const float dmin2 = lx * lx + ly * ly + lz * lz;
     if (dmin2 > L2) return false;
-    // |-d + cv t|^2 = dg2 + cv2 (t - ts)^2 with dg2 the global minimum: t must lie within w of ts
+    // |-d + cv t|^2 = dg2 + cv2 (t - ts)^2 with dg2 the global minimum: t must lie within w of ts.
+    // The cancellation in dg2 (a few ulp of d2) moves w by up to ~2e-3 sqrt(d2 / cv2): covered twice over.
     const float dg2 = fmaxf(d2 - (c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz) * ts, 0.0f);
-    // the cancellation in dg2 (a few ulp of d2) moves w by up to ~2e-3 sqrt(d2 / cv2): covered twice over
-    const float w = sqrt_ub(fmaxf(L2 - dg2, 0.0f) * inv) + 1.0e-3f + 4.0e-3f * sqrt_ub(d2 * inv);
-    const float t_lo = ts - w, t_hi = ts + w;
+    const float wslack = 1.0e-3f + 4.0e-3f * sqrt_ub(d2 * inv);
+    float w = sqrt_ub(fmaxf(L2 - dg2, 0.0f) * inv) + wslack;
+    float t_lo = fmaxf(ts - w, 0.0f), t_hi = fminf(ts + w, 9.5f);
     if (t_hi < 0.0f || t_lo > 9.5f) return false;
+    // Refinement: every feasible t is <= t_hi, so the acceleration term is at most |ca| t_hi^2 / 2
+    // (not |ca| 9.5^2 / 2): shrink the reach and the window accordingly, twice.
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const float Lr = (c.hr + 0.5f * can * t_hi * t_hi) * (1.0f + 1.0e-4f) + 1.0e-2f + 1.0e-5f * sqrt_ub(d2);
+        const float Lr2 = Lr * Lr;
+        const float tcr = fminf(fmaxf(ts, t_lo), t_hi);
+        const float rx = c.cvx * tcr - c.dx, ry = c.cvy * tcr - c.dy, rz = c.cvz * tcr - c.dz;
+        if (rx * rx + ry * ry + rz * rz > Lr2) return false;
+        w = sqrt_ub(fmaxf(Lr2 - dg2, 0.0f) * inv) + wslack;
+        t_lo = fmaxf(fmaxf(ts - w, 0.0f), t_lo);
+        t_hi = fminf(fminf(ts + w, 9.5f), t_hi);
+        if (t_lo > t_hi) return false;
+    }
     m_lo = max((int)floorf(2.0f * t_lo), 0);
     m_hi = min((int)ceilf(2.0f * t_hi), PREDICT_OFFSETS - 1);
     return true;
