@@ -192,7 +192,7 @@ def run_reference(args):
             times.append(t)
     t_mean = float(np.mean(times))
     value = n / t_mean
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "object-updates/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": t_mean * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -417,7 +417,7 @@ def run_b200(args):
             "cpu_baseline": cpu,
             "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     eng.close()
     if world > 1:
         dist.barrier()
@@ -430,6 +430,25 @@ def eng_ncells(bounds, xlo, xhi):
     ny = int((bounds[1][1] - bounds[0][1]) / cell) + 1
     nz = int((bounds[1][2] - bounds[0][2]) / cell) + 1
     return nx * ny * nz
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """NCCL and friends print banners to fd 1; the contract is ONE JSON line on stdout.  Everything
+    but the final line goes to stderr."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
 
 
 def main():
@@ -448,6 +467,7 @@ def main():
         args.objects_per_gpu = {"cfg2_5k_city": 5000, "cfg3_100k_uniform2d": 100_000, "cfg4_1m_clustered3d": PER_GPU_DEFAULT,
                                 "cfg5_10m_skew3d": 1_250_000}[args.workload]
     args.warmup = max(args.warmup, 3)
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
