@@ -307,6 +307,7 @@ struct PredictCoef {
     float dx, dy, dz;
     float uvx, uvy, uvz, uax, uay, uaz;
     float cvx, cvy, cvz, cax, cay, caz;
+    float rvx, rvy, rvz, inv_rv2, lim2;  // sample motion: relative velocity, 1/|rv|^2, (safe_b + 0.405 |ra|)^2
     float safe_b2, hr, hr2;
 };
 __device__ __forceinline__ PredictCoef predict_coef(const float4 &a0, const float4 &a1, const float4 &a2,
@@ -331,7 +332,22 @@ __device__ __forceinline__ PredictCoef predict_coef(const float4 &a0, const floa
     // the 10 samples move the pair by at most |rv|*0.9 + |ra|*0.405 from the offset state
     c.hr = safe_b + rvn * 0.9f + ran * 0.405f;
     c.hr2 = c.hr * c.hr;
+    c.rvx = rvx; c.rvy = rvy; c.rvz = rvz;
+    const float rv2 = rvx * rvx + rvy * rvy + rvz * rvz;
+    c.inv_rv2 = rv2 > 1.0e-12f ? rcp_fast(rv2) : 0.0f;
+    const float lim = (safe_b + ran * 0.405f) * (1.0f + 1.0e-5f) + 1.0e-3f;
+    c.lim2 = lim * lim;
     return c;
+}
+// Can one of the 10 samples after offset time t come within the safe distance?  The samples move
+// along g + rv tau + ra tau^2/2, tau in [0, 0.9]: |.| >= min_tau |g + rv tau| - 0.405 |ra|.
+__device__ __forceinline__ bool offset_may_hit(const PredictCoef &c, float t) {
+    const float h = 0.5f * t * t;
+    const float gx = c.cvx * t + c.cax * h - c.dx, gy = c.cvy * t + c.cay * h - c.dy, gz = c.cvz * t + c.caz * h - c.dz;
+    if (gx * gx + gy * gy + gz * gz > c.hr2) return false;
+    const float tau = fminf(fmaxf(-(gx * c.rvx + gy * c.rvy + gz * c.rvz) * c.inv_rv2, 0.0f), 0.9f);
+    const float ex = gx + c.rvx * tau, ey = gy + c.rvy * tau, ez = gz + c.rvz * tau;
+    return ex * ex + ey * ey + ez * ez <= c.lim2;
 }
 __device__ __forceinline__ float g2_at(const PredictCoef &c, float t) {
     float h = 0.5f * t * t;
@@ -404,14 +420,14 @@ __device__ __forceinline__ u32 predict_scan(WarpShared &ws, const PairParams &P,
                 if (!exact_predict_radius(P, si, sj, pattern, m)) continue;
             }
             ++ncand;
-            if (m >= m_lo && m <= m_hi && g2_at(c, t) <= c.hr2) mask |= 1u << m;
+            if (m >= m_lo && m <= m_hi && offset_may_hit(c, t)) mask |= 1u << m;
         }
         if (ncand) atomicAdd(&ws.cand[ql], ncand);
         return mask;
     }
 #pragma unroll 1
     for (int m = m_lo; m <= m_hi; ++m)
-        if (g2_at(c, 0.5f * (float)m) <= c.hr2) mask |= 1u << m;
+        if (offset_may_hit(c, 0.5f * (float)m)) mask |= 1u << m;
     return mask;
 }
 
