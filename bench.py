@@ -265,7 +265,7 @@ def run_b200(args):
         p["id"] = torch.from_numpy(fid.astype(np.int32)).pin_memory()
         p["pattern"] = torch.full((n,), 2, dtype=torch.uint8).pin_memory()
         pin.append(p)
-    pairs_pin = torch.empty(max_pairs * 48, dtype=torch.uint8).pin_memory()
+    pairs_pin = torch.empty(min(max_pairs, int(args.host_pairs_cap)) * 48, dtype=torch.uint8).pin_memory()
     pairs_host = pairs_pin.numpy().view(N.PAIR_DTYPE)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
@@ -462,6 +462,8 @@ def main():
     ap.add_argument("--objects-per-gpu", type=int, default=None)
     ap.add_argument("--max-pairs", type=int, default=32_000_000)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--host-pairs-cap", type=int, default=32_000_000,
+                    help="pairs per rank the end-to-end leg copies back to (pinned) host memory per frame")
     args = ap.parse_args()
     if args.objects_per_gpu is None:
         args.objects_per_gpu = {"cfg2_5k_city": 5000, "cfg3_100k_uniform2d": 100_000, "cfg4_1m_clustered3d": PER_GPU_DEFAULT,
