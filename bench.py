@@ -240,7 +240,18 @@ def run_b200(args):
         own.append(W.take(f, m))
         own_ids.append(ids_all[m])
     n_own_max = max(len(o["px"]) for o in own)
-    cap = int(n_own_max * (1.6 if world > 1 else 1.0)) + 1024
+    # exact halo sizes (narrow slabs in dense hotspots send the same object to several peers)
+    n_send_max, n_recv_max = 0, 0
+    if world > 1:
+        for f in frames:
+            x = f["px"]
+            owner = (np.searchsorted(hi, x, side="right")).clip(0, world - 1)
+            mine = owner == rank
+            xs = x[mine]
+            n_send = sum(int(((xs >= lo[p] - halo) & (xs < hi[p] + halo)).sum()) for p in range(world) if p != rank)
+            n_recv = int(((x >= lo[rank] - halo) & (x < hi[rank] + halo) & ~mine).sum())
+            n_send_max, n_recv_max = max(n_send_max, n_send), max(n_recv_max, n_recv)
+    cap = int(n_own_max + 1.1 * n_recv_max) + 4096
     max_pairs = int(args.max_pairs)
     # slab bounding box (+ halo) as the static grid bounds: no per-frame bbox round trip
     xlo = max(0.0, float(lo[rank]) - halo) if np.isfinite(lo[rank]) else 0.0
@@ -248,7 +259,7 @@ def run_b200(args):
     eng = FrameEngine(cap, max_pairs, device=local_rank,
                       world_bounds=((xlo, bounds[0][1], bounds[0][2]), (xhi, bounds[1][1], bounds[1][2])), profile=True)
     stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=torch.device("cuda", local_rank))
-    exch = SlabExchange(eng, lo, hi, rank, world, halo, stream, cap_records=int(0.6 * n_own_max) + 1024) if world > 1 else None
+    exch = SlabExchange(eng, lo, hi, rank, world, halo, stream, cap_records=int(1.1 * n_send_max) + 4096) if world > 1 else None
 
     # device-resident copies of the frames (the engine ingests them device-to-device every step)
     dev = []
