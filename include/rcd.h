@@ -115,6 +115,8 @@ typedef struct {
     uint64_t n_written;    /* pairs actually stored (<= max_pairs) */
     uint64_t n_alerts[4];  /* alerts by priority 0..3 (risk >= 0.3) */
     uint64_t n_exact;      /* pairs that took the fp64 re-evaluation path (diagnostic) */
+    uint64_t n_fallback;   /* fp32-settled pairs the fp64 stage had to redo in full: 0 while the guard
+                              bands hold (diagnostic; results are exact either way) */
 } rcd_counts_t;
 
 #define RCD_NUM_STAGES 9

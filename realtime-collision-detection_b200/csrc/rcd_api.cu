@@ -558,6 +558,7 @@ int rcd_counts(rcd_handle h, rcd_counts_t *out) {
     out->n_written = std::min<u64>(c.n_pairs, h->max_pairs);
     for (int k = 0; k < 4; ++k) out->n_alerts[k] = c.n_alerts[k];
     out->n_exact = c.n_exact;
+    out->n_fallback = c.n_fallback;
     return RCD_OK;
 }
 

@@ -43,7 +43,8 @@ class RcdConfig(ctypes.Structure):
 class RcdCounts(ctypes.Structure):
     _fields_ = [("n_objects", ctypes.c_uint64), ("n_owned", ctypes.c_uint64), ("n_candidates", ctypes.c_uint64),
                 ("n_potential", ctypes.c_uint64), ("n_pairs", ctypes.c_uint64), ("n_high_risk", ctypes.c_uint64),
-                ("n_written", ctypes.c_uint64), ("n_alerts", ctypes.c_uint64 * 4), ("n_exact", ctypes.c_uint64)]
+                ("n_written", ctypes.c_uint64), ("n_alerts", ctypes.c_uint64 * 4), ("n_exact", ctypes.c_uint64),
+                ("n_fallback", ctypes.c_uint64)]
 
 
 # numpy mirror of rcd_pair (48 bytes)

@@ -138,7 +138,8 @@ class FrameEngine:
         N.check(self._lib.rcd_counts(self._h, ctypes.byref(c)), self._h)
         return {"n_objects": c.n_objects, "n_owned": c.n_owned, "n_candidates": c.n_candidates,
                 "n_potential": c.n_potential, "n_pairs": c.n_pairs, "n_high_risk": c.n_high_risk,
-                "n_written": c.n_written, "n_alerts": [int(v) for v in c.n_alerts], "n_exact": c.n_exact}
+                "n_written": c.n_written, "n_alerts": [int(v) for v in c.n_alerts], "n_exact": c.n_exact,
+                "n_fallback": c.n_fallback}
 
     def download(self, cap: Optional[int] = None, sort: bool = True, out: Optional[np.ndarray] = None) -> np.ndarray:
         """Emitted pairs as a PAIR_DTYPE array, sorted by (i, j, predicted) unless sort=False.

@@ -33,6 +33,8 @@ def compare_pairs(gpu, ora, mode, rtol=RTOL):
 
 def compare_counts(counts, cand_count, ora, mode, candidates=True):
     """candidates=False: predict frames stepped without RCD_FLAG_COUNT_PREDICT_CANDIDATES."""
+    # pairs settled in fp32 are never contradicted by the fp64 stage: the guard bands hold
+    assert counts.get("n_fallback", 0) == 0, "fp32-resolved pair had to be redone in fp64"
     if candidates:
         assert counts["n_candidates"] == int(ora["counts"][0]), f"{mode} candidate total"
         assert np.array_equal(cand_count[: len(ora["cand_count"])], ora["cand_count"]), f"{mode} per-object candidates"

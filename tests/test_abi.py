@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     from rcd_b200.host import _native as N
     assert ctypes.sizeof(N.RcdConfig) == 4 + 4 + 8 + 8 + 12 + 12
-    assert ctypes.sizeof(N.RcdCounts) == 8 * 12
+    assert ctypes.sizeof(N.RcdCounts) == 8 * 13
     assert N.PAIR_DTYPE.itemsize == 48
     assert N.PAIR_DTYPE.fields["priority"][1] == 44 and N.PAIR_DTYPE.fields["d_closest"][1] == 40
 

@@ -293,3 +293,71 @@ def test_full_size_100k_counts_and_pairs():
         ora = O.frame_A(f64_frame(frame), "predict", pattern_codes=pat, want_potentials=False)
         compare_pairs(got, ora["risks"], "predict")
         compare_counts(e.counts(), e.candidate_counts(), ora, "predict", candidates=False)
+
+
+def test_full_size_1m_sampled_queries_and_symmetry():
+    """configs[3] at full size (1 M mixed vehicles + drones, clustered, 3-D).  The oracle cannot run
+    the whole frame in seconds, so: (a) every 211th object is queried by the oracle against the FULL
+    index and must get exactly the GPU's pairs, detect and predict; (b) size-independent properties:
+    the detect pair set is symmetric with bit-identical values (every term of the reference formula
+    is symmetric) and per-object candidate counts sum to the frame total."""
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    O = _oracle()
+    frame = W.make_workload("cfg4_1m_clustered3d")
+    n = len(frame["px"])
+    stride = 211
+    f64 = f64_frame(frame)
+    with FrameEngine(n, 24_000_000, world_bounds=((0, 0, 0), (31623, 31623, 100))) as e:
+        e.upload(frame)
+        got = e.detect()
+        c = e.counts()
+        assert c["n_pairs"] == len(got) and c["n_fallback"] == 0
+        cand = e.candidate_counts()
+        assert int(cand.astype(np.int64).sum()) == c["n_candidates"]
+        # (b) symmetry
+        fwd = np.stack([got["i"], got["j"]], 1).astype(np.int64)
+        rev = fwd[:, ::-1]
+        order = np.lexsort((rev[:, 1], rev[:, 0]))
+        assert np.array_equal(fwd, rev[order])
+        for col in ("ttc", "distance", "rel_speed", "risk", "cx", "cy", "cz", "priority"):
+            assert np.array_equal(got[col], got[col][order]), col
+        # (a) sampled queries, detect
+        ora = O.frame_A(f64, "detect", want_potentials=False, query_stride=stride)
+        sel = got[got["i"] % stride == 0]
+        compare_pairs(sel, ora["risks"], "detect")
+        q = np.arange(0, n, stride)
+        assert np.array_equal(cand[q], ora["cand_count"][q])
+        # (a) sampled queries, predict
+        pat = W.random_patterns(n, 5)
+        e.set_patterns(pat)
+        got = e.predict()
+        assert e.counts()["n_fallback"] == 0
+        ora = O.frame_A(f64, "predict", pattern_codes=pat, want_potentials=False, query_stride=stride)
+        compare_pairs(got[got["i"] % stride == 0], ora["risks"], "predict")
+
+
+def test_permutation_invariance_and_idempotence():
+    """Shuffling the upload order changes neither the pair set nor any value (ids travel with the
+    objects); stepping the same frame twice gives identical output."""
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 50_000
+    frame = W.hotspot_frame(n, 31, 6000.0, 5, radius_range=(400.0, 900.0))
+    ids = np.arange(n, dtype=np.uint32)
+    perm = np.random.default_rng(7).permutation(n)
+    pat = W.random_patterns(n, 9)
+    with FrameEngine(n, 8_000_000) as e:
+        e.upload(frame, ids=ids)
+        e.set_patterns(pat)
+        a1 = e.predict()
+        a2 = e.predict()
+        assert np.array_equal(a1, a2)
+        e.upload(W.take(frame, perm), ids=ids[perm])
+        e.set_patterns(pat[perm])
+        b = e.predict()
+        assert np.array_equal(a1, b)
+        d1 = e.detect()
+        e.upload(frame, ids=ids)
+        d2 = e.detect()
+        assert np.array_equal(d1, d2) and len(d1) > 100
