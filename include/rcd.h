@@ -209,6 +209,25 @@ int rcd_query_radius(rcd_handle h, uint64_t nq, const float *qx, const float *qy
 int rcd_classify_patterns(rcd_handle h, uint64_t n, uint32_t stride, const double *samples,
                           const uint32_t *count, uint8_t *pattern_out);
 
+/* Trajectory history on the device: replaces CollisionPredictionModel.update_trajectory +
+ * _analyze_trajectory_pattern (collision_detection.py:553-570, 623-711) without re-staging every
+ * vehicle's samples from the host each frame.  The handle keeps a ring of the last `max_history`
+ * (default 100, :539) float64 (x, y, z, t) samples per object slot (= upload order index).
+ * Samples of one object must arrive with non-decreasing timestamps (the reference sorts by
+ * timestamp before classifying; callers with out-of-order samples use rcd_classify_patterns). */
+int rcd_history_configure(rcd_handle h, uint32_t max_history);
+/* Append one sample for each listed slot (slot may be NULL: slots 0..n-1; a slot must not appear
+ * twice in one call).  Host arrays. */
+int rcd_history_append(rcd_handle h, uint64_t n, const uint32_t *slot, const double *x, const double *y,
+                       const double *z, const double *t);
+/* Forget the history of the listed slots (new vehicle in a recycled slot). */
+int rcd_history_reset(rcd_handle h, uint64_t n, const uint32_t *slot);
+/* Copy the history of slot src to slot dst (the host table moved an object, e.g. swap-remove). */
+int rcd_history_move(rcd_handle h, uint32_t dst, uint32_t src);
+/* Classify every uploaded object from its ring and store the codes as the frame's patterns
+ * (what rcd_set_patterns would set); optionally copy the n codes to pattern_out (host, may be NULL). */
+int rcd_history_classify(rcd_handle h, uint8_t *pattern_out);
+
 /* Spatial-slab support: pack every owned object whose x lies within `halo` of
  * peer p's slab [slab_lo[p], slab_hi[p]) -- p != self -- into 52-byte records
  * (11 floats, meta u32 = type | pattern << 8, id u32), grouped by peer.  out_records is a DEVICE

@@ -73,6 +73,9 @@ struct rcd_handle_s {
     Stage stages[3][RCD_NUM_STAGES];  // per frame mode
     int stage_mode = 0;
     float cn_prediction_time = 5.0f, cn_risk_threshold = 0.5f;
+    Sample64 *traj = nullptr;  // trajectory rings, [max_history][cap]
+    u32 *traj_count = nullptr;
+    u32 traj_len = 0;
     u64 launches = 0;
     std::string err;
 };
@@ -336,6 +339,7 @@ int rcd_destroy(rcd_handle h) {
     if (h->bbox_host) cudaFreeHost(h->bbox_host);
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
     cudaFree(h->q2); cudaFree(h->q3);
+    cudaFree(h->traj); cudaFree(h->traj_count);
     if (h->counters_host) cudaFreeHost(h->counters_host);
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) {
@@ -683,6 +687,107 @@ int rcd_classify_patterns(rcd_handle h, uint64_t n, uint32_t stride, const doubl
     if (e != cudaSuccess) return fail(h, e == cudaErrorMemoryAllocation ? RCD_ENOMEM : RCD_ECUDA,
                                       std::string("rcd_classify_patterns: ") + cudaGetErrorString(e));
     ++h->launches;
+    return RCD_OK;
+}
+
+int rcd_history_configure(rcd_handle h, uint32_t max_history) {
+    if (!h) return RCD_EINVAL;
+    if (max_history < 2 || max_history > 4096) return fail(h, RCD_EINVAL, "rcd_history_configure: max_history must be in [2, 4096]");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->traj); cudaFree(h->traj_count);
+    h->traj = nullptr; h->traj_count = nullptr; h->traj_len = 0;
+    CUDA_TRY(h, dev_alloc(&h->traj, (size_t)max_history * h->cap));
+    CUDA_TRY(h, dev_alloc(&h->traj_count, (size_t)h->cap));
+    CUDA_TRY(h, cudaMemsetAsync(h->traj_count, 0, (size_t)h->cap * sizeof(u32), h->stream));
+    h->traj_len = max_history;
+    return RCD_OK;
+}
+
+static int history_ready(rcd_handle h, const char *who) {
+    if (h->traj_len == 0) {
+        int rc = rcd_history_configure(h, 100);  // max_history_length = 100 (collision_detection.py:539)
+        if (rc) return rc;
+    }
+    (void)who;
+    return RCD_OK;
+}
+
+int rcd_history_append(rcd_handle h, uint64_t n, const uint32_t *slot, const double *x, const double *y,
+                       const double *z, const double *t) {
+    if (!h || (n && (!x || !y || !z || !t))) return RCD_EINVAL;
+    if (n > h->cap) return fail(h, RCD_ECAPACITY, "rcd_history_append: n exceeds max_objects");
+    if (n == 0) return RCD_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = history_ready(h, "rcd_history_append");
+    if (rc) return rc;
+    double *d = nullptr;
+    u32 *ds = nullptr;
+    CUDA_TRY(h, dev_alloc(&d, 4 * (size_t)n));
+    cudaError_t e = slot ? dev_alloc(&ds, (size_t)n) : cudaSuccess;
+    const double *src[4] = {x, y, z, t};
+    for (int k = 0; k < 4 && e == cudaSuccess; ++k)
+        e = cudaMemcpyAsync(d + (size_t)k * n, src[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess && slot) e = cudaMemcpyAsync(ds, slot, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_history_append<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((u32)n, ds, d, d + n, d + 2 * n, d + 3 * n, h->traj,
+                                                                             h->traj_count, (u32)h->cap, h->traj_len);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // the staging buffers are freed below
+    cudaFree(d); cudaFree(ds);
+    if (e != cudaSuccess) return fail(h, RCD_ECUDA, std::string("rcd_history_append: ") + cudaGetErrorString(e));
+    ++h->launches;
+    return RCD_OK;
+}
+
+int rcd_history_reset(rcd_handle h, uint64_t n, const uint32_t *slot) {
+    if (!h || (n && !slot)) return RCD_EINVAL;
+    if (n == 0) return RCD_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = history_ready(h, "rcd_history_reset");
+    if (rc) return rc;
+    u32 *ds = nullptr;
+    CUDA_TRY(h, dev_alloc(&ds, (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(ds, slot, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_history_reset<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>((u32)n, ds, h->traj_count, (u32)h->cap);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(ds);
+    if (e != cudaSuccess) return fail(h, RCD_ECUDA, std::string("rcd_history_reset: ") + cudaGetErrorString(e));
+    return RCD_OK;
+}
+
+int rcd_history_move(rcd_handle h, uint32_t dst, uint32_t src) {
+    if (!h) return RCD_EINVAL;
+    if (dst >= h->cap || src >= h->cap) return fail(h, RCD_EINVAL, "rcd_history_move: slot out of range");
+    if (dst == src) return RCD_OK;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = history_ready(h, "rcd_history_move");
+    if (rc) return rc;
+    k_history_move<<<1, 128, 0, h->stream>>>(dst, src, h->traj, h->traj_count, (u32)h->cap, h->traj_len);
+    KERNEL_CHECK(h);
+    return RCD_OK;
+}
+
+int rcd_history_classify(rcd_handle h, uint8_t *pattern_out) {
+    if (!h) return RCD_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc = history_ready(h, "rcd_history_classify");
+    if (rc) return rc;
+    if (h->n) {
+        k_history_classify<<<(unsigned)((h->n + 127) / 128), 128, 0, h->stream>>>((u32)h->n, h->traj, h->traj_count,
+                                                                                  (u32)h->cap, h->traj_len, h->in_pattern);
+        KERNEL_CHECK(h);
+        if (pattern_out) {
+            CUDA_TRY(h, cudaMemcpyAsync(pattern_out, h->in_pattern, (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        }
+    }
+    h->index_valid = false;  // the pattern is packed into the cell-ordered state
+    h->frame_done = false;
     return RCD_OK;
 }
 

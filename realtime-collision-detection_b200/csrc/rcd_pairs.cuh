@@ -991,6 +991,81 @@ k_classify_patterns(u32 n, u32 stride, const double *__restrict__ samples /* [n]
 }
 
 // -------------------------------------------------------------------------------------------------
+// Device-resident trajectory rings: hist[k * cap + slot] = k-th ring entry of the object in `slot`
+// (sample-major, so threads of a warp touch consecutive 32-byte samples), count[slot] = samples ever
+// appended.  Same fp64 arithmetic and summation order as k_classify_patterns.
+// -------------------------------------------------------------------------------------------------
+struct Sample64 {
+    double x, y, z, t;
+};
+
+__global__ void __launch_bounds__(256)
+k_history_append(u32 n, const u32 *__restrict__ slot, const double *__restrict__ x, const double *__restrict__ y,
+                 const double *__restrict__ z, const double *__restrict__ t, Sample64 *__restrict__ hist,
+                 u32 *__restrict__ count, u32 cap, u32 H) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 s = slot ? slot[i] : i;
+    if (s >= cap) return;
+    const u32 c = count[s];
+    Sample64 v;
+    v.x = x[i]; v.y = y[i]; v.z = z[i]; v.t = t[i];
+    hist[(size_t)(c % H) * cap + s] = v;
+    count[s] = c + 1;
+}
+
+__global__ void __launch_bounds__(256) k_history_reset(u32 n, const u32 *__restrict__ slot, u32 *__restrict__ count, u32 cap) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && slot[i] < cap) count[slot[i]] = 0;
+}
+
+__global__ void __launch_bounds__(128) k_history_move(u32 dst, u32 src, Sample64 *__restrict__ hist, u32 *__restrict__ count, u32 cap, u32 H) {
+    for (u32 k = threadIdx.x; k < H; k += blockDim.x) hist[(size_t)k * cap + dst] = hist[(size_t)k * cap + src];
+    if (threadIdx.x == 0) count[dst] = count[src];
+}
+
+__global__ void __launch_bounds__(128)
+k_history_classify(u32 n, const Sample64 *__restrict__ hist, const u32 *__restrict__ count, u32 cap, u32 H,
+                   uint8_t *__restrict__ out) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 total = count[i];
+    const u32 cnt = min(total, H);
+    if (cnt < 2) { out[i] = RCD_PAT_NO_HISTORY; return; }
+    const u32 first = total - cnt;  // ring position of the oldest kept sample is first % H
+    double svx = 0, svy = 0, svz = 0, sax = 0, say = 0, saz = 0;
+    u32 nv = 0, na = 0;
+    double pvx = 0, pvy = 0, pvz = 0, pvt = 0;
+    Sample64 last = hist[(size_t)(first % H) * cap + i];
+    for (u32 k = 1; k < cnt; ++k) {
+        const Sample64 cur = hist[(size_t)((first + k) % H) * cap + i];
+        const double dt = dsub(cur.t, last.t);
+        if (dt > 0) {
+            const double vx = __ddiv_rn(dsub(cur.x, last.x), dt), vy = __ddiv_rn(dsub(cur.y, last.y), dt),
+                         vz = __ddiv_rn(dsub(cur.z, last.z), dt);
+            if (nv > 0) {
+                const double dtv = dsub(cur.t, pvt);
+                if (dtv > 0) {
+                    sax = dadd(sax, __ddiv_rn(dsub(vx, pvx), dtv));
+                    say = dadd(say, __ddiv_rn(dsub(vy, pvy), dtv));
+                    saz = dadd(saz, __ddiv_rn(dsub(vz, pvz), dtv));
+                    ++na;
+                }
+            }
+            svx = dadd(svx, vx); svy = dadd(svy, vy); svz = dadd(svz, vz);
+            ++nv;
+            pvx = vx; pvy = vy; pvz = vz; pvt = cur.t;
+        }
+        last = cur;
+    }
+    if (nv == 0) { out[i] = RCD_PAT_STATIONARY; return; }
+    svx = __ddiv_rn(svx, (double)nv); svy = __ddiv_rn(svy, (double)nv); svz = __ddiv_rn(svz, (double)nv);
+    if (na) { sax = __ddiv_rn(sax, (double)na); say = __ddiv_rn(say, (double)na); saz = __ddiv_rn(saz, (double)na); }
+    const double speed = mag3_d(svx, svy, svz), accel = mag3_d(sax, say, saz);
+    out[i] = speed < 0.1 ? RCD_PAT_STATIONARY : (accel < 0.1 ? RCD_PAT_CONSTANT_VELOCITY : RCD_PAT_ACCELERATING);
+}
+
+// -------------------------------------------------------------------------------------------------
 // Spatial slabs: select / pack / append halo objects.  Record = 13 x u32:
 // 11 floats (px..heading), meta (type | pattern << 8), id.
 // -------------------------------------------------------------------------------------------------

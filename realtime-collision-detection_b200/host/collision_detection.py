@@ -130,6 +130,12 @@ class CollisionDetector:
 
 
 class CollisionPredictionModel:
+    """Trajectory histories live twice: in ``trajectory_history`` (the reference's public attribute)
+    and in ring buffers on the GPU (rcd_history_*), which are fed incrementally, so classifying every
+    vehicle each frame costs one kernel instead of re-staging up to 100 samples per vehicle.  If a
+    vehicle's samples ever arrive out of timestamp order the model switches to staging sorted
+    histories through rcd_classify_patterns (the reference sorts by timestamp, :638)."""
+
     def __init__(self, collision_detector: CollisionDetector):
         self.collision_detector = collision_detector
         self.max_history_length = 100
@@ -140,21 +146,86 @@ class CollisionPredictionModel:
         self._hist_version = 0
         self._pattern_key = None
         self._patterns: Optional[np.ndarray] = None
+        # device rings
+        self._ordered = True
+        self._last_ts: Dict[str, float] = {}
+        self._pending: List[Tuple[str, float, float, float, float]] = []
+        self._events_seen = 0
+        self._ring_generation = -1
 
     def update_trajectory(self, vehicle_id: str, position: Position, timestamp: float) -> None:
         h = self.trajectory_history.setdefault(vehicle_id, [])
         h.append((position, timestamp))
         if len(h) > self.max_history_length:
             self.trajectory_history[vehicle_id] = h[-self.max_history_length:]
+        if timestamp < self._last_ts.get(vehicle_id, float("-inf")):
+            self._ordered = False
+        self._last_ts[vehicle_id] = timestamp
+        if self._ordered:
+            self._pending.append((vehicle_id, position.x, position.y, position.z, timestamp))
         self._hist_version += 1
 
-    def trajectory_patterns(self) -> np.ndarray:
-        """Pattern code of every indexed vehicle (collision_detection.py:623-711), classified on the
-        GPU from the stored histories; 3 = fewer than 2 samples (-> detect path, :590-592)."""
+    # -- device rings ------------------------------------------------------------------------------
+    def _append_rounds(self, engine, samples_by_slot: Dict[int, List[Tuple[float, float, float, float]]]) -> None:
+        """rcd_history_append takes one sample per slot and call: r-th samples go in round r."""
+        r = 0
+        while True:
+            batch = [(s, v[r]) for s, v in samples_by_slot.items() if len(v) > r]
+            if not batch:
+                break
+            arr = np.array([b[1] for b in batch], np.float64).reshape(-1, 4)
+            engine.history_append(np.array([b[0] for b in batch], np.uint32), arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3])
+            r += 1
+
+    def _sync_rings(self, frames) -> None:
         table = self.collision_detector.spatial_index._table
-        key = (self._hist_version, table.version)
-        if key == self._pattern_key and self._patterns is not None:
-            return self._patterns
+        engine = frames.engine
+        if self._ring_generation != frames.engine_generation:
+            # a new handle: rebuild every ring from the host copies
+            engine.history_configure(self.max_history_length)
+            seed = {s: [(p.x, p.y, p.z, t) for p, t in self.trajectory_history.get(table.ids[s], [])]
+                    for s in range(table.n)}
+            self._append_rounds(engine, {s: v for s, v in seed.items() if v})
+            self._ring_generation = frames.engine_generation
+            self._events_seen = len(table.events)
+            self._pending.clear()
+            return
+        reseed = set()
+        for ev in table.events[self._events_seen:]:
+            if ev[0] == "move":
+                engine.history_move(ev[1], ev[2])
+                reseed.discard(ev[2])
+            else:  # a (possibly recycled) slot got a new vehicle
+                reseed.add(ev[1])
+        self._events_seen = len(table.events)
+        by_slot: Dict[int, List[Tuple[float, float, float, float]]] = {}
+        if reseed:
+            live = [s for s in reseed if s < table.n]
+            if live:
+                engine.history_reset(np.array(live, np.uint32))
+            for s in live:  # the reference keeps a removed vehicle's history: it continues on re-insertion
+                hist = self.trajectory_history.get(table.ids[s], [])
+                if hist:
+                    by_slot[s] = [(p.x, p.y, p.z, t) for p, t in hist]
+        reseeded_ids = {table.ids[s] for s in by_slot}
+        for vid, x, y, z, t in self._pending:
+            s = table.slot_of.get(vid)
+            if s is not None and vid not in reseeded_ids:
+                by_slot.setdefault(s, []).append((x, y, z, t))
+        self._pending.clear()
+        self._append_rounds(engine, by_slot)
+
+    def _classify_on_device(self, frames) -> None:
+        table = self.collision_detector.spatial_index._table
+        key = (self._hist_version, table.version, frames.engine_generation)
+        if key != self._pattern_key or frames._flags_uploaded != key:
+            self._sync_rings(frames)
+            self._patterns = frames.engine.history_classify(want_codes=True)
+            self._pattern_key = key
+            frames.flags_set_on_device(key)
+
+    def _classify_staged(self) -> np.ndarray:
+        table = self.collision_detector.spatial_index._table
         n = table.n
         count = np.zeros(n, np.uint32)
         stride = 1
@@ -171,12 +242,29 @@ class CollisionPredictionModel:
                 samples[s, :len(hs)] = [(p.x, p.y, p.z, t) for p, t in hs]
         frames = self.collision_detector.spatial_index._frames
         frames.sync_objects()
-        self._patterns = frames.engine.classify_patterns(samples, count) if n else np.zeros(0, np.uint8)
-        self._pattern_key = key
+        return frames.engine.classify_patterns(samples, count) if n else np.zeros(0, np.uint8)
+
+    def trajectory_patterns(self) -> np.ndarray:
+        """Pattern code of every indexed vehicle (collision_detection.py:623-711), classified on the
+        GPU; 3 = fewer than 2 samples (-> detect path, :590-592)."""
+        frames = self.collision_detector.spatial_index._frames
+        table = self.collision_detector.spatial_index._table
+        if table.n == 0:
+            return np.zeros(0, np.uint8)
+        if self._ordered:
+            frames.sync_objects()
+            self._classify_on_device(frames)
+            return self._patterns
+        key = (self._hist_version, table.version)
+        if key != self._pattern_key or self._patterns is None:
+            self._patterns = self._classify_staged()
+            self._pattern_key = key
         return self._patterns
 
     def _frame(self):
         frames = self.collision_detector.spatial_index._frames
+        if self._ordered:
+            return frames.run(N.MODE_PREDICT, 100.0, 10.0, prepare=self._classify_on_device)
         return frames.run(N.MODE_PREDICT, 100.0, 10.0, flags=self.trajectory_patterns())
 
     def predict_collisions(self, vehicle_id: str) -> List[CollisionRisk]:

@@ -202,6 +202,29 @@ class FrameEngine:
         N.check(self._lib.rcd_classify_patterns(self._h, n, stride, _vp(s), _vp(c), _vp(out)), self._h)
         return out
 
+    # -- device-resident trajectory history ---------------------------------------------------------
+    def history_configure(self, max_history: int = 100) -> None:
+        N.check(self._lib.rcd_history_configure(self._h, int(max_history)), self._h)
+
+    def history_append(self, slots, x, y, z, t) -> None:
+        """One (x, y, z, t) float64 sample for each listed slot (slots=None: 0..n-1)."""
+        xs, ys, zs, ts = (_as(a, np.float64) for a in (x, y, z, t))
+        sl = None if slots is None else _as(slots, np.uint32)
+        N.check(self._lib.rcd_history_append(self._h, int(xs.shape[0]), _vp(sl), _vp(xs), _vp(ys), _vp(zs), _vp(ts)),
+                self._h)
+
+    def history_reset(self, slots) -> None:
+        sl = _as(slots, np.uint32)
+        N.check(self._lib.rcd_history_reset(self._h, int(sl.shape[0]), _vp(sl)), self._h)
+
+    def history_move(self, dst: int, src: int) -> None:
+        N.check(self._lib.rcd_history_move(self._h, int(dst), int(src)), self._h)
+
+    def history_classify(self, want_codes: bool = True) -> Optional[np.ndarray]:
+        out = np.zeros(self.n, np.uint8) if want_codes else None
+        N.check(self._lib.rcd_history_classify(self._h, _vp(out)), self._h)
+        return out
+
     # -- slabs ------------------------------------------------------------------------------
     def halo_pack(self, slab_lo, slab_hi, self_rank: int, halo: float, out_ptr: int, cap: int) -> np.ndarray:
         lo = _as(slab_lo, np.float32)

@@ -26,6 +26,9 @@ class ObjectTable:
         self.flag = np.full(self.capacity, 2, np.uint8)  # pattern code / has-history flag
         self.type_codes: Dict[str, int] = {}
         self.version = 0
+        # slot events since the table was created: ("new", slot, id) / ("move", dst, src); consumers
+        # (the device-resident trajectory rings) keep their own read position
+        self.events: List[Tuple] = []
 
     def _grow(self):
         self.capacity *= 2
@@ -56,6 +59,7 @@ class ObjectTable:
                 self.f[k][s] = 0.0
             self.type[s] = 0
             self.flag[s] = 2
+            self.events.append(("new", s, vid))
         return s
 
     def set_position(self, vid: str, x: float, y: float, z: float) -> int:
@@ -88,6 +92,7 @@ class ObjectTable:
             self.flag[s] = self.flag[last]
             self.ids[s] = moved
             self.slot_of[moved] = s
+            self.events.append(("move", s, last))
         self.ids.pop()
         self.n = last
         self.version += 1
@@ -110,6 +115,7 @@ class FrameCache:
         self._flags_uploaded = None
         self._results: Dict[Tuple, Tuple[np.ndarray, np.ndarray, Dict]] = {}
         self.frames_run = 0
+        self.engine_generation = 0  # bumps whenever a new handle replaces the old one (device state is lost)
 
     def _ensure_engine(self):
         need = max(self.table.n, 1)
@@ -118,6 +124,7 @@ class FrameCache:
                 self.engine.close()
             cap = max(1024, 2 * need)
             self.engine = FrameEngine(cap, max_pairs=max(1 << 16, 32 * cap), device=self.device)
+            self.engine_generation += 1
             self._uploaded = -1
 
     def sync_objects(self, flags: Optional[np.ndarray] = None):
@@ -135,10 +142,21 @@ class FrameCache:
                 self._flags_uploaded = key
                 self._results.clear()
 
-    def run(self, mode: int, radius: float = 100.0, window: float = 10.0, flags: Optional[np.ndarray] = None):
+    def flags_set_on_device(self, key) -> None:
+        """The per-object flags were written on the device (rcd_history_classify): remember which
+        version they belong to and drop memoised frames if they changed."""
+        if key != self._flags_uploaded:
+            self._flags_uploaded = key
+            self._results.clear()
+
+    def run(self, mode: int, radius: float = 100.0, window: float = 10.0, flags: Optional[np.ndarray] = None,
+            prepare=None):
         """(pairs sorted by slot i, CSR starts per slot, counts) of one frame, memoised until the
-        objects change."""
+        objects change.  `prepare(cache)` runs after the objects are on the device and again whenever
+        the handle had to be replaced (it sets device-side flags)."""
         self.sync_objects(flags)
+        if prepare is not None:
+            prepare(self)
         key = (mode, float(radius), float(window))
         hit = self._results.get(key)
         if hit is not None:
@@ -153,9 +171,12 @@ class FrameCache:
             self.engine.close()
             cap = self.engine.max_objects
             self.engine = FrameEngine(cap, max_pairs=int(counts["n_pairs"] * 1.5) + 1024, device=self.device)
+            self.engine_generation += 1
             self._uploaded = -1
             self._flags_uploaded = None
             self.sync_objects(flags)
+            if prepare is not None:
+                prepare(self)
             eng = self.engine
             eng.step(mode, radius, window)
         pairs = eng.download()

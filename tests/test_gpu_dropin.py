@@ -160,3 +160,64 @@ def test_compute_node_classes_match_golden():
         assert all(abs(r.time_to_collision - t) < 1e-3 for r, t in
                    zip(sorted(rs, key=lambda r: int(r.vehicle_id2[1:])), [w[3] for w in want if int(w[0]) == i]))
     assert index.remove("v0") and not index.remove("v0") and index.get_position("v0") is None
+
+
+def _oracle_patterns(model, table):
+    from oracle import oracle as O
+    out = []
+    for s in range(table.n):
+        h = model.trajectory_history.get(table.ids[s], [])
+        out.append(O.pattern([(p.x, p.y, p.z, t) for p, t in h]))
+    return np.array(out, np.uint8)
+
+
+def test_device_trajectory_rings_follow_the_host_histories():
+    """update_trajectory feeds ring buffers on the GPU incrementally; the classes must equal the
+    oracle's classification of the reference-style host histories through ring wrap-around
+    (> 100 samples), vehicle removal (slots are recycled by swap-remove) and re-insertion."""
+    from rcd_b200.host.collision_detection import CollisionDetector, CollisionPredictionModel
+    from rcd_b200.host.models import Position, Vector, Vehicle
+    from rcd_b200.host.spatial_index import SpatialIndex
+    rng = np.random.default_rng(17)
+    det = CollisionDetector(SpatialIndex())
+    model = CollisionPredictionModel(det)
+    n = 60
+    kinds = rng.integers(0, 4, n)  # 0 parked, 1 cruising, 2 accelerating, 3 jittery clock (dt = 0 now and then)
+    pos = rng.uniform(0, 500, (n, 3))
+    vel = rng.uniform(-8, 8, (n, 3))
+    acc = rng.uniform(-1.5, 1.5, (n, 3))
+
+    def vehicle(i, t):
+        k = kinds[i]
+        v = vel[i] * (k > 0)
+        a = acc[i] * (k == 2)
+        p = pos[i] + v * t + 0.5 * a * t * t
+        return Vehicle(id=f"v{i}", position=Position(*map(float, p)), velocity=Vector(*map(float, v)),
+                       acceleration=Vector(*map(float, a)), heading=0.0, size=2.0, type="car", timestamp=t)
+
+    table = det.spatial_index._table
+    t = 0.0
+    for step in range(130):  # 130 samples > max_history_length = 100: the rings wrap
+        t += 0.5 if step % 7 else 0.0  # repeated timestamps (dt = 0) are skipped by the classifier
+        for i in range(n):
+            if i % 5 == 0 and step < 3:
+                continue  # late joiners: some vehicles have fewer than 2 samples at first
+            v = vehicle(i, t)
+            det.update_vehicle(v)
+            model.update_trajectory(v.id, v.position, t)
+        if step in (1, 2, 50, 129):
+            assert np.array_equal(model.trajectory_patterns(), _oracle_patterns(model, table)), step
+        if step == 60:  # remove a few vehicles: the table swap-removes, the rings follow
+            for i in (3, 17, 59, 0):
+                det.remove_vehicle(f"v{i}")
+            assert np.array_equal(model.trajectory_patterns(), _oracle_patterns(model, table))
+    assert model._ordered and set(model.trajectory_patterns().tolist()) >= {0, 1, 2}
+    assert det.spatial_index._frames.engine_generation == 1
+    # predictions use the device-side classes
+    some = table.ids[5]
+    assert isinstance(model.predict_collisions(some), list)
+    # out-of-order timestamps: the model switches to staging sorted histories
+    v = vehicle(7, t - 3.0)
+    model.update_trajectory(v.id, v.position, t - 3.0)
+    assert not model._ordered
+    assert np.array_equal(model.trajectory_patterns(), _oracle_patterns(model, table))
