@@ -470,7 +470,11 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
             CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
             h->pair_blocks[variant] = std::max(1, per_sm) * std::max(1, sms);
         }
-        const unsigned blocks = (unsigned)std::min<u64>((P.ntiles + PAIR_WARPS - 1) / PAIR_WARPS, (u64)h->pair_blocks[variant]);
+        // small frames: share each tile between several warps until the resident warps are used
+        P.splits = 1;
+        while (P.splits < 16 && (u64)P.ntiles * P.splits * 2 <= (u64)h->pair_blocks[variant] * PAIR_WARPS) P.splits *= 2;
+        const u64 items = (u64)P.ntiles * P.splits;
+        const unsigned blocks = (unsigned)std::min<u64>((items + PAIR_WARPS - 1) / PAIR_WARPS, (u64)h->pair_blocks[variant]);
         if (variant == 0) k_pairs<RCD_MODE_DETECT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         else if (variant == 1) k_pairs<RCD_MODE_PREDICT, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         else if (variant == 2) k_pairs<RCD_MODE_PREDICT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);

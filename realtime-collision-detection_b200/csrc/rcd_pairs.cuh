@@ -51,6 +51,7 @@ struct QEntry {
 struct PairParams {
     u32 n;
     u32 ntiles;
+    u32 splits;              // work items per tile (power of two): small frames split a tile's chunks over warps
     GridParams g;
     const float4 *P0, *P1, *P2;
     const u32 *keys;         // sorted cell keys
@@ -563,7 +564,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
         u32 tile = 0;
         if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
         tile = __shfl_sync(FULL_MASK, tile, 0);
-        if (tile >= P.ntiles) break;
+        if (tile >= P.ntiles * P.splits) break;
+        // with few tiles (small frames) each tile is shared by `splits` warps: warp `split` takes the
+        // chunks split, split + splits, ... of every row batch
+        const u32 split = tile % P.splits;
+        tile /= P.splits;
 
         const u32 tile_base = tile * TQ;
         const u32 s = tile_base + lane;
@@ -693,7 +698,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
 
                 // stage chunk c of the flattened spans into buffer c & 1 (cp.async, 2 objects per lane)
                 auto stage = [&](u32 c) {
-                    StageBuf &b = ws.buf[c & 1u];
+                    StageBuf &b = ws.buf[(c / P.splits) & 1u];
 #pragma unroll
                     for (int e = 0; e < CH / TQ; ++e) {
                         u32 slot = lane + e * TQ;
@@ -714,16 +719,16 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                     cp_async_commit();
                 };
 
-                if (nchunks) stage(0);
-                for (u32 c = 0; c < nchunks; ++c) {
-                    if (c + 1 < nchunks) {
-                        stage(c + 1);
+                if (split < nchunks) stage(split);
+                for (u32 c = split; c < nchunks; c += P.splits) {
+                    if (c + P.splits < nchunks) {
+                        stage(c + P.splits);
                         cp_async_wait<1>();
                     } else {
                         cp_async_wait<0>();
                     }
                     __syncwarp();
-                    const StageBuf &b = ws.buf[c & 1u];
+                    const StageBuf &b = ws.buf[(c / P.splits) & 1u];
                     const u32 m = min((u32)CH, total - c * CH);
                     // ---- S1 filter: one query per lane against every staged neighbour --------------
                     // Each lane appends the neighbours inside its reach to a private list in shared memory
@@ -820,10 +825,15 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
         ncand += ws.cand[lane];
         // the filter counted the query itself (distance 0) for radius queries; only the
         // compute-node index returns self (quirk Q8)
-        if (MODE != RCD_MODE_COMPUTE_NODE && owned && radius_query) ncand -= 1;
-        if (owned && P.cand_count) P.cand_count[P.sorted_slot[s]] = ncand;
-        unsigned long long csum = warp_sum((unsigned long long)(owned ? ncand : 0u));
-        if (lane == 0 && csum) atomicAdd(&P.counters->n_candidates, csum);
+        // (with split tiles the self hit is seen by one of the warps, so split 0 subtracts it and the
+        // partial counts are combined with wrapping adds)
+        if (MODE != RCD_MODE_COMPUTE_NODE && owned && radius_query && split == 0) ncand -= 1;
+        if (owned && P.cand_count) {
+            if (P.splits == 1) P.cand_count[P.sorted_slot[s]] = ncand;
+            else if (ncand) atomicAdd(&P.cand_count[P.sorted_slot[s]], ncand);
+        }
+        long long csum = warp_sum((long long)(owned ? (int)ncand : 0));
+        if (lane == 0 && csum) atomicAdd(&P.counters->n_candidates, (unsigned long long)csum);
     }
     unsigned long long p = warp_sum((unsigned long long)n_pot);
     unsigned long long e = warp_sum((unsigned long long)n_exact);
