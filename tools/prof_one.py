@@ -12,7 +12,7 @@ elif name == "1m":
 elif name == "1mc":
     frame, bounds = W.make_workload("cfg4_1m_clustered3d"), ((0, 0, 0), (31623, 31623, 100))
 n = len(frame["px"])
-with FrameEngine(n, 8_000_000, world_bounds=bounds) as e:
+with FrameEngine(n, 40_000_000, world_bounds=bounds) as e:
     e.upload(frame)
     e.set_patterns(np.full(n, 2, np.uint8))
     for r in range(reps):
