@@ -94,6 +94,11 @@ __device__ __forceinline__ int warp_max(int v) {
     for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, o));
     return v;
 }
+__device__ __forceinline__ float warp_minf(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
 __device__ __forceinline__ float warp_maxf(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));

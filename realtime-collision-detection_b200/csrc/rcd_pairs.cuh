@@ -356,79 +356,129 @@ __device__ __forceinline__ float g2_at(const PredictCoef &c, float t) {
     return gx * gx + gy * gy + gz * gz;
 }
 
-// ---- S2a, predict: can the relative trajectory come close at all? -------------------------------------
-// |g(t)| >= |-d + cv t| - |ca| t^2/2 on [0, 9.5]; the linear part is minimal at ts = d.cv / |cv|^2.
-// Returns false when no offset can be hit; otherwise [m_lo, m_hi] bounds the offsets worth testing.
-__device__ __forceinline__ bool predict_window(const PredictCoef &c, int &m_lo, int &m_hi) {
-    const float d2 = c.dx * c.dx + c.dy * c.dy + c.dz * c.dz;
+// ---- S2a / S2b, predict: when can the relative trajectory come close at all? ---------------------------
+// g(t) = -d + cv t + ca t^2/2 is the offset state of the pair (centre_i(t) - predicted_j(t)); an offset
+// at time t can only be hit if |g(t)| <= hr (the 10 samples move the pair by at most hr - safe).
+struct WindowCoef {
+    float dx, dy, dz, cvx, cvy, cvz, cax, cay, caz;
+    float hr;   // safe + band + 0.9 |rv| + 0.405 |ra|, rounded up
+    float can;  // |ca|, rounded up
+    float d2, eps;
+};
+__device__ __forceinline__ WindowCoef window_coef(const float4 &a0, const float4 &a1, const float4 &a2,
+                                                  const float4 &b0, const float4 &b1, const float4 &b2, u32 pattern) {
+    WindowCoef c;
+    const float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f;
+    const float fa = (pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f;
+    c.dx = b0.x - a0.x; c.dy = b0.y - a0.y; c.dz = b0.z - a0.z;
+    c.cvx = a1.x * fv - b1.x; c.cvy = a1.y * fv - b1.y; c.cvz = a1.z * fv - b1.z;
+    c.cax = a2.x * fa - b2.x; c.cay = a2.y * fa - b2.y; c.caz = a2.z * fa - b2.z;
+    const float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;
+    const float rax = a2.x - b2.x, ray = a2.y - b2.y, raz = a2.z - b2.z;
+    const float rvn = sqrt_ub(rvx * rvx + rvy * rvy + rvz * rvz);
+    const float ran = sqrt_ub(rax * rax + ray * ray + raz * raz);
+    c.can = sqrt_ub(c.cax * c.cax + c.cay * c.cay + c.caz * c.caz);
+    c.d2 = c.dx * c.dx + c.dy * c.dy + c.dz * c.dz;
+    const float dn = sqrt_ub(c.d2);
+    const float safe = (a0.w + b0.w) * 0.5f + 5.0f;
+    c.hr = safe + 2.0e-3f + 1.0e-6f * dn + rvn * 0.9f + ran * 0.405f;  // = PredictCoef::hr
+    c.eps = 1.0e-2f + 1.0e-5f * dn;
+    return c;
+}
+// S2a: |g(t)| >= |-d + cv t| - |ca| t^2/2 on [0, 9.5]; the linear part is minimal at ts = d.cv / |cv|^2.
+// False when no offset can be hit.  (Cheap: this runs on every pair the S1 filter lets through.)
+__device__ __forceinline__ bool window_reject_linear(const WindowCoef &c) {
+    const float L = (c.hr + 45.125f * c.can) * (1.0f + 1.0e-4f) + c.eps;
     const float cv2 = c.cvx * c.cvx + c.cvy * c.cvy + c.cvz * c.cvz;
-    const float can = sqrt_ub(c.cax * c.cax + c.cay * c.cay + c.caz * c.caz);
-    const float L = (c.hr + 45.125f * can) * (1.0f + 1.0e-4f) + 1.0e-2f + 1.0e-5f * sqrt_ub(d2);
-    const float L2 = L * L;
-    m_lo = 0;
-    m_hi = PREDICT_OFFSETS - 1;
-    if (!(cv2 > 1.0e-8f)) return d2 <= L2;  // (almost) no relative drift: every offset looks the same
-    const float inv = rcp_fast(cv2);
-    const float ts = (c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz) * inv;
-    // closest point of the linear part on [0, 9.5]
+    if (!(cv2 > 1.0e-8f)) return c.d2 <= L * L;  // (almost) no relative drift: every offset looks the same
+    const float ts = (c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz) * rcp_fast(cv2);
     const float tc = fminf(fmaxf(ts, 0.0f), 9.5f);
     const float lx = c.cvx * tc - c.dx, ly = c.cvy * tc - c.dy, lz = c.cvz * tc - c.dz;
-    const float dmin2 = lx * lx + ly * ly + lz * lz;
-    if (dmin2 > L2) return false;
-    // |-d + cv t|^2 = dg2 + cv2 (t - ts)^2 with dg2 the global minimum: t must lie within w of ts.
-    // The cancellation in dg2 (a few ulp of d2) moves w by up to ~2e-3 sqrt(d2 / cv2): covered twice over.
-    const float dg2 = fmaxf(d2 - (c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz) * ts, 0.0f);
-    const float wslack = 1.0e-3f + 4.0e-3f * sqrt_ub(d2 * inv);
-    float w = sqrt_ub(fmaxf(L2 - dg2, 0.0f) * inv) + wslack;
-    float t_lo = fmaxf(ts - w, 0.0f), t_hi = fminf(ts + w, 9.5f);
-    if (t_hi < 0.0f || t_lo > 9.5f) return false;
-    // Refinement: every feasible t is <= t_hi, so the acceleration term is at most |ca| t_hi^2 / 2
-    // (not |ca| 9.5^2 / 2): shrink the reach and the window accordingly, twice.
+    return lx * lx + ly * ly + lz * lz <= L * L;
+}
+// S2b: the time window [t_lo, t_hi] that can hold a hit, as offsets [m_lo, m_hi].  First the window of
+// the linear part with the whole acceleration term as slack; then, twice, the trajectory is expanded
+// about the middle tm of the current window, g(tm + u) = g0 + g1 u + ca u^2/2 (exact for a quadratic),
+// so only |ca| D^2/2 (D = half width) is left as slack and the window tightens quadratically.
+__device__ __forceinline__ bool predict_window(const WindowCoef &c, int &m_lo, int &m_hi) {
+    const float L = (c.hr + 45.125f * c.can) * (1.0f + 1.0e-4f) + c.eps;
+    const float L2 = L * L;
+    const float cv2 = c.cvx * c.cvx + c.cvy * c.cvy + c.cvz * c.cvz;
+    m_lo = 0;
+    m_hi = PREDICT_OFFSETS - 1;
+    float t_lo = 0.0f, t_hi = 9.5f;
+    if (cv2 > 1.0e-8f) {
+        const float inv = rcp_fast(cv2);
+        const float dcv = c.dx * c.cvx + c.dy * c.cvy + c.dz * c.cvz;
+        const float ts = dcv * inv;
+        const float tc = fminf(fmaxf(ts, 0.0f), 9.5f);
+        const float lx = c.cvx * tc - c.dx, ly = c.cvy * tc - c.dy, lz = c.cvz * tc - c.dz;
+        if (lx * lx + ly * ly + lz * lz > L2) return false;
+        // |-d + cv t|^2 = dg2 + cv2 (t - ts)^2 with dg2 the global minimum: t must lie within w of ts.
+        // The cancellation in dg2 (a few ulp of d2) moves w by up to ~2e-3 sqrt(d2 / cv2): covered twice over.
+        const float dg2 = fmaxf(c.d2 - dcv * ts, 0.0f);
+        const float w = sqrt_ub(fmaxf(L2 - dg2, 0.0f) * inv) + 1.0e-3f + 4.0e-3f * sqrt_ub(c.d2 * inv);
+        t_lo = fmaxf(ts - w, 0.0f);
+        t_hi = fminf(ts + w, 9.5f);
+        if (t_lo > t_hi) return false;
+    } else if (!(c.d2 <= L2)) {
+        return false;
+    }
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-        const float Lr = (c.hr + 0.5f * can * t_hi * t_hi) * (1.0f + 1.0e-4f) + 1.0e-2f + 1.0e-5f * sqrt_ub(d2);
+        const float tm = 0.5f * (t_lo + t_hi);
+        const float D = 0.5f * (t_hi - t_lo) + 1.0e-5f;
+        const float hh = 0.5f * tm * tm;
+        const float g0x = c.cvx * tm + c.cax * hh - c.dx, g0y = c.cvy * tm + c.cay * hh - c.dy,
+                    g0z = c.cvz * tm + c.caz * hh - c.dz;
+        const float g1x = c.cvx + c.cax * tm, g1y = c.cvy + c.cay * tm, g1z = c.cvz + c.caz * tm;
+        const float g12 = g1x * g1x + g1y * g1y + g1z * g1z;
+        const float Lr = (c.hr + 0.5f * c.can * D * D) * (1.0f + 1.0e-4f) + c.eps;
         const float Lr2 = Lr * Lr;
-        const float tcr = fminf(fmaxf(ts, t_lo), t_hi);
-        const float rx = c.cvx * tcr - c.dx, ry = c.cvy * tcr - c.dy, rz = c.cvz * tcr - c.dz;
-        if (rx * rx + ry * ry + rz * rz > Lr2) return false;
-        w = sqrt_ub(fmaxf(Lr2 - dg2, 0.0f) * inv) + wslack;
-        t_lo = fmaxf(fmaxf(ts - w, 0.0f), t_lo);
-        t_hi = fminf(fminf(ts + w, 9.5f), t_hi);
+        const float g02 = g0x * g0x + g0y * g0y + g0z * g0z;
+        if (!(g12 > 1.0e-8f)) {  // no relative drift at tm: |g| >= |g0| - slack over the whole window
+            if (g02 > Lr2) return false;
+            continue;
+        }
+        const float inv1 = rcp_fast(g12);
+        const float us = -(g0x * g1x + g0y * g1y + g0z * g1z) * inv1;  // minimum of the linear part, relative to tm
+        const float uc = fminf(fmaxf(us, -D), D);
+        const float ex = g0x + g1x * uc, ey = g0y + g1y * uc, ez = g0z + g1z * uc;
+        if (ex * ex + ey * ey + ez * ez > Lr2) return false;
+        const float mx = g0x + g1x * us, my = g0y + g1y * us, mz = g0z + g1z * us;  // global minimum, no cancellation
+        const float dgg = mx * mx + my * my + mz * mz;
+        const float w = sqrt_ub(fmaxf(Lr2 - dgg, 0.0f) * inv1) + 1.0e-3f + 4.0e-3f * sqrt_ub(g02 * inv1);
+        t_lo = fmaxf(t_lo, tm + us - w);
+        t_hi = fminf(t_hi, tm + us + w);
         if (t_lo > t_hi) return false;
     }
     m_lo = max((int)floorf(2.0f * t_lo), 0);
     m_hi = min((int)ceilf(2.0f * t_hi), PREDICT_OFFSETS - 1);
-    return true;
+    return m_lo <= m_hi;
 }
 
-// ---- S2b, predict: scan the offsets of the window; bit m set <=> offset m may be hit -----------------
+// ---- diagnostic variant (RCD_STEP_COUNT_CANDIDATES): every offset takes the radius test in k_pairs so that
+// candidates can be counted per query; bit m set <=> offset m is a candidate that may be hit
 template <bool COUNT_CAND>
 __device__ __forceinline__ u32 predict_scan(WarpShared &ws, const PairParams &P, const PredictCoef &c, u32 ql, u32 si,
                                             u32 sj, u32 pattern, int m_lo, int m_hi, u32 &n_exact) {
     u32 mask = 0;
-    if (COUNT_CAND) {
-        // diagnostic variant: every offset takes the radius test so that candidates can be counted
-        const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
-        u32 ncand = 0;
+    const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
+    u32 ncand = 0;
 #pragma unroll 1
-        for (int m = 0; m < PREDICT_OFFSETS; ++m) {
-            float t = 0.5f * (float)m, h = 0.5f * t * t;
-            float ex = c.uvx * t + c.uax * h - c.dx, ey = c.uvy * t + c.uay * h - c.dy, ez = c.uvz * t + c.uaz * h - c.dz;
-            float c2 = ex * ex + ey * ey + ez * ez;
-            if (c2 > R2 * (1.0f + BAND_R2)) continue;
-            if (c2 >= R2 * (1.0f - BAND_R2)) {
-                ++n_exact;
-                if (!exact_predict_radius(P, si, sj, pattern, m)) continue;
-            }
-            ++ncand;
-            if (m >= m_lo && m <= m_hi && offset_may_hit(c, t)) mask |= 1u << m;
+    for (int m = 0; m < PREDICT_OFFSETS; ++m) {
+        float t = 0.5f * (float)m, h = 0.5f * t * t;
+        float ex = c.uvx * t + c.uax * h - c.dx, ey = c.uvy * t + c.uay * h - c.dy, ez = c.uvz * t + c.uaz * h - c.dz;
+        float c2 = ex * ex + ey * ey + ez * ez;
+        if (c2 > R2 * (1.0f + BAND_R2)) continue;
+        if (c2 >= R2 * (1.0f - BAND_R2)) {
+            ++n_exact;
+            if (!exact_predict_radius(P, si, sj, pattern, m)) continue;
         }
-        if (ncand) atomicAdd(&ws.cand[ql], ncand);
-        return mask;
+        ++ncand;
+        if (m >= m_lo && m <= m_hi && offset_may_hit(c, t)) mask |= 1u << m;
     }
-#pragma unroll 1
-    for (int m = m_lo; m <= m_hi; ++m)
-        if (offset_may_hit(c, 0.5f * (float)m)) mask |= 1u << m;
+    if (ncand) atomicAdd(&ws.cand[ql], ncand);
     return mask;
 }
 
@@ -457,7 +507,8 @@ __device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 s
         const int m = __ffs(mask) - 1;
         mask &= mask - 1;
         const float t = 0.5f * (float)m, h = 0.5f * t * t;
-        if (!COUNT_CAND) {  // with COUNT_CAND the radius test was already taken in k_pairs
+        if (!COUNT_CAND) {  // with COUNT_CAND both tests were already taken in k_pairs
+            if (!offset_may_hit(c, t)) continue;  // none of the 10 samples can come within the safe distance
             float ex = c.uvx * t + c.uax * h - c.dx, ey = c.uvy * t + c.uay * h - c.dy, ez = c.uvz * t + c.uaz * h - c.dz;
             float c2 = ex * ex + ey * ey + ez * ez;
             if (c2 > R2 * (1.0f + BAND_R2)) continue;
@@ -598,23 +649,33 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
         const bool radius_query = (MODE != RCD_MODE_PREDICT) || pattern == RCD_PAT_NO_HISTORY;
         const float Rq = (MODE == RCD_MODE_PREDICT) ? PREDICT_RADIUS : P.R;
         const float R2_hi = Rq * Rq * (1.0f + BAND_R2), R2_lo = Rq * Rq * (1.0f - BAND_R2);
-        // reach of this query: how far a neighbour can be and still matter
-        float reach;
+        // Volume a neighbour must lie in to matter: a ball of radius Rq for radius queries; for predict
+        // queries the capsule of radius 100 (+ slack) about the chord of the centre path
+        // c(t) = uv t + ua t^2/2, t in [0, 9.5] (:728-741): the path leaves its chord by at most
+        // |ua| 9.5^2 / 8.  w is the chord, rad the radius.
+        float wx = 0.0f, wy = 0.0f, wz = 0.0f, inv_w2 = 0.0f, rad;
         if (!radius_query) {
-            float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f;
-            float fa = (pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f;
-            float travel = sqrtf(p1.x * p1.x + p1.y * p1.y + p1.z * p1.z) * fv * 9.5f +
-                           sqrtf(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z) * fa * 45.125f;
-            reach = (PREDICT_RADIUS + travel) * (1.0f + 1.0e-5f) + 1.0e-2f;
+            const float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f;
+            const float fa = (pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f;
+            wx = p1.x * fv * 9.5f + p2.x * fa * 45.125f;
+            wy = p1.y * fv * 9.5f + p2.y * fa * 45.125f;
+            wz = p1.z * fv * 9.5f + p2.z * fa * 45.125f;
+            const float uan = sqrtf(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z) * fa;
+            float w2 = wx * wx + wy * wy + wz * wz;
+            rad = (PREDICT_RADIUS + 11.28125f * uan) * (1.0f + 1.0e-5f) + 2.0e-2f + 1.0e-5f * sqrtf(w2);
+            if (!(w2 < 1.0e30f) || !(rad < 1.0e30f)) {  // non-finite motion: scan everything
+                wx = wy = wz = w2 = 0.0f;
+                rad = 1.0e30f;
+            }
+            inv_w2 = w2 > 1.0e-12f ? 1.0f / w2 : 0.0f;
         } else {
-            reach = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
+            rad = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
         }
-        if (!(reach < 1.0e30f)) reach = 1.0e30f;  // non-finite velocity: scan everything
-        const float pass2 = radius_query ? R2_hi : reach * reach;
+        const float pass2 = radius_query ? R2_hi : rad * rad;
         u32 ncand = 0;   // candidates decided by the filter itself
         u32 n1b = 0;     // warp-uniform length of Q1b (predict)
 
-        // S2b on `take` entries from the top of Q1b: scan the window, survivors -> global Q2
+        // S2b on `take` entries from the top of Q1b: time window of the pair -> offsets -> global Q2
         auto run_scan = [&](u32 take) {
             bool keep = false;
             u32 si = 0, sj = 0, mask = 0;
@@ -625,12 +686,16 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                 const float4 a0 = ws.q0[ql], a1 = ws.q1[ql], a2 = ws.q2[ql];
                 const float4 b0 = P.P0[sj], b1 = P.P1[sj], b2 = P.P2[sj];
                 const u32 pat = meta_pattern(__float_as_uint(a2.w));
-                const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
-                int m_lo, m_hi;
-                if (predict_window(c, m_lo, m_hi) || COUNT_CAND) {
-                    mask = predict_scan<COUNT_CAND>(ws, P, c, ql, si, sj, pat, m_lo, m_hi, n_exact);
-                    keep = mask != 0;
+                int m_lo = 0, m_hi = PREDICT_OFFSETS - 1;
+                if (COUNT_CAND) {
+                    const bool in = predict_window(window_coef(a0, a1, a2, b0, b1, b2, pat), m_lo, m_hi);
+                    if (!in) { m_lo = 1; m_hi = 0; }
+                    const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
+                    mask = predict_scan<true>(ws, P, c, ql, si, sj, pat, m_lo, m_hi, n_exact);
+                } else if (predict_window(window_coef(a0, a1, a2, b0, b1, b2, pat), m_lo, m_hi)) {
+                    mask = (2u << m_hi) - (1u << m_lo);  // offsets m_lo..m_hi; k_sample tests each of them
                 }
+                keep = mask != 0;
             }
             __syncwarp();
             n1b -= take;
@@ -648,18 +713,22 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
 
         for (int grp = 0; grp < ngroups; ++grp) {
             const bool active = owned && my_group == grp;
-            const int cxmin = warp_min(active ? cx : 0x7fffffff), cxmax = warp_max(active ? cx : -1);
-            if (cxmax < 0) continue;  // no active query in this group (warp-uniform)
-            const int cymin = warp_min(active ? cy : 0x7fffffff), cymax = warp_max(active ? cy : -1);
-            const int czmin = warp_min(active ? cz : 0x7fffffff), czmax = warp_max(active ? cz : -1);
-            const float hmax = warp_maxf(active ? reach : 0.0f);
-            // |ci - cj| <= floor(H / cell) + 1 for clamped floor() cells (the reference's own bound,
-            // spatial_index.py:246-248); 1e-3 covers the fp32 error of the cell coordinates
-            float srf = floorf(hmax * g.inv_cell + 1.0e-3f) + 1.0f;
-            int sr = (srf < 1.0e6f) ? (int)srf : 1000000;
-            const int x0 = max(cxmin - sr, 0), x1 = min(cxmax + sr, g.nx - 1);
-            const int y0 = max(cymin - sr, 0), y1 = min(cymax + sr, g.ny - 1);
-            const int z0 = max(czmin - sr, 0), z1 = min(czmax + sr, g.nz - 1);
+            if (!__any_sync(FULL_MASK, active)) continue;  // no active query in this group (warp-uniform)
+            // cells of the bounding box of the group's query volumes (cell_coord is monotone, so a
+            // neighbour inside the box in space is inside it in cells; 0.05 m + 1 ulp covers the fp32 sums)
+            const float big = 3.0e38f;
+            const float lox = warp_minf(active ? fminf(p0.x, p0.x + wx) - rad : big);
+            const float hix = warp_maxf(active ? fmaxf(p0.x, p0.x + wx) + rad : -big);
+            const float loy = warp_minf(active ? fminf(p0.y, p0.y + wy) - rad : big);
+            const float hiy = warp_maxf(active ? fmaxf(p0.y, p0.y + wy) + rad : -big);
+            const float loz = warp_minf(active ? fminf(p0.z, p0.z + wz) - rad : big);
+            const float hiz = warp_maxf(active ? fmaxf(p0.z, p0.z + wz) + rad : -big);
+            const int x0 = cell_coord(lox - (0.05f + 4.0e-7f * fabsf(lox)), g.ox, g.inv_cell, g.nx);
+            const int x1 = cell_coord(hix + (0.05f + 4.0e-7f * fabsf(hix)), g.ox, g.inv_cell, g.nx);
+            const int y0 = cell_coord(loy - (0.05f + 4.0e-7f * fabsf(loy)), g.oy, g.inv_cell, g.ny);
+            const int y1 = cell_coord(hiy + (0.05f + 4.0e-7f * fabsf(hiy)), g.oy, g.inv_cell, g.ny);
+            const int z0 = cell_coord(loz - (0.05f + 4.0e-7f * fabsf(loz)), g.oz, g.inv_cell, g.nz);
+            const int z1 = cell_coord(hiz + (0.05f + 4.0e-7f * fabsf(hiz)), g.oz, g.inv_cell, g.nz);
             const int ny_span = y1 - y0 + 1;
             const int nrows = ny_span * (z1 - z0 + 1);
 
@@ -739,6 +808,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                         for (int u = 0; u < 4; ++u) {
                             const float4 b0 = b.p0[min(j0 + u, (u32)CH - 1)];
                             float dx = b0.x - p0.x, dy = b0.y - p0.y, dz = b0.z - p0.z;
+                            if (MODE == RCD_MODE_PREDICT) {  // distance to the chord (w = 0 for radius queries)
+                                const float sc = __saturatef((dx * wx + dy * wy + dz * wz) * inv_w2);
+                                dx -= sc * wx; dy -= sc * wy; dz -= sc * wz;
+                            }
                             float d2 = dx * dx + dy * dy + dz * dz;
                             const bool pass = active && (j0 + u < m) && d2 <= pass2;
                             if (pass) {
@@ -791,9 +864,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                                 } else if (COUNT_CAND) {
                                     to_scan = true;
                                 } else {
-                                    const PredictCoef co = predict_coef(a0, a1, a2, b0, b1, b2, pat);
-                                    int m_lo, m_hi;
-                                    to_scan = predict_window(co, m_lo, m_hi);
+                                    to_scan = window_reject_linear(window_coef(a0, a1, a2, b0, b1, b2, pat));
                                 }
                             }
                         }
