@@ -271,6 +271,8 @@ __device__ __noinline__ u32 finish_entry_inline(const PairParams &P, u32 si, u32
 
 // ---- S2, detect: temporal filter + closest approach in fp32 (collision_detection.py:244-292) ------
 // returns true when the pair must be decided in fp64
+// COUNT_ALL: the S1 filter did not count the pairs certainly within the radius (predict mode)
+template <bool COUNT_ALL>
 __device__ __forceinline__ bool narrow_detect(WarpShared &ws, u32 ql, const float4 &a0, const float4 &a1,
                                               const float4 &a2, const float4 &b0, const float4 &b1, const float4 &b2,
                                               float R, float T, u32 &n_exact) {
@@ -280,6 +282,8 @@ __device__ __forceinline__ bool narrow_detect(WarpShared &ws, u32 ql, const floa
     if (d2 >= R2 * (1.0f - BAND_R2)) {  // the filter could not decide the radius test (spatial_index.py:268)
         ++n_exact;
         if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, R)) return false;
+        atomicAdd(&ws.cand[ql], 1u);
+    } else if (COUNT_ALL) {
         atomicAdd(&ws.cand[ql], 1u);
     }
     float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;  // rel_velocity = self - other
@@ -665,13 +669,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
             rad = (PREDICT_RADIUS + 11.28125f * uan) * (1.0f + 1.0e-5f) + 2.0e-2f + 1.0e-5f * sqrtf(w2);
             if (!(w2 < 1.0e30f) || !(rad < 1.0e30f)) {  // non-finite motion: scan everything
                 wx = wy = wz = w2 = 0.0f;
-                rad = 1.0e30f;
+                rad = 1.0e18f;
             }
             inv_w2 = w2 > 1.0e-12f ? 1.0f / w2 : 0.0f;
         } else {
             rad = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
         }
-        const float pass2 = radius_query ? R2_hi : rad * rad;
+        const float pass2_own = radius_query ? R2_hi : rad * rad;
         u32 ncand = 0;   // candidates decided by the filter itself
         u32 n1b = 0;     // warp-uniform length of Q1b (predict)
 
@@ -714,6 +718,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
         for (int grp = 0; grp < ngroups; ++grp) {
             const bool active = owned && my_group == grp;
             if (!__any_sync(FULL_MASK, active)) continue;  // no active query in this group (warp-uniform)
+            const float pass2 = active ? pass2_own : -1.0f;     // d2 <= -1 never holds
             // cells of the bounding box of the group's query volumes (cell_coord is monotone, so a
             // neighbour inside the box in space is inside it in cells; 0.05 m + 1 ulp covers the fp32 sums)
             const float big = 3.0e38f;
@@ -783,6 +788,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                             cp_async16(&b.p1[slot], P.P1 + src);
                             cp_async16(&b.p2[slot], P.P2 + src);
                             b.pos[slot] = src;
+                        } else {  // pad the last chunk with an object no query can reach
+                            b.p0[slot] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
                         }
                     }
                     cp_async_commit();
@@ -803,21 +810,21 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                     // Each lane appends the neighbours inside its reach to a private list in shared memory
                     // (no warp vote per test); the lists are then consumed 32 pairs at a time.
                     u32 cnt = 0;
-                    for (u32 j0 = 0; j0 < m; j0 += 4) {
+                    for (u32 j0 = 0; j0 < m; j0 += 4) {  // (the last chunk is padded: no bound check per test)
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            const float4 b0 = b.p0[min(j0 + u, (u32)CH - 1)];
+                            const float4 b0 = b.p0[j0 + u];
                             float dx = b0.x - p0.x, dy = b0.y - p0.y, dz = b0.z - p0.z;
                             if (MODE == RCD_MODE_PREDICT) {  // distance to the chord (w = 0 for radius queries)
                                 const float sc = __saturatef((dx * wx + dy * wy + dz * wz) * inv_w2);
                                 dx -= sc * wx; dy -= sc * wy; dz -= sc * wz;
                             }
-                            float d2 = dx * dx + dy * dy + dz * dz;
-                            const bool pass = active && (j0 + u < m) && d2 <= pass2;
-                            if (pass) {
+                            const float d2 = dx * dx + dy * dy + dz * dz;
+                            if (d2 <= pass2) {
                                 ws.plist[cnt][lane] = (unsigned char)(j0 + u);
                                 ++cnt;
-                                if (radius_query && d2 < R2_lo) ++ncand;  // certainly within the radius
+                                // certainly within the radius (predict counts its rare radius queries in S2)
+                                if (MODE != RCD_MODE_PREDICT && d2 < R2_lo) ++ncand;
                             }
                         }
                     }
@@ -858,9 +865,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                             } else if (sj != si) {  // _spatial_filtering strips self (:224-225)
                                 const u32 pat = meta_pattern(__float_as_uint(a2.w));
                                 if (MODE == RCD_MODE_DETECT) {
-                                    keep = narrow_detect(ws, ql, a0, a1, a2, b0, b1, b2, P.R, P.T, n_exact);
+                                    keep = narrow_detect<false>(ws, ql, a0, a1, a2, b0, b1, b2, P.R, P.T, n_exact);
                                 } else if (pat == RCD_PAT_NO_HISTORY) {
-                                    keep = narrow_detect(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, n_exact);
+                                    keep = narrow_detect<true>(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, n_exact);
                                 } else if (COUNT_CAND) {
                                     to_scan = true;
                                 } else {
@@ -898,7 +905,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
         // compute-node index returns self (quirk Q8)
         // (with split tiles the self hit is seen by one of the warps, so split 0 subtracts it and the
         // partial counts are combined with wrapping adds)
-        if (MODE != RCD_MODE_COMPUTE_NODE && owned && radius_query && split == 0) ncand -= 1;
+        // (predict counts its radius queries in S2, after self has been stripped)
+        if (MODE == RCD_MODE_DETECT && owned && split == 0) ncand -= 1;
         if (owned && P.cand_count) {
             if (P.splits == 1) P.cand_count[P.sorted_slot[s]] = ncand;
             else if (ncand) atomicAdd(&P.cand_count[P.sorted_slot[s]], ncand);
@@ -914,30 +922,201 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
     }
 }
 
-// k_sample (predict): one queued pair per thread -> offsets that survive the fp32 samples -> Q3
+// k_sample (predict): Q2 -> Q3.  A warp takes 32 queued pairs at a time and works through them in
+// phases with different lane assignments, so that every phase runs with (almost) full warps although
+// the pairs carry different numbers of offsets:
+//   1. lane = pair            : gather both objects, derive the pair's coefficients -> shared memory
+//   2. lane = (pair, offset)  : can the offset be hit at all (offset_may_hit)?  is the neighbour within
+//                               100 m of the predicted centre (:801-803)?  survivors -> item list
+//   3. lane = surviving item  : the 10 samples of the offset (:322-342) in fp32 -> first sample inside
+//                               safe + band and its squared distance -> shared memory
+//   4. lane = pair            : merge over the offsets (max risk, earliest offset on ties, :848-865)
+//                               -> 0 / RESOLVED | m | k << 8 / mask of the offsets fp64 must decide
+// sample_predict() above is the same decision for one pair on one thread (queue-overflow fallback).
 constexpr int STAGE_THREADS = 128;
+constexpr int STAGE_WARPS = STAGE_THREADS / 32;
+constexpr int SC = 25;  // coefficients per pair (odd stride: conflict-free)
+enum { SC_D = 0, SC_CV = 3, SC_CA = 6, SC_RV = 9, SC_RA = 12, SC_UV = 15, SC_UA = 18, SC_HR2 = 21, SC_INVRV2 = 22,
+       SC_LIM2 = 23, SC_SAFEB2 = 24 };
+struct SampleShared {
+    float coef[32][SC];
+    float r2first[32][PREDICT_OFFSETS];
+    unsigned char first[32][PREDICT_OFFSETS];  // first sample within safe + band (valid where hit_mask is set)
+    u32 hit_mask[32];                          // offsets with a sample within safe + band
+    unsigned short items[64];                  // pair | offset << 5
+};
 
 template <bool COUNT_CAND>
-__global__ void __launch_bounds__(STAGE_THREADS) k_sample(PairParams P) {
+__global__ void __launch_bounds__(STAGE_THREADS, 4) k_sample(PairParams P) {
+    __shared__ SampleShared shared[STAGE_WARPS];
+    SampleShared &sh = shared[threadIdx.x >> 5];
+    const u32 lane = threadIdx.x & 31u;
     const unsigned long long n = min(P.counters->n_q2, (unsigned long long)P.qcap);
-    const unsigned long long stride = (unsigned long long)gridDim.x * STAGE_THREADS;
-    const unsigned long long rounds = (n + stride - 1) / stride;
+    const unsigned long long nbatch = (n + 31) / 32;
+    const unsigned long long wstride = (unsigned long long)gridDim.x * STAGE_WARPS;
+    const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
     u32 n_exact = 0;
-    for (unsigned long long r = 0; r < rounds; ++r) {  // uniform trip count: global_push is warp-wide
-        const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
-        bool keep = false;
+    for (unsigned long long batch = (unsigned long long)blockIdx.x * STAGE_WARPS + (threadIdx.x >> 5); batch < nbatch;
+         batch += wstride) {
+        // ---- 1. lane = pair ------------------------------------------------------------------------
+        const unsigned long long k = batch * 32 + lane;
         QEntry e;
         e.si = e.sj = e.mask = 0;
+        float safe = 5.0f, band = 0.0f;
         if (k < n) {
             e = P.q2[k];
-            e.mask = sample_predict<COUNT_CAND>(P, e.si, e.sj, e.mask, n_exact);
-            keep = e.mask != 0;
+            const float4 a0 = P.P0[e.si], a1 = P.P1[e.si], a2 = P.P2[e.si];
+            const float4 b0 = P.P0[e.sj], b1 = P.P1[e.sj], b2 = P.P2[e.sj];
+            const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, meta_pattern(__float_as_uint(a2.w)));
+            float *o = sh.coef[lane];
+            o[SC_D] = c.dx; o[SC_D + 1] = c.dy; o[SC_D + 2] = c.dz;
+            o[SC_CV] = c.cvx; o[SC_CV + 1] = c.cvy; o[SC_CV + 2] = c.cvz;
+            o[SC_CA] = c.cax; o[SC_CA + 1] = c.cay; o[SC_CA + 2] = c.caz;
+            o[SC_RV] = c.rvx; o[SC_RV + 1] = c.rvy; o[SC_RV + 2] = c.rvz;
+            o[SC_RA] = a2.x - b2.x; o[SC_RA + 1] = a2.y - b2.y; o[SC_RA + 2] = a2.z - b2.z;
+            o[SC_UV] = c.uvx; o[SC_UV + 1] = c.uvy; o[SC_UV + 2] = c.uvz;
+            o[SC_UA] = c.uax; o[SC_UA + 1] = c.uay; o[SC_UA + 2] = c.uaz;
+            o[SC_HR2] = c.hr2; o[SC_INVRV2] = c.inv_rv2; o[SC_LIM2] = c.lim2; o[SC_SAFEB2] = c.safe_b2;
+            safe = (a0.w + b0.w) * 0.5f + 5.0f;
+            band = sqrtf(c.safe_b2) - safe;  // the guard band of predict_coef
         }
-        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, keep, e.si, e.sj, e.mask))
-            finish_entry_inline<RCD_MODE_PREDICT>(P, e.si, e.sj, e.mask);
+        const u32 mask = e.mask & ((1u << PREDICT_OFFSETS) - 1u);
+        sh.hit_mask[lane] = 0;
+        const u32 cnt = (u32)__popc(mask);
+        u32 off = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 t = __shfl_up_sync(FULL_MASK, off, o);
+            if (lane >= (u32)o) off += t;
+        }
+        const u32 total = __shfl_sync(FULL_MASK, off, 31);
+        off -= cnt;
+        __syncwarp();
+
+        // ---- 3. lane = item: the 10 samples of one offset of one pair ---------------------------------
+        u32 n_items = 0;  // warp-uniform length of the item list
+        auto run_samples = [&](u32 take) {
+            if (lane < take) {
+                const u32 it = sh.items[n_items - take + lane];
+                const u32 pr = it & 31u, m = it >> 5;
+                const float *c = sh.coef[pr];
+                const float t = 0.5f * (float)m, h = 0.5f * t * t;
+                const float gx = c[SC_CV] * t + c[SC_CA] * h - c[SC_D], gy = c[SC_CV + 1] * t + c[SC_CA + 1] * h - c[SC_D + 1],
+                            gz = c[SC_CV + 2] * t + c[SC_CA + 2] * h - c[SC_D + 2];
+                const float rvx = c[SC_RV], rvy = c[SC_RV + 1], rvz = c[SC_RV + 2];
+                const float rax = c[SC_RA], ray = c[SC_RA + 1], raz = c[SC_RA + 2];
+                const float safe_b2 = c[SC_SAFEB2];
+                int first = -1;
+                float r2first = 0.0f;
+#pragma unroll
+                for (int kk = PREDICT_STEPS - 1; kk >= 0; --kk) {  // descending: the last assignment is the first sample
+                    const float tau = 0.1f * (float)kk, hh = 0.5f * tau * tau;
+                    const float rx = gx + rvx * tau + rax * hh, ry = gy + rvy * tau + ray * hh, rz = gz + rvz * tau + raz * hh;
+                    const float r2 = rx * rx + ry * ry + rz * rz;
+                    if (r2 <= safe_b2) { first = kk; r2first = r2; }
+                }
+                if (first >= 0) {
+                    sh.first[pr][m] = (unsigned char)first;
+                    sh.r2first[pr][m] = r2first;
+                    atomicOr(&sh.hit_mask[pr], 1u << m);
+                }
+            }
+            n_items -= take;
+            __syncwarp();
+        };
+
+        // ---- 2. lane = (pair, offset) ---------------------------------------------------------------------
+        for (u32 fbase = 0; fbase < total; fbase += 32) {
+            const u32 f = fbase + lane;
+            u32 pr = 0;
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const u32 cand = pr + step;
+                const u32 v = __shfl_sync(FULL_MASK, off, cand & 31u);
+                if (cand < 32u && v <= f) pr = cand;
+            }
+            const u32 pr_off = __shfl_sync(FULL_MASK, off, pr);
+            u32 pr_mask = __shfl_sync(FULL_MASK, mask, pr);
+            bool pass = false;
+            u32 m = 0;
+            if (f < total) {
+                if (COUNT_CAND) {  // sparse mask: r-th set bit
+                    for (u32 r = f - pr_off; r > 0; --r) pr_mask &= pr_mask - 1;
+                    m = (u32)__ffs(pr_mask) - 1u;
+                } else {           // k_pairs queues whole windows: consecutive offsets
+                    m = (u32)__ffs(pr_mask) - 1u + (f - pr_off);
+                }
+                pass = true;
+                if (!COUNT_CAND) {  // with COUNT_CAND both tests were already taken in k_pairs
+                    const float *c = sh.coef[pr];
+                    const float t = 0.5f * (float)m, h = 0.5f * t * t;
+                    const float dx = c[SC_D], dy = c[SC_D + 1], dz = c[SC_D + 2];
+                    // offset_may_hit(): none of the 10 samples can come within the safe distance otherwise
+                    const float gx = c[SC_CV] * t + c[SC_CA] * h - dx, gy = c[SC_CV + 1] * t + c[SC_CA + 1] * h - dy,
+                                gz = c[SC_CV + 2] * t + c[SC_CA + 2] * h - dz;
+                    const float rvx = c[SC_RV], rvy = c[SC_RV + 1], rvz = c[SC_RV + 2];
+                    pass = gx * gx + gy * gy + gz * gz <= c[SC_HR2];
+                    if (pass) {
+                        const float tau = fminf(fmaxf(-(gx * rvx + gy * rvy + gz * rvz) * c[SC_INVRV2], 0.0f), 0.9f);
+                        const float ex = gx + rvx * tau, ey = gy + rvy * tau, ez = gz + rvz * tau;
+                        pass = ex * ex + ey * ey + ez * ez <= c[SC_LIM2];
+                    }
+                    if (pass) {  // neighbour within 100 m of the predicted centre?
+                        const float ux = c[SC_UV] * t + c[SC_UA] * h - dx, uy = c[SC_UV + 1] * t + c[SC_UA + 1] * h - dy,
+                                    uz = c[SC_UV + 2] * t + c[SC_UA + 2] * h - dz;
+                        const float c2 = ux * ux + uy * uy + uz * uz;
+                        pass = c2 <= R2 * (1.0f + BAND_R2);
+                        if (pass && c2 >= R2 * (1.0f - BAND_R2)) {
+                            ++n_exact;
+                            const QEntry pe = P.q2[batch * 32 + pr];
+                            pass = exact_predict_radius(P, pe.si, pe.sj, meta_pattern(__float_as_uint(P.P2[pe.si].w)), (int)m);
+                        }
+                    }
+                }
+            }
+            const u32 bal = __ballot_sync(FULL_MASK, pass);
+            if (bal) {
+                if (pass) sh.items[n_items + __popc(bal & lanemask_lt())] = (unsigned short)(pr | (m << 5));
+                n_items += __popc(bal);
+                __syncwarp();
+                if (n_items >= 32) run_samples(32);
+            }
+        }
+        if (n_items) run_samples(n_items);
+        __syncwarp();
+
+        // ---- 4. lane = pair: merge over the offsets ------------------------------------------------------
+        const float safe_in = fmaxf(safe - band, 0.0f), safe_in2 = safe_in * safe_in;
+        const float inv_safe = 1.0f / safe;
+        u32 maybe_mask = 0;      // offsets with a sample inside safe + band
+        bool doubt = false;      // some decisive sample lies inside the band
+        float best = -1.0f, second = -1.0f;
+        int best_m = -1, best_k = 0;
+        u32 rest = sh.hit_mask[lane];  // the other offsets have no sample within safe + band: certainly no hit
+        while (rest) {
+            const int m = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const u32 first = sh.first[lane][m];
+            const float r2first = sh.r2first[lane][m];
+            maybe_mask |= 1u << m;
+            if (r2first > safe_in2) { doubt = true; continue; }  // the first candidate sample is inside the band
+            // certain hit at sample `first`, and every earlier sample is certainly outside: the parts of the
+            // risk that differ between offsets (collision_detection.py:371-374) decide the merge
+            const float part = 0.3f * (1.0f - sqrtf(r2first) * inv_safe) + 0.3f * (1.0f - 0.01f * (float)first);
+            if (part > best) { second = best; best = part; best_m = m; best_k = (int)first; }
+            else if (part > second) second = part;
+        }
+        u32 word = 0;
+        if (maybe_mask) {
+            // a runner-up within 1e-4 (fp32 error of `part` is ~1e-5) or any sample in the band: fp64 decides
+            word = (doubt || best_m < 0 || best - second <= 1.0e-4f) ? maybe_mask : (RESOLVED | (u32)best_m | ((u32)best_k << 8));
+        }
+        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, word != 0, e.si, e.sj, word))
+            finish_entry_inline<RCD_MODE_PREDICT>(P, e.si, e.sj, word);
+        __syncwarp();  // the next batch overwrites this warp's shared memory
     }
     unsigned long long ex = warp_sum((unsigned long long)n_exact);
-    if ((threadIdx.x & 31u) == 0 && ex) atomicAdd(&P.counters->n_exact, ex);
+    if (lane == 0 && ex) atomicAdd(&P.counters->n_exact, ex);
 }
 
 // k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp
