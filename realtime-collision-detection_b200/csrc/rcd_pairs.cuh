@@ -76,7 +76,9 @@ constexpr float BAND_R2 = 2.0e-5f;
 // shared-memory state of one warp
 struct StageBuf {
     float4 p0[CH], p1[CH], p2[CH];
-    u32 pos[CH];  // position in cell order of the staged object
+    u32 pos[CH];         // position in cell order of the staged object
+    float4 xy[CH / 2];   // positions again, two objects side by side for the packed S1 filter: {x0, x1, y0, y1}
+    float2 zz[CH / 2];   //                                                                     {z0, z1}
 };
 struct WarpShared {
     StageBuf buf[2];
@@ -96,6 +98,27 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2: two lanes of fp32 per instruction; a float2 built
+// from one scalar becomes the broadcast operand form)
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) { return *reinterpret_cast<unsigned long long *>(&v); }
+__device__ __forceinline__ float2 bits_f2(unsigned long long v) { return *reinterpret_cast<float2 *>(&v); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return bits_f2(d);
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 // sqrt(x) rounded up a little: only ever used for conservative bounds (MUFU.SQRT, ~1 ulp)
 __device__ __forceinline__ float sqrt_ub(float x) {
@@ -212,6 +235,10 @@ __device__ __noinline__ EmitRec exact_predict(const PairParams &P, u32 si, u32 s
 // Queue entries whose winning offset m and first hit sample k were already settled in fp32 with
 // every margin wide open carry RESOLVED | m | k << 8: one fp64 evaluation yields the emitted values.
 constexpr u32 RESOLVED = 1u << 31;
+// Queue entries of radius queries whose fp32 distance lies inside the guard band of the radius carry
+// RADIUS_UNDECIDED: the exact stage takes the radius test (spatial_index.py:268) before anything else
+// and counts the candidate.  k_pairs itself never evaluates fp64.
+constexpr u32 RADIUS_UNDECIDED = 1u << 30;
 
 // predict, full fallback: every offset, radius test included (collision_detection.py:789-865)
 __device__ __noinline__ EmitRec exact_predict_all(const PairParams &P, u32 si, u32 sj, u32 pattern) {
@@ -253,6 +280,15 @@ __device__ __noinline__ EmitRec exact_compute_node(const PairParams &P, u32 si, 
 // the exact stage for one queue entry
 template <int MODE>
 __device__ __forceinline__ EmitRec exact_entry(const PairParams &P, u32 si, u32 sj, u32 mask) {
+    if (mask & RADIUS_UNDECIDED) {
+        const float4 a0 = P.P0[si], b0 = P.P0[sj];
+        const float R = (MODE == RCD_MODE_PREDICT) ? PREDICT_RADIUS : P.R;
+        if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, R)) return no_rec();
+        atomicAdd(&P.counters->n_candidates, 1ULL);
+        if (P.cand_count) atomicAdd(&P.cand_count[P.sorted_slot[si]], 1u);
+        if (MODE == RCD_MODE_COMPUTE_NODE && si == sj) return no_rec();  // the index returns self (quirk Q8)
+        mask = 0;
+    }
     if (MODE == RCD_MODE_DETECT) return exact_detect(P, si, sj, P.T, P.steps);
     if (MODE == RCD_MODE_COMPUTE_NODE) return exact_compute_node(P, si, sj);
     if (mask == 0) return exact_detect(P, si, sj, 10.0f, 100);  // pattern 3: detect defaults (:592)
@@ -275,17 +311,15 @@ __device__ __noinline__ u32 finish_entry_inline(const PairParams &P, u32 si, u32
 template <bool COUNT_ALL>
 __device__ __forceinline__ bool narrow_detect(WarpShared &ws, u32 ql, const float4 &a0, const float4 &a1,
                                               const float4 &a2, const float4 &b0, const float4 &b1, const float4 &b2,
-                                              float R, float T, u32 &n_exact) {
+                                              float R, float T, bool &undecided) {
     const float R2 = R * R;
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;  // rel_position = other - self
     float d2 = dx * dx + dy * dy + dz * dz;
-    if (d2 >= R2 * (1.0f - BAND_R2)) {  // the filter could not decide the radius test (spatial_index.py:268)
-        ++n_exact;
-        if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, R)) return false;
-        atomicAdd(&ws.cand[ql], 1u);
-    } else if (COUNT_ALL) {
-        atomicAdd(&ws.cand[ql], 1u);
-    }
+    // fp32 cannot decide the radius test inside the guard band (spatial_index.py:268): the exact stage does.
+    // (detect: the S1 filter made that call when it counted the candidate; predict: made here)
+    if (COUNT_ALL) undecided = d2 >= R2 * (1.0f - BAND_R2);
+    if (undecided) return true;
+    if (COUNT_ALL) atomicAdd(&ws.cand[ql], 1u);
     float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;  // rel_velocity = self - other
     float rs2 = rvx * rvx + rvy * rvy + rvz * rvz;
     if (rs2 < 0.0099f) return false;  // rel_speed < 0.1 with margin (0.1^2 = 0.01)
@@ -549,15 +583,11 @@ __device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 s
 // ---- S2, compute-node pair function in fp32 (compute_node.py:258-292) --------------------------------
 __device__ __forceinline__ bool narrow_compute_node(WarpShared &ws, const PairParams &P, u32 ql, const float4 &a0,
                                                     const float4 &a1, const float4 &a2, const float4 &b0,
-                                                    const float4 &b1, const float4 &b2, bool self, u32 &n_exact) {
+                                                    const float4 &b1, const float4 &b2, bool self, bool &undecided) {
     const float R2 = P.R * P.R;
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;
     float d2 = dx * dx + dy * dy + dz * dz;
-    if (d2 >= R2 * (1.0f - BAND_R2)) {
-        ++n_exact;
-        if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, P.R)) return false;
-        atomicAdd(&ws.cand[ql], 1u);  // query_nearby returns the querying vehicle too (quirk Q8)
-    }
+    if (undecided) return true;  // fp32 could not decide the radius test (compute_node.py:113-116)
     if (self) return false;                              // compute_node.py:251-252
     if (d2 > 2500.0f * (1.0f + BAND_R2)) return false;   // current_distance > 50
     if (meta_pattern(__float_as_uint(a2.w)) == 0u || meta_pattern(__float_as_uint(b2.w)) == 0u)
@@ -608,7 +638,10 @@ __device__ __forceinline__ bool global_push(QEntry *q, u32 cap, unsigned long lo
 }
 
 template <int MODE, bool COUNT_CAND>
-__global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
+#ifndef RCD_PAIR_MIN_BLOCKS
+#define RCD_PAIR_MIN_BLOCKS 6
+#endif
+__global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(PairParams P) {
     __shared__ WarpShared shared[PAIR_WARPS];
     WarpShared &ws = shared[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31u;
@@ -703,8 +736,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
             }
             __syncwarp();
             n1b -= take;
-            if (!global_push(P.q2, P.qcap, &P.counters->n_q2, keep, si, sj, mask))
-                finish_predict_pair<COUNT_CAND>(P, si, sj, mask);  // queue full: finish the pair here
+            const bool pushed = global_push(P.q2, P.qcap, &P.counters->n_q2, keep, si, sj, mask);
+            if (!pushed) finish_predict_pair<COUNT_CAND>(P, si, sj, mask);  // queue full: finish the pair here
         };
 
         // a tile that crosses a cell-row boundary is processed as two groups (first row / the rest)
@@ -803,29 +836,49 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                     } else {
                         cp_async_wait<0>();
                     }
+                    StageBuf &b = ws.buf[(c / P.splits) & 1u];
+                    {   // each lane copied its own slot: lay the positions out pairwise for the packed filter
+                        const float4 own = b.p0[lane];
+                        float *xy = reinterpret_cast<float *>(&b.xy[lane >> 1]);
+                        xy[lane & 1u] = own.x;
+                        xy[2u + (lane & 1u)] = own.y;
+                        reinterpret_cast<float *>(&b.zz[lane >> 1])[lane & 1u] = own.z;
+                    }
                     __syncwarp();
-                    const StageBuf &b = ws.buf[(c / P.splits) & 1u];
                     const u32 m = min((u32)CH, total - c * CH);
                     // ---- S1 filter: one query per lane against every staged neighbour --------------
                     // Each lane appends the neighbours inside its reach to a private list in shared memory
                     // (no warp vote per test); the lists are then consumed 32 pairs at a time.
                     u32 cnt = 0;
+                    auto s1_push = [&](u32 j, float d2) {
+                        if (d2 <= pass2) {
+                            // radius queries: bit 7 = inside the guard band of the radius, the exact stage
+                            // decides; otherwise certainly within it (predict counts its rare radius
+                            // queries in S2)
+                            const bool certain = d2 < R2_lo;
+                            ws.plist[cnt][lane] = (unsigned char)(j | ((MODE != RCD_MODE_PREDICT && !certain) ? 0x80u : 0u));
+                            ++cnt;
+                            if (MODE != RCD_MODE_PREDICT && certain) ++ncand;
+                        }
+                    };
                     for (u32 j0 = 0; j0 < m; j0 += 4) {  // (the last chunk is padded: no bound check per test)
 #pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float4 b0 = b.p0[j0 + u];
-                            float dx = b0.x - p0.x, dy = b0.y - p0.y, dz = b0.z - p0.z;
+                        for (u32 u = 0; u < 2; ++u) {    // two neighbours per packed instruction
+                            const float4 xy = b.xy[(j0 >> 1) + u];
+                            const float2 zz = b.zz[(j0 >> 1) + u];
+                            float2 dx = add2(make_float2(xy.x, xy.y), splat2(-p0.x));
+                            float2 dy = add2(make_float2(xy.z, xy.w), splat2(-p0.y));
+                            float2 dz = add2(zz, splat2(-p0.z));
                             if (MODE == RCD_MODE_PREDICT) {  // distance to the chord (w = 0 for radius queries)
-                                const float sc = __saturatef((dx * wx + dy * wy + dz * wz) * inv_w2);
-                                dx -= sc * wx; dy -= sc * wy; dz -= sc * wz;
+                                const float2 dot = fma2(dz, splat2(wz), fma2(dy, splat2(wy), mul2(dx, splat2(wx))));
+                                const float2 sc = make_float2(__saturatef(dot.x * inv_w2), __saturatef(dot.y * inv_w2));
+                                dx = fma2(sc, splat2(-wx), dx);
+                                dy = fma2(sc, splat2(-wy), dy);
+                                dz = fma2(sc, splat2(-wz), dz);
                             }
-                            const float d2 = dx * dx + dy * dy + dz * dz;
-                            if (d2 <= pass2) {
-                                ws.plist[cnt][lane] = (unsigned char)(j0 + u);
-                                ++cnt;
-                                // certainly within the radius (predict counts its rare radius queries in S2)
-                                if (MODE != RCD_MODE_PREDICT && d2 < R2_lo) ++ncand;
-                            }
+                            const float2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                            s1_push(j0 + 2u * u, d2.x);
+                            s1_push(j0 + 2u * u + 1u, d2.y);
                         }
                     }
                     // exclusive scan of the list lengths: pair f of the chunk belongs to the last lane o
@@ -851,9 +904,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                             if (cand < 32u && v <= f) ql = cand;
                         }
                         const u32 ql_off = __shfl_sync(FULL_MASK, off, ql);
-                        const u32 jj = (lane < take) ? ws.plist[f - ql_off][ql] : 0u;
+                        const u32 entry = (lane < take) ? ws.plist[f - ql_off][ql] : 0u;
+                        const u32 jj = entry & 31u;
                         const u32 si = tile_base + ql;
                         bool keep = false;     // -> global Q3 (exact stage)
+                        bool undecided = (entry & 0x80u) != 0;  // ... which has to take the radius test first
                         bool to_scan = false;  // -> Q1b (predict window scan)
                         u32 sj = 0;
                         if (lane < take) {
@@ -861,13 +916,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                             const float4 b0 = b.p0[jj], b1 = b.p1[jj], b2 = b.p2[jj];
                             sj = b.pos[jj];
                             if (MODE == RCD_MODE_COMPUTE_NODE) {
-                                keep = narrow_compute_node(ws, P, ql, a0, a1, a2, b0, b1, b2, sj == si, n_exact);
+                                keep = narrow_compute_node(ws, P, ql, a0, a1, a2, b0, b1, b2, sj == si, undecided);
                             } else if (sj != si) {  // _spatial_filtering strips self (:224-225)
                                 const u32 pat = meta_pattern(__float_as_uint(a2.w));
                                 if (MODE == RCD_MODE_DETECT) {
-                                    keep = narrow_detect<false>(ws, ql, a0, a1, a2, b0, b1, b2, P.R, P.T, n_exact);
+                                    keep = narrow_detect<false>(ws, ql, a0, a1, a2, b0, b1, b2, P.R, P.T, undecided);
                                 } else if (pat == RCD_PAT_NO_HISTORY) {
-                                    keep = narrow_detect<true>(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, n_exact);
+                                    keep = narrow_detect<true>(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, undecided);
                                 } else if (COUNT_CAND) {
                                     to_scan = true;
                                 } else {
@@ -888,8 +943,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 6) k_pairs(PairParams P) {
                                 if (n1b >= 32) run_scan(32);
                             }
                         }
-                        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, keep, si, sj, 0u))
-                            n_pot += finish_entry_inline<MODE>(P, si, sj, 0u);  // queue full: decide here
+                        const u32 word = undecided ? RADIUS_UNDECIDED : 0u;
+                        const bool pushed = global_push(P.q3, P.qcap, &P.counters->n_q3, keep, si, sj, word);
+                        if (!pushed) n_pot += finish_entry_inline<MODE>(P, si, sj, word);  // queue full: decide here
                     }
                     __syncwarp();
                 }

@@ -11,7 +11,7 @@ from typing import Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG, "librcd_b200.so")
+LIB_PATH = os.environ.get("RCD_B200_LIB") or os.path.join(_PKG, "librcd_b200.so")  # override: kernel-tuning experiments only
 
 RCD_OK, RCD_EINVAL, RCD_ENODEVICE, RCD_ENOMEM, RCD_ECUDA, RCD_ECAPACITY, RCD_ESTATE = 0, -1, -2, -3, -4, -5, -6
 MODE_DETECT, MODE_PREDICT, MODE_COMPUTE_NODE = 0, 1, 2
