@@ -228,6 +228,48 @@ int rcd_history_move(rcd_handle h, uint32_t dst, uint32_t src);
  * (what rcd_set_patterns would set); optionally copy the n codes to pattern_out (host, may be NULL). */
 int rcd_history_classify(rcd_handle h, uint8_t *pattern_out);
 
+/* ---- batched ingest ---------------------------------------------------------
+ * The reference receives one JSON message per vehicle update (src/test/vehicle_simulator.py:721-752)
+ * and rebuilds a Vehicle from it in Python (src/collision/warning_system.py:638-678).  rcd_ingest_*
+ * decodes whole buffers of those messages on the host into fixed records; rcd_apply_records scatters
+ * the records into the device-resident frame state and trajectory rings. */
+typedef struct {
+    double x, y, z;      /* position, float64 as on the wire (the ring keeps float64, the frame state fp32) */
+    double timestamp;
+    float vx, vy, vz, ax, ay, az, size, heading;
+    uint32_t slot;       /* dense object index = position in the frame (rcd_ingest interns the id string) */
+    uint8_t type;        /* interned type string */
+    uint8_t seq;         /* how many earlier records of the same batch carry the same slot */
+    uint16_t reserved;
+} rcd_record;            /* 72 bytes */
+
+typedef struct rcd_ingest_s *rcd_ingest;
+int rcd_ingest_create(rcd_ingest *out);
+int rcd_ingest_destroy(rcd_ingest g);
+const char *rcd_ingest_last_error(rcd_ingest g);
+/* Decode every message in buf[0, len): JSON objects separated by whitespace / newlines / commas,
+ * optionally inside one array.  threads: 0 = all host cores, 1 = sequential; with more than one thread
+ * (and len >= 1 MiB) the buffer is cut at newlines, so a message must not contain a raw newline
+ * (json.dumps never emits one).  Messages that are malformed or lack a field the reference reads are
+ * skipped and counted in *n_bad (the reference logs and drops them, warning_system.py:677-678).
+ * *n_out = messages decoded (RCD_ECAPACITY if > cap), *max_seq = largest rcd_record.seq of the batch.
+ * Needs no CUDA device. */
+int rcd_ingest_decode_json(rcd_ingest g, const char *buf, uint64_t len, int32_t threads, rcd_record *out,
+                           uint64_t cap, uint64_t *n_out, uint64_t *n_bad, uint32_t *max_seq);
+int rcd_ingest_counts(rcd_ingest g, uint64_t *n_ids, uint64_t *n_types);
+/* interned strings (UTF-8, not NUL-terminated; valid until the next decode call) */
+int rcd_ingest_id_name(rcd_ingest g, uint32_t slot, const char **name, uint32_t *len);
+int rcd_ingest_type_name(rcd_ingest g, uint32_t code, const char **name, uint32_t *len);
+int rcd_ingest_lookup(rcd_ingest g, const char *id, uint32_t len, uint32_t *slot); /* RCD_ESTATE if unknown */
+
+/* Apply n decoded records to the frame: state[slot] = record for every record, in seq order
+ * (N x CollisionDetector.update_vehicle, collision_detection.py:74-85), and -- if the trajectory rings
+ * are configured (rcd_history_configure) and append_history != 0 -- one ring sample per record
+ * (N x update_trajectory, :553-570).  n_objects = frame size afterwards (>= every slot + 1, >= the
+ * current size; objects without a record keep their state).  records: host or device memory (src). */
+int rcd_apply_records(rcd_handle h, uint64_t n, const rcd_record *records, uint32_t max_seq,
+                      uint64_t n_objects, int32_t append_history, int32_t src);
+
 /* Spatial-slab support: pack every owned object whose x lies within `halo` of
  * peer p's slab [slab_lo[p], slab_hi[p]) -- p != self -- into 52-byte records
  * (11 floats, meta u32 = type | pattern << 8, id u32), grouped by peer.  out_records is a DEVICE

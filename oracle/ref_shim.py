@@ -350,3 +350,57 @@ def run_B(frame, has_history: Sequence[bool], radius: float = 100.0) -> Dict[str
     cands.sort()
     risks.sort()
     return {"candidates": cands, "risks": risks}
+
+
+# ----------------------------------------------------------------------------------------
+# Ingest driver: EarlyWarningSystem._handle_vehicle_position (warning_system.py:638-678) on raw
+# message texts.  One more repair is needed to execute it at all:
+#   R7  warning_system uses `Vector` without importing it (:656) -> bind models.Vector there.
+# The handler is run on an instance created without __init__ (its constructor needs the broker),
+# with recording stand-ins for the two objects it calls.
+# ----------------------------------------------------------------------------------------
+def run_handle_position_A(texts: Sequence[str]) -> List[Any]:
+    """For every message text: None if the reference drops it, else the tuple
+    (id, px, py, pz, vx, vy, vz, ax, ay, az, heading, size, type, timestamp) of the Vehicle it
+    hands to update_vehicle, after checking that update_trajectory got the same position/time."""
+    import json
+
+    ref = load_reference()
+    ws = ref.warning_system
+    ws.Vector = ref.Vector  # R7
+
+    class _Rec:
+        def __init__(self):
+            self.vehicle = None
+            self.traj = None
+
+        def update_vehicle(self, v):
+            self.vehicle = v
+
+        def update_trajectory(self, vid, pos, ts):
+            self.traj = (vid, pos, ts)
+
+    class _Msg:
+        def __init__(self, value):
+            self.value = value
+
+    out: List[Any] = []
+    for t in texts:
+        rec = _Rec()
+        sys_ = object.__new__(ws.EarlyWarningSystem)
+        sys_.collision_detector = rec
+        sys_.prediction_model = rec
+        try:
+            value = json.loads(t)  # what the broker hands over (messaging.py deserialises with json)
+        except Exception:
+            out.append(None)
+            continue
+        sys_._handle_vehicle_position(_Msg(value))
+        v = rec.vehicle
+        if v is None or rec.traj is None:
+            out.append(None)
+            continue
+        assert rec.traj[0] == v.id and rec.traj[1] is v.position and rec.traj[2] is v.timestamp
+        out.append((v.id, v.position.x, v.position.y, v.position.z, v.velocity.x, v.velocity.y, v.velocity.z,
+                    v.acceleration.x, v.acceleration.y, v.acceleration.z, v.heading, v.size, v.type, v.timestamp))
+    return out

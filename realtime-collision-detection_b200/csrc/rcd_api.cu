@@ -11,6 +11,8 @@
 #include "rcd_common.cuh"
 #include "rcd_index.cuh"
 #include "rcd_pairs.cuh"
+#include "rcd_ingest.cuh"
+#include "rcd_ingest.hpp"
 
 using namespace rcd;
 
@@ -791,6 +793,58 @@ int rcd_history_classify(rcd_handle h, uint8_t *pattern_out) {
         }
     }
     h->index_valid = false;  // the pattern is packed into the cell-ordered state
+    h->frame_done = false;
+    return RCD_OK;
+}
+
+int rcd_apply_records(rcd_handle h, uint64_t n, const rcd_record *records, uint32_t max_seq, uint64_t n_objects,
+                      int32_t append_history, int32_t src) {
+    if (!h || (n && !records)) return RCD_EINVAL;
+    if (n_objects > h->cap) return fail(h, RCD_ECAPACITY, "rcd_apply_records: n_objects exceeds max_objects");
+    if (n_objects < h->n) return fail(h, RCD_EINVAL, "rcd_apply_records: n_objects is smaller than the current frame");
+    if (n > 0xffffffffull / 16) return fail(h, RCD_ECAPACITY, "rcd_apply_records: batch too large");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (append_history) {
+        int rc = history_ready(h, "rcd_apply_records");
+        if (rc) return rc;
+    }
+    const bool hist = append_history && h->traj;
+    for (int m = 0; m < 3; ++m)
+        for (int s = 0; s < RCD_NUM_STAGES; ++s) h->stages[m][s].used = false;
+    h->stage_mode = 0;
+    stage_begin(h, RCD_STAGE_UPLOAD);
+    if (n_objects > h->n) {
+        const u32 fresh = (u32)(n_objects - h->n);
+        k_init_slots<<<(fresh + 255) / 256, 256, 0, h->stream>>>((u32)h->n, (u32)n_objects, h->in_id, h->in_pattern);
+        KERNEL_CHECK(h);
+    }
+    const unsigned long long *dev = reinterpret_cast<const unsigned long long *>(records);
+    unsigned long long *staged = nullptr;
+    if (n && src == RCD_SRC_HOST) {
+        CUDA_TRY(h, dev_alloc(&staged, (size_t)n * RECORD_WORDS));
+        cudaError_t e = cudaMemcpyAsync(staged, records, (size_t)n * sizeof(rcd_record), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { cudaFree(staged); return fail(h, RCD_ECUDA, std::string("rcd_apply_records: ") + cudaGetErrorString(e)); }
+        dev = staged;
+    }
+    MutableState st;
+    for (int k = 0; k < 11; ++k) st.f[k] = h->in_f[k];
+    st.type = h->in_type; st.pattern = h->in_pattern; st.id = h->in_id;
+    cudaError_t e = cudaSuccess;
+    for (u32 seq = 0; n && seq <= max_seq && e == cudaSuccess; ++seq) {
+        k_apply_records<<<(unsigned)((n + APPLY_THREADS - 1) / APPLY_THREADS), APPLY_THREADS, 0, h->stream>>>(
+            (u32)n, dev, seq, (u32)n_objects, st, hist ? h->traj : nullptr, h->traj_count, (u32)h->cap, h->traj_len);
+        e = cudaGetLastError();
+        ++h->launches;
+    }
+    stage_end(h, RCD_STAGE_UPLOAD);
+    if (staged) {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // the staging buffer is freed below
+        cudaFree(staged);
+    }
+    if (e != cudaSuccess) return fail(h, RCD_ECUDA, std::string("rcd_apply_records: ") + cudaGetErrorString(e));
+    h->n = n_objects;
+    h->n_owned = n_objects;
+    h->index_valid = false;
     h->frame_done = false;
     return RCD_OK;
 }

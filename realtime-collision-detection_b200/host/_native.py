@@ -32,6 +32,8 @@ SYMBOLS = (
     "rcd_download_candidate_counts", "rcd_query_radius", "rcd_classify_patterns", "rcd_halo_pack",
     "rcd_halo_append", "rcd_history_configure", "rcd_history_append", "rcd_history_reset", "rcd_history_move",
     "rcd_history_classify", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_sync",
+    "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
+    "rcd_ingest_counts", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
 )
 
 
@@ -54,6 +56,12 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("ttc", "<f4"), ("distance", 
                        ("d_closest", "<f4"), ("priority", "i1"), ("offset", "u1"), ("predicted", "u1"),
                        ("reserved", "u1")])
 assert PAIR_DTYPE.itemsize == 48
+
+# numpy mirror of rcd_record (72 bytes): one decoded vehicle message
+RECORD_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("timestamp", "<f8"), ("vx", "<f4"), ("vy", "<f4"),
+                         ("vz", "<f4"), ("ax", "<f4"), ("ay", "<f4"), ("az", "<f4"), ("size", "<f4"),
+                         ("heading", "<f4"), ("slot", "<u4"), ("type", "u1"), ("seq", "u1"), ("reserved", "<u2")])
+assert RECORD_DTYPE.itemsize == 72
 
 
 class NativeError(RuntimeError):
@@ -107,9 +115,20 @@ def load() -> ctypes.CDLL:
     L.rcd_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
     L.rcd_launch_count.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_sync.argtypes = [vp]
+    L.rcd_ingest_create.argtypes = [ctypes.POINTER(vp)]
+    L.rcd_ingest_destroy.argtypes = [vp]
+    L.rcd_ingest_last_error.restype = ctypes.c_char_p
+    L.rcd_ingest_last_error.argtypes = [vp]
+    L.rcd_ingest_decode_json.argtypes = [vp, vp, u64, i32, vp, u64, ctypes.POINTER(u64), ctypes.POINTER(u64),
+                                         ctypes.POINTER(u32)]
+    L.rcd_ingest_counts.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.rcd_ingest_id_name.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(u32)]
+    L.rcd_ingest_type_name.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(u32)]
+    L.rcd_ingest_lookup.argtypes = [vp, ctypes.c_char_p, u32, ctypes.POINTER(u32)]
+    L.rcd_apply_records.argtypes = [vp, u64, vp, u32, u64, i32, i32]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("rcd_last_error", "rcd_version"):
+        if name not in ("rcd_last_error", "rcd_version", "rcd_ingest_last_error"):
             fn.restype = ctypes.c_int
     _lib = L
     return L

@@ -93,6 +93,19 @@ class FrameEngine:
     def upload_host_ptrs(self, n: int, ptrs: Sequence[int], type_ptr: int = 0, id_ptr: int = 0) -> None:
         self.upload_ptrs(n, ptrs, type_ptr, id_ptr, N.SRC_HOST)
 
+    def apply_records(self, records: np.ndarray, n_objects: int, max_seq: int = 0, history: bool = True) -> None:
+        """Scatter decoded vehicle messages (``_native.RECORD_DTYPE``, see ``ingest.py``) into the frame:
+        N x update_vehicle + N x update_trajectory (warning_system.py:638-678) in one call."""
+        rec = np.ascontiguousarray(records, dtype=N.RECORD_DTYPE)
+        N.check(self._lib.rcd_apply_records(self._h, int(rec.shape[0]), _vp(rec) if rec.shape[0] else None, int(max_seq),
+                                            int(n_objects), 1 if history else 0, N.SRC_HOST), self._h)
+        self.n = int(n_objects)
+
+    def apply_records_device(self, n: int, ptr: int, n_objects: int, max_seq: int = 0, history: bool = True) -> None:
+        N.check(self._lib.rcd_apply_records(self._h, int(n), ctypes.c_void_p(int(ptr)), int(max_seq), int(n_objects),
+                                            1 if history else 0, N.SRC_DEVICE), self._h)
+        self.n = int(n_objects)
+
     def set_patterns_ptr(self, n: int, ptr: int, src: int) -> None:
         N.check(self._lib.rcd_set_patterns(self._h, int(n), ctypes.c_void_p(int(ptr)) if ptr else None, int(src)),
                 self._h)

@@ -109,6 +109,21 @@ def scalars_fixture(name):
     print(name, np.bincount(classes), len(near))
 
 
+def ingest_fixture(name):
+    """EarlyWarningSystem._handle_vehicle_position (warning_system.py:638-678, shim repair R7) on the
+    message texts of tests/ingest_cases.py: per message, dropped or the Vehicle fields."""
+    import json
+    from tests import ingest_cases as C
+    texts = C.seeded_messages(400, 77) + [t for t, _ in C.edge_messages()]
+    got = S.run_handle_position_A(texts)
+    rows = []
+    for t, g in zip(texts, got):
+        rows.append({"text": t, "vehicle": None if g is None else [g[0]] + [repr(float(x)) for x in g[1:12]] + [g[12], repr(float(g[13]))]})
+    with open(os.path.join(HERE, name), "w") as f:
+        json.dump(rows, f, ensure_ascii=True, indent=0)
+    print(name, len(rows), "messages,", sum(r["vehicle"] is None for r in rows), "dropped")
+
+
 def main():
     if not S.reference_available():
         raise SystemExit("needs /root/reference")
@@ -130,6 +145,7 @@ def main():
     fb = W.uniform_frame(600, 106, map_size=160.0, drone_fraction=0.2)
     implB_fixture("implB_dense.npz", fb, np.random.default_rng(3).random(600) < 0.9)
     scalars_fixture("scalars.npz")
+    ingest_fixture("ingest_messages.json")
 
 
 if __name__ == "__main__":
