@@ -270,6 +270,54 @@ int rcd_ingest_lookup(rcd_ingest g, const char *id, uint32_t len, uint32_t *slot
 int rcd_apply_records(rcd_handle h, uint64_t n, const rcd_record *records, uint32_t max_seq,
                       uint64_t n_objects, int32_t append_history, int32_t src);
 
+/* ---- alert lifecycle on the device --------------------------------------------
+ * Replaces the per-risk dict walk of AlertManager.process_collision_risks / update_alert / create_alert
+ * (src/collision/warning_system.py:259-285, 120-197), _cleanup_expired_alerts (:488-517) and
+ * acknowledge_alert (:199-213): one alert per directed pair (i, j) lives in a device hash table; a
+ * frame's emitted pairs are folded into it without leaving the device and only the changes come back. */
+enum {
+    RCD_ALERT_REFRESHED = 0,        /* existing alert updated, same priority (not reported unless asked for) */
+    RCD_ALERT_CREATED = 1,          /* create_alert: no alert existed for (i, j) */
+    RCD_ALERT_PRIORITY_CHANGED = 2, /* update_alert with a different priority (the reference re-queues it) */
+    RCD_ALERT_EXPIRED = 3           /* removed by the cleanup: acknowledged, or older than max_age */
+};
+typedef struct {
+    uint32_t i, j;        /* caller ids: vehicle_id, other_vehicle_id */
+    uint32_t alert_id;    /* running number given at creation (the reference draws a uuid) */
+    float risk, ttc;      /* risk_level, time_to_collision after the update */
+    int8_t priority;      /* after the update */
+    int8_t old_priority;  /* before it (-1: none) */
+    uint8_t kind;         /* RCD_ALERT_* */
+    uint8_t acknowledged;
+    double timestamp;     /* AlertInfo.timestamp: `now` of the last update */
+} rcd_alert_event;        /* 32 bytes */
+typedef struct {
+    uint64_t n_events;    /* events produced by the call (only min(n_events, cap) were stored) */
+    uint64_t n_created, n_changed, n_refreshed, n_expired;
+    uint64_t n_live;      /* alerts in the table after the call */
+    uint64_t n_dropped;   /* risks that found the table full (size it with rcd_alerts_configure) */
+} rcd_alert_stats;
+/* Allocate (or reset) the table for up to max_alerts live alerts. */
+int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts);
+/* process_collision_risks on every pair the last rcd_step(s) of this frame emitted (risk >= 0.3 only,
+ * :273), with time.time() = now.  events (host, may be NULL with cap 0) receives the CREATED and
+ * PRIORITY_CHANGED events, plus the REFRESHED ones if report_refreshed != 0; order is not deterministic. */
+int rcd_alerts_update(rcd_handle h, double now, int32_t report_refreshed, rcd_alert_event *events, uint64_t cap,
+                      rcd_alert_stats *stats);
+/* The same for an explicit list of risks (host array of rcd_pair; i, j, ttc, risk, priority and predicted
+ * are read; a pair with priority < 0 is skipped).  If (i, j) occurs more than once, a non-predicted entry
+ * is applied before a predicted one; other duplicates are the caller's to split into separate calls. */
+int rcd_alerts_update_pairs(rcd_handle h, const rcd_pair *pairs, uint64_t n, double now, int32_t report_refreshed,
+                            rcd_alert_event *events, uint64_t cap, rcd_alert_stats *stats);
+/* _cleanup_expired_alerts: drop every alert that is acknowledged or has now - timestamp > max_age
+ * (the reference uses 30.0); events receives one EXPIRED event per dropped alert. */
+int rcd_alerts_expire(rcd_handle h, double now, double max_age, rcd_alert_event *events, uint64_t cap,
+                      rcd_alert_stats *stats);
+/* acknowledge_alert for the alerts of the listed (i, j) pairs; *n_found = how many existed. */
+int rcd_alerts_acknowledge(rcd_handle h, uint64_t n, const uint32_t *i, const uint32_t *j, uint64_t *n_found);
+/* Every live alert, sorted by (i, j), as event records with kind = RCD_ALERT_REFRESHED. */
+int rcd_alerts_download(rcd_handle h, rcd_alert_event *out, uint64_t cap, uint64_t *n_out);
+
 /* Spatial-slab support: pack every owned object whose x lies within `halo` of
  * peer p's slab [slab_lo[p], slab_hi[p]) -- p != self -- into 52-byte records
  * (11 floats, meta u32 = type | pattern << 8, id u32), grouped by peer.  out_records is a DEVICE

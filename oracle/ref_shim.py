@@ -404,3 +404,66 @@ def run_handle_position_A(texts: Sequence[str]) -> List[Any]:
         out.append((v.id, v.position.x, v.position.y, v.position.z, v.velocity.x, v.velocity.y, v.velocity.z,
                     v.acceleration.x, v.acceleration.y, v.acceleration.z, v.heading, v.size, v.type, v.timestamp))
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# Alert lifecycle driver: the reference's AlertManager table logic (warning_system.py:120-213,
+# 259-285, 488-517) on a scripted scenario with a controlled clock.  The manager is created
+# without __init__ (which needs the broker); only the three dict/list attributes its table methods
+# use are set, exactly as __init__ sets them (:61-66).
+# ----------------------------------------------------------------------------------------
+def run_alert_scenario_A(script) -> List[Any]:
+    """script: list of ("process", now, [(vid, other, risk, ttc, distance)]) | ("ack", [(vid, other)]) |
+    ("cleanup", now).  Returns, per op, (events, table) with events = sorted [(kind, vid, other, priority,
+    old_priority)] and table = sorted [(vid, other, risk, ttc, priority, timestamp, acknowledged)]."""
+    ref = load_reference()
+    ws = ref.warning_system
+
+    class _Clock:
+        now = 0.0
+
+        @staticmethod
+        def time():
+            return _Clock.now
+
+    real_time = ws.time
+    ws.time = _Clock
+    try:
+        am = object.__new__(ws.AlertManager)
+        am.alerts, am.vehicle_alerts, am.alert_queue = {}, {}, []
+        out = []
+        for op in script:
+            events = []
+            if op[0] == "process":
+                _Clock.now = op[1]
+                before = {(a.vehicle_id, a.other_vehicle_id): (a.id, a.priority) for a in am.alerts.values()}
+                risks = [ref.CollisionRiskA(id=f"r{k}", vehicle_id=v, other_vehicle_id=o, time_to_collision=ttc, distance=d,
+                                            relative_speed=0.0, risk_level=r, collision_position=None, timestamp=op[1])
+                         for k, (v, o, r, ttc, d) in enumerate(op[2])]
+                got = am.process_collision_risks(risks)
+                for a in got:
+                    key = (a.vehicle_id, a.other_vehicle_id)
+                    if key not in before or before[key][0] != a.id:
+                        events.append(("created", key[0], key[1], a.priority, -1))
+                    else:
+                        old = before[key][1]
+                        events.append(("changed" if a.priority != old else "refreshed", key[0], key[1], a.priority, old))
+                # a priority change must have re-queued the alert (:186-191); every alert is queued once
+                assert sorted(x.id for x in am.alert_queue) == sorted(am.alerts)
+            elif op[0] == "ack":
+                for v, o in op[1]:
+                    aid = am.vehicle_alerts.get(v, {}).get(o)
+                    if aid is not None:
+                        am.acknowledge_alert(aid)
+            elif op[0] == "cleanup":
+                _Clock.now = op[1]
+                before = {(a.vehicle_id, a.other_vehicle_id) for a in am.alerts.values()}
+                am._cleanup_expired_alerts()
+                after = {(a.vehicle_id, a.other_vehicle_id) for a in am.alerts.values()}
+                events = [("expired", v, o, -1, -1) for v, o in before - after]
+            table = sorted((a.vehicle_id, a.other_vehicle_id, a.risk_level, a.time_to_collision, a.priority, a.timestamp,
+                            bool(a.acknowledged)) for a in am.alerts.values())
+            out.append((sorted(events), table))
+        return out
+    finally:
+        ws.time = real_time

@@ -12,6 +12,7 @@
 #include "rcd_index.cuh"
 #include "rcd_pairs.cuh"
 #include "rcd_ingest.cuh"
+#include "rcd_alerts.cuh"
 #include "rcd_ingest.hpp"
 
 using namespace rcd;
@@ -79,6 +80,13 @@ struct rcd_handle_s {
     u32 *traj_count = nullptr;
     u32 traj_len = 0;
     u64 launches = 0;
+    // alert table (rcd_alerts.cuh)
+    AlertEntry *alert_tab[2] = {nullptr, nullptr};
+    int alert_cur = 0;
+    u64 alert_cap = 0, alert_ev_cap = 0;
+    rcd_alert_event *alert_ev = nullptr;
+    AlertCounters *alert_counters = nullptr;
+    AlertCounters *alert_counters_host = nullptr;  // pinned
     std::string err;
 };
 
@@ -342,6 +350,8 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
     cudaFree(h->q2); cudaFree(h->q3);
     cudaFree(h->traj); cudaFree(h->traj_count);
+    cudaFree(h->alert_tab[0]); cudaFree(h->alert_tab[1]); cudaFree(h->alert_ev); cudaFree(h->alert_counters);
+    if (h->alert_counters_host) cudaFreeHost(h->alert_counters_host);
     if (h->counters_host) cudaFreeHost(h->counters_host);
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) {
@@ -846,6 +856,171 @@ int rcd_apply_records(rcd_handle h, uint64_t n, const rcd_record *records, uint3
     h->n_owned = n_objects;
     h->index_valid = false;
     h->frame_done = false;
+    return RCD_OK;
+}
+
+// ---- alert lifecycle -------------------------------------------------------------------------------------
+static int alerts_ready(rcd_handle h, const char *who) {
+    if (!h->alert_cap) return fail(h, RCD_ESTATE, std::string(who) + ": call rcd_alerts_configure first");
+    return RCD_OK;
+}
+static void alert_stats_out(rcd_handle h, rcd_alert_stats *st) {
+    if (!st) return;
+    const AlertCounters &c = *h->alert_counters_host;
+    st->n_events = c.n_events; st->n_created = c.n_created; st->n_changed = c.n_changed;
+    st->n_refreshed = c.n_refreshed; st->n_expired = c.n_expired; st->n_live = c.n_live; st->n_dropped = c.n_dropped;
+}
+// zero the per-call counters (n_live and next_id persist), run `launch`, bring counters + events back
+extern "C++" {
+template <typename F>
+static int alerts_call(rcd_handle h, rcd_alert_event *events, uint64_t cap, rcd_alert_stats *stats, bool reset_live, F launch) {
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemsetAsync(h->alert_counters, 0, offsetof(AlertCounters, n_live), h->stream));
+    if (reset_live) CUDA_TRY(h, cudaMemsetAsync(&h->alert_counters->n_live, 0, sizeof(unsigned long long), h->stream));
+    int rc = launch();
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->alert_counters_host, h->alert_counters, sizeof(AlertCounters), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const u64 n_ev = std::min<u64>(std::min<u64>(h->alert_counters_host->n_events, h->alert_ev_cap), cap);
+    if (n_ev && events)
+        CUDA_TRY(h, cudaMemcpy(events, h->alert_ev, (size_t)n_ev * sizeof(rcd_alert_event), cudaMemcpyDeviceToHost));
+    alert_stats_out(h, stats);
+    return RCD_OK;
+}
+}  // extern "C++"
+
+int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts) {
+    if (!h || max_alerts == 0 || max_alerts > (1ull << 31)) return h ? fail(h, RCD_EINVAL, "rcd_alerts_configure: max_alerts must be in [1, 2^31]") : RCD_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->alert_tab[0]); cudaFree(h->alert_tab[1]); cudaFree(h->alert_ev); cudaFree(h->alert_counters);
+    if (h->alert_counters_host) cudaFreeHost(h->alert_counters_host);
+    h->alert_tab[0] = h->alert_tab[1] = nullptr; h->alert_ev = nullptr; h->alert_counters = nullptr; h->alert_counters_host = nullptr;
+    h->alert_cap = 0;
+    u64 cap = 1024;
+    while (cap < 2 * max_alerts) cap <<= 1;  // load factor <= 0.5
+    CUDA_TRY(h, dev_alloc(&h->alert_tab[0], (size_t)cap));
+    CUDA_TRY(h, dev_alloc(&h->alert_tab[1], (size_t)cap));
+    CUDA_TRY(h, dev_alloc(&h->alert_ev, (size_t)max_alerts));
+    CUDA_TRY(h, dev_alloc(&h->alert_counters, 1));
+    CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void **>(&h->alert_counters_host), sizeof(AlertCounters)));
+    CUDA_TRY(h, cudaMemsetAsync(h->alert_tab[0], 0xff, (size_t)cap * sizeof(AlertEntry), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->alert_counters, 0, sizeof(AlertCounters), h->stream));
+    h->alert_cur = 0;
+    h->alert_cap = cap;
+    h->alert_ev_cap = max_alerts;
+    return RCD_OK;
+}
+
+static int alerts_update_impl(rcd_handle h, const rcd_pair *dev_pairs, u64 n_max, const unsigned long long *n_dev, double now,
+                              int32_t report_refreshed, rcd_alert_event *events, uint64_t cap, rcd_alert_stats *stats) {
+    return alerts_call(h, events, cap, stats, false, [&]() -> int {
+        if (n_max == 0) return RCD_OK;
+        int sms = 0;
+        CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        const unsigned blocks = (unsigned)std::min<u64>((n_max + ALERT_THREADS - 1) / ALERT_THREADS, (u64)std::max(1, sms) * 8);
+        for (int pass = 0; pass < 2; ++pass) {
+            k_alert_update<<<blocks, ALERT_THREADS, 0, h->stream>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
+                                                                    h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
+                                                                    h->alert_counters, report_refreshed);
+            KERNEL_CHECK(h);
+        }
+        return RCD_OK;
+    });
+}
+
+int rcd_alerts_update(rcd_handle h, double now, int32_t report_refreshed, rcd_alert_event *events, uint64_t cap,
+                      rcd_alert_stats *stats) {
+    if (!h) return RCD_EINVAL;
+    int rc = alerts_ready(h, "rcd_alerts_update");
+    if (rc) return rc;
+    if (!h->frame_done) return fail(h, RCD_ESTATE, "rcd_alerts_update: no frame has been stepped");
+    return alerts_update_impl(h, h->out, h->max_pairs, &h->counters->n_pairs, now, report_refreshed, events, cap, stats);
+}
+
+int rcd_alerts_update_pairs(rcd_handle h, const rcd_pair *pairs, uint64_t n, double now, int32_t report_refreshed,
+                            rcd_alert_event *events, uint64_t cap, rcd_alert_stats *stats) {
+    if (!h || (n && !pairs)) return RCD_EINVAL;
+    int rc = alerts_ready(h, "rcd_alerts_update_pairs");
+    if (rc) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    rcd_pair *staged = nullptr;
+    if (n) {
+        CUDA_TRY(h, dev_alloc(&staged, (size_t)n));
+        cudaError_t e = cudaMemcpyAsync(staged, pairs, (size_t)n * sizeof(rcd_pair), cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) { cudaFree(staged); return fail(h, RCD_ECUDA, std::string("rcd_alerts_update_pairs: ") + cudaGetErrorString(e)); }
+    }
+    rc = alerts_update_impl(h, staged, n, nullptr, now, report_refreshed, events, cap, stats);  // synchronises
+    cudaFree(staged);
+    return rc;
+}
+
+int rcd_alerts_expire(rcd_handle h, double now, double max_age, rcd_alert_event *events, uint64_t cap, rcd_alert_stats *stats) {
+    if (!h) return RCD_EINVAL;
+    int rc = alerts_ready(h, "rcd_alerts_expire");
+    if (rc) return rc;
+    rc = alerts_call(h, events, cap, stats, true, [&]() -> int {
+        AlertEntry *src = h->alert_tab[h->alert_cur], *dst = h->alert_tab[h->alert_cur ^ 1];
+        CUDA_TRY(h, cudaMemsetAsync(dst, 0xff, (size_t)h->alert_cap * sizeof(AlertEntry), h->stream));
+        int sms = 0;
+        CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        const unsigned blocks = (unsigned)std::min<u64>((h->alert_cap + ALERT_THREADS - 1) / ALERT_THREADS, (u64)std::max(1, sms) * 8);
+        k_alert_expire<<<blocks, ALERT_THREADS, 0, h->stream>>>(src, h->alert_cap, now, max_age, dst, h->alert_ev, h->alert_ev_cap,
+                                                                h->alert_counters);
+        KERNEL_CHECK(h);
+        return RCD_OK;
+    });
+    if (rc == RCD_OK) h->alert_cur ^= 1;
+    return rc;
+}
+
+int rcd_alerts_acknowledge(rcd_handle h, uint64_t n, const uint32_t *i, const uint32_t *j, uint64_t *n_found) {
+    if (!h || (n && (!i || !j))) return RCD_EINVAL;
+    int rc = alerts_ready(h, "rcd_alerts_acknowledge");
+    if (rc) return rc;
+    if (n_found) *n_found = 0;
+    if (n == 0) return RCD_OK;
+    if (n > 0xffffffffull) return fail(h, RCD_ECAPACITY, "rcd_alerts_acknowledge: too many pairs");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    u32 *d = nullptr;
+    CUDA_TRY(h, dev_alloc(&d, 2 * (size_t)n + 1));
+    cudaError_t e = cudaMemcpyAsync(d, i, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, j, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d + 2 * n, 0, sizeof(u32), h->stream);
+    if (e == cudaSuccess) {
+        k_alert_ack<<<(unsigned)((n + ALERT_THREADS - 1) / ALERT_THREADS), ALERT_THREADS, 0, h->stream>>>(
+            d, d + n, (u32)n, h->alert_tab[h->alert_cur], h->alert_cap - 1, d + 2 * n);
+        e = cudaGetLastError();
+        ++h->launches;
+    }
+    u32 found = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&found, d + 2 * n, sizeof(u32), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(h, RCD_ECUDA, std::string("rcd_alerts_acknowledge: ") + cudaGetErrorString(e));
+    if (n_found) *n_found = found;
+    return RCD_OK;
+}
+
+int rcd_alerts_download(rcd_handle h, rcd_alert_event *out, uint64_t cap, uint64_t *n_out) {
+    if (!h || !n_out || (cap && !out)) return RCD_EINVAL;
+    int rc = alerts_ready(h, "rcd_alerts_download");
+    if (rc) return rc;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    rcd_alert_stats st;
+    rc = alerts_call(h, out, cap, &st, false, [&]() -> int {
+        int sms = 0;
+        CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+        const unsigned blocks = (unsigned)std::min<u64>((h->alert_cap + ALERT_THREADS - 1) / ALERT_THREADS, (u64)std::max(1, sms) * 8);
+        k_alert_dump<<<blocks, ALERT_THREADS, 0, h->stream>>>(h->alert_tab[h->alert_cur], h->alert_cap, h->alert_ev, h->alert_ev_cap,
+                                                              h->alert_counters);
+        KERNEL_CHECK(h);
+        return RCD_OK;
+    });
+    if (rc) return rc;
+    const u64 n = std::min<u64>(std::min<u64>(st.n_events, h->alert_ev_cap), cap);
+    std::sort(out, out + n, [](const rcd_alert_event &a, const rcd_alert_event &b) { return a.i != b.i ? a.i < b.i : a.j < b.j; });
+    *n_out = n;
     return RCD_OK;
 }
 

@@ -584,7 +584,6 @@ __device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 s
 __device__ __forceinline__ bool narrow_compute_node(WarpShared &ws, const PairParams &P, u32 ql, const float4 &a0,
                                                     const float4 &a1, const float4 &a2, const float4 &b0,
                                                     const float4 &b1, const float4 &b2, bool self, bool &undecided) {
-    const float R2 = P.R * P.R;
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;
     float d2 = dx * dx + dy * dy + dz * dz;
     if (undecided) return true;  // fp32 could not decide the radius test (compute_node.py:113-116)

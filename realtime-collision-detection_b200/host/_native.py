@@ -34,6 +34,8 @@ SYMBOLS = (
     "rcd_history_classify", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_sync",
     "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
     "rcd_ingest_counts", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
+    "rcd_alerts_configure", "rcd_alerts_update", "rcd_alerts_update_pairs", "rcd_alerts_expire",
+    "rcd_alerts_acknowledge", "rcd_alerts_download",
 )
 
 
@@ -56,6 +58,19 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("ttc", "<f4"), ("distance", 
                        ("d_closest", "<f4"), ("priority", "i1"), ("offset", "u1"), ("predicted", "u1"),
                        ("reserved", "u1")])
 assert PAIR_DTYPE.itemsize == 48
+
+# numpy mirror of rcd_alert_event (32 bytes)
+ALERT_REFRESHED, ALERT_CREATED, ALERT_PRIORITY_CHANGED, ALERT_EXPIRED = 0, 1, 2, 3
+ALERT_EVENT_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("alert_id", "<u4"), ("risk", "<f4"), ("ttc", "<f4"),
+                              ("priority", "i1"), ("old_priority", "i1"), ("kind", "u1"), ("acknowledged", "u1"),
+                              ("timestamp", "<f8")])
+assert ALERT_EVENT_DTYPE.itemsize == 32
+
+
+class RcdAlertStats(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_uint64) for k in ("n_events", "n_created", "n_changed", "n_refreshed", "n_expired",
+                                               "n_live", "n_dropped")]
+
 
 # numpy mirror of rcd_record (72 bytes): one decoded vehicle message
 RECORD_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("timestamp", "<f8"), ("vx", "<f4"), ("vy", "<f4"),
@@ -126,6 +141,13 @@ def load() -> ctypes.CDLL:
     L.rcd_ingest_type_name.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(u32)]
     L.rcd_ingest_lookup.argtypes = [vp, ctypes.c_char_p, u32, ctypes.POINTER(u32)]
     L.rcd_apply_records.argtypes = [vp, u64, vp, u32, u64, i32, i32]
+    f64 = ctypes.c_double
+    L.rcd_alerts_configure.argtypes = [vp, u64]
+    L.rcd_alerts_update.argtypes = [vp, f64, i32, vp, u64, ctypes.POINTER(RcdAlertStats)]
+    L.rcd_alerts_update_pairs.argtypes = [vp, vp, u64, f64, i32, vp, u64, ctypes.POINTER(RcdAlertStats)]
+    L.rcd_alerts_expire.argtypes = [vp, f64, f64, vp, u64, ctypes.POINTER(RcdAlertStats)]
+    L.rcd_alerts_acknowledge.argtypes = [vp, u64, vp, vp, ctypes.POINTER(u64)]
+    L.rcd_alerts_download.argtypes = [vp, vp, u64, ctypes.POINTER(u64)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("rcd_last_error", "rcd_version", "rcd_ingest_last_error"):

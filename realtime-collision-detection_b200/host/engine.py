@@ -238,6 +238,49 @@ class FrameEngine:
         N.check(self._lib.rcd_history_classify(self._h, _vp(out)), self._h)
         return out
 
+    # -- alert lifecycle (warning_system.py:120-197, 259-285, 488-517) ----------------------
+    def alerts_configure(self, max_alerts: int) -> None:
+        N.check(self._lib.rcd_alerts_configure(self._h, int(max_alerts)), self._h)
+        self._alert_cap = int(max_alerts)
+
+    @staticmethod
+    def _alert_stats(st: "N.RcdAlertStats") -> Dict[str, int]:
+        return {k: int(getattr(st, k)) for k, _ in N.RcdAlertStats._fields_}
+
+    def _alert_events(self, cap: Optional[int]) -> np.ndarray:
+        return np.zeros(self._alert_cap if cap is None else int(cap), dtype=N.ALERT_EVENT_DTYPE)
+
+    def alerts_update(self, now: float, report_refreshed: bool = False, cap: Optional[int] = None):
+        """process_collision_risks on the pairs of the last frame; returns (events, stats)."""
+        ev, st = self._alert_events(cap), N.RcdAlertStats()
+        N.check(self._lib.rcd_alerts_update(self._h, float(now), 1 if report_refreshed else 0, _vp(ev), ev.shape[0],
+                                            ctypes.byref(st)), self._h)
+        return ev[: min(int(st.n_events), ev.shape[0])], self._alert_stats(st)
+
+    def alerts_update_pairs(self, pairs: np.ndarray, now: float, report_refreshed: bool = False, cap: Optional[int] = None):
+        p = np.ascontiguousarray(pairs, dtype=N.PAIR_DTYPE)
+        ev, st = self._alert_events(cap), N.RcdAlertStats()
+        N.check(self._lib.rcd_alerts_update_pairs(self._h, _vp(p) if p.shape[0] else None, p.shape[0], float(now),
+                                                  1 if report_refreshed else 0, _vp(ev), ev.shape[0], ctypes.byref(st)), self._h)
+        return ev[: min(int(st.n_events), ev.shape[0])], self._alert_stats(st)
+
+    def alerts_expire(self, now: float, max_age: float = 30.0, cap: Optional[int] = None):
+        ev, st = self._alert_events(cap), N.RcdAlertStats()
+        N.check(self._lib.rcd_alerts_expire(self._h, float(now), float(max_age), _vp(ev), ev.shape[0], ctypes.byref(st)), self._h)
+        return ev[: min(int(st.n_events), ev.shape[0])], self._alert_stats(st)
+
+    def alerts_acknowledge(self, i, j) -> int:
+        ii, jj = _as(i, np.uint32), _as(j, np.uint32)
+        found = ctypes.c_uint64()
+        N.check(self._lib.rcd_alerts_acknowledge(self._h, ii.shape[0], _vp(ii), _vp(jj), ctypes.byref(found)), self._h)
+        return int(found.value)
+
+    def alerts_download(self, cap: Optional[int] = None) -> np.ndarray:
+        ev = self._alert_events(cap)
+        n = ctypes.c_uint64()
+        N.check(self._lib.rcd_alerts_download(self._h, _vp(ev), ev.shape[0], ctypes.byref(n)), self._h)
+        return ev[: int(n.value)]
+
     # -- slabs ------------------------------------------------------------------------------
     def halo_pack(self, slab_lo, slab_hi, self_rank: int, halo: float, out_ptr: int, cap: int) -> np.ndarray:
         lo = _as(slab_lo, np.float32)

@@ -69,5 +69,41 @@ class AlertManager:
         self.stats["active_alerts"] = len(self.alerts)
         return out
 
+    # -- device table (csrc/rcd_alerts.cuh): the same lifecycle for whole frames ----------------------
+    def attach_engine(self, engine, id_of, max_alerts: int = 1 << 20) -> None:
+        """Keep the alert table on the GPU next to the frames of ``engine`` (a ``FrameEngine``);
+        ``id_of(k)`` maps the caller ids of the pairs back to vehicle id strings."""
+        self._engine, self._id_of = engine, id_of
+        engine.alerts_configure(max_alerts)
+
+    def _alert_from_event(self, e) -> AlertInfo:
+        vid, other = self._id_of(int(e["i"])), self._id_of(int(e["j"]))
+        risk = CollisionRisk(id="", vehicle_id=vid, other_vehicle_id=other, time_to_collision=float(e["ttc"]), distance=float("nan"),
+                             relative_speed=0.0, risk_level=float(e["risk"]), collision_position=None, timestamp=float(e["timestamp"]))
+        msg = self._generate_alert_message(risk) if float(e["risk"]) >= RISK_LEVEL_MEDIUM else \
+            f"NOTICE: vehicle {other} is close - keep a safe distance"
+        return AlertInfo(id=f"alert-{int(e['alert_id'])}", vehicle_id=vid, other_vehicle_id=other, risk_level=float(e["risk"]),
+                         time_to_collision=float(e["ttc"]), message=msg, priority=int(e["priority"]),
+                         timestamp=float(e["timestamp"]), acknowledged=bool(e["acknowledged"]))
+
+    def process_frame(self, now: Optional[float] = None, report_refreshed: bool = False) -> List[AlertInfo]:
+        """process_collision_risks (:259-285) for every risk of the engine's last frame, on the device.
+        Returns only what the reference's queue would hear about: created alerts and priority changes
+        (plus refreshed ones on request)."""
+        ev, st = self._engine.alerts_update(time.time() if now is None else now, report_refreshed)
+        self.stats["total_alerts"] += st["n_created"]
+        self.stats["active_alerts"] = st["n_live"]
+        return [self._alert_from_event(e) for e in ev]
+
+    def cleanup_expired(self, now: Optional[float] = None, max_age: float = 30.0) -> List[Tuple[str, str]]:
+        """_cleanup_expired_alerts (:488-517); returns the (vehicle, other) keys that were dropped."""
+        ev, st = self._engine.alerts_expire(time.time() if now is None else now, max_age)
+        self.stats["active_alerts"] = st["n_live"]
+        return [(self._id_of(int(e["i"])), self._id_of(int(e["j"]))) for e in ev]
+
+    def acknowledge(self, vehicle_id_index: int, other_vehicle_index: int) -> bool:
+        """acknowledge_alert (:199-213) addressed by the pair's caller ids."""
+        return self._engine.alerts_acknowledge([vehicle_id_index], [other_vehicle_index]) == 1
+
     def get_stats(self):
         return dict(self.stats)

@@ -124,6 +124,21 @@ def ingest_fixture(name):
     print(name, len(rows), "messages,", sum(r["vehicle"] is None for r in rows), "dropped")
 
 
+def alerts_fixture(name):
+    """AlertManager's table methods (warning_system.py:120-213, 259-285, 488-517) on the scripted scenario
+    of tests/alert_cases.py, controlled clock: per op the events and the whole table."""
+    import json
+    from tests import alert_cases as A
+    script = A.scenario()
+    got = S.run_alert_scenario_A(script)
+    rows = [{"events": [list(e) for e in ev], "table": [[t[0], t[1], repr(t[2]), repr(t[3]), t[4], repr(t[5]), t[6]] for t in tab]}
+            for ev, tab in got]
+    import gzip
+    with gzip.GzipFile(os.path.join(HERE, name), "w", mtime=0) as f:
+        f.write(json.dumps(rows).encode())
+    print(name, len(rows), "ops,", sum(len(r["events"]) for r in rows), "events, final table", len(rows[-1]["table"]))
+
+
 def main():
     if not S.reference_available():
         raise SystemExit("needs /root/reference")
@@ -146,6 +161,7 @@ def main():
     implB_fixture("implB_dense.npz", fb, np.random.default_rng(3).random(600) < 0.9)
     scalars_fixture("scalars.npz")
     ingest_fixture("ingest_messages.json")
+    alerts_fixture("alert_scenario.json.gz")
 
 
 if __name__ == "__main__":
