@@ -502,6 +502,7 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         const unsigned sb = (unsigned)std::min<u64>((u64)h->stage_blocks, (h->n + STAGE_THREADS - 1) / STAGE_THREADS + 1);
         if (variant == 1 || variant == 2) {
             stage_begin(h, RCD_STAGE_SAMPLE);
+            // k_sample is compiled for 8 resident blocks per SM: the fixed grid is exactly one wave
             if (variant == 1) k_sample<false><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
             else k_sample<true><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
             KERNEL_CHECK(h);

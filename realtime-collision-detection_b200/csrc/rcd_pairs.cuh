@@ -1002,7 +1002,10 @@ struct SampleShared {
 };
 
 template <bool COUNT_CAND>
-__global__ void __launch_bounds__(STAGE_THREADS, 4) k_sample(PairParams P) {
+#ifndef RCD_SAMPLE_MIN_BLOCKS
+#define RCD_SAMPLE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(STAGE_THREADS, RCD_SAMPLE_MIN_BLOCKS) k_sample(PairParams P) {
     __shared__ SampleShared shared[STAGE_WARPS];
     SampleShared &sh = shared[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31u;
