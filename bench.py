@@ -291,8 +291,7 @@ def run_b200(args):
         eng.set_patterns_device(n, d["pattern"].data_ptr())
         if exch is not None:
             exch.exchange()
-        eng.step(N.MODE_DETECT)
-        eng.step(N.MODE_PREDICT, append=True)
+        eng.step(N.MODE_PREDICT, with_detect=True)  # detect-all + predict-all, one sweep
 
     def frame_e2e(k: int):
         p = pin[k % len(pin)]
@@ -301,8 +300,7 @@ def run_b200(args):
         eng.set_patterns_host_ptr(n, p["pattern"].data_ptr())
         if exch is not None:
             exch.exchange()
-        eng.step(N.MODE_DETECT)
-        eng.step(N.MODE_PREDICT, append=True)
+        eng.step(N.MODE_PREDICT, with_detect=True)  # detect-all + predict-all, one sweep
         return eng.download(sort=False, out=pairs_host)  # delivery only: consumers group on their own
 
     def barrier():
@@ -374,8 +372,7 @@ def run_b200(args):
             n = int(p["px"].shape[0])
             e.upload_host_ptrs(n, [p[f].data_ptr() for f in FRAME_FIELDS], p["type"].data_ptr(), p["id"].data_ptr())
             e.set_patterns_host_ptr(n, p["pattern"].data_ptr())
-            e.step(N.MODE_DETECT)
-            e.step(N.MODE_PREDICT, append=True)
+            e.step(N.MODE_PREDICT, with_detect=True)
             return e.download(sort=False, out=buf)
 
         def lane_worker(which, ks):

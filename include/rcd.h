@@ -58,6 +58,13 @@ enum {
  * one frame (src/test/performance_test.py:794-813); that is rcd_step(DETECT) followed by
  * rcd_step(PREDICT | RCD_STEP_APPEND) on the same index. */
 #define RCD_STEP_APPEND 0x100
+/* OR-ed into RCD_MODE_PREDICT: the predict pass also runs detect_collisions(search_radius, time_window)
+ * for every object, in the same sweep over the neighbourhoods -- the result (pairs, totals) is that of
+ * rcd_step(DETECT, r, t) followed by rcd_step(PREDICT | RCD_STEP_APPEND), i.e. the reference harness's
+ * frame (performance_test.py:794-813), for one pass over the data.  With search_radius = 100 and
+ * time_window = 10 (the reference's defaults) the two are fused in one kernel; other values run the two
+ * passes back to back.  Per-object candidate counts then cover both parts. */
+#define RCD_STEP_WITH_DETECT 0x200
 
 enum { RCD_SRC_HOST = 0, RCD_SRC_DEVICE = 1 };
 

@@ -69,7 +69,7 @@ struct rcd_handle_s {
     QEntry *q2 = nullptr, *q3 = nullptr;
     u32 qcap = 0;
     int stage_blocks = 0;
-    int pair_blocks[4] = {0, 0, 0, 0};  // resident blocks per SM x SMs, per kernel variant
+    int pair_blocks[5] = {0, 0, 0, 0, 0};  // resident blocks per SM x SMs, per kernel variant
     bool frame_done = false;
     int last_mode = -1;
 
@@ -428,8 +428,19 @@ int rcd_set_owned(rcd_handle h, uint64_t n_owned) {
 int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window) {
     if (!h) return RCD_EINVAL;
     const bool append = (mode & RCD_STEP_APPEND) != 0;
-    mode &= ~RCD_STEP_APPEND;
+    const bool with_detect = (mode & RCD_STEP_WITH_DETECT) != 0;
+    mode &= ~(RCD_STEP_APPEND | RCD_STEP_WITH_DETECT);
     if (mode < RCD_MODE_DETECT || mode > RCD_MODE_COMPUTE_NODE) return fail(h, RCD_EINVAL, "rcd_step: unknown mode");
+    if (with_detect && mode != RCD_MODE_PREDICT) return fail(h, RCD_EINVAL, "rcd_step: RCD_STEP_WITH_DETECT goes with RCD_MODE_PREDICT");
+    bool fused = false;
+    if (with_detect) {
+        fused = search_radius == PREDICT_RADIUS && time_window == 10.0f && !(h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES);
+        if (!fused) {  // other parameters: the two passes back to back
+            int rc2 = rcd_step(h, RCD_MODE_DETECT | (append ? RCD_STEP_APPEND : 0), search_radius, time_window);
+            if (rc2) return rc2;
+            return rcd_step(h, RCD_MODE_PREDICT | RCD_STEP_APPEND, search_radius, time_window);
+        }
+    }
     if (append && !h->frame_done) return fail(h, RCD_ESTATE, "rcd_step: RCD_STEP_APPEND needs a previous step of this frame");
     if (!(search_radius > 0.0f) || !std::isfinite(search_radius)) return fail(h, RCD_EINVAL, "rcd_step: search_radius must be positive");
     if (mode == RCD_MODE_DETECT && !(time_window >= 0.0f)) return fail(h, RCD_EINVAL, "rcd_step: time_window must be >= 0");
@@ -471,12 +482,13 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_q2, 0, 2 * sizeof(unsigned long long), h->stream));
         const bool count = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) != 0;
         // persistent launch: as many blocks as can be resident, warps pull tiles from a counter
-        const int variant = mode == RCD_MODE_DETECT ? 0 : (mode == RCD_MODE_COMPUTE_NODE ? 3 : (count ? 2 : 1));
+        const int variant = fused ? 4 : mode == RCD_MODE_DETECT ? 0 : (mode == RCD_MODE_COMPUTE_NODE ? 3 : (count ? 2 : 1));
         if (h->pair_blocks[variant] == 0) {
             int per_sm = 0, sms = 0;
             const void *fn = variant == 0 ? (const void *)k_pairs<RCD_MODE_DETECT, true>
                            : variant == 1 ? (const void *)k_pairs<RCD_MODE_PREDICT, false>
                            : variant == 2 ? (const void *)k_pairs<RCD_MODE_PREDICT, true>
+                           : variant == 4 ? (const void *)k_pairs<MODE_PREDICT_WITH_DETECT, false>
                                           : (const void *)k_pairs<RCD_MODE_COMPUTE_NODE, true>;
             CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PAIR_THREADS, 0));
             CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -490,6 +502,7 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         if (variant == 0) k_pairs<RCD_MODE_DETECT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         else if (variant == 1) k_pairs<RCD_MODE_PREDICT, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         else if (variant == 2) k_pairs<RCD_MODE_PREDICT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+        else if (variant == 4) k_pairs<MODE_PREDICT_WITH_DETECT, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         else k_pairs<RCD_MODE_COMPUTE_NODE, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
         KERNEL_CHECK(h);
         stage_end(h, RCD_STAGE_PAIRS);
@@ -500,10 +513,10 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
             h->stage_blocks = std::max(1, sms) * 8;
         }
         const unsigned sb = (unsigned)std::min<u64>((u64)h->stage_blocks, (h->n + STAGE_THREADS - 1) / STAGE_THREADS + 1);
-        if (variant == 1 || variant == 2) {
+        if (variant == 1 || variant == 2 || variant == 4) {
             stage_begin(h, RCD_STAGE_SAMPLE);
             // k_sample is compiled for 8 resident blocks per SM: the fixed grid is exactly one wave
-            if (variant == 1) k_sample<false><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+            if (variant == 1 || variant == 4) k_sample<false><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
             else k_sample<true><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
             KERNEL_CHECK(h);
             stage_end(h, RCD_STAGE_SAMPLE);
@@ -511,6 +524,7 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         stage_begin(h, RCD_STAGE_EXACT);
         if (variant == 0) k_exact<RCD_MODE_DETECT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         else if (variant == 3) k_exact<RCD_MODE_COMPUTE_NODE><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        else if (variant == 4) k_exact<MODE_PREDICT_WITH_DETECT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         else k_exact<RCD_MODE_PREDICT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         KERNEL_CHECK(h);
         stage_end(h, RCD_STAGE_EXACT);

@@ -139,6 +139,7 @@ struct EmitRec {
     float ttc, dist, rs, risk, cx, cy, cz, tcl, dcl;
     int prio, offset;
     bool hit, predicted, high;  // high: risk > 0.7 decided in fp64 (stats["high_risk_collisions"])
+    bool twice;                 // emit (and count) the record twice (ENTRY_TWICE)
     u32 potential;              // detect: the pair passed stage 2 (stats["potential_collisions"])
 };
 
@@ -152,6 +153,7 @@ __device__ __forceinline__ EmitRec make_rec(u32 si, u32 sj, double ttc, double d
     r.tcl = (float)tcl; r.dcl = (float)dcl;
     r.prio = prio; r.offset = offset;
     r.hit = true; r.predicted = predicted; r.high = risk > 0.7;
+    r.twice = false;
     r.potential = 0;
     return r;
 }
@@ -161,6 +163,7 @@ __device__ __forceinline__ EmitRec no_rec() {
     r.ttc = r.dist = r.rs = r.risk = r.cx = r.cy = r.cz = r.tcl = r.dcl = 0.0f;
     r.prio = -1; r.offset = 255;
     r.hit = false; r.predicted = false; r.high = false;
+    r.twice = false;
     r.potential = 0;
     return r;
 }
@@ -186,10 +189,12 @@ __device__ __forceinline__ void store_pair(const PairParams &P, unsigned long lo
 // per-thread emission (queue-overflow fallbacks only; the exact stage aggregates per warp)
 __device__ __noinline__ void thread_emit(const PairParams &P, const EmitRec &e) {
     if (!e.hit) return;
-    unsigned long long pos = atomicAdd(&P.counters->n_pairs, 1ULL);
-    if (e.high) atomicAdd(&P.counters->n_high_risk, 1ULL);
-    if (e.prio >= 0) atomicAdd(&P.counters->n_alerts[e.prio], 1ULL);
+    const unsigned long long copies = e.twice ? 2ULL : 1ULL;
+    unsigned long long pos = atomicAdd(&P.counters->n_pairs, copies);
+    if (e.high) atomicAdd(&P.counters->n_high_risk, copies);
+    if (e.prio >= 0) atomicAdd(&P.counters->n_alerts[e.prio], copies);
     store_pair(P, pos, e);
+    if (e.twice) store_pair(P, pos + 1, e);
 }
 
 // ---- fp64 decisions (rare) ---------------------------------------------------------------------------
@@ -239,6 +244,14 @@ constexpr u32 RESOLVED = 1u << 31;
 // RADIUS_UNDECIDED: the exact stage takes the radius test (spatial_index.py:268) before anything else
 // and counts the candidate.  k_pairs itself never evaluates fp64.
 constexpr u32 RADIUS_UNDECIDED = 1u << 30;
+// Internal frame mode of rcd_step(RCD_MODE_PREDICT | RCD_STEP_WITH_DETECT): the predict pass also runs
+// detect_collisions(100.0, 10.0) for every object on the pairs it streams anyway (the ball of radius 100
+// about an object lies inside its predict capsule).  Objects without history (pattern 3) then owe the same
+// risk twice -- once as detect_collisions, once as the fall-back of predict_collisions (:590-592) -- which
+// their queue entries carry as ENTRY_TWICE.
+constexpr int MODE_PREDICT_WITH_DETECT = 3;
+constexpr u32 ENTRY_TWICE = 1u << 29;
+__host__ __device__ constexpr bool is_predict(int mode) { return mode == RCD_MODE_PREDICT || mode == MODE_PREDICT_WITH_DETECT; }
 
 // predict, full fallback: every offset, radius test included (collision_detection.py:789-865)
 __device__ __noinline__ EmitRec exact_predict_all(const PairParams &P, u32 si, u32 sj, u32 pattern) {
@@ -280,21 +293,28 @@ __device__ __noinline__ EmitRec exact_compute_node(const PairParams &P, u32 si, 
 // the exact stage for one queue entry
 template <int MODE>
 __device__ __forceinline__ EmitRec exact_entry(const PairParams &P, u32 si, u32 sj, u32 mask) {
+    const bool twice = (mask & ENTRY_TWICE) != 0;
+    mask &= ~ENTRY_TWICE;
     if (mask & RADIUS_UNDECIDED) {
         const float4 a0 = P.P0[si], b0 = P.P0[sj];
-        const float R = (MODE == RCD_MODE_PREDICT) ? PREDICT_RADIUS : P.R;
+        const float R = is_predict(MODE) ? PREDICT_RADIUS : P.R;
         if (!exact_within_radius(a0.x, a0.y, a0.z, b0.x, b0.y, b0.z, R)) return no_rec();
-        atomicAdd(&P.counters->n_candidates, 1ULL);
-        if (P.cand_count) atomicAdd(&P.cand_count[P.sorted_slot[si]], 1u);
+        atomicAdd(&P.counters->n_candidates, twice ? 2ULL : 1ULL);
+        if (P.cand_count) atomicAdd(&P.cand_count[P.sorted_slot[si]], twice ? 2u : 1u);
         if (MODE == RCD_MODE_COMPUTE_NODE && si == sj) return no_rec();  // the index returns self (quirk Q8)
         mask = 0;
     }
-    if (MODE == RCD_MODE_DETECT) return exact_detect(P, si, sj, P.T, P.steps);
-    if (MODE == RCD_MODE_COMPUTE_NODE) return exact_compute_node(P, si, sj);
-    if (mask == 0) return exact_detect(P, si, sj, 10.0f, 100);  // pattern 3: detect defaults (:592)
-    const u32 pattern = meta_pattern(__float_as_uint(P.P2[si].w));
-    if (mask & RESOLVED) return exact_predict_resolved(P, si, sj, pattern, (int)(mask & 31u), (int)((mask >> 8) & 15u));
-    return exact_predict(P, si, sj, pattern, mask);
+    EmitRec e;
+    if (MODE == RCD_MODE_DETECT) e = exact_detect(P, si, sj, P.T, P.steps);
+    else if (MODE == RCD_MODE_COMPUTE_NODE) e = exact_compute_node(P, si, sj);
+    else if (mask == 0) e = exact_detect(P, si, sj, 10.0f, 100);  // pattern 3 / fused detect: the defaults (:592)
+    else {
+        const u32 pattern = meta_pattern(__float_as_uint(P.P2[si].w));
+        e = (mask & RESOLVED) ? exact_predict_resolved(P, si, sj, pattern, (int)(mask & 31u), (int)((mask >> 8) & 15u))
+                              : exact_predict(P, si, sj, pattern, mask);
+    }
+    if (twice) { e.twice = true; e.potential *= 2u; }
+    return e;
 }
 
 // queue-full fallback: decide and emit the pair in place (correct, slower, out of line)
@@ -311,15 +331,16 @@ __device__ __noinline__ u32 finish_entry_inline(const PairParams &P, u32 si, u32
 template <bool COUNT_ALL>
 __device__ __forceinline__ bool narrow_detect(WarpShared &ws, u32 ql, const float4 &a0, const float4 &a1,
                                               const float4 &a2, const float4 &b0, const float4 &b1, const float4 &b2,
-                                              float R, float T, bool &undecided) {
+                                              float R, float T, bool &undecided, u32 count_weight = 1u) {
     const float R2 = R * R;
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;  // rel_position = other - self
     float d2 = dx * dx + dy * dy + dz * dz;
+    if (COUNT_ALL && d2 > R2 * (1.0f + BAND_R2)) return false;  // certainly outside the radius
     // fp32 cannot decide the radius test inside the guard band (spatial_index.py:268): the exact stage does.
     // (detect: the S1 filter made that call when it counted the candidate; predict: made here)
     if (COUNT_ALL) undecided = d2 >= R2 * (1.0f - BAND_R2);
     if (undecided) return true;
-    if (COUNT_ALL) atomicAdd(&ws.cand[ql], 1u);
+    if (COUNT_ALL) atomicAdd(&ws.cand[ql], count_weight);
     float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;  // rel_velocity = self - other
     float rs2 = rvx * rvx + rvy * rvy + rvz * rvz;
     if (rs2 < 0.0099f) return false;  // rel_speed < 0.1 with margin (0.1^2 = 0.01)
@@ -682,8 +703,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
         const bool owned = valid && (meta & META_OWNED);
         const u32 pattern = meta_pattern(meta);
         // queries that take the radius-R test in the filter (detect-like); the others are predict queries
-        const bool radius_query = (MODE != RCD_MODE_PREDICT) || pattern == RCD_PAT_NO_HISTORY;
-        const float Rq = (MODE == RCD_MODE_PREDICT) ? PREDICT_RADIUS : P.R;
+        const bool radius_query = !is_predict(MODE) || pattern == RCD_PAT_NO_HISTORY;
+        const float Rq = is_predict(MODE) ? PREDICT_RADIUS : P.R;
         const float R2_hi = Rq * Rq * (1.0f + BAND_R2), R2_lo = Rq * Rq * (1.0f - BAND_R2);
         // Volume a neighbour must lie in to matter: a ball of radius Rq for radius queries; for predict
         // queries the capsule of radius 100 (+ slack) about the chord of the centre path
@@ -855,9 +876,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
                             // decides; otherwise certainly within it (predict counts its rare radius
                             // queries in S2)
                             const bool certain = d2 < R2_lo;
-                            ws.plist[cnt][lane] = (unsigned char)(j | ((MODE != RCD_MODE_PREDICT && !certain) ? 0x80u : 0u));
+                            ws.plist[cnt][lane] = (unsigned char)(j | ((!is_predict(MODE) && !certain) ? 0x80u : 0u));
                             ++cnt;
-                            if (MODE != RCD_MODE_PREDICT && certain) ++ncand;
+                            if (!is_predict(MODE) && certain) ++ncand;
                         }
                     };
                     for (u32 j0 = 0; j0 < m; j0 += 4) {  // (the last chunk is padded: no bound check per test)
@@ -868,7 +889,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
                             float2 dx = add2(make_float2(xy.x, xy.y), splat2(-p0.x));
                             float2 dy = add2(make_float2(xy.z, xy.w), splat2(-p0.y));
                             float2 dz = add2(zz, splat2(-p0.z));
-                            if (MODE == RCD_MODE_PREDICT) {  // distance to the chord (w = 0 for radius queries)
+                            if (is_predict(MODE)) {  // distance to the chord (w = 0 for radius queries)
                                 const float2 dot = fma2(dz, splat2(wz), fma2(dy, splat2(wy), mul2(dx, splat2(wx))));
                                 const float2 sc = make_float2(__saturatef(dot.x * inv_w2), __saturatef(dot.y * inv_w2));
                                 dx = fma2(sc, splat2(-wx), dx);
@@ -909,6 +930,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
                         bool keep = false;     // -> global Q3 (exact stage)
                         bool undecided = (entry & 0x80u) != 0;  // ... which has to take the radius test first
                         bool to_scan = false;  // -> Q1b (predict window scan)
+                        bool twice = false;    // fused mode, object without history: the risk is owed twice
                         u32 sj = 0;
                         if (lane < take) {
                             const float4 a0 = ws.q0[ql], a1 = ws.q1[ql], a2 = ws.q2[ql];
@@ -920,16 +942,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
                                 const u32 pat = meta_pattern(__float_as_uint(a2.w));
                                 if (MODE == RCD_MODE_DETECT) {
                                     keep = narrow_detect<false>(ws, ql, a0, a1, a2, b0, b1, b2, P.R, P.T, undecided);
-                                } else if (pat == RCD_PAT_NO_HISTORY) {
-                                    keep = narrow_detect<true>(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, undecided);
-                                } else if (COUNT_CAND) {
-                                    to_scan = true;
                                 } else {
-                                    to_scan = window_reject_linear(window_coef(a0, a1, a2, b0, b1, b2, pat));
+                                    const bool nohist = pat == RCD_PAT_NO_HISTORY;
+                                    if (nohist || MODE == MODE_PREDICT_WITH_DETECT) {
+                                        twice = nohist && MODE == MODE_PREDICT_WITH_DETECT;
+                                        keep = narrow_detect<true>(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, undecided,
+                                                                   twice ? 2u : 1u);
+                                    }
+                                    if (!nohist) to_scan = COUNT_CAND ? true : window_reject_linear(window_coef(a0, a1, a2, b0, b1, b2, pat));
                                 }
                             }
                         }
-                        if (MODE == RCD_MODE_PREDICT) {
+                        if (is_predict(MODE)) {
                             const u32 bal = __ballot_sync(FULL_MASK, to_scan);
                             if (bal) {
                                 if (to_scan) {
@@ -942,7 +966,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
                                 if (n1b >= 32) run_scan(32);
                             }
                         }
-                        const u32 word = undecided ? RADIUS_UNDECIDED : 0u;
+                        const u32 word = (undecided ? RADIUS_UNDECIDED : 0u) | (twice ? ENTRY_TWICE : 0u);
                         const bool pushed = global_push(P.q3, P.qcap, &P.counters->n_q3, keep, si, sj, word);
                         if (!pushed) n_pot += finish_entry_inline<MODE>(P, si, sj, word);  // queue full: decide here
                     }
@@ -951,7 +975,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
             }
         }
         // ---- end of tile ------------------------------------------------------------------------------
-        if (MODE == RCD_MODE_PREDICT) {
+        if (is_predict(MODE)) {
             if (n1b) run_scan(n1b);  // Q1b refers to this tile's queries
         }
         __syncwarp();
@@ -1192,7 +1216,7 @@ __global__ void __launch_bounds__(STAGE_THREADS) k_exact(PairParams P) {
             const QEntry q = P.q3[k];
             e = exact_entry<MODE>(P, q.si, q.sj, q.mask);
             n_pot += e.potential;
-            n_exact += (MODE == RCD_MODE_PREDICT && q.mask && !(q.mask & RESOLVED)) ? (u32)__popc(q.mask) : 1u;
+            n_exact += (is_predict(MODE) && (q.mask & 0xfffffu) && !(q.mask & RESOLVED)) ? (u32)__popc(q.mask & 0xfffffu) : 1u;
         }
         const u32 ballot = __ballot_sync(FULL_MASK, e.hit);
         if (ballot) {
@@ -1204,6 +1228,21 @@ __global__ void __launch_bounds__(STAGE_THREADS) k_exact(PairParams P) {
                 store_pair(P, base + __popc(ballot & lanemask_lt()), e);
                 n_high += e.high ? 1u : 0u;
                 if (e.prio >= 0) n_prio[e.prio] += 1u;
+            }
+        }
+        if (MODE == MODE_PREDICT_WITH_DETECT) {  // second copy of the records that are owed twice
+            const bool again = e.hit && e.twice;
+            const u32 b2 = __ballot_sync(FULL_MASK, again);
+            if (b2) {
+                unsigned long long base = 0;
+                const u32 leader = __ffs(b2) - 1;
+                if (lane == leader) base = atomicAdd(&P.counters->n_pairs, (unsigned long long)__popc(b2));
+                base = __shfl_sync(FULL_MASK, base, leader);
+                if (again) {
+                    store_pair(P, base + __popc(b2 & lanemask_lt()), e);
+                    n_high += e.high ? 1u : 0u;
+                    if (e.prio >= 0) n_prio[e.prio] += 1u;
+                }
             }
         }
     }

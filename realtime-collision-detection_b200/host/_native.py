@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("RCD_B200_LIB") or os.path.join(_PKG, "librcd_b200.so"
 RCD_OK, RCD_EINVAL, RCD_ENODEVICE, RCD_ENOMEM, RCD_ECUDA, RCD_ECAPACITY, RCD_ESTATE = 0, -1, -2, -3, -4, -5, -6
 MODE_DETECT, MODE_PREDICT, MODE_COMPUTE_NODE = 0, 1, 2
 STEP_APPEND = 0x100
+STEP_WITH_DETECT = 0x200
 SRC_HOST, SRC_DEVICE = 0, 1
 PAT_STATIONARY, PAT_CONSTANT_VELOCITY, PAT_ACCELERATING, PAT_NO_HISTORY = 0, 1, 2, 3
 FLAG_PROFILE = 1

@@ -139,8 +139,12 @@ class FrameEngine:
         N.check(self._lib.rcd_invalidate(self._h), self._h)
 
     # -- frames -----------------------------------------------------------------------------
-    def step(self, mode: int, search_radius: float = 100.0, time_window: float = 10.0, append: bool = False) -> None:
-        m = int(mode) | (N.STEP_APPEND if append else 0)
+    def step(self, mode: int, search_radius: float = 100.0, time_window: float = 10.0, append: bool = False,
+             with_detect: bool = False) -> None:
+        """One frame for every owned object.  ``append``: keep the pairs / totals of the previous step of this
+        frame.  ``with_detect`` (predict mode): also run detect_collisions(search_radius, time_window) in the
+        same pass -- the result of step(DETECT) + step(PREDICT, append=True) for one sweep over the data."""
+        m = int(mode) | (N.STEP_APPEND if append else 0) | (N.STEP_WITH_DETECT if with_detect else 0)
         N.check(self._lib.rcd_step(self._h, m, float(search_radius), float(time_window)), self._h)
 
     def build_index(self, cell_radius: float = 100.0) -> None:

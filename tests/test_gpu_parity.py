@@ -361,3 +361,34 @@ def test_permutation_invariance_and_idempotence():
         e.upload(frame, ids=ids)
         d2 = e.detect()
         assert np.array_equal(d1, d2) and len(d1) > 100
+
+
+@pytest.mark.parametrize("case", ["mixed_patterns", "all_accelerating", "other_radius"])
+def test_fused_detect_predict_equals_the_two_passes(case):
+    """rcd_step(PREDICT | WITH_DETECT) must return exactly what step(DETECT) + step(PREDICT | APPEND) returns:
+    same records (byte for byte after the sorted download), same totals."""
+    from rcd_b200.host import _native as N, workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 6000
+    frame = W.uniform_frame(n, 61, map_size=1100.0, drone_fraction=0.3)
+    pat = W.random_patterns(n, 9, p=(0.1, 0.3, 0.4, 0.2)) if case != "all_accelerating" else np.full(n, 2, np.uint8)
+    R, T = (100.0, 10.0) if case != "other_radius" else (60.0, 4.0)
+    with FrameEngine(n, 1 << 21) as a, FrameEngine(n, 1 << 21) as b:
+        for e in (a, b):
+            e.upload(frame)
+            e.set_patterns(pat)
+        a.step(N.MODE_DETECT, R, T)
+        a.step(N.MODE_PREDICT, R, T, append=True)
+        b.step(N.MODE_PREDICT, R, T, with_detect=True)
+        pa, pb = a.download(), b.download()
+        ca, cb = a.counts(), b.counts()
+        assert len(pa) > 2000 and (pa["predicted"] == 0).sum() > 200 and (pa["predicted"] == 1).sum() > 200
+        assert pa.tobytes() == pb.tobytes()
+        for k in ("n_pairs", "n_candidates", "n_potential", "n_high_risk", "n_alerts", "n_objects", "n_owned"):
+            assert ca[k] == cb[k], k
+        assert cb["n_fallback"] == 0
+        if case == "mixed_patterns":  # objects without history owe every risk twice (detect + predict fall-back)
+            nohist = np.flatnonzero(pat == 3)
+            twice = pb[np.isin(pb["i"], nohist)]
+            assert len(twice) > 0 and len(twice) % 2 == 0
+            assert twice[0::2].tobytes() == twice[1::2].tobytes()
