@@ -131,6 +131,9 @@ def load() -> ctypes.CDLL:
     L.rcd_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
     L.rcd_launch_count.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_sync.argtypes = [vp]
+    if not hasattr(L, "rcd_ingest_create") and os.environ.get("RCD_B200_LIB"):
+        _lib = L
+        return L
     L.rcd_ingest_create.argtypes = [ctypes.POINTER(vp)]
     L.rcd_ingest_destroy.argtypes = [vp]
     L.rcd_ingest_last_error.restype = ctypes.c_char_p
@@ -150,6 +153,8 @@ def load() -> ctypes.CDLL:
     L.rcd_alerts_acknowledge.argtypes = [vp, u64, vp, vp, ctypes.POINTER(u64)]
     L.rcd_alerts_download.argtypes = [vp, vp, u64, ctypes.POINTER(u64)]
     for name in SYMBOLS:
+        if not hasattr(L, name) and os.environ.get("RCD_B200_LIB"):
+            continue  # an older build loaded for an A/B kernel experiment
         fn = getattr(L, name)
         if name not in ("rcd_last_error", "rcd_version", "rcd_ingest_last_error"):
             fn.restype = ctypes.c_int

@@ -37,6 +37,27 @@ for mode in ("detect", "predict"):
         ora = O.frame_A(W.frame_to_f64(frame), mode, pattern_codes=pat if mode == "predict" else None, threads=8)["risks"]
         compare_pairs(both, ora, mode)
         print(f"{mode}: {len(both)} pairs over {world} slabs == oracle; halo on rank 0: {nh}", flush=True)
+# fused frame (detect + predict in one sweep): the union over the owners equals the two oracle results together
+eng.upload(W.take(frame, mine), ids=ids[mine])
+eng.set_patterns(pat[mine])
+ex.exchange()
+eng.step(N.MODE_PREDICT, with_detect=True)
+got = eng.download()
+gathered = [None] * world
+dist.all_gather_object(gathered, got)
+if rank == 0:
+    both = np.concatenate(gathered)
+    for mode, flag in (("detect", 0), ("predict", 1)):
+        part = np.sort(both[both["predicted"] == flag], order=["i", "j"])
+        f64 = W.frame_to_f64(frame)
+        ora = O.frame_A(f64, mode, pattern_codes=pat if mode == "predict" else None, threads=8)["risks"]
+        if mode == "predict":  # objects without history fall back to detect: those risks are not `predicted`
+            ora = ora[ora["offset"] >= 0]
+        else:
+            nohist = O.frame_A(f64, "predict", pattern_codes=pat, threads=8)["risks"]
+            ora = np.sort(np.concatenate([ora, nohist[nohist["offset"] < 0]]), order=["i", "j"])
+        compare_pairs(part, ora, mode)
+    print(f"fused: {len(both)} pairs over {world} slabs == detect oracle + predict oracle", flush=True)
 dist.barrier()
 eng.close()
 dist.destroy_process_group()

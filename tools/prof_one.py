@@ -17,6 +17,9 @@ with FrameEngine(n, 40_000_000, world_bounds=bounds) as e:
     e.set_patterns(np.full(n, 2, np.uint8))
     for r in range(reps):
         e.invalidate()
-        e.step(N.MODE_DETECT if mode == "detect" else N.MODE_PREDICT)
+        if mode == "fused":
+            e.step(N.MODE_PREDICT, with_detect=True)
+        else:
+            e.step(N.MODE_DETECT if mode == "detect" else N.MODE_PREDICT)
         e.sync()
     print(e.counts())
