@@ -392,3 +392,121 @@ def test_fused_detect_predict_equals_the_two_passes(case):
             twice = pb[np.isin(pb["i"], nohist)]
             assert len(twice) > 0 and len(twice) % 2 == 0
             assert twice[0::2].tobytes() == twice[1::2].tobytes()
+
+
+def _fused_oracle(frame, pat):
+    """What the fused frame must emit: detect for everyone + predict for everyone (objects without
+    history fall back to detect there too: those risks are not `predicted`)."""
+    O = _oracle()
+    f64 = f64_frame(frame)
+    d = O.frame_A(f64, "detect")["risks"]
+    p = O.frame_A(f64, "predict", pattern_codes=pat)["risks"]
+    det = np.sort(np.concatenate([d, p[p["offset"] < 0]]), order=["i", "j"])
+    return det, p[p["offset"] >= 0]
+
+
+def _check_fused(e, frame, pat):
+    from rcd_b200.host import _native as N
+    e.upload(frame)
+    e.set_patterns(pat)
+    e.step(N.MODE_PREDICT, with_detect=True)
+    got = e.download()
+    det, pred = _fused_oracle(frame, pat)
+    compare_pairs(got[got["predicted"] == 0], det, "detect")
+    compare_pairs(got[got["predicted"] == 1], pred, "predict")
+    c = e.counts()
+    assert c["n_pairs"] == len(det) + len(pred) and c["n_fallback"] == 0
+    return got
+
+
+def test_predict_far_from_the_origin_and_outside_static_bounds():
+    """fp32 slack of the capsule / window tests at 90 km coordinates (ulp = 8 mm), and predict queries whose
+    capsules reach beyond the configured grid (clamped border cells)."""
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 6000
+    frame = W.uniform_frame(n, 81, map_size=1400.0, drone_fraction=0.3)
+    for k in ("px", "py"):
+        frame[k] = (frame[k] + np.float32(90000.0)).astype(np.float32)
+    pat = W.random_patterns(n, 82, p=(0.1, 0.3, 0.5, 0.1))
+    for bounds in (None, ((90400.0, 90400.0, 20.0), (91000.0, 91000.0, 60.0))):
+        with FrameEngine(n, 1 << 21, world_bounds=bounds) as e:
+            got = _check_fused(e, frame, pat)
+            assert (got["predicted"] == 1).sum() > 300
+
+
+def test_fast_and_hard_accelerating_objects():
+    """Capsules several hundred metres long, chord slack of tens of metres, windows bent by 3 m/s^2."""
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 5000
+    frame = W.uniform_frame(n, 83, map_size=2500.0, drone_fraction=0.3)
+    rng = np.random.default_rng(84)
+    for k in ("vx", "vy"):
+        frame[k] = (frame[k] * rng.uniform(0.0, 4.0, n)).astype(np.float32)  # up to ~80 m/s
+    for k in ("ax", "ay", "az"):
+        frame[k] = rng.uniform(-3.0, 3.0, n).astype(np.float32)
+    pat = W.random_patterns(n, 85, p=(0.05, 0.25, 0.65, 0.05))
+    with FrameEngine(n, 1 << 21) as e:
+        got = _check_fused(e, frame, pat)
+        assert (got["predicted"] == 1).sum() > 100
+
+
+def test_queue_overflow_is_finished_in_place():
+    """Inter-kernel queues hold 2 * max_pairs + 64 Ki entries; beyond that every stage finishes its pairs
+    in place.  Totals stay exact, the first max_pairs records are real records."""
+    from rcd_b200.host import _native as N, workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 12000
+    frame = W.uniform_frame(n, 86, map_size=520.0, drone_fraction=0.3)  # ~1400 neighbours within 100 m each
+    pat = W.random_patterns(n, 87, p=(0.1, 0.3, 0.5, 0.1))
+    det, pred = _fused_oracle(frame, pat)
+    assert len(pred) > 200_000  # far more queue entries than the 65 k + 128 the tiny buffers give
+    with FrameEngine(n, 64) as small, FrameEngine(n, 1 << 22) as big:
+        for e in (small, big):
+            e.upload(frame)
+            e.set_patterns(pat)
+        big.step(N.MODE_PREDICT, with_detect=True)
+        everything = big.download()
+        for fused in (True, False):
+            if fused:
+                small.step(N.MODE_PREDICT, with_detect=True)
+            else:
+                small.step(N.MODE_DETECT)
+                small.step(N.MODE_PREDICT, append=True)
+            c = small.counts()
+            assert c["n_pairs"] == len(det) + len(pred) == len(everything) and c["n_written"] == 64
+            assert c["n_high_risk"] == big.counts()["n_high_risk"] and c["n_alerts"] == big.counts()["n_alerts"]
+            got = small.download(sort=False)
+            keys = set(zip(everything["i"].tolist(), everything["j"].tolist(), everything["predicted"].tolist()))
+            assert len(got) == 64 and all((int(r["i"]), int(r["j"]), int(r["predicted"])) in keys for r in got)
+
+
+def test_non_finite_state_does_not_disturb_the_rest():
+    """The reference raises inside get_grid_id for NaN / inf coordinates (int(nan)) and its caller drops the update;
+    here such objects simply never pair with anything, and every other object's result is untouched."""
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 3000
+    frame = W.uniform_frame(n, 88, map_size=700.0, drone_fraction=0.3)
+    pat = W.random_patterns(n, 89)
+    bad = np.arange(0, n, 97)
+    clean = np.setdiff1d(np.arange(n), bad)
+    dirty = {k: v.copy() for k, v in frame.items()}
+    dirty["px"][bad[0::3]] = np.nan
+    dirty["vx"][bad[1::3]] = np.inf
+    dirty["ay"][bad[2::3]] = np.nan
+    with FrameEngine(n, 1 << 21) as e:
+        sub = W.take(frame, clean)
+        want = _check_fused(e, sub, pat[clean])
+        from rcd_b200.host import _native as N
+        e.upload(dirty)
+        e.set_patterns(pat)
+        e.step(N.MODE_PREDICT, with_detect=True)
+        got = e.download()
+        got = got[~np.isin(got["i"], bad) & ~np.isin(got["j"], bad)]
+        remap = np.full(n, -1, np.int64)
+        remap[clean] = np.arange(len(clean))
+        g = got.copy()
+        g["i"], g["j"] = remap[got["i"]], remap[got["j"]]
+        assert g.tobytes() == want.tobytes()
