@@ -1202,8 +1202,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_SAMPLE_MIN_BLOCKS) k_sample
 }
 
 // k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp
+#ifndef RCD_EXACT_MIN_BLOCKS
+#define RCD_EXACT_MIN_BLOCKS 4
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(STAGE_THREADS) k_exact(PairParams P) {
+__global__ void __launch_bounds__(STAGE_THREADS, RCD_EXACT_MIN_BLOCKS) k_exact(PairParams P) {
     const unsigned long long n = min(P.counters->n_q3, (unsigned long long)P.qcap);
     const unsigned long long stride = (unsigned long long)gridDim.x * STAGE_THREADS;
     const unsigned long long rounds = (n + stride - 1) / stride;
