@@ -200,6 +200,17 @@ int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out);
  * sort on their own, or only stream the pairs onwards. */
 int rcd_download_unsorted(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out);
 
+/* Pipelined delivery: start handing the frame just stepped over to the host and return at once.  The
+ * handle keeps two pair buffers and two sets of totals; the next rcd_upload / rcd_step may be issued
+ * immediately and writes into the other set, so the device->host copy of frame k (on the handle's copy
+ * stream) overlaps the kernels of frame k + 1.  rcd_download_finish waits for frame k, copies
+ * min(n_written, cap) pairs (emission order, like rcd_download_unsorted) to `out` -- pinned host memory
+ * for a copy that really overlaps -- and returns that frame's totals.  One download in flight at a time.
+ * Between begin and finish the totals / pairs of frame k stay readable through rcd_counts,
+ * rcd_download*, rcd_alerts_update until the next rcd_step. */
+int rcd_download_begin(rcd_handle h, rcd_pair *out, uint64_t cap);
+int rcd_download_finish(rcd_handle h, rcd_counts_t *counts, uint64_t *n_out);
+
 /* Per-object broad-phase candidate counts of the last frame, in upload order (n entries). */
 int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n);
 

@@ -80,6 +80,15 @@ struct rcd_handle_s {
     u32 *traj_count = nullptr;
     u32 traj_len = 0;
     u64 launches = 0;
+    // pipelined delivery (rcd_download_begin / _finish): twin pair buffer + totals, copy stream
+    rcd_pair *out_alt = nullptr;
+    Counters *counters_alt = nullptr;
+    Counters *pend_counters_host = nullptr;  // pinned snapshot of the pending frame's totals
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t pend_event = nullptr;
+    bool flip_pending = false, download_pending = false;
+    rcd_pair *pend_dev = nullptr, *pend_out = nullptr;
+    u64 pend_cap = 0, pend_n = 0, pend_n_owned = 0;
     // alert table (rcd_alerts.cuh)
     AlertEntry *alert_tab[2] = {nullptr, nullptr};
     int alert_cur = 0;
@@ -350,6 +359,10 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
     cudaFree(h->q2); cudaFree(h->q3);
     cudaFree(h->traj); cudaFree(h->traj_count);
+    cudaFree(h->out_alt); cudaFree(h->counters_alt);
+    if (h->pend_counters_host) cudaFreeHost(h->pend_counters_host);
+    if (h->pend_event) cudaEventDestroy(h->pend_event);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     cudaFree(h->alert_tab[0]); cudaFree(h->alert_tab[1]); cudaFree(h->alert_ev); cudaFree(h->alert_counters);
     if (h->alert_counters_host) cudaFreeHost(h->alert_counters_host);
     if (h->counters_host) cudaFreeHost(h->counters_host);
@@ -446,6 +459,11 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     if (mode == RCD_MODE_DETECT && !(time_window >= 0.0f)) return fail(h, RCD_EINVAL, "rcd_step: time_window must be >= 0");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (!append) h->launches = 0;
+    if (!append && h->flip_pending) {  // the previous frame is being delivered: write into the twin buffers
+        std::swap(h->out, h->out_alt);
+        std::swap(h->counters, h->counters_alt);
+        h->flip_pending = false;
+    }
     h->frame_done = false;
     h->stage_mode = mode;
     for (int s = RCD_STAGE_KEYS; s <= RCD_STAGE_EXACT; ++s) h->stages[mode][s].used = false;
@@ -631,6 +649,58 @@ int rcd_download(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
 
 int rcd_download_unsorted(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n_out) {
     return download_impl(h, out, cap, n_out, false);
+}
+
+int rcd_download_begin(rcd_handle h, rcd_pair *out, uint64_t cap) {
+    if (!h || (cap && !out)) return RCD_EINVAL;
+    if (!h->frame_done) return fail(h, RCD_ESTATE, "rcd_download_begin: no frame has been stepped");
+    if (h->download_pending) return fail(h, RCD_ESTATE, "rcd_download_begin: a download is already in flight");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->out_alt) {
+        CUDA_TRY(h, dev_alloc(&h->out_alt, (size_t)h->max_pairs));
+        CUDA_TRY(h, dev_alloc(&h->counters_alt, 1));
+        CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void **>(&h->pend_counters_host), sizeof(Counters)));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->pend_event, cudaEventDisableTiming));
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->pend_counters_host, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->pend_event, h->stream));
+    h->pend_dev = h->out;
+    h->pend_out = out;
+    h->pend_cap = cap;
+    h->pend_n = h->n;
+    h->pend_n_owned = h->n_owned;
+    h->download_pending = true;
+    h->flip_pending = true;
+    return RCD_OK;
+}
+
+int rcd_download_finish(rcd_handle h, rcd_counts_t *counts, uint64_t *n_out) {
+    if (!h || !n_out) return RCD_EINVAL;
+    if (!h->download_pending) return fail(h, RCD_ESTATE, "rcd_download_finish: no download in flight");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventSynchronize(h->pend_event));  // the frame is complete; later work keeps running
+    const Counters &c = *h->pend_counters_host;
+    const u64 m = std::min<u64>(std::min<u64>(c.n_pairs, h->max_pairs), h->pend_cap);
+    if (m) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->pend_out, h->pend_dev, (size_t)m * sizeof(rcd_pair), cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    }
+    if (counts) {
+        counts->n_objects = h->pend_n;
+        counts->n_owned = h->pend_n_owned;
+        counts->n_candidates = c.n_candidates;
+        counts->n_potential = c.n_potential;
+        counts->n_pairs = c.n_pairs;
+        counts->n_high_risk = c.n_high_risk;
+        counts->n_written = std::min<u64>(c.n_pairs, h->max_pairs);
+        for (int k = 0; k < 4; ++k) counts->n_alerts[k] = c.n_alerts[k];
+        counts->n_exact = c.n_exact;
+        counts->n_fallback = c.n_fallback;
+    }
+    *n_out = m;
+    h->download_pending = false;
+    return RCD_OK;
 }
 
 int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n) {

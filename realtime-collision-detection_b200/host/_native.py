@@ -36,7 +36,7 @@ SYMBOLS = (
     "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
     "rcd_ingest_counts", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
     "rcd_alerts_configure", "rcd_alerts_update", "rcd_alerts_update_pairs", "rcd_alerts_expire",
-    "rcd_alerts_acknowledge", "rcd_alerts_download",
+    "rcd_alerts_acknowledge", "rcd_alerts_download", "rcd_download_begin", "rcd_download_finish",
 )
 
 
@@ -118,6 +118,9 @@ def load() -> ctypes.CDLL:
     L.rcd_download.argtypes = [vp, vp, u64, ctypes.POINTER(u64)]
     L.rcd_download_unsorted.argtypes = [vp, vp, u64, ctypes.POINTER(u64)]
     L.rcd_download_candidate_counts.argtypes = [vp, vp, u64]
+    if hasattr(L, "rcd_download_begin"):
+        L.rcd_download_begin.argtypes = [vp, vp, u64]
+        L.rcd_download_finish.argtypes = [vp, ctypes.POINTER(RcdCounts), ctypes.POINTER(u64)]
     L.rcd_query_radius.argtypes = [vp, u64, vp, vp, vp, f32, vp, vp, u64]
     L.rcd_classify_patterns.argtypes = [vp, u64, u32, vp, vp, vp]
     L.rcd_halo_pack.argtypes = [vp, i32, i32, vp, vp, f32, vp, u64, vp]

@@ -172,6 +172,21 @@ class FrameEngine:
         N.check(fn(self._h, _vp(out), m, ctypes.byref(got)), self._h)
         return out[: got.value]
 
+    def download_begin(self, out: np.ndarray) -> None:
+        """Start delivering the frame just stepped into ``out`` (PAIR_DTYPE, ideally pinned) and return at
+        once: the next upload / step can be issued while the copy runs (the handle has twin pair buffers)."""
+        self._pending_out = out
+        N.check(self._lib.rcd_download_begin(self._h, _vp(out), int(out.shape[0])), self._h)
+
+    def download_finish(self) -> Tuple[np.ndarray, Dict[str, int]]:
+        """Wait for the pending delivery; returns (pairs in emission order, totals of that frame)."""
+        c, n = N.RcdCounts(), ctypes.c_uint64()
+        N.check(self._lib.rcd_download_finish(self._h, ctypes.byref(c), ctypes.byref(n)), self._h)
+        out, self._pending_out = self._pending_out, None
+        d = {k: int(getattr(c, k)) for k, _ in N.RcdCounts._fields_ if k != "n_alerts"}
+        d["n_alerts"] = [int(v) for v in c.n_alerts]
+        return out[: int(n.value)], d
+
     def candidate_counts(self) -> np.ndarray:
         out = np.zeros(int(self.counts()["n_objects"]), np.uint32)
         N.check(self._lib.rcd_download_candidate_counts(self._h, _vp(out), out.shape[0]), self._h)

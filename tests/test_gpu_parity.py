@@ -510,3 +510,37 @@ def test_non_finite_state_does_not_disturb_the_rest():
         g = got.copy()
         g["i"], g["j"] = remap[got["i"]], remap[got["j"]]
         assert g.tobytes() == want.tobytes()
+
+
+def test_pipelined_download_delivers_each_frame_while_the_next_one_runs():
+    """rcd_download_begin / _finish: frame k arrives complete although frame k + 1 was uploaded and stepped
+    in between (twin pair buffers and totals); the synchronous calls keep seeing the newest frame."""
+    from rcd_b200.host import _native as N, workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 5000
+    frames = [W.uniform_frame(n, 91 + k, map_size=900.0, drone_fraction=0.3) for k in range(4)]
+    pat = W.random_patterns(n, 95)
+    with FrameEngine(n, 1 << 20) as ref, FrameEngine(n, 1 << 20) as e:
+        want = []
+        for f in frames:
+            ref.upload(f); ref.set_patterns(pat); ref.step(N.MODE_PREDICT, with_detect=True)
+            want.append((ref.download(), ref.counts()))
+        bufs = [np.zeros(1 << 20, dtype=N.PAIR_DTYPE) for _ in range(2)]
+        got = []
+        for k, f in enumerate(frames):
+            e.upload(f); e.set_patterns(pat); e.step(N.MODE_PREDICT, with_detect=True)
+            if k:
+                pairs, counts = e.download_finish()  # frame k - 1, after frame k was already enqueued
+                got.append((pairs.copy(), counts))   # (the host buffer is reused two frames later)
+            e.download_begin(bufs[k % 2])
+            with pytest.raises(N.NativeError):
+                e.download_begin(bufs[k % 2])        # one delivery at a time
+            assert e.counts()["n_pairs"] == want[k][1]["n_pairs"]  # newest frame through the synchronous calls
+        got.append(e.download_finish())
+        for (pairs, counts), (w_pairs, w_counts) in zip(got, want):
+            p = np.sort(pairs, order=["i", "j", "predicted"], kind="stable")
+            assert p.tobytes() == w_pairs.tobytes()
+            for key in ("n_pairs", "n_candidates", "n_potential", "n_high_risk", "n_alerts", "n_objects"):
+                assert counts[key] == w_counts[key], key
+        with pytest.raises(N.NativeError):
+            e.download_finish()
