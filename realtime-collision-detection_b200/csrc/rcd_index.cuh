@@ -111,65 +111,57 @@ __device__ __forceinline__ void st_status(u32 *p, u32 v) {
 }
 
 // lanes of the warp holding the same 8-bit digit: eight independent ballots pipeline far better
-// than one MATCH.ANY (whose latency the ranking chain would pay once per item)
-__device__ __forceinline__ u32 match_digit(u32 digit, bool valid) {
-    u32 peers = __ballot_sync(FULL_MASK, valid);
+// than one MATCH.ANY (whose latency the ranking chain would pay once per item).  Written in PTX so that
+// every bit costs four instructions (test, vote, select, and-xor) instead of the seven nvcc makes of the
+// C++ form: peers &= vote ^ (bit ? 0 : ~0).
+__device__ __forceinline__ u32 match_digit(u32 digit, u32 peers /* lanes that take part */) {
 #pragma unroll
     for (int b = 0; b < RADIX_BITS; ++b) {
-        const bool bit = (digit >> b) & 1u;
-        const u32 vote = __ballot_sync(FULL_MASK, bit);
-        peers &= bit ? vote : ~vote;
+        u32 t;
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 v, m, a;\n\t"
+            "and.b32 a, %1, %2;\n\t"
+            "setp.ne.u32 p, a, 0;\n\t"
+            "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"
+            "selp.b32 m, 0, 0xffffffff, p;\n\t"
+            "xor.b32 %0, v, m;\n\t}"
+            : "=r"(t) : "r"(digit), "r"(1u << b));
+        peers &= t;
     }
     return peers;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
-k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
-                u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 n, int shift,
-                const u32 *__restrict__ digit_base /* [RADIX] exclusive, this pass */,
-                u32 *tile_status /* [tiles][RADIX], zeroed */, u32 *tile_counter) {
-    __shared__ u32 s_warp_hist[SORT_WARPS][RADIX];
-    __shared__ u32 s_digit_excl[RADIX];
-    __shared__ u32 s_global_base[RADIX];
-    __shared__ u32 s_scan[SORT_WARPS];
-    __shared__ u32 s_keys[SORT_TILE];
-    __shared__ u32 s_vals[SORT_TILE];
-    __shared__ u32 s_tile;
-
+// One tile of one pass.  FULL: the tile holds SORT_TILE keys (every tile but the last): no bound checks.
+template <bool FULL>
+__device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
+                                              u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 tile,
+                                              u32 tile_count, int shift, const u32 *__restrict__ digit_base,
+                                              u32 *tile_status, u32 (*s_warp_hist)[RADIX], u32 *s_digit_excl,
+                                              u32 *s_global_base, u32 *s_scan, uint2 *s_kv) {
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (int k = tid; k < SORT_WARPS * RADIX; k += SORT_THREADS) (&s_warp_hist[0][0])[k] = 0;
-    __syncthreads();
-    const u32 tile = s_tile;
     const u32 tile_base = tile * SORT_TILE;
-    const u32 tile_count = min((u32)SORT_TILE, n - tile_base);
-
     // ---- load (warp-striped: item k of lane l is element warp*ITEMS*32 + k*32 + l) and rank ----
     u32 key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
     const u32 warp_base = warp * (SORT_ITEMS * 32);
+    const u32 *kin = keys_in + tile_base + warp_base + lane;
+    const u32 *vin = vals_in + tile_base + warp_base + lane;
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
-        u32 local = warp_base + k * 32 + lane;
-        bool valid = local < tile_count;
-        key[k] = valid ? __ldcs(keys_in + tile_base + local) : 0xffffffffu;
-        val[k] = valid ? __ldcs(vals_in + tile_base + local) : 0u;
+        const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
+        key[k] = valid ? __ldcs(kin + k * 32) : 0xffffffffu;
+        val[k] = valid ? __ldcs(vin + k * 32) : 0u;
     }
     const u32 lt = lanemask_lt();
+    u32 *my_hist = s_warp_hist[warp];
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
-        u32 local = warp_base + k * 32 + lane;
-        bool valid = local < tile_count;
-        u32 digit = (key[k] >> shift) & (RADIX - 1);
+        const u32 digit = (key[k] >> shift) & (RADIX - 1);
         // invalid lanes are in nobody's group and do not touch the counters
-        u32 group = match_digit(digit, valid);
-        if (!valid) group = 1u << lane;
-        u32 leader = __ffs(group) - 1;
-        u32 before = 0;
-        if (valid && lane == leader) {
-            before = s_warp_hist[warp][digit];
-            s_warp_hist[warp][digit] = before + __popc(group);
-        }
-        before = __shfl_sync(FULL_MASK, before, leader);
+        const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
+        const u32 group = match_digit(digit, FULL ? FULL_MASK : __ballot_sync(FULL_MASK, valid));
+        // every lane of a group reads the counter (one broadcast per digit), the lowest lane advances it
+        const u32 before = my_hist[digit];
+        __syncwarp();
+        if ((group & lt) == 0 && valid) my_hist[digit] = before + __popc(group);
         rank[k] = before + __popc(group & lt);
         __syncwarp();
     }
@@ -231,29 +223,52 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
     s_global_base[tid] = digit_base[tid] + excl - s_digit_excl[tid];
     __syncthreads();
 
-    // ---- scatter into shared memory in sorted order, then write runs to global ----------------
+    // ---- scatter (key, value) into shared memory in sorted order, then write runs to global ------
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
-        u32 local = warp_base + k * 32 + lane;
-        if (local < tile_count) {
-            u32 digit = (key[k] >> shift) & (RADIX - 1);
-            u32 pos = s_digit_excl[digit] + s_warp_hist[warp][digit] + rank[k];
-            s_keys[pos] = key[k];
-            s_vals[pos] = val[k];
+        if (FULL || warp_base + k * 32 + lane < tile_count) {
+            const u32 digit = (key[k] >> shift) & (RADIX - 1);
+            const u32 pos = s_digit_excl[digit] + my_hist[digit] + rank[k];
+            s_kv[pos] = make_uint2(key[k], val[k]);
         }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
-        u32 idx = k * SORT_THREADS + tid;
-        if (idx < tile_count) {
-            u32 kk = s_keys[idx];
-            u32 digit = (kk >> shift) & (RADIX - 1);
-            u32 out = s_global_base[digit] + idx;
-            keys_out[out] = kk;
-            vals_out[out] = s_vals[idx];
+        const u32 idx = k * SORT_THREADS + tid;
+        if (FULL || idx < tile_count) {
+            const uint2 kv = s_kv[idx];
+            const u32 out = s_global_base[(kv.x >> shift) & (RADIX - 1)] + idx;
+            keys_out[out] = kv.x;
+            vals_out[out] = kv.y;
         }
     }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS)
+k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
+                u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 n, int shift,
+                const u32 *__restrict__ digit_base /* [RADIX] exclusive, this pass */,
+                u32 *tile_status /* [tiles][RADIX], zeroed */, u32 *tile_counter) {
+    __shared__ u32 s_warp_hist[SORT_WARPS][RADIX];
+    __shared__ u32 s_digit_excl[RADIX];
+    __shared__ u32 s_global_base[RADIX];
+    __shared__ u32 s_scan[SORT_WARPS];
+    __shared__ uint2 s_kv[SORT_TILE];
+    __shared__ u32 s_tile;
+
+    const u32 tid = threadIdx.x;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int k = tid; k < SORT_WARPS * RADIX; k += SORT_THREADS) (&s_warp_hist[0][0])[k] = 0;
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u32 tile_count = min((u32)SORT_TILE, n - tile * SORT_TILE);
+    if (tile_count == SORT_TILE)
+        onesweep_tile<true>(keys_in, vals_in, keys_out, vals_out, tile, tile_count, shift, digit_base, tile_status, s_warp_hist,
+                            s_digit_excl, s_global_base, s_scan, s_kv);
+    else
+        onesweep_tile<false>(keys_in, vals_in, keys_out, vals_out, tile, tile_count, shift, digit_base, tile_status, s_warp_hist,
+                             s_digit_excl, s_global_base, s_scan, s_kv);
 }
 
 // -------------------------------------------------------------------------------------------------
