@@ -195,6 +195,17 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
         for (u32 w = 0; w < warp; ++w) base += s_scan[w];
         s_digit_excl[tid] = base + incl - total;
     }
+    __syncthreads();
+    // ---- scatter (key, value) into shared memory in sorted order.  Done BEFORE the look-back: it needs
+    // only tile-local offsets, and the predecessors' prefixes have that much longer to arrive.
+#pragma unroll
+    for (int k = 0; k < SORT_ITEMS; ++k) {
+        if (FULL || warp_base + k * 32 + lane < tile_count) {
+            const u32 digit = (key[k] >> shift) & (RADIX - 1);
+            const u32 pos = s_digit_excl[digit] + my_hist[digit] + rank[k];
+            s_kv[pos] = make_uint2(key[k], val[k]);
+        }
+    }
     // ---- decoupled look-back for digit `tid` ----------------------------------------------------
     // Up to LOOKBACK predecessors are fetched with independent loads and then consumed in order, so a
     // long run of AGGREGATE tiles costs one memory latency per batch instead of one per tile.
@@ -223,16 +234,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     s_global_base[tid] = digit_base[tid] + excl - s_digit_excl[tid];
     __syncthreads();
 
-    // ---- scatter (key, value) into shared memory in sorted order, then write runs to global ------
-#pragma unroll
-    for (int k = 0; k < SORT_ITEMS; ++k) {
-        if (FULL || warp_base + k * 32 + lane < tile_count) {
-            const u32 digit = (key[k] >> shift) & (RADIX - 1);
-            const u32 pos = s_digit_excl[digit] + my_hist[digit] + rank[k];
-            s_kv[pos] = make_uint2(key[k], val[k]);
-        }
-    }
-    __syncthreads();
+    // ---- write the sorted tile's runs to global ------------------------------------------------
 #pragma unroll
     for (int k = 0; k < SORT_ITEMS; ++k) {
         const u32 idx = k * SORT_THREADS + tid;
@@ -245,7 +247,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS)
+__global__ void __launch_bounds__(SORT_THREADS, 3)
 k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                 u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 n, int shift,
                 const u32 *__restrict__ digit_base /* [RADIX] exclusive, this pass */,
