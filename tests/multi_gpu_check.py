@@ -1,4 +1,5 @@
-"""Multi-GPU correctness check (run under torchrun on N GPUs): slabs + NCCL halo exchange, the
+"""Multi-GPU parity test (not collected by pytest: run under torchrun on N GPUs,
+`python -m torch.distributed.run --nproc-per-node N tests/multi_gpu_check.py`): slabs + NCCL halo exchange, the
 union of the owners' pairs must equal the single-domain oracle result."""
 import os, sys
 import numpy as np

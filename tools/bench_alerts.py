@@ -38,13 +38,31 @@ with FrameEngine(n, 32_000_000, world_bounds=((0, 0, 0), (31623, 31623, 100))) a
     pairs = e.download(sort=False)
 for r in rows:
     print(json.dumps(r))
-# reference port on a sample of the same risks
-from oracle import oracle as O  # noqa: E402
+# the reference's dict walk (warning_system.py:259-285, 120-197) on a sample of the same risks
+def priority(risk, ttc):
+    if risk >= 0.8 and ttc < 3.0:
+        return 3
+    if risk >= 0.8 or ttc < 5.0:
+        return 2
+    return 1 if risk >= 0.6 else 0
+
+
+def dict_walk(table, risks, now):
+    for i, j, risk, ttc in risks:
+        if risk < 0.3:
+            continue
+        a = table.get((i, j))
+        if a is None:
+            table[(i, j)] = [risk, ttc, priority(risk, ttc), now]
+        else:
+            a[0], a[1], a[2], a[3] = risk, ttc, priority(risk, ttc), now
+
+
 sample = pairs[pairs["priority"] >= 0][:300_000]
 risks = [(int(p["i"]), int(p["j"]), float(p["risk"]), float(p["ttc"])) for p in sample]
-t = O.AlertTable()
+table = {}
 t0 = time.perf_counter()
-t.process(risks, 10.0)
-t.process(risks, 10.5)
+dict_walk(table, risks, 10.0)
+dict_walk(table, risks, 10.5)
 dt = time.perf_counter() - t0
-print(json.dumps({"what": "reference dict walk (Python port, 1 core), create + refresh", "risks": 2 * len(risks), "risks_per_s": round(2 * len(risks) / dt)}))
+print(json.dumps({"what": "reference dict walk (Python, 1 core), create + refresh", "risks": 2 * len(risks), "risks_per_s": round(2 * len(risks) / dt)}))

@@ -24,11 +24,21 @@ msgs = [base[k % len(base)].replace(f'"vehicle-{k % len(base)}"', f'"vehicle-{k}
 text = "\n".join(msgs).encode()
 print(json.dumps({"what": "generated", "messages": n, "bytes": len(text), "s": round(time.perf_counter() - t0, 2)}))
 
-# reference path (port): json.loads + the field reads of _handle_vehicle_position, per message
-from oracle import oracle as O  # noqa: E402
+# reference path: json.loads + the field reads of _handle_vehicle_position, per message
+def python_path(text):
+    """What the reference does per message (warning_system.py:638-678): json.loads + the field reads."""
+    try:
+        d = json.loads(text)
+        return (d["id"], d["position"]["x"], d["position"]["y"], d["position"]["z"], d["velocity"]["x"], d["velocity"]["y"],
+                d["velocity"]["z"], d["acceleration"]["x"], d["acceleration"]["y"], d["acceleration"]["z"], d["heading"],
+                d["size"], d["type"], d["timestamp"])
+    except Exception:
+        return None
+
+
 sample = msgs[: min(n, 200_000)]
 t0 = time.perf_counter()
-ok = sum(O.parse_vehicle_message(m) is not None for m in sample)
+ok = sum(python_path(m) is not None for m in sample)
 dt = time.perf_counter() - t0
 print(json.dumps({"what": "reference per-message parse (Python, 1 core)", "messages": len(sample), "ok": ok,
                   "msgs_per_s": round(len(sample) / dt), "MB_per_s": round(sum(map(len, sample)) / dt / 1e6, 1)}))
