@@ -345,18 +345,19 @@ __device__ __forceinline__ bool narrow_detect(WarpShared &ws, u32 ql, const floa
     float rs2 = rvx * rvx + rvy * rvy + rvz * rvz;
     if (rs2 < 0.0099f) return false;  // rel_speed < 0.1 with margin (0.1^2 = 0.01)
     float dot = dx * rvx + dy * rvy + dz * rvz;
-    float edot = 4.0e-6f * sqrtf(d2 * rs2) + 1.0e-20f;
+    float edot = 4.0e-6f * sqrt_ub(d2 * rs2) + 1.0e-20f;  // (bounds only need upper estimates: MUFU sqrt / rcp)
     // dot > 0: either (dot > 0 and cur > 5) or time_to_closest < 0 rejects the pair (:273, :280)
     if (dot > edot) return false;
     if (-dot > T * rs2 * (1.0f + 1.0e-5f) + edot) return false;  // time_to_closest > time_window
-    float tc = fmaxf(-dot, 0.0f) / rs2;
+    const float inv_rs2 = rcp_fast(rs2);
+    float tc = fmaxf(-dot, 0.0f) * inv_rs2;
     float rax = a2.x - b2.x, ray = a2.y - b2.y, raz = a2.z - b2.z;
     float h = 0.5f * tc * tc;
     float ex = rvx * tc + rax * h - dx, ey = rvy * tc + ray * h - dy, ez = rvz * tc + raz * h - dz;
     float cd2 = ex * ex + ey * ey + ez * ez;
     float safe = (a0.w + b0.w) * 0.5f + 5.0f;
-    float tcerr = edot / rs2 + 4.0e-6f * tc;
-    float band = 2.0e-3f + 2.0f * (sqrtf(rs2) + sqrtf(rax * rax + ray * ray + raz * raz) * tc) * tcerr;
+    float tcerr = edot * inv_rs2 * (1.0f + 1.0e-6f) + 4.0e-6f * tc;  // 4e-6 tc also covers the rcp (1 ulp)
+    float band = 2.0e-3f + 2.0f * (sqrt_ub(rs2) + sqrt_ub(rax * rax + ray * ray + raz * raz) * tc) * tcerr;
     float thr = safe + band;
     return cd2 <= thr * thr;
 }
