@@ -271,7 +271,8 @@ const char *rcd_ingest_last_error(rcd_ingest g);
  * (json.dumps never emits one).  Messages that are malformed or lack a field the reference reads are
  * skipped and counted in *n_bad (the reference logs and drops them, warning_system.py:677-678).
  * *n_out = messages decoded (RCD_ECAPACITY if > cap), *max_seq = largest rcd_record.seq of the batch.
- * Needs no CUDA device. */
+ * Limits of the record format: at most 255 distinct type strings per rcd_ingest and at most 255 messages
+ * for one vehicle in one call (RCD_ECAPACITY beyond).  Needs no CUDA device. */
 int rcd_ingest_decode_json(rcd_ingest g, const char *buf, uint64_t len, int32_t threads, rcd_record *out,
                            uint64_t cap, uint64_t *n_out, uint64_t *n_bad, uint32_t *max_seq);
 int rcd_ingest_counts(rcd_ingest g, uint64_t *n_ids, uint64_t *n_types);

@@ -139,3 +139,54 @@ def test_fresh_messages_against_the_live_reference():
         assert len(rec) == len(want) == 300
         for r, w in zip(rec, want):
             _check_record(g, r, [w[0]] + [repr(float(x)) for x in w[1:12]] + [w[12], repr(float(w[13]))])
+
+
+def test_mutated_messages_never_disagree_with_the_python_path():
+    """Seeded fuzz: random deletions / insertions / replacements in valid messages.  The decoder must accept
+    exactly the texts the reference path accepts (json.loads + the handler's field reads), with identical
+    values -- except that a complete message followed by garbage is one message plus one dropped message
+    for a stream decoder, where json.loads rejects the whole text ("Extra data")."""
+    from oracle import oracle as O
+    from rcd_b200.host.ingest import VehicleIngest
+    rng = random.Random(20261018)
+    base = C.seeded_messages(120, 3) + [t for t, _ in C.edge_messages()]
+    alphabet = list('{}[]":,.-+eE0123456789 \\ntrue falsnNaInity\t') + ['\\u00e9', '\\ud83d', '"x"', '"y"', '"id"']
+
+    def mutate(s):
+        s = list(s)
+        for _ in range(rng.choice([1, 1, 2, 3, 6])):
+            op, pos = rng.random(), rng.randrange(len(s) + 1)
+            if op < 0.35 and s:
+                del s[min(pos, len(s) - 1)]
+            elif op < 0.7:
+                s.insert(pos, rng.choice(alphabet))
+            elif s:
+                s[min(pos, len(s) - 1)] = rng.choice(alphabet)
+        return "".join(s).replace("\n", " ")
+
+    g = VehicleIngest(threads=1)
+    accepted = dropped = 0
+    for k in range(6000):
+        if k % 100 == 0:  # fresh id / type tables: the mutations invent type strings (limit 255 per table)
+            g.close()
+            g = VehicleIngest(threads=1)
+        m = mutate(rng.choice(base))
+        want = O.parse_vehicle_message(m)
+        rec, _ = g.decode(m)
+        if want is None:
+            try:
+                json.loads(m)
+                extra = False
+            except json.JSONDecodeError as e:
+                extra = e.msg == "Extra data"
+            except RecursionError:
+                continue
+            assert len(rec) == 0 or extra, m
+            dropped += 1
+            continue
+        assert len(rec) == 1, m
+        vals = [float(v) for v in (*want["position"], *want["velocity"], *want["acceleration"], want["heading"], want["size"])]
+        _check_record(g, rec[0], [want["id"]] + [repr(v) for v in vals] + [want["type"], repr(float(want["timestamp"]))])
+        accepted += 1
+    g.close()
+    assert accepted > 500 and dropped > 2000
