@@ -80,6 +80,33 @@ struct rcd_handle_s {
     u32 *traj_count = nullptr;
     u32 traj_len = 0;
     u64 launches = 0;
+    // CUDA-graph replay of rcd_step (RCD_FLAG_GRAPH)
+    struct StepKey {
+        int32_t mode = -1;
+        float R = 0, T = 0, pt = 0, thr = 0, index_cell_req = 0;
+        u64 n = 0, n_owned = 0;
+        int index_valid = 0, sorted_buf = 0, frame_done = 0;
+        const void *out = nullptr;
+        bool operator==(const StepKey &o) const {
+            return mode == o.mode && R == o.R && T == o.T && pt == o.pt && thr == o.thr && index_cell_req == o.index_cell_req &&
+                   n == o.n && n_owned == o.n_owned && index_valid == o.index_valid && sorted_buf == o.sorted_buf &&
+                   frame_done == o.frame_done && out == o.out;
+        }
+    };
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        StepKey key;
+        GridParams grid = {};
+        float index_cell_req = 0;
+        int sorted_buf = 0, last_mode = 0;
+        u64 launches = 0;
+    };
+    StepGraph graphs[4];
+    int graph_next = 0;
+    StepKey graph_candidates[4];  // keys seen recently (twin pair buffers make consecutive frames alternate)
+    int graph_cand_next = 0;
+    bool graph_broken = false;
+    u64 graph_replays = 0;
     // pipelined delivery (rcd_download_begin / _finish): twin pair buffer + totals, copy stream
     rcd_pair *out_alt = nullptr;
     Counters *counters_alt = nullptr;
@@ -359,6 +386,8 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
     cudaFree(h->q2); cudaFree(h->q3);
     cudaFree(h->traj); cudaFree(h->traj_count);
+    for (auto &g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     cudaFree(h->out_alt); cudaFree(h->counters_alt);
     if (h->pend_counters_host) cudaFreeHost(h->pend_counters_host);
     if (h->pend_event) cudaEventDestroy(h->pend_event);
@@ -438,7 +467,7 @@ int rcd_set_owned(rcd_handle h, uint64_t n_owned) {
     return RCD_OK;
 }
 
-int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window) {
+static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time_window) {
     if (!h) return RCD_EINVAL;
     const bool append = (mode & RCD_STEP_APPEND) != 0;
     const bool with_detect = (mode & RCD_STEP_WITH_DETECT) != 0;
@@ -449,9 +478,9 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     if (with_detect) {
         fused = search_radius == PREDICT_RADIUS && time_window == 10.0f && !(h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES);
         if (!fused) {  // other parameters: the two passes back to back
-            int rc2 = rcd_step(h, RCD_MODE_DETECT | (append ? RCD_STEP_APPEND : 0), search_radius, time_window);
+            int rc2 = step_impl(h, RCD_MODE_DETECT | (append ? RCD_STEP_APPEND : 0), search_radius, time_window);
             if (rc2) return rc2;
-            return rcd_step(h, RCD_MODE_PREDICT | RCD_STEP_APPEND, search_radius, time_window);
+            return step_impl(h, RCD_MODE_PREDICT | RCD_STEP_APPEND, search_radius, time_window);
         }
     }
     if (append && !h->frame_done) return fail(h, RCD_ESTATE, "rcd_step: RCD_STEP_APPEND needs a previous step of this frame");
@@ -552,6 +581,112 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     stage_end(h, RCD_STAGE_TOTAL);
     h->frame_done = true;
     h->last_mode = mode;
+    return RCD_OK;
+}
+
+// RCD_FLAG_GRAPH: the launch sequence of a step is a pure function of the key below (every other kernel
+// argument is a buffer that lives as long as the handle).  First sighting of a key: run normally and
+// remember it; second sighting in a row: capture, instantiate, launch; from then on: one graph launch plus the
+// host-side state changes step_impl would have made.
+int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window) {
+    if (!h) return RCD_EINVAL;
+    const bool want = (h->flags & RCD_FLAG_GRAPH) && !(h->flags & RCD_FLAG_PROFILE) && h->world_static && !h->graph_broken &&
+                      h->n > 0 && h->n_owned > 0;
+    if (!want) return step_impl(h, mode, search_radius, time_window);
+    const bool append = (mode & RCD_STEP_APPEND) != 0;
+    const bool flip = !append && h->flip_pending;
+    rcd_handle_s::StepKey key;
+    key.mode = mode; key.R = search_radius; key.T = time_window;
+    key.pt = h->cn_prediction_time; key.thr = h->cn_risk_threshold;
+    key.n = h->n; key.n_owned = h->n_owned;
+    key.index_valid = h->index_valid ? 1 : 0;
+    key.index_cell_req = h->index_valid ? h->index_cell_req : 0.0f;
+    key.sorted_buf = h->index_valid ? h->sorted_buf : 0;
+    key.frame_done = append ? (h->frame_done ? 1 : 0) : 0;
+    key.out = flip ? (const void *)h->out_alt : (const void *)h->out;
+    for (auto &g : h->graphs) {
+        if (!g.exec || !(g.key == key)) continue;
+        // ---- replay ----
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        if (flip) {
+            std::swap(h->out, h->out_alt);
+            std::swap(h->counters, h->counters_alt);
+            h->flip_pending = false;
+        }
+        h->frame_done = false;
+        CUDA_TRY(h, cudaGraphLaunch(g.exec, h->stream));
+        h->launches = (append ? h->launches : 0) + g.launches;
+        h->grid = g.grid;
+        h->index_valid = true;
+        h->index_cell_req = g.index_cell_req;
+        h->sorted_buf = g.sorted_buf;
+        h->stage_mode = g.last_mode;
+        h->last_mode = g.last_mode;
+        h->frame_done = true;
+        ++h->graph_replays;
+        return RCD_OK;
+    }
+    bool seen = false;
+    for (auto &c : h->graph_candidates) seen = seen || c == key;
+    if (!seen) {  // first sighting: run it, remember it
+        h->graph_candidates[h->graph_cand_next] = key;
+        h->graph_cand_next = (h->graph_cand_next + 1) % 4;
+        return step_impl(h, mode, search_radius, time_window);
+    }
+    // ---- second sighting: capture ----
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    struct Saved {
+        rcd_pair *out, *out_alt; Counters *counters, *counters_alt; bool flip_pending, frame_done, index_valid;
+        float index_cell_req; int sorted_buf, last_mode, stage_mode; GridParams grid; u64 launches;
+    } pre = {h->out, h->out_alt, h->counters, h->counters_alt, h->flip_pending, h->frame_done, h->index_valid,
+             h->index_cell_req, h->sorted_buf, h->last_mode, h->stage_mode, h->grid, h->launches};
+    auto restore = [&]() {
+        h->out = pre.out; h->out_alt = pre.out_alt; h->counters = pre.counters; h->counters_alt = pre.counters_alt;
+        h->flip_pending = pre.flip_pending; h->frame_done = pre.frame_done; h->index_valid = pre.index_valid;
+        h->index_cell_req = pre.index_cell_req; h->sorted_buf = pre.sorted_buf; h->last_mode = pre.last_mode;
+        h->stage_mode = pre.stage_mode; h->grid = pre.grid; h->launches = pre.launches;
+    };
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = RCD_OK;
+    if (e == cudaSuccess) {
+        rc = step_impl(h, mode, search_radius, time_window);
+        cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        if (e2 != cudaSuccess) e = e2;
+    }
+    if (e == cudaSuccess && rc == RCD_OK && graph) e = cudaGraphInstantiate(&exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess || rc != RCD_OK || !exec) {  // not capturable here: never try again, run the step for real
+        (void)cudaGetLastError();
+        if (exec) cudaGraphExecDestroy(exec);
+        restore();
+        h->graph_broken = true;
+        return step_impl(h, mode, search_radius, time_window);
+    }
+    e = cudaGraphLaunch(exec, h->stream);
+    if (e != cudaSuccess) {
+        cudaGraphExecDestroy(exec);
+        restore();
+        h->graph_broken = true;
+        return step_impl(h, mode, search_radius, time_window);
+    }
+    rcd_handle_s::StepGraph &slot = h->graphs[h->graph_next];
+    h->graph_next = (h->graph_next + 1) % 4;
+    if (slot.exec) cudaGraphExecDestroy(slot.exec);
+    slot.exec = exec;
+    slot.key = key;
+    slot.grid = h->grid;
+    slot.index_cell_req = h->index_cell_req;
+    slot.sorted_buf = h->sorted_buf;
+    slot.last_mode = h->last_mode;
+    slot.launches = h->launches - (append ? pre.launches : 0);
+    return RCD_OK;
+}
+
+int rcd_graph_replays(rcd_handle h, uint64_t *n) {
+    if (!h || !n) return RCD_EINVAL;
+    *n = h->graph_replays;
     return RCD_OK;
 }
 

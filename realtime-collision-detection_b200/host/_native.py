@@ -21,6 +21,7 @@ SRC_HOST, SRC_DEVICE = 0, 1
 PAT_STATIONARY, PAT_CONSTANT_VELOCITY, PAT_ACCELERATING, PAT_NO_HISTORY = 0, 1, 2, 3
 FLAG_PROFILE = 1
 FLAG_COUNT_PREDICT_CANDIDATES = 2
+FLAG_GRAPH = 4
 NUM_STAGES = 9
 STAGE_NAMES = ("upload", "keys", "sort", "reorder", "pairs", "sample", "exact", "download", "total")
 HALO_RECORD_WORDS = 13
@@ -36,7 +37,7 @@ SYMBOLS = (
     "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
     "rcd_ingest_counts", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
     "rcd_alerts_configure", "rcd_alerts_update", "rcd_alerts_update_pairs", "rcd_alerts_expire",
-    "rcd_alerts_acknowledge", "rcd_alerts_download", "rcd_download_begin", "rcd_download_finish",
+    "rcd_alerts_acknowledge", "rcd_alerts_download", "rcd_download_begin", "rcd_download_finish", "rcd_graph_replays",
 )
 
 
@@ -133,6 +134,8 @@ def load() -> ctypes.CDLL:
     L.rcd_stage_ms.argtypes = [vp, i32, vp]
     L.rcd_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
     L.rcd_launch_count.argtypes = [vp, ctypes.POINTER(u64)]
+    if hasattr(L, "rcd_graph_replays"):
+        L.rcd_graph_replays.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_sync.argtypes = [vp]
     if not hasattr(L, "rcd_ingest_create") and os.environ.get("RCD_B200_LIB"):
         _lib = L

@@ -28,13 +28,13 @@ class FrameEngine:
 
     def __init__(self, max_objects: int, max_pairs: Optional[int] = None, device: int = 0,
                  world_bounds: Optional[Tuple[Sequence[float], Sequence[float]]] = None, profile: bool = False,
-                 count_predict_candidates: bool = False):
+                 count_predict_candidates: bool = False, graph: bool = False):
         self._lib = N.load()
         self._h = ctypes.c_void_p()
         cfg = N.RcdConfig()
         cfg.device = int(device)
         cfg.flags = (N.FLAG_PROFILE if profile else 0) | (
-            N.FLAG_COUNT_PREDICT_CANDIDATES if count_predict_candidates else 0)
+            N.FLAG_COUNT_PREDICT_CANDIDATES if count_predict_candidates else 0) | (N.FLAG_GRAPH if graph else 0)
         cfg.max_objects = int(max(1, max_objects))
         cfg.max_pairs = int(max_pairs if max_pairs is not None else max(4096, 16 * max_objects))
         if world_bounds is None:
@@ -331,6 +331,11 @@ class FrameEngine:
         v = ctypes.c_uint64(0)
         N.check(self._lib.rcd_launch_count(self._h, ctypes.byref(v)), self._h)
         return int(v.value)
+
+    def graph_replays(self) -> int:
+        n = ctypes.c_uint64()
+        N.check(self._lib.rcd_graph_replays(self._h, ctypes.byref(n)), self._h)
+        return int(n.value)
 
     def sync(self) -> None:
         N.check(self._lib.rcd_sync(self._h), self._h)

@@ -544,3 +544,43 @@ def test_pipelined_download_delivers_each_frame_while_the_next_one_runs():
                 assert counts[key] == w_counts[key], key
         with pytest.raises(N.NativeError):
             e.download_finish()
+
+
+def test_graph_replay_gives_the_same_frames():
+    """RCD_FLAG_GRAPH: after a shape has been seen twice, rcd_step replays a captured CUDA graph.  Results must
+    not depend on it -- new data every frame, pipelined delivery (alternating pair buffers), append steps."""
+    from rcd_b200.host import _native as N, workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 5000
+    bounds = ((0.0, 0.0, 0.0), (900.0, 900.0, 100.0))
+    frames = [W.uniform_frame(n, 101 + k, map_size=900.0, drone_fraction=0.3) for k in range(8)]
+    pat = W.random_patterns(n, 111)
+    with FrameEngine(n, 1 << 20, world_bounds=bounds) as ref, FrameEngine(n, 1 << 20, world_bounds=bounds, graph=True) as e:
+        bufs = [np.zeros(1 << 20, dtype=N.PAIR_DTYPE) for _ in range(2)]
+        got, want = [], []
+        for k, f in enumerate(frames):
+            ref.upload(f); ref.set_patterns(pat); ref.step(N.MODE_PREDICT, with_detect=True)
+            want.append((ref.download(), ref.counts()))
+            e.upload(f); e.set_patterns(pat); e.step(N.MODE_PREDICT, with_detect=True)
+            if k:
+                pairs, counts = e.download_finish()
+                got.append((pairs.copy(), counts))
+            e.download_begin(bufs[k % 2])
+        pairs, counts = e.download_finish()
+        got.append((pairs.copy(), counts))
+        assert e.graph_replays() >= 3  # two buffer sets: each shape is seen, captured, then replayed
+        for (pairs, counts), (w_pairs, w_counts) in zip(got, want):
+            assert np.sort(pairs, order=["i", "j", "predicted"], kind="stable").tobytes() == w_pairs.tobytes()
+            for key in ("n_pairs", "n_candidates", "n_potential", "n_high_risk", "n_alerts"):
+                assert counts[key] == w_counts[key], key
+        # two-step frames (detect, then predict appended), other radius, repeated: still identical
+        before = e.graph_replays()
+        for k in range(4):
+            f = frames[k]
+            for eng in (ref, e):
+                eng.upload(f); eng.set_patterns(pat)
+                eng.step(N.MODE_DETECT, 60.0, 4.0)
+                eng.step(N.MODE_PREDICT, append=True)
+            assert e.download().tobytes() == ref.download().tobytes()
+            assert e.counts() == ref.counts()
+        assert e.graph_replays() > before
