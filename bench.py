@@ -262,7 +262,9 @@ def run_b200(args):
     xlo = max(0.0, float(lo[rank]) - halo) if np.isfinite(lo[rank]) else 0.0
     xhi = min(side, float(hi[rank]) + halo) if np.isfinite(hi[rank]) else side
     eng_bounds = ((xlo, bounds[0][1], bounds[0][2]), (xhi, bounds[1][1], bounds[1][2]))
-    eng = FrameEngine(cap, max_pairs, device=local_rank, world_bounds=eng_bounds, profile=True)
+    # --graph: rcd_step is replayed as a CUDA graph (RCD_FLAG_GRAPH), which excludes the per-stage events; the stage
+    # breakdown then comes from a few extra frames on a profiled twin engine after the timed regions
+    eng = FrameEngine(cap, max_pairs, device=local_rank, world_bounds=eng_bounds, profile=not args.graph, graph=args.graph)
     stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=torch.device("cuda", local_rank))
     exch = SlabExchange(eng, lo, hi, rank, world, halo, stream, cap_records=int(1.1 * n_send_max) + 4096) if world > 1 else None
 
@@ -334,10 +336,11 @@ def run_b200(args):
         frame_resident(k)
         ev[k][1].record(stream)
         # per-stage times of this frame (synchronises after the frame's end event was recorded)
-        for mode in (N.MODE_DETECT, N.MODE_PREDICT):
-            for name, ms in eng.stage_ms(mode).items():
-                key = ("detect." if mode == N.MODE_DETECT else "predict.") + name
-                stage_acc[key] = stage_acc.get(key, 0.0) + ms
+        if not args.graph:
+            for mode in (N.MODE_DETECT, N.MODE_PREDICT):
+                for name, ms in eng.stage_ms(mode).items():
+                    key = ("detect." if mode == N.MODE_DETECT else "predict.") + name
+                    stage_acc[key] = stage_acc.get(key, 0.0) + ms
         launches[0] += eng.launch_count() + (exch.launches_last if exch is not None else 0)
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -405,6 +408,21 @@ def run_b200(args):
         if float(t_both[0]) < float(t_both[1]):
             t_e2e, inflight, e2e_lat, d2h = t_pipe, 2, lat_pipe, d2h_pipe
     clocks = sampler.stop() if rank == 0 else None
+    graph_replays = eng.graph_replays() if args.graph else 0
+    if args.graph:  # stage breakdown on a profiled twin (outside every timed region)
+        prof = FrameEngine(cap, max_pairs, device=local_rank, world_bounds=eng_bounds, profile=True)
+        keep, eng = eng, prof
+        ex_keep, exch = exch, (SlabExchange(prof, lo, hi, rank, world, halo,
+                                            torch.cuda.ExternalStream(prof.cuda_stream(), device=torch.device("cuda", local_rank)),
+                                            cap_records=int(1.1 * n_send_max) + 4096) if world > 1 else None)
+        for k in range(args.steps):
+            frame_resident(k)
+            for mode in (N.MODE_DETECT, N.MODE_PREDICT):
+                for name, ms in eng.stage_ms(mode).items():
+                    key = ("detect." if mode == N.MODE_DETECT else "predict.") + name
+                    stage_acc[key] = stage_acc.get(key, 0.0) + ms
+        eng, exch = keep, ex_keep
+        prof.close()
 
     # ---- reduce over ranks (max time, summed counts) -----------------------------------------------
     n_own_mean = float(np.mean([len(o["px"]) for o in own]))
@@ -459,7 +477,8 @@ def run_b200(args):
             "config": {"workload": f"{args.workload}: {desc}", "objects": int(objs), "objects_per_gpu": args.objects_per_gpu,
                        "frame": "ingest + index + detect-all + predict-all (performance_test.py:794-813)",
                        "partition": f"{world} x-slabs, halo {halo:.0f} m, NCCL all_to_all" if world > 1 else "single GPU",
-                       "l2": "flushed with a 256 MiB write before every timed frame", "max_pairs": max_pairs},
+                       "l2": "flushed with a 256 MiB write before every timed frame", "max_pairs": max_pairs,
+                       "cuda_graph": bool(args.graph), "graph_replays": int(graph_replays)},
             "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
                            "p99_reference_rule": float(np.sort(lat)[min(len(lat) - 1, int(len(lat) * 0.99))]),
                            "max": float(lat.max())},
@@ -523,6 +542,8 @@ def main():
     ap.add_argument("--objects-per-gpu", type=int, default=None)
     ap.add_argument("--max-pairs", type=int, default=32_000_000)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay rcd_step as a CUDA graph (RCD_FLAG_GRAPH): for the small, launch-bound configs")
     ap.add_argument("--e2e-inflight", type=int, default=2,
                     help="frames in flight in the end-to-end leg at N=1 (2 = result copy overlaps the next frame)")
     ap.add_argument("--host-pairs-cap", type=int, default=32_000_000,
