@@ -5,19 +5,25 @@
 //
 //   k_pairs  : persistent.  A tile is 32 consecutive objects in cell order, handled by ONE warp
 //              (one lane per querying object); warps take tiles from an atomic counter, so dense
-//              regions spread over all SMs.  The warp finds the cell rows that can hold neighbours
-//              of its queries, flattens their contiguous spans and streams them through its own
-//              slice of shared memory in double-buffered chunks (cp.async); there is no block-wide
-//              barrier, everything is warp-synchronous.
-//                S1 filter : lane = query; every staged neighbour is tested with one broadcast
-//                            LDS.128 and a squared distance; survivors are compacted with
-//                            __ballot_sync into a shared-memory queue of (query, neighbour) pairs.
-//                S2 narrow : lane = pair, 32 queued pairs at a time.  detect: temporal filter +
-//                            closest approach.  predict: closest approach of the relative
-//                            trajectory rejects most pairs outright; the rest are compacted again
-//                            and the offsets inside the reachable time window are scanned.
-//              Survivors go to global queues (warp-aggregated atomics).
-//   k_sample : (predict) lane = pair; per surviving offset: radius test + the 10 samples.
+//              regions spread over all SMs.  Every query has a volume a neighbour must lie in to
+//              matter -- a ball of radius R, or (predict) the capsule of radius 100 m about the chord
+//              of the predicted centre path -- and the warp streams the cell rows under the bounding
+//              box of its queries' volumes through its own slice of shared memory in double-buffered
+//              chunks (cp.async); there is no block-wide barrier, everything is warp-synchronous.
+//                S1 filter : lane = query; every staged neighbour is tested against the lane's
+//                            volume, two neighbours per packed fp32 instruction (FADD2 / FFMA2);
+//                            hits go to per-lane lists in shared memory.
+//                S2a       : lane = pair, 32 listed pairs at a time.  detect: temporal filter +
+//                            closest approach.  predict: linear closest approach of the relative
+//                            trajectory; survivors are compacted by ballot into a warp queue.
+//                S2b       : lane = queued pair: the time window that can hold a hit (trajectory
+//                            re-expanded about the middle of the window, twice) -> offsets m_lo..m_hi.
+//              Survivors go to global queues (warp-aggregated atomics).  No fp64 here: radius tests
+//              inside the fp32 guard band are flagged for k_exact.  MODE_PREDICT_WITH_DETECT runs the
+//              detect narrow phase on the pairs of the predict sweep (one pass for both).
+//   k_sample : (predict) a warp takes 32 queued pairs through four phases with different lane
+//              assignments (pair / (pair, offset) / surviving item / pair): per offset the reach and
+//              radius tests, then the 10 samples, then the max-risk merge.
 //   k_exact  : lane = pair; the decision is taken in fp64 in the reference's operation order
 //              (rcd_exact.cuh), merged over offsets, emitted through one 64-bit atomic cursor and
 //              classified (alert priority).
