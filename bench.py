@@ -451,7 +451,7 @@ def run_b200(args):
         npass = max(1, -(-int(np.ceil(np.log2(max(2, eng_ncells(bounds, xlo, xhi))))) // 8))
         model = {
             "keys": 102.0 * n_loc, "sort": (16.0 * npass) * n_loc, "reorder": 108.0 * n_loc,
-            "pairs": 56.0 * n_loc, "sample": 0.0, "exact": 0.0,
+            "pairs": 56.0 * n_loc, "narrow": 0.0, "exact": 0.0, "qorder": 0.0,
         }
         kernels = {}
         for key, ms in stage_ms.items():

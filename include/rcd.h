@@ -131,18 +131,19 @@ typedef struct {
                               bands hold (diagnostic; results are exact either way) */
 } rcd_counts_t;
 
-#define RCD_NUM_STAGES 9
+#define RCD_NUM_STAGES 10
 /* stage indices for rcd_stage_ms */
 enum {
     RCD_STAGE_UPLOAD = 0,  /* host->device copies of the SoA state */
-    RCD_STAGE_KEYS = 1,    /* k_cell_keys + k_scan_hist: cell keys + digit histograms */
+    RCD_STAGE_KEYS = 1,    /* k_pack_keys + k_scan_hist: cell keys + digit histograms */
     RCD_STAGE_SORT = 2,    /* k_onesweep_pass x passes */
-    RCD_STAGE_REORDER = 3, /* k_reorder: gather into cell order + cell ranges */
-    RCD_STAGE_PAIRS = 4,   /* k_pairs: pair enumeration + fp32 narrow phase */
-    RCD_STAGE_SAMPLE = 5,  /* k_sample (predict): radius test + 10 samples per surviving offset */
+    RCD_STAGE_REORDER = 3, /* k_reorder + k_cell_table: gather into cell order + dense cell table */
+    RCD_STAGE_PAIRS = 4,   /* k_pairs: pair enumeration, radius test + closest-approach filter (fp32) */
+    RCD_STAGE_NARROW = 5,  /* k_narrow: fp32 narrow phase (temporal filter; predict: window, 10 samples per offset) */
     RCD_STAGE_EXACT = 6,   /* k_exact: fp64 decision, merge, emit, alert class */
     RCD_STAGE_DOWNLOAD = 7,
-    RCD_STAGE_TOTAL = 8
+    RCD_STAGE_TOTAL = 8,
+    RCD_STAGE_QORDER = 9   /* k_query_keys + k_onesweep_pass x 3: query order (tiles of overlapping query volumes) */
 };
 
 int rcd_version(void);

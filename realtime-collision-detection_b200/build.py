@@ -16,7 +16,6 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librcd_b200.so")
 SOURCES = ["rcd_api.cu"]
-HEADERS = ["rcd_common.cuh", "rcd_index.cuh", "rcd_exact.cuh", "rcd_pairs.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas=-v",
@@ -34,7 +33,7 @@ def up_to_date() -> bool:
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]  # every source and header under csrc/
     deps += [os.path.join(os.path.dirname(HERE), "include", "rcd.h"), os.path.abspath(__file__)]
     return all(os.path.getmtime(d) <= t for d in deps)
 

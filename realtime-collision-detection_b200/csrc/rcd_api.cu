@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -50,8 +51,12 @@ struct rcd_handle_s {
     float4 *P0 = nullptr, *P1 = nullptr, *P2 = nullptr;
     float4 *U = nullptr;  // packed 48-byte records in upload order
     u32 *sorted_slot = nullptr;
-    u32 *cell_start = nullptr, *cell_end = nullptr;
+    u32 *cell_begin = nullptr;  // [cells_cap + 1] dense cell table
     u32 cells_cap = 0;
+    float cell_scale = 0.5f;    // grid cell edge (x, y) as a fraction of the query radius
+    u32 *qkeys[2] = {}, *qvals[2] = {};  // query order: Morton keys of the query volumes + permutation
+    int q_sorted_buf = 0;
+    int qorder_kind = 0;        // 0 none, 1 balls (radius queries), 2 capsules (predict queries)
 
     bool world_static = false;
     float wmin[3] = {}, wmax[3] = {};
@@ -66,9 +71,15 @@ struct rcd_handle_s {
     Counters *counters_host = nullptr;  // pinned
     u32 *cand_count = nullptr;
     u32 *pair_tile_counter = nullptr;
-    QEntry *q2 = nullptr, *q3 = nullptr;
+    QEntry *q3 = nullptr;
     u32 qcap = 0;
-    int stage_blocks = 0;
+    uint2 *qa = nullptr;        // pair queue k_pairs -> k_narrow
+    u32 *qa_fill = nullptr;
+    u32 qa_blocks_cap = 0;
+    uint4 *ovf = nullptr;       // tiles (or rests of tiles) left to the overflow pass of k_pairs
+    u32 ovf_cap = 0;
+    int stage_blocks = 0, stage_blocks_sms = 148;
+    int narrow_blocks[5] = {0, 0, 0, 0, 0};
     int pair_blocks[5] = {0, 0, 0, 0, 0};  // resident blocks per SM x SMs, per kernel variant
     bool frame_done = false;
     int last_mode = -1;
@@ -85,12 +96,12 @@ struct rcd_handle_s {
         int32_t mode = -1;
         float R = 0, T = 0, pt = 0, thr = 0, index_cell_req = 0;
         u64 n = 0, n_owned = 0;
-        int index_valid = 0, sorted_buf = 0, frame_done = 0;
+        int index_valid = 0, sorted_buf = 0, frame_done = 0, qorder_kind = 0, q_sorted_buf = 0;
         const void *out = nullptr;
         bool operator==(const StepKey &o) const {
             return mode == o.mode && R == o.R && T == o.T && pt == o.pt && thr == o.thr && index_cell_req == o.index_cell_req &&
                    n == o.n && n_owned == o.n_owned && index_valid == o.index_valid && sorted_buf == o.sorted_buf &&
-                   frame_done == o.frame_done && out == o.out;
+                   frame_done == o.frame_done && qorder_kind == o.qorder_kind && q_sorted_buf == o.q_sorted_buf && out == o.out;
         }
     };
     struct StepGraph {
@@ -98,7 +109,7 @@ struct rcd_handle_s {
         StepKey key;
         GridParams grid = {};
         float index_cell_req = 0;
-        int sorted_buf = 0, last_mode = 0;
+        int sorted_buf = 0, last_mode = 0, qorder_kind = 0, q_sorted_buf = 0;
         u64 launches = 0;
     };
     StepGraph graphs[4];
@@ -174,12 +185,15 @@ InputState input_state(rcd_handle h) {
     return in;
 }
 
-// Grid for a requested minimum cell edge.  cell = cell_req * 1.002 + 0.02 keeps two objects within
-// cell_req of each other in adjacent cells despite the fp32 rounding of (x - origin) / cell (up to
-// ~1e-4 cells at 100 km coordinates; the stencil radius adds 1e-3 cells of slack, rcd_pairs.cuh).
-GridParams make_grid(const float *wmin, const float *wmax, float cell_req, u32 cells_cap) {
+// Grid for a query radius.  The pair kernel and the radius queries walk the cells under the bounding box of
+// their query volumes, so any cell size is exact (cell_coord is monotone); the x/y edge is a fraction of
+// the query radius (finer cells = tighter boxes in dense regions, more rows per box), the z edge is the
+// radius itself (the reference's worlds are ~100 m high).  Cells grow until the grid fits cells_cap.
+GridParams make_grid(const float *wmin, const float *wmax, float cell_req, float cell_scale, u32 cells_cap) {
     GridParams g;
-    double cell = (double)cell_req * 1.002 + 0.02;
+    double cell_z = (double)cell_req * 1.002 + 0.02;
+    if (!(cell_z > 1e-3)) cell_z = 1e-3;
+    double cell = cell_z * (double)cell_scale;
     if (!(cell > 1e-3)) cell = 1e-3;
     double ext[3];
     for (int d = 0; d < 3; ++d) {
@@ -187,16 +201,19 @@ GridParams make_grid(const float *wmin, const float *wmax, float cell_req, u32 c
         ext[d] = (e > 0 && std::isfinite(e)) ? e : 0.0;
     }
     for (;;) {
-        double nx = std::floor(ext[0] / cell) + 1, ny = std::floor(ext[1] / cell) + 1, nz = std::floor(ext[2] / cell) + 1;
+        double nx = std::floor(ext[0] / cell) + 1, ny = std::floor(ext[1] / cell) + 1, nz = std::floor(ext[2] / cell_z) + 1;
         if (nx * ny * nz <= (double)cells_cap) {
             g.nx = (int)nx; g.ny = (int)ny; g.nz = (int)nz;
             break;
         }
         cell *= 1.25;
+        cell_z *= 1.25;
     }
     g.ox = wmin[0]; g.oy = wmin[1]; g.oz = wmin[2];
     g.cell = (float)cell;
     g.inv_cell = (float)(1.0 / cell);
+    g.cell_z = (float)cell_z;
+    g.inv_cell_z = (float)(1.0 / cell_z);
     g.ncells = (u32)g.nx * (u32)g.ny * (u32)g.nz;
     return g;
 }
@@ -212,9 +229,10 @@ int build_index(rcd_handle h, float cell_req) {
     const u32 n = (u32)h->n;
     if (h->index_valid && h->index_cell_req == cell_req) return RCD_OK;
     h->index_valid = false;
+    h->qorder_kind = 0;
     if (n == 0) {
         float z[3] = {0, 0, 0};
-        h->grid = make_grid(z, z, cell_req, h->cells_cap);
+        h->grid = make_grid(z, z, cell_req, h->cell_scale, h->cells_cap);
         h->index_valid = true;
         h->index_cell_req = cell_req;
         return RCD_OK;
@@ -234,7 +252,7 @@ int build_index(rcd_handle h, float cell_req) {
             if (!(h->wmin[d] <= h->wmax[d])) h->wmin[d] = h->wmax[d] = 0.0f;  // no finite coordinate
         }
     }
-    h->grid = make_grid(h->wmin, h->wmax, cell_req, h->cells_cap);
+    h->grid = make_grid(h->wmin, h->wmax, cell_req, h->cell_scale, h->cells_cap);
     const GridParams g = h->grid;
     const int passes = key_passes(g.ncells);
     const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
@@ -243,8 +261,6 @@ int build_index(rcd_handle h, float cell_req) {
     CUDA_TRY(h, cudaMemsetAsync(h->hist, 0, MAX_PASSES * RADIX * sizeof(u32), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->tile_status, 0, (size_t)passes * tiles * RADIX * sizeof(u32), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->tile_counter, 0, MAX_PASSES * sizeof(u32), h->stream));
-    CUDA_TRY(h, cudaMemsetAsync(h->cell_start, 0, (size_t)g.ncells * sizeof(u32), h->stream));
-    CUDA_TRY(h, cudaMemsetAsync(h->cell_end, 0, (size_t)g.ncells * sizeof(u32), h->stream));
     {
         int blocks = (int)std::min<u64>(((u64)n + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
         k_pack_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(input_state(h), n, (u32)h->n_owned, g, passes, h->keys[0],
@@ -269,12 +285,49 @@ int build_index(rcd_handle h, float cell_req) {
 
     stage_begin(h, RCD_STAGE_REORDER);
     k_reorder<<<(n + REORDER_THREADS - 1) / REORDER_THREADS, REORDER_THREADS, 0, h->stream>>>(
-        h->keys[cur], h->vals[cur], n, h->U, h->P0, h->P1, h->P2, h->sorted_slot, h->cell_start,
-        h->cell_end);
+        h->vals[cur], n, h->U, h->P0, h->P1, h->P2, h->sorted_slot);
+    KERNEL_CHECK(h);
+    k_cell_table<<<(g.ncells + CT_CELLS - 1) / CT_CELLS, CT_THREADS, 0, h->stream>>>(h->keys[cur], n, g.ncells, h->cell_begin);
     KERNEL_CHECK(h);
     stage_end(h, RCD_STAGE_REORDER);
     h->index_valid = true;
     h->index_cell_req = cell_req;
+    return RCD_OK;
+}
+
+// Query order for the pair kernel (k_query_keys + the same onesweep passes): tiles of 32 queries whose
+// volumes overlap.  kind 1: balls about the objects; kind 2: capsules of the predict queries.
+int build_query_order(rcd_handle h, int kind) {
+    const u32 n = (u32)h->n;
+    if (h->qorder_kind == kind || n == 0) return RCD_OK;
+    const GridParams g = h->grid;
+    const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    stage_begin(h, RCD_STAGE_QORDER);
+    CUDA_TRY(h, cudaMemsetAsync(h->hist, 0, MAX_PASSES * RADIX * sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->tile_status, 0, (size_t)QKEY_PASSES * tiles * RADIX * sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->tile_counter, 0, MAX_PASSES * sizeof(u32), h->stream));
+    QueryKeyParams q;
+    q.ox = g.ox; q.oy = g.oy;
+    const double ex = std::max((double)g.nx * g.cell, 1e-3), ey = std::max((double)g.ny * g.cell, 1e-3);
+    q.inv_res_x = (float)(2048.0 / ex);
+    q.inv_res_y = (float)(2048.0 / ey);
+    q.capsule = kind == 2 ? 1 : 0;
+    const int blocks = (int)std::min<u64>(((u64)n + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
+    k_query_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(h->P0, h->P1, h->P2, n, q, h->qkeys[0], h->qvals[0], h->hist);
+    KERNEL_CHECK(h);
+    k_scan_hist<<<1, RADIX, 0, h->stream>>>(h->hist, QKEY_PASSES);
+    KERNEL_CHECK(h);
+    int cur = 0;
+    for (int p = 0; p < QKEY_PASSES; ++p) {
+        k_onesweep_pass<<<tiles, SORT_THREADS, 0, h->stream>>>(
+            h->qkeys[cur], h->qvals[cur], h->qkeys[cur ^ 1], h->qvals[cur ^ 1], n, p * RADIX_BITS,
+            h->hist + p * RADIX, h->tile_status + (size_t)p * tiles * RADIX, h->tile_counter + p);
+        KERNEL_CHECK(h);
+        cur ^= 1;
+    }
+    stage_end(h, RCD_STAGE_QORDER);
+    h->q_sorted_buf = cur;
+    h->qorder_kind = kind;
     return RCD_OK;
 }
 
@@ -346,20 +399,33 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->P2, cap));
     CREATE_TRY(dev_alloc(&h->U, 3 * (cap + 4)));
     CREATE_TRY(dev_alloc(&h->sorted_slot, cap));
-    CREATE_TRY(dev_alloc(&h->cell_start, h->cells_cap));
-    CREATE_TRY(dev_alloc(&h->cell_end, h->cells_cap));
+    CREATE_TRY(dev_alloc(&h->cell_begin, (size_t)h->cells_cap + 1));
+    for (int k = 0; k < 2; ++k) {
+        CREATE_TRY(dev_alloc(&h->qkeys[k], cap + 4));
+        CREATE_TRY(dev_alloc(&h->qvals[k], cap + 4));
+    }
+    if (const char *e = getenv("RCD_CELL_SCALE")) {  // kernel-tuning experiments only
+        const double v = atof(e);
+        if (v >= 0.05 && v <= 4.0) h->cell_scale = (float)v;
+    }
     CREATE_TRY(dev_alloc(&h->bbox_dev, 6));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->bbox_host), 6 * sizeof(int)));
     CREATE_TRY(dev_alloc(&h->out, (size_t)h->max_pairs));
     CREATE_TRY(dev_alloc(&h->counters, 1));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->counters_host), sizeof(Counters)));
     CREATE_TRY(dev_alloc(&h->cand_count, cap));
-    CREATE_TRY(dev_alloc(&h->pair_tile_counter, 1));
+    CREATE_TRY(dev_alloc(&h->pair_tile_counter, 2));
     // the fp32 stages forward about 5 candidate entries per emitted pair on clustered frames; a full
     // queue is not an error (the pair is then finished in place) but it is slower
     h->qcap = (u32)std::min<u64>(6 * h->max_pairs + 65536, 1ull << 28);
-    CREATE_TRY(dev_alloc(&h->q2, (size_t)h->qcap));
     CREATE_TRY(dev_alloc(&h->q3, (size_t)h->qcap));
+    // the S1 filter forwards ~60 (predict) / ~20 (detect) pairs per object at the density of the bench frame;
+    // the pair queue is handed out in blocks of QA_BLOCK entries, one per warp at a time
+    h->qa_blocks_cap = (u32)std::max<u64>(h->qcap / QA_BLOCK, 1);
+    CREATE_TRY(dev_alloc(&h->qa, (size_t)h->qa_blocks_cap * QA_BLOCK));
+    CREATE_TRY(dev_alloc(&h->qa_fill, (size_t)h->qa_blocks_cap));
+    h->ovf_cap = (u32)(cap / TQ + 65536);  // >= work items of a frame (tiles x splits)
+    CREATE_TRY(dev_alloc(&h->ovf, (size_t)h->ovf_cap));
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) {
             CREATE_TRY(cudaEventCreate(&h->stages[m][s].begin));
@@ -381,10 +447,12 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->hist); cudaFree(h->tile_status); cudaFree(h->tile_counter);
     cudaFree(h->P0); cudaFree(h->P1); cudaFree(h->P2); cudaFree(h->sorted_slot);
     cudaFree(h->U);
-    cudaFree(h->cell_start); cudaFree(h->cell_end); cudaFree(h->bbox_dev);
+    cudaFree(h->cell_begin); cudaFree(h->bbox_dev);
+    for (int k = 0; k < 2; ++k) { cudaFree(h->qkeys[k]); cudaFree(h->qvals[k]); }
+    cudaFree(h->qa); cudaFree(h->qa_fill); cudaFree(h->ovf);
     if (h->bbox_host) cudaFreeHost(h->bbox_host);
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
-    cudaFree(h->q2); cudaFree(h->q3);
+    cudaFree(h->q3);
     cudaFree(h->traj); cudaFree(h->traj_count);
     for (auto &g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -496,61 +564,101 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
     h->frame_done = false;
     h->stage_mode = mode;
     for (int s = RCD_STAGE_KEYS; s <= RCD_STAGE_EXACT; ++s) h->stages[mode][s].used = false;
+    h->stages[mode][RCD_STAGE_QORDER].used = false;
     stage_begin(h, RCD_STAGE_TOTAL);
     const float cell_req = (mode == RCD_MODE_PREDICT) ? PREDICT_RADIUS : search_radius;
     int rc = build_index(h, cell_req);
     if (rc) return rc;
 
+    if (h->n && h->n_owned) {
+        rc = build_query_order(h, mode == RCD_MODE_PREDICT ? 2 : 1);
+        if (rc) return rc;
+    }
     stage_begin(h, RCD_STAGE_PAIRS);
     if (!append) CUDA_TRY(h, cudaMemsetAsync(h->counters, 0, sizeof(Counters), h->stream));
     if (h->n) CUDA_TRY(h, cudaMemsetAsync(h->cand_count, 0, (size_t)h->n * sizeof(u32), h->stream));
     if (h->n && h->n_owned) {
         PairParams P;
         P.n = (u32)h->n;
+        P.n_owned = (u32)h->n_owned;
         P.g = h->grid;
         P.P0 = h->P0; P.P1 = h->P1; P.P2 = h->P2;
-        P.keys = h->keys[h->sorted_buf];
+        P.qorder = h->qvals[h->q_sorted_buf];
         P.sorted_slot = h->sorted_slot;
         P.in_id = h->in_id;
-        P.cell_start = h->cell_start; P.cell_end = h->cell_end;
+        P.cell_begin = h->cell_begin;
         P.R = search_radius;
         P.T = time_window;
         P.steps = (int)((double)time_window / 0.1);  // int(time_window / time_step), collision_detection.py:322
         P.pt = h->cn_prediction_time;  // CollisionDetector(prediction_time=5.0, risk_threshold=0.5), compute_node.py:218
         P.threshold = h->cn_risk_threshold;
+        // T1 window of the S1 filter: detect looks at [0, time_window]; the predict modes at [0, 10] (offsets up
+        // to 9.5 s, and detect_collisions(100, 10) for objects without history / the fused detect pass)
+        if (mode == RCD_MODE_DETECT) {
+            P.tm = P.D = 0.5f * time_window;
+            P.use_t1 = time_window <= 64.0f ? 1 : 0;  // (longer windows: the quadratic slack passes everything anyway)
+        } else {
+            P.tm = P.D = 5.0f;
+            P.use_t1 = mode == RCD_MODE_PREDICT ? 1 : 0;
+        }
+        P.D *= 1.0f + 1.0e-6f;
         P.out = h->out;
         P.out_cap = h->max_pairs;
         P.counters = h->counters;
         P.cand_count = h->cand_count;
-        P.ntiles = (u32)((h->n + TQ - 1) / TQ);
+        P.ntiles = (u32)((h->n_owned + TQ - 1) / TQ);
         P.tile_counter = h->pair_tile_counter;
-        P.q2 = h->q2; P.q3 = h->q3; P.qcap = h->qcap;
-        CUDA_TRY(h, cudaMemsetAsync(h->pair_tile_counter, 0, sizeof(u32), h->stream));
-        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_q2, 0, 2 * sizeof(unsigned long long), h->stream));
+        P.qa = h->qa; P.qa_fill = h->qa_fill; P.qa_blocks_cap = h->qa_blocks_cap;
+        P.ovf = h->ovf; P.ovf_cap = h->ovf_cap;
+        P.q3 = h->q3; P.qcap = h->qcap;
+        CUDA_TRY(h, cudaMemsetAsync(h->pair_tile_counter, 0, 2 * sizeof(u32), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_qa_blocks, 0, 3 * sizeof(unsigned long long), h->stream));
         const bool count = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) != 0;
         // persistent launch: as many blocks as can be resident, warps pull tiles from a counter
         const int variant = fused ? 4 : mode == RCD_MODE_DETECT ? 0 : (mode == RCD_MODE_COMPUTE_NODE ? 3 : (count ? 2 : 1));
         if (h->pair_blocks[variant] == 0) {
             int per_sm = 0, sms = 0;
-            const void *fn = variant == 0 ? (const void *)k_pairs<RCD_MODE_DETECT, true>
-                           : variant == 1 ? (const void *)k_pairs<RCD_MODE_PREDICT, false>
-                           : variant == 2 ? (const void *)k_pairs<RCD_MODE_PREDICT, true>
-                           : variant == 4 ? (const void *)k_pairs<MODE_PREDICT_WITH_DETECT, false>
-                                          : (const void *)k_pairs<RCD_MODE_COMPUTE_NODE, true>;
-            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PAIR_THREADS, 0));
+            const void *fn = variant == 0 ? (const void *)k_pairs<RCD_MODE_DETECT, false, false>
+                           : variant == 1 ? (const void *)k_pairs<RCD_MODE_PREDICT, false, false>
+                           : variant == 2 ? (const void *)k_pairs<RCD_MODE_PREDICT, true, false>
+                           : variant == 4 ? (const void *)k_pairs<MODE_PREDICT_WITH_DETECT, false, false>
+                                          : (const void *)k_pairs<RCD_MODE_COMPUTE_NODE, false, false>;
+            const void *fn2 = variant == 0 ? (const void *)k_narrow<RCD_MODE_DETECT, false>
+                            : variant == 1 ? (const void *)k_narrow<RCD_MODE_PREDICT, false>
+                            : variant == 2 ? (const void *)k_narrow<RCD_MODE_PREDICT, true>
+                            : variant == 4 ? (const void *)k_narrow<MODE_PREDICT_WITH_DETECT, false>
+                                           : (const void *)k_narrow<RCD_MODE_COMPUTE_NODE, false>;
             CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+            h->stage_blocks_sms = std::max(1, sms);
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PAIR_THREADS, 0));
             h->pair_blocks[variant] = std::max(1, per_sm) * std::max(1, sms);
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn2, STAGE_THREADS, 0));
+            h->narrow_blocks[variant] = std::max(1, per_sm) * std::max(1, sms);
         }
         // small frames: share each tile between several warps until the resident warps are used
         P.splits = 1;
         while (P.splits < 16 && (u64)P.ntiles * P.splits * 2 <= (u64)h->pair_blocks[variant] * PAIR_WARPS) P.splits *= 2;
         const u64 items = (u64)P.ntiles * P.splits;
         const unsigned blocks = (unsigned)std::min<u64>((items + PAIR_WARPS - 1) / PAIR_WARPS, (u64)h->pair_blocks[variant]);
-        if (variant == 0) k_pairs<RCD_MODE_DETECT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
-        else if (variant == 1) k_pairs<RCD_MODE_PREDICT, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
-        else if (variant == 2) k_pairs<RCD_MODE_PREDICT, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
-        else if (variant == 4) k_pairs<MODE_PREDICT_WITH_DETECT, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
-        else k_pairs<RCD_MODE_COMPUTE_NODE, true><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+        // the regular pass, then the overflow pass (returns at once unless the pair queue ran out)
+        const unsigned oblocks = std::min(blocks, (unsigned)h->stage_blocks_sms * 4u);
+        if (variant == 0) {
+            k_pairs<RCD_MODE_DETECT, false, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+            k_pairs<RCD_MODE_DETECT, false, true><<<oblocks, PAIR_THREADS, 0, h->stream>>>(P);
+        } else if (variant == 1) {
+            k_pairs<RCD_MODE_PREDICT, false, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+            k_pairs<RCD_MODE_PREDICT, false, true><<<oblocks, PAIR_THREADS, 0, h->stream>>>(P);
+        } else if (variant == 2) {
+            k_pairs<RCD_MODE_PREDICT, true, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+            k_pairs<RCD_MODE_PREDICT, true, true><<<oblocks, PAIR_THREADS, 0, h->stream>>>(P);
+        } else if (variant == 4) {
+            k_pairs<MODE_PREDICT_WITH_DETECT, false, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+            k_pairs<MODE_PREDICT_WITH_DETECT, false, true><<<oblocks, PAIR_THREADS, 0, h->stream>>>(P);
+        } else {
+            k_pairs<RCD_MODE_COMPUTE_NODE, false, false><<<blocks, PAIR_THREADS, 0, h->stream>>>(P);
+            k_pairs<RCD_MODE_COMPUTE_NODE, false, true><<<oblocks, PAIR_THREADS, 0, h->stream>>>(P);
+        }
+        ++h->launches;
         KERNEL_CHECK(h);
         stage_end(h, RCD_STAGE_PAIRS);
         // the later stages read their queue lengths on the device: fixed grids, no host round trip
@@ -559,15 +667,18 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
             CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
             h->stage_blocks = std::max(1, sms) * 8;
         }
-        const unsigned sb = (unsigned)std::min<u64>((u64)h->stage_blocks, (h->n + STAGE_THREADS - 1) / STAGE_THREADS + 1);
-        if (variant == 1 || variant == 2 || variant == 4) {
-            stage_begin(h, RCD_STAGE_SAMPLE);
-            // k_sample is compiled for 8 resident blocks per SM: the fixed grid is exactly one wave
-            if (variant == 1 || variant == 4) k_sample<false><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-            else k_sample<true><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        stage_begin(h, RCD_STAGE_NARROW);
+        {
+            const unsigned nb = (unsigned)std::min<u64>((u64)h->narrow_blocks[variant], items * 2 / STAGE_WARPS + 1);
+            if (variant == 0) k_narrow<RCD_MODE_DETECT, false><<<nb, STAGE_THREADS, 0, h->stream>>>(P);
+            else if (variant == 1) k_narrow<RCD_MODE_PREDICT, false><<<nb, STAGE_THREADS, 0, h->stream>>>(P);
+            else if (variant == 2) k_narrow<RCD_MODE_PREDICT, true><<<nb, STAGE_THREADS, 0, h->stream>>>(P);
+            else if (variant == 4) k_narrow<MODE_PREDICT_WITH_DETECT, false><<<nb, STAGE_THREADS, 0, h->stream>>>(P);
+            else k_narrow<RCD_MODE_COMPUTE_NODE, false><<<nb, STAGE_THREADS, 0, h->stream>>>(P);
             KERNEL_CHECK(h);
-            stage_end(h, RCD_STAGE_SAMPLE);
         }
+        stage_end(h, RCD_STAGE_NARROW);
+        const unsigned sb = (unsigned)std::min<u64>((u64)h->stage_blocks, (h->n + STAGE_THREADS - 1) / STAGE_THREADS + 1);
         stage_begin(h, RCD_STAGE_EXACT);
         if (variant == 0) k_exact<RCD_MODE_DETECT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         else if (variant == 3) k_exact<RCD_MODE_COMPUTE_NODE><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
@@ -602,6 +713,8 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     key.index_valid = h->index_valid ? 1 : 0;
     key.index_cell_req = h->index_valid ? h->index_cell_req : 0.0f;
     key.sorted_buf = h->index_valid ? h->sorted_buf : 0;
+    key.qorder_kind = h->index_valid ? h->qorder_kind : 0;
+    key.q_sorted_buf = (h->index_valid && h->qorder_kind) ? h->q_sorted_buf : 0;
     key.frame_done = append ? (h->frame_done ? 1 : 0) : 0;
     key.out = flip ? (const void *)h->out_alt : (const void *)h->out;
     for (auto &g : h->graphs) {
@@ -620,6 +733,8 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         h->index_valid = true;
         h->index_cell_req = g.index_cell_req;
         h->sorted_buf = g.sorted_buf;
+        h->qorder_kind = g.qorder_kind;
+        h->q_sorted_buf = g.q_sorted_buf;
         h->stage_mode = g.last_mode;
         h->last_mode = g.last_mode;
         h->frame_done = true;
@@ -637,14 +752,15 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     CUDA_TRY(h, cudaSetDevice(h->device));
     struct Saved {
         rcd_pair *out, *out_alt; Counters *counters, *counters_alt; bool flip_pending, frame_done, index_valid;
-        float index_cell_req; int sorted_buf, last_mode, stage_mode; GridParams grid; u64 launches;
+        float index_cell_req; int sorted_buf, last_mode, stage_mode; GridParams grid; u64 launches; int qorder_kind, q_sorted_buf;
     } pre = {h->out, h->out_alt, h->counters, h->counters_alt, h->flip_pending, h->frame_done, h->index_valid,
-             h->index_cell_req, h->sorted_buf, h->last_mode, h->stage_mode, h->grid, h->launches};
+             h->index_cell_req, h->sorted_buf, h->last_mode, h->stage_mode, h->grid, h->launches, h->qorder_kind, h->q_sorted_buf};
     auto restore = [&]() {
         h->out = pre.out; h->out_alt = pre.out_alt; h->counters = pre.counters; h->counters_alt = pre.counters_alt;
         h->flip_pending = pre.flip_pending; h->frame_done = pre.frame_done; h->index_valid = pre.index_valid;
         h->index_cell_req = pre.index_cell_req; h->sorted_buf = pre.sorted_buf; h->last_mode = pre.last_mode;
         h->stage_mode = pre.stage_mode; h->grid = pre.grid; h->launches = pre.launches;
+        h->qorder_kind = pre.qorder_kind; h->q_sorted_buf = pre.q_sorted_buf;
     };
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -679,6 +795,8 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     slot.grid = h->grid;
     slot.index_cell_req = h->index_cell_req;
     slot.sorted_buf = h->sorted_buf;
+    slot.qorder_kind = h->qorder_kind;
+    slot.q_sorted_buf = h->q_sorted_buf;
     slot.last_mode = h->last_mode;
     slot.launches = h->launches - (append ? pre.launches : 0);
     return RCD_OK;
@@ -870,7 +988,7 @@ int rcd_query_radius(rcd_handle h, uint64_t nq, const float *qx, const float *qy
     cudaMemsetAsync(&h->counters->n_query_hits, 0, sizeof(unsigned long long), h->stream);
     const unsigned blocks = (unsigned)((nq * 32 + 127) / 128);
     k_query_radius<<<blocks, 128, 0, h->stream>>>((u32)nq, dq, dq + nq, dq + 2 * nq, radius, h->grid, (u32)h->n, h->P0,
-                                                   h->keys[h->sorted_buf], h->sorted_slot, dhits, cap, h->counters);
+                                                   h->cell_begin, h->sorted_slot, dhits, cap, h->counters);
     e = cudaGetLastError();
     unsigned long long total = 0;
     if (e == cudaSuccess)

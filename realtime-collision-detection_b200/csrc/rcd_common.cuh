@@ -29,8 +29,10 @@ constexpr int PREDICT_STEPS = 10;         // int(1.0 / 0.1), :821 + :322
 // other are always within floor(H / cell) + 1 cells after clamping ("grid").
 struct GridParams {
     float ox, oy, oz;  // origin
-    float cell;        // cell edge (>= search radius)
+    float cell;        // cell edge in x and y (any size: queries walk the cells under their bounding box)
     float inv_cell;
+    float cell_z;      // cell edge in z (coarser: the worlds of the reference are ~100 m high)
+    float inv_cell_z;
     int nx, ny, nz;
     u32 ncells;
 };
@@ -46,7 +48,7 @@ __device__ __forceinline__ int cell_coord(float x, float o, float inv_cell, int 
 __device__ __forceinline__ u32 cell_key(const GridParams &g, float x, float y, float z) {
     int cx = cell_coord(x, g.ox, g.inv_cell, g.nx);
     int cy = cell_coord(y, g.oy, g.inv_cell, g.ny);
-    int cz = cell_coord(z, g.oz, g.inv_cell, g.nz);
+    int cz = cell_coord(z, g.oz, g.inv_cell_z, g.nz);
     return (u32)((cz * g.ny + cy) * g.nx + cx);
 }
 
@@ -66,8 +68,10 @@ struct Counters {
     unsigned long long n_alerts[4];
     unsigned long long n_exact;
     unsigned long long n_query_hits;  // rcd_query_radius
-    // lengths of the global queues between k_pairs / k_sample / k_exact (reset before every step)
-    unsigned long long n_q2, n_q3;
+    // blocks of the pair queue handed out by k_pairs / length of the queue between k_narrow and k_exact
+    // (reset before every step)
+    unsigned long long n_qa_blocks, n_q3;
+    unsigned long long n_overflow;  // parts of tiles k_pairs left to its overflow pass (pair queue full)
     unsigned long long n_fallback;  // resolved entries the exact stage had to redo in full (expected 0)
 };
 

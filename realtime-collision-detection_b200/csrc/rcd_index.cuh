@@ -274,30 +274,156 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
 }
 
 // -------------------------------------------------------------------------------------------------
-// K4: gather the packed planes into cell order and mark the cell ranges.
-// Algorithmic bytes: 8 N (key + perm) + 48 N gathered + 52 N written = 108 N (+ 8 B per occupied cell);
+// K4: gather the packed planes into cell order.
+// Algorithmic bytes: 8 N (key + perm) + 48 N gathered + 52 N written = 108 N;
 // a 48-byte record spans exactly two 32-byte sectors, so DRAM traffic is about 124 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int REORDER_THREADS = 256;
 
 __global__ void __launch_bounds__(REORDER_THREADS)
-k_reorder(const u32 *__restrict__ keys, const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
-          float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2,
-          u32 *__restrict__ sorted_slot, u32 *__restrict__ cell_start, u32 *__restrict__ cell_end) {
+k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U, float4 *__restrict__ P0,
+          float4 *__restrict__ P1, float4 *__restrict__ P2, u32 *__restrict__ sorted_slot) {
     u32 s = blockIdx.x * REORDER_THREADS + threadIdx.x;
     if (s >= n) return;
-    const u32 key = keys[s];
-    const u32 src = perm[s];
-    const u32 prev = (s > 0) ? keys[s - 1] : 0xffffffffu;
-    const u32 next = (s + 1 < n) ? keys[s + 1] : 0xffffffffu;
-    if (s == 0 || key != prev) cell_start[key] = s;
-    if (s + 1 == n || key != next) cell_end[key] = s + 1;
+    const u32 src = __ldcs(perm + s);
     const float4 *rec = U + 3 * (size_t)src;
     const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
     P0[s] = a;
     P1[s] = b;
     P2[s] = c;
     sorted_slot[s] = src;
+}
+
+// lower bound in the sorted key array
+__device__ __forceinline__ u32 lower_bound_keys(const u32 *__restrict__ keys, u32 n, u32 key) {
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        u32 mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// -------------------------------------------------------------------------------------------------
+// K5: dense cell table.  cell_begin[c] = position in cell order of the first object whose cell is
+// >= c, for every c in [0, ncells]; the objects of the cell run [c0, c1] of one grid row are then
+// cell_begin[c0] .. cell_begin[c1 + 1] -- two loads, whatever the cell size.  One block owns
+// CT_CELLS consecutive cells: two binary searches give its slice of the sorted keys, the first
+// object of every occupied cell is marked in shared memory, a suffix-minimum fills the empty cells.
+// Every entry is written every frame (no memset).  Bytes: 4 N read + 4 C written.
+// -------------------------------------------------------------------------------------------------
+constexpr int CT_THREADS = 256;
+constexpr int CT_PER_THREAD = 4;
+constexpr int CT_CELLS = CT_THREADS * CT_PER_THREAD;
+
+__global__ void __launch_bounds__(CT_THREADS)
+k_cell_table(const u32 *__restrict__ keys, u32 n, u32 ncells, u32 *__restrict__ cell_begin) {
+    __shared__ u32 s_first[CT_CELLS];
+    __shared__ u32 s_warp_min[CT_THREADS / 32];
+    __shared__ u32 s_range[2];
+    const u32 c0 = blockIdx.x * CT_CELLS;
+    const u32 c1 = min(c0 + (u32)CT_CELLS, ncells);  // exclusive
+    if (threadIdx.x < 2) s_range[threadIdx.x] = lower_bound_keys(keys, n, threadIdx.x == 0 ? c0 : c1);
+#pragma unroll
+    for (int k = 0; k < CT_PER_THREAD; ++k) s_first[threadIdx.x + k * CT_THREADS] = 0xffffffffu;
+    __syncthreads();
+    const u32 s0 = s_range[0], s1 = s_range[1];
+    for (u32 s = s0 + threadIdx.x; s < s1; s += CT_THREADS) {
+        const u32 key = keys[s];
+        if (s == s0 || keys[s - 1] != key) s_first[key - c0] = s;
+    }
+    __syncthreads();
+    // suffix minimum over the block's cells, seeded with s1 (= first object of any later cell)
+    u32 v[CT_PER_THREAD];
+    u32 run = 0xffffffffu;
+#pragma unroll
+    for (int k = CT_PER_THREAD - 1; k >= 0; --k) {
+        run = min(run, s_first[threadIdx.x * CT_PER_THREAD + k]);
+        v[k] = run;
+    }
+    u32 suf = run;  // inclusive suffix minimum over the threads of the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_down_sync(FULL_MASK, suf, o);
+        if (lane_id() + o < 32) suf = min(suf, t);
+    }
+    if (lane_id() == 0) s_warp_min[threadIdx.x >> 5] = suf;
+    __syncthreads();
+    u32 later = s1;  // minimum over everything after this thread
+    for (u32 w = (threadIdx.x >> 5) + 1; w < CT_THREADS / 32; ++w) later = min(later, s_warp_min[w]);
+    const u32 next = __shfl_down_sync(FULL_MASK, suf, 1);
+    if (lane_id() < 31) later = min(later, next);
+#pragma unroll
+    for (int k = 0; k < CT_PER_THREAD; ++k) {
+        const u32 c = c0 + threadIdx.x * CT_PER_THREAD + k;
+        if (c < c1) cell_begin[c] = min(v[k], later);
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cell_begin[ncells] = n;
+}
+
+// -------------------------------------------------------------------------------------------------
+// K6: query order.  The pair kernel walks the cell rows under the bounding box of a tile's 32 query
+// volumes, so a tile should hold queries whose volumes overlap: objects are keyed by the 2-D Morton
+// code of the centre of their volume -- the object itself for radius queries, the middle of the chord
+// of the predicted centre path (collision_detection.py:728-741) for predict queries -- and sorted;
+// consecutive 32 objects are then a compact tile at any density.  Halo copies (not queried) get the
+// top key and end up behind the last tile.  Bytes: 48 N read + 8 N written, then the sort passes.
+// -------------------------------------------------------------------------------------------------
+constexpr int QKEY_BITS = 11;                       // per axis
+constexpr u32 QKEY_NOT_QUERIED = 1u << (2 * QKEY_BITS);  // bit 22: sorts behind every query
+constexpr int QKEY_PASSES = 3;                      // 23 bits
+
+__device__ __forceinline__ u32 spread_bits_2d(u32 v) {  // 11 bits -> every other bit
+    v &= 0x7ffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+struct QueryKeyParams {
+    float ox, oy;          // origin of the key lattice
+    float inv_res_x, inv_res_y;
+    int capsule;           // 1: predict queries are keyed by the middle of their chord
+};
+
+__global__ void __launch_bounds__(KEYS_THREADS)
+k_query_keys(const float4 *__restrict__ P0, const float4 *__restrict__ P1, const float4 *__restrict__ P2, u32 n,
+             QueryKeyParams q, u32 *__restrict__ keys, u32 *__restrict__ vals, u32 *__restrict__ hist) {
+    __shared__ u32 s_hist[QKEY_PASSES][RADIX];
+    for (int k = threadIdx.x; k < QKEY_PASSES * RADIX; k += KEYS_THREADS) (&s_hist[0][0])[k] = 0;
+    __syncthreads();
+    const u32 stride = gridDim.x * KEYS_THREADS;
+    for (u32 s = blockIdx.x * KEYS_THREADS + threadIdx.x; s < n; s += stride) {
+        const float4 p0 = P0[s];
+        const float4 p2 = P2[s];
+        const u32 meta = __float_as_uint(p2.w);
+        u32 key = QKEY_NOT_QUERIED;
+        if (meta & META_OWNED) {
+            float x = p0.x, y = p0.y;
+            const u32 pattern = meta_pattern(meta);
+            if (q.capsule && pattern != RCD_PAT_NO_HISTORY) {
+                const float4 p1 = P1[s];
+                const float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 4.75f : 0.0f;
+                const float fa = (pattern == RCD_PAT_ACCELERATING) ? 22.5625f : 0.0f;
+                const float mx = x + p1.x * fv + p2.x * fa, my = y + p1.y * fv + p2.y * fa;
+                if (fabsf(mx) < 1.0e30f && fabsf(my) < 1.0e30f) { x = mx; y = my; }
+            }
+            const float fx = fminf(fmaxf((x - q.ox) * q.inv_res_x, 0.0f), 2047.0f);  // NaN -> 0
+            const float fy = fminf(fmaxf((y - q.oy) * q.inv_res_y, 0.0f), 2047.0f);
+            key = spread_bits_2d((u32)fx) | (spread_bits_2d((u32)fy) << 1);
+        }
+        keys[s] = key;
+        vals[s] = s;
+#pragma unroll
+        for (int p = 0; p < QKEY_PASSES; ++p) atomicAdd(&s_hist[p][(key >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < QKEY_PASSES * RADIX; k += KEYS_THREADS) {
+        u32 c = (&s_hist[0][0])[k];
+        if (c) atomicAdd(&hist[k], c);
+    }
 }
 
 // bounding box of the positions (auto grid): ordered-int atomics

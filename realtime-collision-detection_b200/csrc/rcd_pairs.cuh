@@ -1,29 +1,33 @@
 // Pair enumeration + narrow phase + classification.
 //
-// Three small kernels per frame, connected by compact queues in global memory, so that every
-// stage runs with full warps and each kernel's hot loop stays I-cache resident:
+// Three kernels per frame, connected by compact queues in global memory, so that every stage runs
+// with full warps and each kernel's hot loop stays small:
 //
-//   k_pairs  : persistent.  A tile is 32 consecutive objects in cell order, handled by ONE warp
-//              (one lane per querying object); warps take tiles from an atomic counter, so dense
-//              regions spread over all SMs.  Every query has a volume a neighbour must lie in to
-//              matter -- a ball of radius R, or (predict) the capsule of radius 100 m about the chord
-//              of the predicted centre path -- and the warp streams the cell rows under the bounding
-//              box of its queries' volumes through its own slice of shared memory in double-buffered
-//              chunks (cp.async); there is no block-wide barrier, everything is warp-synchronous.
-//                S1 filter : lane = query; every staged neighbour is tested against the lane's
-//                            volume, two neighbours per packed fp32 instruction (FADD2 / FFMA2);
-//                            hits go to per-lane lists in shared memory.
-//                S2a       : lane = pair, 32 listed pairs at a time.  detect: temporal filter +
-//                            closest approach.  predict: linear closest approach of the relative
-//                            trajectory; survivors are compacted by ballot into a warp queue.
-//                S2b       : lane = queued pair: the time window that can hold a hit (trajectory
-//                            re-expanded about the middle of the window, twice) -> offsets m_lo..m_hi.
-//              Survivors go to global queues (warp-aggregated atomics).  No fp64 here: radius tests
-//              inside the fp32 guard band are flagged for k_exact.  MODE_PREDICT_WITH_DETECT runs the
-//              detect narrow phase on the pairs of the predict sweep (one pass for both).
-//   k_sample : (predict) a warp takes 32 queued pairs through four phases with different lane
-//              assignments (pair / (pair, offset) / surviving item / pair): per offset the reach and
-//              radius tests, then the 10 samples, then the max-risk merge.
+//   k_pairs  : persistent, the S1 filter only.  A tile is 32 queries in *query order* (Morton order of
+//              the centres of the query volumes, rcd_index.cuh), handled by ONE warp with one lane per
+//              query; warps take tiles from an atomic counter.  Every query has a volume a neighbour
+//              must lie in to matter -- a ball of radius R, or (predict) the capsule of radius 100 m
+//              about the chord of the predicted centre path -- and the warp streams the cell rows under
+//              the bounding box of its queries' volumes through its own slice of shared memory
+//              (cp.async one chunk of 32 neighbours ahead, re-laid two neighbours side by side).  For
+//              every (query, neighbour) the lane takes, in packed fp32 (FADD2 / FFMA2, two neighbours
+//              per instruction):
+//                * the radius test |p_j - p_i| <= R where the mode has one (candidate counts; pairs inside
+//                  the fp32 guard band of the radius are flagged for the exact stage), and
+//                * T1: can the relative trajectory come close at all?  The trajectory of the pair is
+//                  expanded about the middle tm of the time window, g(tm + u) = g0 + g1 u + ca u^2 / 2 with
+//                  g0 = centre_i(tm) - pos_j(tm) and g1 the relative velocity at tm -- differences of
+//                  per-object quantities, so the neighbour's half is computed once when it is staged --
+//                  and the linear part must come within  L = A_i + B_j + 0.9 |g1|  on |u| <= D, where
+//                  A_i, B_j bound the safe distance, the motion of the 10 samples and |ca| D^2 / 2.
+//              Survivors (about 1 in 20) are appended to the pair queue QA, which warps fill in private
+//              2048-entry blocks (one global atomic per block, not per push).
+//   k_narrow : QA -> Q3.  A warp takes 32 queued pairs (lane = pair): detect narrow phase (temporal
+//              filter + closest approach) and, for predict queries, the time window that can hold a hit
+//              (trajectory re-expanded about the middle of the window, twice) -> offsets m_lo..m_hi; then
+//              the per-offset work in three more phases with different lane assignments
+//              ((pair, offset) / surviving item / pair): reach and radius tests, the 10 samples, the
+//              max-risk merge.
 //   k_exact  : lane = pair; the decision is taken in fp64 in the reference's operation order
 //              (rcd_exact.cuh), merged over offsets, emitted through one 64-bit atomic cursor and
 //              classified (alert priority).
@@ -38,6 +42,7 @@
 //                                                       src/collision/warning_system.py:259-311
 #pragma once
 #include "rcd_common.cuh"
+#include "rcd_index.cuh"
 #include "rcd_exact.cuh"
 
 namespace rcd {
@@ -46,56 +51,70 @@ constexpr int TQ = 32;            // queries per tile = one warp
 constexpr int PAIR_WARPS = 4;     // warps (independent tiles) per block
 constexpr int PAIR_THREADS = PAIR_WARPS * 32;
 constexpr int CH = 32;            // neighbours staged per chunk (1 per lane)
-constexpr int ROW_SCAN_MAX = 32;  // rows up to this many cells wide are scanned cell by cell
-constexpr int QCAP1B = 64;        // Q1b capacity (<= 31 carried + 32 pushed)
+constexpr int QA_BLOCK = 2048;    // entries of the pair queue a warp reserves at a time (>= TQ * CH)
+constexpr u32 QA_INR = 1u << 30;  // entry flag: certainly within the radius (and counted as a candidate)
+constexpr u32 QA_UND = 1u << 31;  // entry flag: inside the fp32 guard band of the radius: k_exact decides and counts
+constexpr u32 QA_SI_MASK = (1u << 30) - 1u;
+constexpr u32 QA_NO_BLOCK = 0xffffffffu;
 
-// one queued pair between kernels: positions in cell order + offset mask (predict)
+// one queued pair between k_narrow and k_exact: positions in cell order + offset mask (predict)
 struct QEntry {
     u32 si, sj, mask;
 };
 
 struct PairParams {
-    u32 n;
+    u32 n;                   // objects (owned + halo)
+    u32 n_owned;             // queries
     u32 ntiles;
     u32 splits;              // work items per tile (power of two): small frames split a tile's chunks over warps
     GridParams g;
     const float4 *P0, *P1, *P2;
-    const u32 *keys;         // sorted cell keys
+    const u32 *qorder;       // query order -> position in cell order
     const u32 *sorted_slot;  // cell order -> upload slot
     const u32 *in_id;        // upload slot -> caller id
-    const u32 *cell_start, *cell_end;
+    const u32 *cell_begin;   // [ncells + 1]
     float R, T;              // search radius / time window (detect)
     int steps;               // int(T / 0.1)
     float pt, threshold;     // compute-node: prediction_time, risk_threshold
+    // T1: middle and half width of the time window, on/off
+    float tm, D;
+    int use_t1;
     rcd_pair *out;
     unsigned long long out_cap;
     Counters *counters;
     u32 *tile_counter;
     u32 *cand_count;         // per upload slot
-    QEntry *q2, *q3;         // global queues: -> k_sample, -> k_exact
-    u32 qcap;                // capacity of each
+    uint2 *qa;               // pair queue k_pairs -> k_narrow: {si | flags, sj}
+    u32 *qa_fill;            // entries used in every QA block
+    u32 qa_blocks_cap;
+    uint4 *ovf;              // work of k_pairs left to its overflow pass: {work item, row batch, chunk, -}
+    u32 ovf_cap;
+    QEntry *q3;              // k_narrow -> k_exact
+    u32 qcap;
 };
 
 // relative guard band of the fp32 radius test (fp32 error of d2 is < 1e-6 relative)
 constexpr float BAND_R2 = 2.0e-5f;
 
-// shared-memory state of one warp
-struct StageBuf {
-    float4 p0[CH], p1[CH], p2[CH];
-    u32 pos[CH];         // position in cell order of the staged object
-    float4 xy[CH / 2];   // positions again, two objects side by side for the packed S1 filter: {x0, x1, y0, y1}
-    float2 zz[CH / 2];   //                                                                     {z0, z1}
+// shared-memory state of one warp of k_pairs
+struct StagePacked {      // a chunk of 32 neighbours, two side by side per entry (operands of the packed filter)
+    float4 xy[CH / 2];    // {x0, x1, y0, y1}                      current position
+    float4 zb[CH / 2];    // {z0, z1, B0, B1}                      ... and the neighbour's half of the T1 bound
+    float4 nxy[CH / 2];   // {-Nx0, -Nx1, -Ny0, -Ny1}              N = position at tm, negated
+    float4 nzv[CH / 2];   // {-Nz0, -Nz1, -NVx0, -NVx1}            NV = velocity at tm, negated
+    float4 nvyz[CH / 2];  // {-NVy0, -NVy1, -NVz0, -NVz1}
+    float4 naxy[CH / 2];  // {-ax0, -ax1, -ay0, -ay1}              acceleration, negated
+    float2 naz[CH / 2];   // {-az0, -az1}
+    u32 pos[CH];          // position in cell order of the staged object
 };
 struct WarpShared {
-    StageBuf buf[2];
-    float4 q0[TQ], q1[TQ], q2[TQ];  // the tile's own (querying) objects
-    unsigned char plist[CH][TQ];    // S1: per-lane lists of staged indices inside the lane's reach
-    u32 q1b_pos[QCAP1B];            // Q1b (predict): neighbour position in cell order
-    unsigned char q1b_ql[QCAP1B];   //                query lane
-    u32 cand[TQ];                   // candidates resolved outside the filter (per query)
+    float4 r0[CH], r1[CH], r2[CH];  // landing zone of the cp.async copies (the chunk after the one being filtered)
+    StagePacked buf[2];
+    unsigned char plist[CH][TQ];    // per-lane lists of the staged neighbours that passed: index | flags
     u32 row_lo[TQ];
     u32 row_prefix[TQ + 1];
 };
+constexpr u32 PL_INR = 0x40u, PL_UND = 0x80u;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -331,22 +350,13 @@ __device__ __noinline__ u32 finish_entry_inline(const PairParams &P, u32 si, u32
     return e.potential;
 }
 
-// ---- S2, detect: temporal filter + closest approach in fp32 (collision_detection.py:244-292) ------
-// returns true when the pair must be decided in fp64
-// COUNT_ALL: the S1 filter did not count the pairs certainly within the radius (predict mode)
-template <bool COUNT_ALL>
-__device__ __forceinline__ bool narrow_detect(WarpShared &ws, u32 ql, const float4 &a0, const float4 &a1,
-                                              const float4 &a2, const float4 &b0, const float4 &b1, const float4 &b2,
-                                              float R, float T, bool &undecided, u32 count_weight = 1u) {
-    const float R2 = R * R;
+// ---- narrow phase, detect: temporal filter + closest approach in fp32 (collision_detection.py:244-292) ------
+// returns true when the pair must be decided in fp64.  The radius test was taken by the S1 filter (QA_INR /
+// QA_UND): pairs inside the guard band of the radius go to the exact stage without passing through here.
+__device__ __forceinline__ bool narrow_detect(const float4 &a0, const float4 &a1, const float4 &a2, const float4 &b0,
+                                              const float4 &b1, const float4 &b2, float T) {
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;  // rel_position = other - self
     float d2 = dx * dx + dy * dy + dz * dz;
-    if (COUNT_ALL && d2 > R2 * (1.0f + BAND_R2)) return false;  // certainly outside the radius
-    // fp32 cannot decide the radius test inside the guard band (spatial_index.py:268): the exact stage does.
-    // (detect: the S1 filter made that call when it counted the candidate; predict: made here)
-    if (COUNT_ALL) undecided = d2 >= R2 * (1.0f - BAND_R2);
-    if (undecided) return true;
-    if (COUNT_ALL) atomicAdd(&ws.cand[ql], count_weight);
     float rvx = a1.x - b1.x, rvy = a1.y - b1.y, rvz = a1.z - b1.z;  // rel_velocity = self - other
     float rs2 = rvx * rvx + rvy * rvy + rvz * rvz;
     if (rs2 < 0.0099f) return false;  // rel_speed < 0.1 with margin (0.1^2 = 0.01)
@@ -525,9 +535,8 @@ __device__ __forceinline__ bool predict_window(const WindowCoef &c, int &m_lo, i
 
 // ---- diagnostic variant (RCD_STEP_COUNT_CANDIDATES): every offset takes the radius test in k_pairs so that
 // candidates can be counted per query; bit m set <=> offset m is a candidate that may be hit
-template <bool COUNT_CAND>
-__device__ __forceinline__ u32 predict_scan(WarpShared &ws, const PairParams &P, const PredictCoef &c, u32 ql, u32 si,
-                                            u32 sj, u32 pattern, int m_lo, int m_hi, u32 &n_exact) {
+__device__ __forceinline__ u32 predict_scan(const PairParams &P, const PredictCoef &c, u32 si, u32 sj, u32 pattern,
+                                            int m_lo, int m_hi, u32 &n_exact) {
     u32 mask = 0;
     const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
     u32 ncand = 0;
@@ -544,7 +553,10 @@ __device__ __forceinline__ u32 predict_scan(WarpShared &ws, const PairParams &P,
         ++ncand;
         if (m >= m_lo && m <= m_hi && offset_may_hit(c, t)) mask |= 1u << m;
     }
-    if (ncand) atomicAdd(&ws.cand[ql], ncand);
+    if (ncand) {
+        atomicAdd(&P.counters->n_candidates, (unsigned long long)ncand);
+        if (P.cand_count) atomicAdd(&P.cand_count[P.sorted_slot[si]], ncand);
+    }
     return mask;
 }
 
@@ -609,9 +621,9 @@ __device__ __forceinline__ u32 sample_predict(const PairParams &P, u32 si, u32 s
 }
 
 // ---- S2, compute-node pair function in fp32 (compute_node.py:258-292) --------------------------------
-__device__ __forceinline__ bool narrow_compute_node(WarpShared &ws, const PairParams &P, u32 ql, const float4 &a0,
-                                                    const float4 &a1, const float4 &a2, const float4 &b0,
-                                                    const float4 &b1, const float4 &b2, bool self, bool &undecided) {
+__device__ __forceinline__ bool narrow_compute_node(const PairParams &P, const float4 &a0, const float4 &a1,
+                                                    const float4 &a2, const float4 &b0, const float4 &b1,
+                                                    const float4 &b2, bool self, bool undecided) {
     float dx = b0.x - a0.x, dy = b0.y - a0.y, dz = b0.z - a0.z;
     float d2 = dx * dx + dy * dy + dz * dz;
     if (undecided) return true;  // fp32 could not decide the radius test (compute_node.py:113-116)
@@ -636,16 +648,6 @@ __device__ __noinline__ void finish_predict_pair(const PairParams &P, u32 si, u3
     if (m2) finish_entry_inline<RCD_MODE_PREDICT>(P, si, sj, m2);
 }
 
-// lower bound in the sorted key array
-__device__ __forceinline__ u32 lower_bound_keys(const u32 *__restrict__ keys, u32 n, u32 key) {
-    u32 lo = 0, hi = n;
-    while (lo < hi) {
-        u32 mid = (lo + hi) >> 1;
-        if (keys[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
 // warp-aggregated append to a global queue; returns false for the lanes whose entry did not fit
 __device__ __forceinline__ bool global_push(QEntry *q, u32 cap, unsigned long long *count, bool flag, u32 si, u32 sj,
                                             u32 mask) {
@@ -663,70 +665,141 @@ __device__ __forceinline__ bool global_push(QEntry *q, u32 cap, unsigned long lo
     q[at] = e;
     return true;
 }
+// predict: the offsets of the pair (si, sj) the later phases have to look at (0: none)
+template <bool COUNT_CAND>
+__device__ __forceinline__ u32 predict_mask(const PairParams &P, const float4 &a0, const float4 &a1, const float4 &a2,
+                                            const float4 &b0, const float4 &b1, const float4 &b2, u32 si, u32 sj,
+                                            u32 pat, u32 &n_exact) {
+    int m_lo = 0, m_hi = PREDICT_OFFSETS - 1;
+    if (COUNT_CAND) {  // diagnostic: every offset takes the radius test here so that candidates can be counted
+        const bool in = predict_window(window_coef(a0, a1, a2, b0, b1, b2, pat), m_lo, m_hi);
+        if (!in) { m_lo = 1; m_hi = 0; }
+        const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
+        return predict_scan(P, c, si, sj, pat, m_lo, m_hi, n_exact);
+    }
+    if (predict_window(window_coef(a0, a1, a2, b0, b1, b2, pat), m_lo, m_hi))
+        return (2u << m_hi) - (1u << m_lo);  // offsets m_lo..m_hi; the per-offset phases test each of them
+    return 0u;
+}
 
+// pair-queue-full fallback of k_pairs: everything k_narrow and k_exact would do for one pair, in place
+// (correct, slower, out of line)
 template <int MODE, bool COUNT_CAND>
+__device__ __noinline__ u32 narrow_entry_inline(const PairParams &P, u32 si_flags, u32 sj) {
+    const u32 si = si_flags & QA_SI_MASK;
+    const bool inr = (si_flags & QA_INR) != 0, und = (si_flags & QA_UND) != 0;
+    if (si == sj && MODE != RCD_MODE_COMPUTE_NODE) return 0u;  // _spatial_filtering strips self (:224-225)
+    const float4 a0 = P.P0[si], a1 = P.P1[si], a2 = P.P2[si];
+    const float4 b0 = P.P0[sj], b1 = P.P1[sj], b2 = P.P2[sj];
+    u32 n_pot = 0;
+    if (MODE == RCD_MODE_DETECT) {
+        if (und || narrow_detect(a0, a1, a2, b0, b1, b2, P.T))
+            n_pot += finish_entry_inline<MODE>(P, si, sj, und ? RADIUS_UNDECIDED : 0u);
+    } else if (MODE == RCD_MODE_COMPUTE_NODE) {
+        if (narrow_compute_node(P, a0, a1, a2, b0, b1, b2, si == sj, und))
+            finish_entry_inline<MODE>(P, si, sj, und ? RADIUS_UNDECIDED : 0u);
+    } else {
+        const u32 pat = meta_pattern(__float_as_uint(a2.w));
+        const bool nohist = pat == RCD_PAT_NO_HISTORY;
+        if ((nohist || MODE == MODE_PREDICT_WITH_DETECT) && (inr || und)) {
+            const bool twice = nohist && MODE == MODE_PREDICT_WITH_DETECT;
+            if (und || narrow_detect(a0, a1, a2, b0, b1, b2, 10.0f))
+                n_pot += finish_entry_inline<MODE>(P, si, sj, (und ? RADIUS_UNDECIDED : 0u) | (twice ? ENTRY_TWICE : 0u));
+        }
+        if (!nohist) {
+            u32 dummy = 0;
+            const u32 mask = predict_mask<COUNT_CAND>(P, a0, a1, a2, b0, b1, b2, si, sj, pat, dummy);
+            if (mask) finish_predict_pair<COUNT_CAND>(P, si, sj, mask);
+        }
+    }
+    return n_pot;
+}
+
+__device__ __forceinline__ float abs3(float x, float y, float z) { return fabsf(x) + fabsf(y) + fabsf(z); }
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// k_pairs: the S1 filter (see the head of this file).
+// -------------------------------------------------------------------------------------------------
+// SLOW: the overflow pass.  A warp of the regular pass that finds the pair queue full records where it stopped
+// (work item, row batch, chunk) and moves on; the overflow pass redoes exactly those parts and finishes every
+// surviving pair in place (narrow phase, fp64 decision, emission -- out of line, one pair per thread).  It is
+// launched after every regular pass and returns at once when nothing was recorded, so the regular pass carries
+// no call in its loops.
+template <int MODE, bool COUNT_CAND, bool SLOW>
 #ifndef RCD_PAIR_MIN_BLOCKS
-#define RCD_PAIR_MIN_BLOCKS 6
+#define RCD_PAIR_MIN_BLOCKS 8
 #endif
-__global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(PairParams P) {
+__global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) k_pairs(PairParams P) {
     __shared__ WarpShared shared[PAIR_WARPS];
     WarpShared &ws = shared[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31u;
     const GridParams g = P.g;
-    u32 n_exact = 0, n_pot = 0;  // per-lane statistics, flushed once at the end
+    constexpr bool PRED = is_predict(MODE);
+    constexpr bool FUSED = MODE == MODE_PREDICT_WITH_DETECT;
+    constexpr bool USE_CAPSULE = PRED && COUNT_CAND;  // diagnostic variant: every neighbour inside the capsule goes on
+    const bool t1_on = MODE != RCD_MODE_COMPUTE_NODE && !USE_CAPSULE && P.use_t1 != 0;  // (uniform)
+    const float tm = P.tm, D = P.D, h2 = 0.5f * tm * tm;
+    const float Rq = PRED ? PREDICT_RADIUS : P.R;
+    const float R2_hi = Rq * Rq * (1.0f + BAND_R2), R2_lo = Rq * Rq * (1.0f - BAND_R2);
+    const float FAR = 3.0e38f;
+    u32 n_pot = 0;                                // per-lane statistics, flushed once at the end
+    u32 qa_block = QA_NO_BLOCK, qa_used = 0;      // this warp's block of the pair queue (uniform)
+    bool qa_full = false;                         // (uniform) the pair queue has no block left
+    const u32 n_redo = SLOW ? (u32)min(P.counters->n_overflow, (unsigned long long)P.ovf_cap) : 0u;
 
     for (;;) {
         u32 tile = 0;
-        if (lane == 0) tile = atomicAdd(P.tile_counter, 1u);
+        if (lane == 0) tile = atomicAdd(P.tile_counter + (SLOW ? 1 : 0), 1u);
         tile = __shfl_sync(FULL_MASK, tile, 0);
+        int rbase0 = 0;        // where to start: the beginning, or (overflow pass) where the regular pass stopped
+        u32 c_first = 0xffffffffu;
+        if (SLOW) {
+            if (tile >= n_redo) break;
+            const uint4 rec = P.ovf[tile];
+            tile = rec.x;
+            rbase0 = (int)rec.y;
+            c_first = rec.z;
+        }
         if (tile >= P.ntiles * P.splits) break;
+        const u32 item = tile;
         // with few tiles (small frames) each tile is shared by `splits` warps: warp `split` takes the
         // chunks split, split + splits, ... of every row batch
         const u32 split = tile % P.splits;
         tile /= P.splits;
 
-        const u32 tile_base = tile * TQ;
-        const u32 s = tile_base + lane;
-        const bool valid = s < P.n;
+        const u32 qi = tile * TQ + lane;
+        const bool valid = qi < P.n_owned;
+        u32 s = 0;
         float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0;
-        int cx = 0, cy = 0, cz = 0;
-        u32 meta = 0;
         if (valid) {
+            s = P.qorder[qi];
             p0 = P.P0[s];
             p1 = P.P1[s];
             p2 = P.P2[s];
-            meta = __float_as_uint(p2.w);
-            u32 key = P.keys[s];
-            cx = (int)(key % (u32)g.nx);
-            u32 row = key / (u32)g.nx;
-            cy = (int)(row % (u32)g.ny);
-            cz = (int)(row / (u32)g.ny);
         }
-        __syncwarp();  // the previous tile's readers of ws.q* are done
-        ws.q0[lane] = p0;
-        ws.q1[lane] = p1;
-        ws.q2[lane] = p2;
-        ws.cand[lane] = 0;
-        const bool owned = valid && (meta & META_OWNED);
-        const u32 pattern = meta_pattern(meta);
-        // queries that take the radius-R test in the filter (detect-like); the others are predict queries
-        const bool radius_query = !is_predict(MODE) || pattern == RCD_PAT_NO_HISTORY;
-        const float Rq = is_predict(MODE) ? PREDICT_RADIUS : P.R;
-        const float R2_hi = Rq * Rq * (1.0f + BAND_R2), R2_lo = Rq * Rq * (1.0f - BAND_R2);
+        const u32 pattern = meta_pattern(__float_as_uint(p2.w));
+        // queries that take the radius-R test (detect-like); the others are predict queries
+        const bool radius_query = !PRED || pattern == RCD_PAT_NO_HISTORY;
+        const bool counts = valid && (radius_query || FUSED);  // in-radius neighbours are candidates of this query
         // Volume a neighbour must lie in to matter: a ball of radius Rq for radius queries; for predict
         // queries the capsule of radius 100 (+ slack) about the chord of the centre path
         // c(t) = uv t + ua t^2/2, t in [0, 9.5] (:728-741): the path leaves its chord by at most
         // |ua| 9.5^2 / 8.  w is the chord, rad the radius.
         float wx = 0.0f, wy = 0.0f, wz = 0.0f, inv_w2 = 0.0f, rad;
+        const float fv = radius_query ? 1.0f : ((pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f);
+        const float fa = radius_query ? 1.0f : ((pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f);
+        const float an = sqrt_ub(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z);  // |a_i|, rounded up
         if (!radius_query) {
-            const float fv = (pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f;
-            const float fa = (pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f;
             wx = p1.x * fv * 9.5f + p2.x * fa * 45.125f;
             wy = p1.y * fv * 9.5f + p2.y * fa * 45.125f;
             wz = p1.z * fv * 9.5f + p2.z * fa * 45.125f;
-            const float uan = sqrtf(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z) * fa;
             float w2 = wx * wx + wy * wy + wz * wz;
-            rad = (PREDICT_RADIUS + 11.28125f * uan) * (1.0f + 1.0e-5f) + 2.0e-2f + 1.0e-5f * sqrtf(w2);
+            rad = (PREDICT_RADIUS + 11.28125f * an * fa) * (1.0f + 1.0e-5f) + 2.0e-2f + 1.0e-5f * sqrtf(w2);
             if (!(w2 < 1.0e30f) || !(rad < 1.0e30f)) {  // non-finite motion: scan everything
                 wx = wy = wz = w2 = 0.0f;
                 rad = 1.0e18f;
@@ -735,290 +808,327 @@ __global__ void __launch_bounds__(PAIR_THREADS, RCD_PAIR_MIN_BLOCKS) k_pairs(Pai
         } else {
             rad = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
         }
-        const float pass2_own = radius_query ? R2_hi : rad * rad;
-        u32 ncand = 0;   // candidates decided by the filter itself
-        u32 n1b = 0;     // warp-uniform length of Q1b (predict)
+        // T1: this query's half.  Radius queries follow their true motion (the detect trajectory, :229-294),
+        // predict queries the motion of their pattern (:728-741): M = centre at tm, MV = its velocity there.
+        const float uvx = p1.x * fv, uvy = p1.y * fv, uvz = p1.z * fv;
+        const float uax = p2.x * fa, uay = p2.y * fa, uaz = p2.z * fa;
+        const float Mx = fmaf(uax, h2, fmaf(uvx, tm, p0.x)), My = fmaf(uay, h2, fmaf(uvy, tm, p0.y)),
+                    Mz = fmaf(uaz, h2, fmaf(uvz, tm, p0.z));
+        const float MVx = fmaf(uax, tm, uvx), MVy = fmaf(uay, tm, uvy), MVz = fmaf(uaz, tm, uvz);
+        // L = A_i + B_j + krv |g1| + kq |Ua_i - a_j| bounds: the safe distance, guard bands, the motion of the 10
+        // samples (0.9 |rv| + 0.405 |ra|, predict only), |ca| D^2 / 2 and the fp32 rounding of M, MV (x4), with
+        // |rv| <= |g1| + |v_i - uv_i| + tm |Ua_i - a_j|,  |ra| <= |Ua_i - a_j| + |a_i - Ua_i|,  |ca| = |Ua_i - a_j|
+        // (Ua_i = ua_i: the acceleration the query's centre path follows).
+        float A, krv, kq;
+        {
+            const float err = 5.0e-7f * (abs3(p0.x, p0.y, p0.z) + tm * abs3(uvx, uvy, uvz) + h2 * abs3(uax, uay, uaz)) +
+                              5.0e-7f * D * (abs3(uvx, uvy, uvz) + tm * abs3(uax, uay, uaz));
+            if (radius_query) {
+                A = 0.5f * p0.w + 5.0f + 2.0e-2f + err;
+                krv = 0.0f;
+                kq = 0.5f * D * D * (1.0f + 1.2e-4f);
+            } else {
+                const float dvx = p1.x - uvx, dvy = p1.y - uvy, dvz = p1.z - uvz;
+                const float dvn = sqrt_ub(dvx * dvx + dvy * dvy + dvz * dvz);
+                A = 0.5f * p0.w + 5.0f + 2.0e-2f + 0.405f * an * (1.0f - fa) + 0.9f * dvn + err;
+                krv = 0.9f * (1.0f + 1.2e-4f);
+                kq = (0.405f + 0.9f * tm + 0.5f * D * D) * (1.0f + 1.2e-4f);
+            }
+            A *= 1.0f + 1.0e-4f;
+        }
+        // what passes, per lane:  (t1 && d2 < dmaxA) || d2 < dmaxB || inside the guard band of the radius
+        float R2lo_l = -1.0f, R2hi_l = -1.0f, dmaxA = -1.0f, dmaxB = -1.0f;
+        if (counts) { R2lo_l = R2_lo; R2hi_l = R2_hi; }
+        if (valid) {
+            if (MODE == RCD_MODE_COMPUTE_NODE) dmaxB = fminf(R2_lo, 2500.0f * (1.0f + 2.0f * BAND_R2));  // current_distance <= 50
+            else if (radius_query) { if (t1_on) dmaxA = R2_lo; else dmaxB = R2_lo; }
+            else {
+                dmaxA = FAR;
+                if (FUSED && pattern != RCD_PAT_ACCELERATING) dmaxB = R2_lo;  // detect follows another trajectory: all of them
+            }
+        }
+        const float rad2 = rad * rad;
+        u32 ncand = 0;  // candidates decided by the filter itself
 
-        // S2b on `take` entries from the top of Q1b: time window of the pair -> offsets -> global Q2
-        auto run_scan = [&](u32 take) {
-            bool keep = false;
-            u32 si = 0, sj = 0, mask = 0;
-            if (lane < take) {
-                const u32 ql = ws.q1b_ql[n1b - take + lane];
-                sj = ws.q1b_pos[n1b - take + lane];
-                si = tile_base + ql;
-                const float4 a0 = ws.q0[ql], a1 = ws.q1[ql], a2 = ws.q2[ql];
-                const float4 b0 = P.P0[sj], b1 = P.P1[sj], b2 = P.P2[sj];
-                const u32 pat = meta_pattern(__float_as_uint(a2.w));
-                int m_lo = 0, m_hi = PREDICT_OFFSETS - 1;
-                if (COUNT_CAND) {
-                    const bool in = predict_window(window_coef(a0, a1, a2, b0, b1, b2, pat), m_lo, m_hi);
-                    if (!in) { m_lo = 1; m_hi = 0; }
-                    const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
-                    mask = predict_scan<true>(ws, P, c, ql, si, sj, pat, m_lo, m_hi, n_exact);
-                } else if (predict_window(window_coef(a0, a1, a2, b0, b1, b2, pat), m_lo, m_hi)) {
-                    mask = (2u << m_hi) - (1u << m_lo);  // offsets m_lo..m_hi; k_sample tests each of them
+        // cells of the bounding box of the tile's query volumes (cell_coord is monotone, so a
+        // neighbour inside the box in space is inside it in cells; 0.05 m + 1 ulp covers the fp32 sums)
+        const float big = 3.0e38f;
+        const float lox = warp_minf(valid ? fminf(p0.x, p0.x + wx) - rad : big);
+        const float hix = warp_maxf(valid ? fmaxf(p0.x, p0.x + wx) + rad : -big);
+        const float loy = warp_minf(valid ? fminf(p0.y, p0.y + wy) - rad : big);
+        const float hiy = warp_maxf(valid ? fmaxf(p0.y, p0.y + wy) + rad : -big);
+        const float loz = warp_minf(valid ? fminf(p0.z, p0.z + wz) - rad : big);
+        const float hiz = warp_maxf(valid ? fmaxf(p0.z, p0.z + wz) + rad : -big);
+        const int x0 = cell_coord(lox - (0.05f + 4.0e-7f * fabsf(lox)), g.ox, g.inv_cell, g.nx);
+        const int x1 = cell_coord(hix + (0.05f + 4.0e-7f * fabsf(hix)), g.ox, g.inv_cell, g.nx);
+        const int y0 = cell_coord(loy - (0.05f + 4.0e-7f * fabsf(loy)), g.oy, g.inv_cell, g.ny);
+        const int y1 = cell_coord(hiy + (0.05f + 4.0e-7f * fabsf(hiy)), g.oy, g.inv_cell, g.ny);
+        const int z0 = cell_coord(loz - (0.05f + 4.0e-7f * fabsf(loz)), g.oz, g.inv_cell_z, g.nz);
+        const int z1 = cell_coord(hiz + (0.05f + 4.0e-7f * fabsf(hiz)), g.oz, g.inv_cell_z, g.nz);
+        const int ny_span = y1 - y0 + 1;
+        const int nrows = ny_span * (z1 - z0 + 1);
+
+        bool stopped = false;  // (uniform) regular pass: the pair queue ran out in this tile
+        if (!SLOW && qa_full) {  // nothing can be queued any more: hand the whole tile to the overflow pass
+            if (lane == 0) {
+                const unsigned long long k = atomicAdd(&P.counters->n_overflow, 1ULL);
+                if (k < P.ovf_cap) P.ovf[k] = make_uint4(item, 0u, split, 0u);
+            }
+            stopped = true;
+        }
+        for (int rbase = rbase0; rbase < nrows && !stopped; rbase += TQ) {
+            // ---- span of one cell row per lane: two loads from the dense cell table ------------------
+            u32 lo = 0, rcnt = 0;
+            if ((int)lane + rbase < nrows) {
+                const int rr = rbase + (int)lane;
+                const int yy = y0 + rr % ny_span, zz = z0 + rr / ny_span;
+                const u32 c0 = (u32)((zz * g.ny + yy) * g.nx + x0);
+                const u32 first = P.cell_begin[c0], last = P.cell_begin[c0 + (u32)(x1 - x0) + 1u];
+                lo = first;
+                rcnt = last - first;
+            }
+            u32 incl = rcnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                u32 t = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= (u32)o) incl += t;
+            }
+            __syncwarp();  // previous batch's readers of row_* are done
+            ws.row_lo[lane] = lo;
+            ws.row_prefix[lane] = incl - rcnt;
+            if (lane == 31) ws.row_prefix[TQ] = incl;
+            __syncwarp();
+            const u32 total = ws.row_prefix[TQ];
+            const u32 nchunks = (total + CH - 1) / CH;
+
+            // chunk c of the flattened spans: cp.async of the lane's own object into the landing zone
+            auto stage = [&](u32 c, StagePacked &b) {
+                const u32 f = c * CH + lane;
+                if (f < total) {
+                    int a = 0, z = TQ - 1;  // last row r with prefix[r] <= f
+                    while (a < z) {
+                        int mid = (a + z + 1) >> 1;
+                        if (ws.row_prefix[mid] <= f) a = mid; else z = mid - 1;
+                    }
+                    const u32 src = ws.row_lo[a] + (f - ws.row_prefix[a]);
+                    cp_async16(&ws.r0[lane], P.P0 + src);
+                    cp_async16(&ws.r1[lane], P.P1 + src);
+                    cp_async16(&ws.r2[lane], P.P2 + src);
+                    b.pos[lane] = src;
                 }
-                keep = mask != 0;
+                cp_async_commit();
+            };
+            // ... and, once it has landed, the lane's object as operands of the packed filter: the position, and
+            // the neighbour's half of T1 (N = position at tm, NV = velocity at tm, B = its share of the bound).
+            // The last chunk is padded with an object no query can reach instead of bound checks per test.
+            auto relayout = [&](u32 c, StagePacked &b) {
+                const u32 f = c * CH + lane;
+                float x = 1.0e30f, y = 1.0e30f, z = 1.0e30f, B = 0.0f;
+                float nx = -1.0e18f, ny = -1.0e18f, nz = -1.0e18f, nvx = 0.0f, nvy = 0.0f, nvz = 0.0f, nax = 0.0f, nay = 0.0f, naz = 0.0f;
+                if (f < total) {
+                    const float4 q0 = ws.r0[lane], q1 = ws.r1[lane], q2 = ws.r2[lane];
+                    x = q0.x; y = q0.y; z = q0.z;
+                    if (t1_on) {
+                        nx = -fmaf(q2.x, h2, fmaf(q1.x, tm, q0.x));
+                        ny = -fmaf(q2.y, h2, fmaf(q1.y, tm, q0.y));
+                        nz = -fmaf(q2.z, h2, fmaf(q1.z, tm, q0.z));
+                        nvx = -fmaf(q2.x, tm, q1.x);
+                        nvy = -fmaf(q2.y, tm, q1.y);
+                        nvz = -fmaf(q2.z, tm, q1.z);
+                        const float err = 5.0e-7f * (abs3(q0.x, q0.y, q0.z) + tm * abs3(q1.x, q1.y, q1.z) + h2 * abs3(q2.x, q2.y, q2.z)) +
+                                          5.0e-7f * D * (abs3(q1.x, q1.y, q1.z) + tm * abs3(q2.x, q2.y, q2.z));
+                        B = (0.5f * q0.w + err) * (1.0f + 1.0e-4f);
+                        nax = -q2.x; nay = -q2.y; naz = -q2.z;
+                    }
+                }
+                const u32 e = lane >> 1, h = lane & 1u;
+                float *xy = reinterpret_cast<float *>(&b.xy[e]);
+                xy[h] = x; xy[2u + h] = y;
+                float *zb = reinterpret_cast<float *>(&b.zb[e]);
+                zb[h] = z; zb[2u + h] = B;
+                if (t1_on) {
+                    float *nxy = reinterpret_cast<float *>(&b.nxy[e]);
+                    nxy[h] = nx; nxy[2u + h] = ny;
+                    float *nzv = reinterpret_cast<float *>(&b.nzv[e]);
+                    nzv[h] = nz; nzv[2u + h] = nvx;
+                    float *nvyz = reinterpret_cast<float *>(&b.nvyz[e]);
+                    nvyz[h] = nvy; nvyz[2u + h] = nvz;
+                    float *naxy = reinterpret_cast<float *>(&b.naxy[e]);
+                    naxy[h] = nax; naxy[2u + h] = nay;
+                    reinterpret_cast<float *>(&b.naz[e])[h] = naz;
+                }
+            };
+
+            u32 kbuf = 0;
+            const u32 c_begin = (SLOW && rbase == rbase0) ? c_first : split;
+            if (c_begin < nchunks) {
+                stage(c_begin, ws.buf[0]);
+                cp_async_wait<0>();
+                relayout(c_begin, ws.buf[0]);
             }
             __syncwarp();
-            n1b -= take;
-            const bool pushed = global_push(P.q2, P.qcap, &P.counters->n_q2, keep, si, sj, mask);
-            if (!pushed) finish_predict_pair<COUNT_CAND>(P, si, sj, mask);  // queue full: finish the pair here
-        };
-
-        // a tile that crosses a cell-row boundary is processed as two groups (first row / the rest)
-        // so that each group's cell box stays tight
-        const u32 my_row = (u32)(cy + cz * g.ny);
-        const u32 first_row = __shfl_sync(FULL_MASK, my_row, 0);
-        const int my_group = (valid && my_row != first_row) ? 1 : 0;
-        const int ngroups = __any_sync(FULL_MASK, my_group) ? 2 : 1;
-        __syncwarp();
-
-        for (int grp = 0; grp < ngroups; ++grp) {
-            const bool active = owned && my_group == grp;
-            if (!__any_sync(FULL_MASK, active)) continue;  // no active query in this group (warp-uniform)
-            const float pass2 = active ? pass2_own : -1.0f;     // d2 <= -1 never holds
-            // cells of the bounding box of the group's query volumes (cell_coord is monotone, so a
-            // neighbour inside the box in space is inside it in cells; 0.05 m + 1 ulp covers the fp32 sums)
-            const float big = 3.0e38f;
-            const float lox = warp_minf(active ? fminf(p0.x, p0.x + wx) - rad : big);
-            const float hix = warp_maxf(active ? fmaxf(p0.x, p0.x + wx) + rad : -big);
-            const float loy = warp_minf(active ? fminf(p0.y, p0.y + wy) - rad : big);
-            const float hiy = warp_maxf(active ? fmaxf(p0.y, p0.y + wy) + rad : -big);
-            const float loz = warp_minf(active ? fminf(p0.z, p0.z + wz) - rad : big);
-            const float hiz = warp_maxf(active ? fmaxf(p0.z, p0.z + wz) + rad : -big);
-            const int x0 = cell_coord(lox - (0.05f + 4.0e-7f * fabsf(lox)), g.ox, g.inv_cell, g.nx);
-            const int x1 = cell_coord(hix + (0.05f + 4.0e-7f * fabsf(hix)), g.ox, g.inv_cell, g.nx);
-            const int y0 = cell_coord(loy - (0.05f + 4.0e-7f * fabsf(loy)), g.oy, g.inv_cell, g.ny);
-            const int y1 = cell_coord(hiy + (0.05f + 4.0e-7f * fabsf(hiy)), g.oy, g.inv_cell, g.ny);
-            const int z0 = cell_coord(loz - (0.05f + 4.0e-7f * fabsf(loz)), g.oz, g.inv_cell, g.nz);
-            const int z1 = cell_coord(hiz + (0.05f + 4.0e-7f * fabsf(hiz)), g.oz, g.inv_cell, g.nz);
-            const int ny_span = y1 - y0 + 1;
-            const int nrows = ny_span * (z1 - z0 + 1);
-
-            for (int rbase = 0; rbase < nrows; rbase += TQ) {
-                // ---- span of one cell row per lane -------------------------------------------
-                u32 lo = 0, cnt = 0;
-                if ((int)lane + rbase < nrows) {
-                    int rr = rbase + (int)lane;
-                    int yy = y0 + rr % ny_span, zz = z0 + rr / ny_span;
-                    u32 c0 = (u32)((zz * g.ny + yy) * g.nx + x0), c1 = c0 + (u32)(x1 - x0);
-                    u32 first = 0xffffffffu, last = 0;
-                    if (x1 - x0 < ROW_SCAN_MAX) {
-                        for (u32 c = c0; c <= c1; ++c) {
-                            u32 st_ = P.cell_start[c], en = P.cell_end[c];
-                            if (en > st_) { first = min(first, st_); last = max(last, en); }
-                        }
-                    } else {
-                        first = lower_bound_keys(P.keys, P.n, c0);
-                        last = lower_bound_keys(P.keys, P.n, c1 + 1);
+            for (u32 c = c_begin; c < nchunks; c += P.splits, kbuf ^= 1u) {
+                StagePacked &b = ws.buf[kbuf];
+                const bool more = c + P.splits < nchunks;
+                if (more) stage(c + P.splits, ws.buf[kbuf ^ 1u]);  // in flight while this chunk is filtered
+                const u32 m = min((u32)CH, total - c * CH);
+                // ---- S1: one query per lane against every staged neighbour, two per packed instruction -----
+                // Each lane appends what passes to a private list in shared memory (no warp vote per test).
+                u32 cnt = 0, nc = 0;
+                const u32 npair = (m + 1u) >> 1;
+                for (u32 u = 0; u < npair; ++u) {
+                    const float4 xy = b.xy[u];
+                    const float4 zb = b.zb[u];
+                    const float2 dx = add2(make_float2(xy.x, xy.y), splat2(-p0.x));  // p_j - p_i
+                    const float2 dy = add2(make_float2(xy.z, xy.w), splat2(-p0.y));
+                    const float2 dz = add2(make_float2(zb.x, zb.y), splat2(-p0.z));
+                    const float2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    bool ta = true, tb = true;
+                    if (USE_CAPSULE) {  // distance to the chord (w = 0 for radius queries)
+                        const float2 dot = fma2(dz, splat2(wz), fma2(dy, splat2(wy), mul2(dx, splat2(wx))));
+                        const float2 sc = make_float2(__saturatef(dot.x * inv_w2), __saturatef(dot.y * inv_w2));
+                        const float2 ex = fma2(sc, splat2(-wx), dx), ey = fma2(sc, splat2(-wy), dy), ez = fma2(sc, splat2(-wz), dz);
+                        const float2 e2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+                        ta = e2.x <= rad2;
+                        tb = e2.y <= rad2;
+                    } else if (t1_on) {
+                        const float4 nxy = b.nxy[u], nzv = b.nzv[u], nvyz = b.nvyz[u];
+                        const float2 gx = add2(make_float2(nxy.x, nxy.y), splat2(Mx));   // g0 = M_i - N_j
+                        const float2 gy = add2(make_float2(nxy.z, nxy.w), splat2(My));
+                        const float2 gz = add2(make_float2(nzv.x, nzv.y), splat2(Mz));
+                        const float2 hx = add2(make_float2(nzv.z, nzv.w), splat2(MVx));  // g1 = MV_i - NV_j
+                        const float2 hy = add2(make_float2(nvyz.x, nvyz.y), splat2(MVy));
+                        const float2 hz = add2(make_float2(nvyz.z, nvyz.w), splat2(MVz));
+                        const float2 g12 = fma2(hz, hz, fma2(hy, hy, mul2(hx, hx)));
+                        const float2 dot = fma2(gz, hz, fma2(gy, hy, mul2(gx, hx)));
+                        const float2 g12c = make_float2(fmaxf(g12.x, 1.0e-12f), fmaxf(g12.y, 1.0e-12f));
+                        const float2 r = make_float2(rsqrt_fast(g12c.x), rsqrt_fast(g12c.y));
+                        const float2 sn = mul2(g12c, r);                 // |g1| (to ~3e-7)
+                        const float2 um = mul2(dot, mul2(r, r));          // -(minimum of the linear part, relative to tm)
+                        const float2 uc = make_float2(fminf(fmaxf(-um.x, -D), D), fminf(fmaxf(-um.y, -D), D));
+                        const float2 lx = fma2(hx, uc, gx), ly = fma2(hy, uc, gy), lz = fma2(hz, uc, gz);
+                        const float2 l2 = fma2(lz, lz, fma2(ly, ly, mul2(lx, lx)));
+                        const float4 naxy = b.naxy[u];
+                        const float2 naz = b.naz[u];
+                        const float2 qx = add2(make_float2(naxy.x, naxy.y), splat2(uax));  // Ua_i - a_j
+                        const float2 qy = add2(make_float2(naxy.z, naxy.w), splat2(uay));
+                        const float2 qz = add2(naz, splat2(uaz));
+                        const float2 q2 = fma2(qz, qz, fma2(qy, qy, mul2(qx, qx)));
+                        const float2 q2c = make_float2(fmaxf(q2.x, 1.0e-30f), fmaxf(q2.y, 1.0e-30f));
+                        const float2 qn = mul2(q2c, make_float2(rsqrt_fast(q2c.x), rsqrt_fast(q2c.y)));
+                        const float2 L = fma2(splat2(kq), qn, fma2(splat2(krv), sn, add2(make_float2(zb.z, zb.w), splat2(A))));
+                        const float2 L2 = mul2(L, L);
+                        ta = l2.x <= L2.x;
+                        tb = l2.y <= L2.y;
                     }
-                    if (last > first) { lo = first; cnt = last - first; }
+                    {
+                        const bool inr = d2.x < R2lo_l;
+                        const bool und = !inr && d2.x <= R2hi_l;
+                        if ((ta && d2.x < dmaxA) || d2.x < dmaxB || und) {
+                            ws.plist[cnt][lane] = (unsigned char)((2u * u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
+                            ++cnt;
+                        }
+                        nc += inr ? 1u : 0u;
+                    }
+                    {
+                        const bool inr = d2.y < R2lo_l;
+                        const bool und = !inr && d2.y <= R2hi_l;
+                        if ((tb && d2.y < dmaxA) || d2.y < dmaxB || und) {
+                            ws.plist[cnt][lane] = (unsigned char)((2u * u + 1u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
+                            ++cnt;
+                        }
+                        nc += inr ? 1u : 0u;
+                    }
                 }
-                u32 incl = cnt;
+                // ---- survivors -> pair queue (the warp's private block; a new one when this one is full) -------
+                u32 off = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    u32 t = __shfl_up_sync(FULL_MASK, incl, o);
-                    if (lane >= (u32)o) incl += t;
+                    u32 t = __shfl_up_sync(FULL_MASK, off, o);
+                    if (lane >= (u32)o) off += t;
                 }
-                __syncwarp();  // previous batch's readers of row_* are done
-                ws.row_lo[lane] = lo;
-                ws.row_prefix[lane] = incl - cnt;
-                if (lane == 31) ws.row_prefix[TQ] = incl;
+                const u32 total_pairs = __shfl_sync(FULL_MASK, off, 31);
+                off -= cnt;
+                if (SLOW) {  // overflow pass: finish every survivor here
+                    for (u32 k = 0; k < cnt; ++k) {
+                        const u32 code = ws.plist[k][lane];
+                        n_pot += narrow_entry_inline<MODE, COUNT_CAND>(
+                            P, s | ((code & PL_INR) ? QA_INR : 0u) | ((code & PL_UND) ? QA_UND : 0u), b.pos[code & 31u]);
+                    }
+                } else if (total_pairs) {
+                    if (qa_block == QA_NO_BLOCK || qa_used + total_pairs > (u32)QA_BLOCK) {
+                        u32 nb = 0;
+                        if (lane == 0) {
+                            if (qa_block < P.qa_blocks_cap) P.qa_fill[qa_block] = qa_used;
+                            nb = (u32)min(atomicAdd(&P.counters->n_qa_blocks, 1ULL), 0xfffffffeULL);
+                        }
+                        qa_block = __shfl_sync(FULL_MASK, nb, 0);
+                        qa_used = 0;
+                    }
+                    if (qa_block >= P.qa_blocks_cap) {  // queue full: the overflow pass redoes the tile from this chunk on
+                        if (lane == 0) {
+                            const unsigned long long k = atomicAdd(&P.counters->n_overflow, 1ULL);
+                            if (k < P.ovf_cap) P.ovf[k] = make_uint4(item, (u32)rbase, c, 0u);
+                        }
+                        qa_full = true;
+                        stopped = true;
+                        qa_block = QA_NO_BLOCK;
+                        if (more) cp_async_wait<0>();
+                        __syncwarp();
+                        break;
+                    }
+                    uint2 *dst = P.qa + ((size_t)qa_block * QA_BLOCK + qa_used + off);
+                    for (u32 k = 0; __any_sync(FULL_MASK, k < cnt); ++k) {
+                        if (k < cnt) {
+                            const u32 code = ws.plist[k][lane];
+                            dst[k] = make_uint2(s | ((code & PL_INR) ? QA_INR : 0u) | ((code & PL_UND) ? QA_UND : 0u),
+                                                b.pos[code & 31u]);
+                        }
+                    }
+                    qa_used += total_pairs;
+                }
+                ncand += nc;  // (a chunk handed to the overflow pass is counted there)
+                if (more) {
+                    cp_async_wait<0>();
+                    relayout(c + P.splits, ws.buf[kbuf ^ 1u]);
+                }
                 __syncwarp();
-                const u32 total = ws.row_prefix[TQ];
-                const u32 nchunks = (total + CH - 1) / CH;
-
-                // stage chunk c of the flattened spans into buffer c & 1 (cp.async, 2 objects per lane)
-                auto stage = [&](u32 c) {
-                    StageBuf &b = ws.buf[(c / P.splits) & 1u];
-#pragma unroll
-                    for (int e = 0; e < CH / TQ; ++e) {
-                        u32 slot = lane + e * TQ;
-                        u32 f = c * CH + slot;
-                        if (f < total) {
-                            int a = 0, z = TQ - 1;  // last row r with prefix[r] <= f
-                            while (a < z) {
-                                int mid = (a + z + 1) >> 1;
-                                if (ws.row_prefix[mid] <= f) a = mid; else z = mid - 1;
-                            }
-                            u32 src = ws.row_lo[a] + (f - ws.row_prefix[a]);
-                            cp_async16(&b.p0[slot], P.P0 + src);
-                            cp_async16(&b.p1[slot], P.P1 + src);
-                            cp_async16(&b.p2[slot], P.P2 + src);
-                            b.pos[slot] = src;
-                        } else {  // pad the last chunk with an object no query can reach
-                            b.p0[slot] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, 0.0f);
-                        }
-                    }
-                    cp_async_commit();
-                };
-
-                if (split < nchunks) stage(split);
-                for (u32 c = split; c < nchunks; c += P.splits) {
-                    if (c + P.splits < nchunks) {
-                        stage(c + P.splits);
-                        cp_async_wait<1>();
-                    } else {
-                        cp_async_wait<0>();
-                    }
-                    StageBuf &b = ws.buf[(c / P.splits) & 1u];
-                    {   // each lane copied its own slot: lay the positions out pairwise for the packed filter
-                        const float4 own = b.p0[lane];
-                        float *xy = reinterpret_cast<float *>(&b.xy[lane >> 1]);
-                        xy[lane & 1u] = own.x;
-                        xy[2u + (lane & 1u)] = own.y;
-                        reinterpret_cast<float *>(&b.zz[lane >> 1])[lane & 1u] = own.z;
-                    }
-                    __syncwarp();
-                    const u32 m = min((u32)CH, total - c * CH);
-                    // ---- S1 filter: one query per lane against every staged neighbour --------------
-                    // Each lane appends the neighbours inside its reach to a private list in shared memory
-                    // (no warp vote per test); the lists are then consumed 32 pairs at a time.
-                    u32 cnt = 0;
-                    auto s1_push = [&](u32 j, float d2) {
-                        if (d2 <= pass2) {
-                            // radius queries: bit 7 = inside the guard band of the radius, the exact stage
-                            // decides; otherwise certainly within it (predict counts its rare radius
-                            // queries in S2)
-                            const bool certain = d2 < R2_lo;
-                            ws.plist[cnt][lane] = (unsigned char)(j | ((!is_predict(MODE) && !certain) ? 0x80u : 0u));
-                            ++cnt;
-                            if (!is_predict(MODE) && certain) ++ncand;
-                        }
-                    };
-                    for (u32 j0 = 0; j0 < m; j0 += 4) {  // (the last chunk is padded: no bound check per test)
-#pragma unroll
-                        for (u32 u = 0; u < 2; ++u) {    // two neighbours per packed instruction
-                            const float4 xy = b.xy[(j0 >> 1) + u];
-                            const float2 zz = b.zz[(j0 >> 1) + u];
-                            float2 dx = add2(make_float2(xy.x, xy.y), splat2(-p0.x));
-                            float2 dy = add2(make_float2(xy.z, xy.w), splat2(-p0.y));
-                            float2 dz = add2(zz, splat2(-p0.z));
-                            if (is_predict(MODE)) {  // distance to the chord (w = 0 for radius queries)
-                                const float2 dot = fma2(dz, splat2(wz), fma2(dy, splat2(wy), mul2(dx, splat2(wx))));
-                                const float2 sc = make_float2(__saturatef(dot.x * inv_w2), __saturatef(dot.y * inv_w2));
-                                dx = fma2(sc, splat2(-wx), dx);
-                                dy = fma2(sc, splat2(-wy), dy);
-                                dz = fma2(sc, splat2(-wz), dz);
-                            }
-                            const float2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-                            s1_push(j0 + 2u * u, d2.x);
-                            s1_push(j0 + 2u * u + 1u, d2.y);
-                        }
-                    }
-                    // exclusive scan of the list lengths: pair f of the chunk belongs to the last lane o
-                    // with off[o] <= f
-                    u32 off = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        u32 t = __shfl_up_sync(FULL_MASK, off, o);
-                        if (lane >= (u32)o) off += t;
-                    }
-                    const u32 total_pairs = __shfl_sync(FULL_MASK, off, 31);
-                    off -= cnt;
-                    __syncwarp();
-                    for (u32 fbase = 0; fbase < total_pairs; fbase += 32) {
-                        // ---- S2 on up to 32 pairs ------------------------------------------------------
-                        const u32 f = fbase + lane;
-                        const u32 take = min(total_pairs - fbase, 32u);
-                        u32 ql = 0;
-#pragma unroll
-                        for (int step = 16; step > 0; step >>= 1) {
-                            const u32 cand = ql + step;
-                            const u32 v = __shfl_sync(FULL_MASK, off, cand & 31u);
-                            if (cand < 32u && v <= f) ql = cand;
-                        }
-                        const u32 ql_off = __shfl_sync(FULL_MASK, off, ql);
-                        const u32 entry = (lane < take) ? ws.plist[f - ql_off][ql] : 0u;
-                        const u32 jj = entry & 31u;
-                        const u32 si = tile_base + ql;
-                        bool keep = false;     // -> global Q3 (exact stage)
-                        bool undecided = (entry & 0x80u) != 0;  // ... which has to take the radius test first
-                        bool to_scan = false;  // -> Q1b (predict window scan)
-                        bool twice = false;    // fused mode, object without history: the risk is owed twice
-                        u32 sj = 0;
-                        if (lane < take) {
-                            const float4 a0 = ws.q0[ql], a1 = ws.q1[ql], a2 = ws.q2[ql];
-                            const float4 b0 = b.p0[jj], b1 = b.p1[jj], b2 = b.p2[jj];
-                            sj = b.pos[jj];
-                            if (MODE == RCD_MODE_COMPUTE_NODE) {
-                                keep = narrow_compute_node(ws, P, ql, a0, a1, a2, b0, b1, b2, sj == si, undecided);
-                            } else if (sj != si) {  // _spatial_filtering strips self (:224-225)
-                                const u32 pat = meta_pattern(__float_as_uint(a2.w));
-                                if (MODE == RCD_MODE_DETECT) {
-                                    keep = narrow_detect<false>(ws, ql, a0, a1, a2, b0, b1, b2, P.R, P.T, undecided);
-                                } else {
-                                    const bool nohist = pat == RCD_PAT_NO_HISTORY;
-                                    if (nohist || MODE == MODE_PREDICT_WITH_DETECT) {
-                                        twice = nohist && MODE == MODE_PREDICT_WITH_DETECT;
-                                        keep = narrow_detect<true>(ws, ql, a0, a1, a2, b0, b1, b2, PREDICT_RADIUS, 10.0f, undecided,
-                                                                   twice ? 2u : 1u);
-                                    }
-                                    if (!nohist) to_scan = COUNT_CAND ? true : window_reject_linear(window_coef(a0, a1, a2, b0, b1, b2, pat));
-                                }
-                            }
-                        }
-                        if (is_predict(MODE)) {
-                            const u32 bal = __ballot_sync(FULL_MASK, to_scan);
-                            if (bal) {
-                                if (to_scan) {
-                                    const u32 at = n1b + __popc(bal & lanemask_lt());
-                                    ws.q1b_pos[at] = sj;
-                                    ws.q1b_ql[at] = (unsigned char)ql;
-                                }
-                                n1b += __popc(bal);
-                                __syncwarp();
-                                if (n1b >= 32) run_scan(32);
-                            }
-                        }
-                        const u32 word = (undecided ? RADIUS_UNDECIDED : 0u) | (twice ? ENTRY_TWICE : 0u);
-                        const bool pushed = global_push(P.q3, P.qcap, &P.counters->n_q3, keep, si, sj, word);
-                        if (!pushed) n_pot += finish_entry_inline<MODE>(P, si, sj, word);  // queue full: decide here
-                    }
-                    __syncwarp();
-                }
             }
         }
         // ---- end of tile ------------------------------------------------------------------------------
-        if (is_predict(MODE)) {
-            if (n1b) run_scan(n1b);  // Q1b refers to this tile's queries
-        }
-        __syncwarp();
-        ncand += ws.cand[lane];
-        // the filter counted the query itself (distance 0) for radius queries; only the
-        // compute-node index returns self (quirk Q8)
-        // (with split tiles the self hit is seen by one of the warps, so split 0 subtracts it and the
-        // partial counts are combined with wrapping adds)
-        // (predict counts its radius queries in S2, after self has been stripped)
-        if (MODE == RCD_MODE_DETECT && owned && split == 0) ncand -= 1;
-        if (owned && P.cand_count) {
-            if (P.splits == 1) P.cand_count[P.sorted_slot[s]] = ncand;
+        // the filter counted the query itself (distance 0); only the compute-node index returns self (quirk Q8).
+        // (with split tiles the self hit is seen by one of the warps, so split 0 subtracts it and the partial
+        // counts are combined with wrapping adds).  Objects without history owe every candidate twice in the
+        // fused frame: once as detect_collisions, once as the fall-back of predict_collisions (:590-592).
+        const bool self_seen = (p0.x - p0.x) == 0.0f && (p0.y - p0.y) == 0.0f && (p0.z - p0.z) == 0.0f;  // finite position
+        if (!SLOW && MODE != RCD_MODE_COMPUTE_NODE && counts && split == 0 && self_seen) ncand -= 1u;
+        if (FUSED && pattern == RCD_PAT_NO_HISTORY) ncand *= 2u;
+        if (counts && P.cand_count) {
+            if (!SLOW && P.splits == 1) P.cand_count[P.sorted_slot[s]] = ncand;
             else if (ncand) atomicAdd(&P.cand_count[P.sorted_slot[s]], ncand);
         }
-        long long csum = warp_sum((long long)(owned ? (int)ncand : 0));
+        long long csum = warp_sum((long long)(counts ? (int)ncand : 0));
         if (lane == 0 && csum) atomicAdd(&P.counters->n_candidates, (unsigned long long)csum);
     }
+    if (!SLOW && lane == 0 && qa_block < P.qa_blocks_cap) P.qa_fill[qa_block] = qa_used;
     unsigned long long p = warp_sum((unsigned long long)n_pot);
-    unsigned long long e = warp_sum((unsigned long long)n_exact);
-    if (lane == 0) {
-        if (p) atomicAdd(&P.counters->n_potential, p);
-        if (e) atomicAdd(&P.counters->n_exact, e);
-    }
+    if (lane == 0 && p) atomicAdd(&P.counters->n_potential, p);
 }
 
-// k_sample (predict): Q2 -> Q3.  A warp takes 32 queued pairs at a time and works through them in
-// phases with different lane assignments, so that every phase runs with (almost) full warps although
-// the pairs carry different numbers of offsets:
-//   1. lane = pair            : gather both objects, derive the pair's coefficients -> shared memory
+// -------------------------------------------------------------------------------------------------
+// k_narrow: QA -> Q3.  A warp takes 32 queued pairs at a time and works through them in phases with
+// different lane assignments, so that every phase runs with (almost) full warps although the pairs
+// carry different numbers of offsets:
+//   1. lane = pair            : gather both objects; detect narrow phase (-> Q3); predict: the time window
+//                               that can hold a hit -> offsets, coefficients of the pair -> shared memory
 //   2. lane = (pair, offset)  : can the offset be hit at all (offset_may_hit)?  is the neighbour within
 //                               100 m of the predicted centre (:801-803)?  survivors -> item list
 //   3. lane = surviving item  : the 10 samples of the offset (:322-342) in fp32 -> first sample inside
 //                               safe + band and its squared distance -> shared memory
 //   4. lane = pair            : merge over the offsets (max risk, earliest offset on ties, :848-865)
 //                               -> 0 / RESOLVED | m | k << 8 / mask of the offsets fp64 must decide
-// sample_predict() above is the same decision for one pair on one thread (queue-overflow fallback).
+// sample_predict() above is the decision of phases 2-4 for one pair on one thread (queue-overflow fallback).
+// -------------------------------------------------------------------------------------------------
 constexpr int STAGE_THREADS = 128;
 constexpr int STAGE_WARPS = STAGE_THREADS / 32;
 constexpr int SC = 25;  // coefficients per pair (odd stride: conflict-free)
@@ -1029,48 +1139,85 @@ struct SampleShared {
     float r2first[32][PREDICT_OFFSETS];
     unsigned char first[32][PREDICT_OFFSETS];  // first sample within safe + band (valid where hit_mask is set)
     u32 hit_mask[32];                          // offsets with a sample within safe + band
+    u32 si[32], sj[32];
     unsigned short items[64];                  // pair | offset << 5
 };
+constexpr int QA_BATCHES_PER_BLOCK = QA_BLOCK / 32;
 
-template <bool COUNT_CAND>
-#ifndef RCD_SAMPLE_MIN_BLOCKS
-#define RCD_SAMPLE_MIN_BLOCKS 8
+template <int MODE, bool COUNT_CAND>
+#ifndef RCD_NARROW_MIN_BLOCKS
+#define RCD_NARROW_MIN_BLOCKS 6
 #endif
-__global__ void __launch_bounds__(STAGE_THREADS, RCD_SAMPLE_MIN_BLOCKS) k_sample(PairParams P) {
+__global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow(PairParams P) {
     __shared__ SampleShared shared[STAGE_WARPS];
     SampleShared &sh = shared[threadIdx.x >> 5];
+    constexpr bool PRED = is_predict(MODE);
+    constexpr bool FUSED = MODE == MODE_PREDICT_WITH_DETECT;
     const u32 lane = threadIdx.x & 31u;
-    const unsigned long long n = min(P.counters->n_q2, (unsigned long long)P.qcap);
-    const unsigned long long nbatch = (n + 31) / 32;
+    const unsigned long long nblocks = min(P.counters->n_qa_blocks, (unsigned long long)P.qa_blocks_cap);
+    const unsigned long long nbatch = nblocks * QA_BATCHES_PER_BLOCK;
     const unsigned long long wstride = (unsigned long long)gridDim.x * STAGE_WARPS;
     const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
-    u32 n_exact = 0;
+    u32 n_exact = 0, n_pot = 0;
     for (unsigned long long batch = (unsigned long long)blockIdx.x * STAGE_WARPS + (threadIdx.x >> 5); batch < nbatch;
          batch += wstride) {
+        const u32 blk = (u32)(batch / QA_BATCHES_PER_BLOCK), within = (u32)(batch % QA_BATCHES_PER_BLOCK) * 32u;
+        const u32 fill = P.qa_fill[blk];
+        if (within >= fill) continue;  // (uniform) the warp that owned the block stopped before this batch
         // ---- 1. lane = pair ------------------------------------------------------------------------
-        const unsigned long long k = batch * 32 + lane;
-        QEntry e;
-        e.si = e.sj = e.mask = 0;
+        u32 si = 0, sj = 0, mask = 0, det_word = 0;
+        bool det_keep = false;
         float safe = 5.0f, band = 0.0f;
-        if (k < n) {
-            e = P.q2[k];
-            const float4 a0 = P.P0[e.si], a1 = P.P1[e.si], a2 = P.P2[e.si];
-            const float4 b0 = P.P0[e.sj], b1 = P.P1[e.sj], b2 = P.P2[e.sj];
-            const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, meta_pattern(__float_as_uint(a2.w)));
-            float *o = sh.coef[lane];
-            o[SC_D] = c.dx; o[SC_D + 1] = c.dy; o[SC_D + 2] = c.dz;
-            o[SC_CV] = c.cvx; o[SC_CV + 1] = c.cvy; o[SC_CV + 2] = c.cvz;
-            o[SC_CA] = c.cax; o[SC_CA + 1] = c.cay; o[SC_CA + 2] = c.caz;
-            o[SC_RV] = c.rvx; o[SC_RV + 1] = c.rvy; o[SC_RV + 2] = c.rvz;
-            o[SC_RA] = a2.x - b2.x; o[SC_RA + 1] = a2.y - b2.y; o[SC_RA + 2] = a2.z - b2.z;
-            o[SC_UV] = c.uvx; o[SC_UV + 1] = c.uvy; o[SC_UV + 2] = c.uvz;
-            o[SC_UA] = c.uax; o[SC_UA + 1] = c.uay; o[SC_UA + 2] = c.uaz;
-            o[SC_HR2] = c.hr2; o[SC_INVRV2] = c.inv_rv2; o[SC_LIM2] = c.lim2; o[SC_SAFEB2] = c.safe_b2;
-            safe = (a0.w + b0.w) * 0.5f + 5.0f;
-            band = sqrtf(c.safe_b2) - safe;  // the guard band of predict_coef
+        if (within + lane < fill) {
+            const uint2 e = P.qa[(size_t)blk * QA_BLOCK + within + lane];
+            si = e.x & QA_SI_MASK;
+            sj = e.y;
+            const bool inr = (e.x & QA_INR) != 0, und = (e.x & QA_UND) != 0;
+            if (si != sj || MODE == RCD_MODE_COMPUTE_NODE) {  // _spatial_filtering strips self (:224-225)
+                const float4 a0 = P.P0[si], a1 = P.P1[si], a2 = P.P2[si];
+                const float4 b0 = P.P0[sj], b1 = P.P1[sj], b2 = P.P2[sj];
+                if (MODE == RCD_MODE_DETECT) {
+                    det_keep = und || narrow_detect(a0, a1, a2, b0, b1, b2, P.T);
+                    det_word = und ? RADIUS_UNDECIDED : 0u;
+                } else if (MODE == RCD_MODE_COMPUTE_NODE) {
+                    det_keep = narrow_compute_node(P, a0, a1, a2, b0, b1, b2, si == sj, und);
+                    det_word = und ? RADIUS_UNDECIDED : 0u;
+                } else {
+                    const u32 pat = meta_pattern(__float_as_uint(a2.w));
+                    const bool nohist = pat == RCD_PAT_NO_HISTORY;
+                    if ((nohist || FUSED) && (inr || und)) {  // detect_collisions(100.0, 10.0): the defaults (:592)
+                        const bool twice = nohist && FUSED;
+                        det_keep = und || narrow_detect(a0, a1, a2, b0, b1, b2, 10.0f);
+                        det_word = (und ? RADIUS_UNDECIDED : 0u) | (twice ? ENTRY_TWICE : 0u);
+                    }
+                    if (!nohist) {
+                        mask = predict_mask<COUNT_CAND>(P, a0, a1, a2, b0, b1, b2, si, sj, pat, n_exact);
+                        if (mask) {
+                            const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
+                            float *o = sh.coef[lane];
+                            o[SC_D] = c.dx; o[SC_D + 1] = c.dy; o[SC_D + 2] = c.dz;
+                            o[SC_CV] = c.cvx; o[SC_CV + 1] = c.cvy; o[SC_CV + 2] = c.cvz;
+                            o[SC_CA] = c.cax; o[SC_CA + 1] = c.cay; o[SC_CA + 2] = c.caz;
+                            o[SC_RV] = c.rvx; o[SC_RV + 1] = c.rvy; o[SC_RV + 2] = c.rvz;
+                            o[SC_RA] = a2.x - b2.x; o[SC_RA + 1] = a2.y - b2.y; o[SC_RA + 2] = a2.z - b2.z;
+                            o[SC_UV] = c.uvx; o[SC_UV + 1] = c.uvy; o[SC_UV + 2] = c.uvz;
+                            o[SC_UA] = c.uax; o[SC_UA + 1] = c.uay; o[SC_UA + 2] = c.uaz;
+                            o[SC_HR2] = c.hr2; o[SC_INVRV2] = c.inv_rv2; o[SC_LIM2] = c.lim2; o[SC_SAFEB2] = c.safe_b2;
+                            safe = (a0.w + b0.w) * 0.5f + 5.0f;
+                            band = sqrtf(c.safe_b2) - safe;  // the guard band of predict_coef
+                        }
+                    }
+                }
+            }
         }
-        const u32 mask = e.mask & ((1u << PREDICT_OFFSETS) - 1u);
+        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, det_keep, si, sj, det_word))
+            n_pot += finish_entry_inline<MODE>(P, si, sj, det_word);  // queue full: decide here
+        if (!PRED) continue;
+        mask &= (1u << PREDICT_OFFSETS) - 1u;
+        if (!__any_sync(FULL_MASK, mask != 0)) continue;
         sh.hit_mask[lane] = 0;
+        sh.si[lane] = si;
+        sh.sj[lane] = sj;
         const u32 cnt = (u32)__popc(mask);
         u32 off = cnt;
 #pragma unroll
@@ -1132,11 +1279,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_SAMPLE_MIN_BLOCKS) k_sample
                 if (COUNT_CAND) {  // sparse mask: r-th set bit
                     for (u32 r = f - pr_off; r > 0; --r) pr_mask &= pr_mask - 1;
                     m = (u32)__ffs(pr_mask) - 1u;
-                } else {           // k_pairs queues whole windows: consecutive offsets
+                } else {           // phase 1 queues whole windows: consecutive offsets
                     m = (u32)__ffs(pr_mask) - 1u + (f - pr_off);
                 }
                 pass = true;
-                if (!COUNT_CAND) {  // with COUNT_CAND both tests were already taken in k_pairs
+                if (!COUNT_CAND) {  // with COUNT_CAND both tests were already taken in phase 1
                     const float *c = sh.coef[pr];
                     const float t = 0.5f * (float)m, h = 0.5f * t * t;
                     const float dx = c[SC_D], dy = c[SC_D + 1], dz = c[SC_D + 2];
@@ -1157,8 +1304,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_SAMPLE_MIN_BLOCKS) k_sample
                         pass = c2 <= R2 * (1.0f + BAND_R2);
                         if (pass && c2 >= R2 * (1.0f - BAND_R2)) {
                             ++n_exact;
-                            const QEntry pe = P.q2[batch * 32 + pr];
-                            pass = exact_predict_radius(P, pe.si, pe.sj, meta_pattern(__float_as_uint(P.P2[pe.si].w)), (int)m);
+                            const u32 psi = sh.si[pr], psj = sh.sj[pr];
+                            pass = exact_predict_radius(P, psi, psj, meta_pattern(__float_as_uint(P.P2[psi].w)), (int)m);
                         }
                     }
                 }
@@ -1200,12 +1347,16 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_SAMPLE_MIN_BLOCKS) k_sample
             // a runner-up within 1e-4 (fp32 error of `part` is ~1e-5) or any sample in the band: fp64 decides
             word = (doubt || best_m < 0 || best - second <= 1.0e-4f) ? maybe_mask : (RESOLVED | (u32)best_m | ((u32)best_k << 8));
         }
-        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, word != 0, e.si, e.sj, word))
-            finish_entry_inline<RCD_MODE_PREDICT>(P, e.si, e.sj, word);
+        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, word != 0, si, sj, word))
+            finish_entry_inline<RCD_MODE_PREDICT>(P, si, sj, word);
         __syncwarp();  // the next batch overwrites this warp's shared memory
     }
     unsigned long long ex = warp_sum((unsigned long long)n_exact);
-    if (lane == 0 && ex) atomicAdd(&P.counters->n_exact, ex);
+    unsigned long long pt = warp_sum((unsigned long long)n_pot);
+    if (lane == 0) {
+        if (ex) atomicAdd(&P.counters->n_exact, ex);
+        if (pt) atomicAdd(&P.counters->n_potential, pt);
+    }
 }
 
 // k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp
@@ -1276,7 +1427,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_EXACT_MIN_BLOCKS) k_exact(P
 // -------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_query_radius(u32 nq, const float *__restrict__ qx, const float *__restrict__ qy, const float *__restrict__ qz,
-               float radius, GridParams g, u32 n, const float4 *__restrict__ P0, const u32 *__restrict__ keys,
+               float radius, GridParams g, u32 n, const float4 *__restrict__ P0, const u32 *__restrict__ cell_begin,
                const u32 *__restrict__ sorted_slot, uint2 *__restrict__ hits, unsigned long long cap,
                Counters *counters) {
     const u32 lane = threadIdx.x & 31u;
@@ -1284,22 +1435,19 @@ k_query_radius(u32 nq, const float *__restrict__ qx, const float *__restrict__ q
     if (qi >= nq) return;
     const float x = qx[qi], y = qy[qi], z = qz[qi];
     const float R2 = radius * radius;
-    int cx = cell_coord(x, g.ox, g.inv_cell, g.nx), cy = cell_coord(y, g.oy, g.inv_cell, g.ny),
-        cz = cell_coord(z, g.oz, g.inv_cell, g.nz);
-    // a query point may lie outside the grid: widen the stencil by its distance to the box
-    float ex = fmaxf(fmaxf(g.ox - x, x - (g.ox + g.nx * g.cell)), 0.0f);
-    float ey = fmaxf(fmaxf(g.oy - y, y - (g.oy + g.ny * g.cell)), 0.0f);
-    float ez = fmaxf(fmaxf(g.oz - z, z - (g.oz + g.nz * g.cell)), 0.0f);
-    (void)ex; (void)ey; (void)ez;  // clamping is non-expanding: the plain stencil already suffices
-    float srf = floorf(radius * g.inv_cell + 1.0e-3f) + 1.0f;
-    int sr = (srf < 1.0e6f) ? (int)srf : 1000000;
-    const int x0 = max(cx - sr, 0), x1 = min(cx + sr, g.nx - 1);
-    const int y0 = max(cy - sr, 0), y1 = min(cy + sr, g.ny - 1);
-    const int z0 = max(cz - sr, 0), z1 = min(cz + sr, g.nz - 1);
+    // cells under the bounding box of the ball (cell_coord is monotone and clamps: objects outside the
+    // grid sit in its border cells, a query point outside the grid reaches them through the same clamp)
+    const float r = radius * (1.0f + 1.0e-5f) + 1.0e-3f;
+    const int x0 = cell_coord(x - r - (0.05f + 4.0e-7f * fabsf(x)), g.ox, g.inv_cell, g.nx);
+    const int x1 = cell_coord(x + r + (0.05f + 4.0e-7f * fabsf(x)), g.ox, g.inv_cell, g.nx);
+    const int y0 = cell_coord(y - r - (0.05f + 4.0e-7f * fabsf(y)), g.oy, g.inv_cell, g.ny);
+    const int y1 = cell_coord(y + r + (0.05f + 4.0e-7f * fabsf(y)), g.oy, g.inv_cell, g.ny);
+    const int z0 = cell_coord(z - r - (0.05f + 4.0e-7f * fabsf(z)), g.oz, g.inv_cell_z, g.nz);
+    const int z1 = cell_coord(z + r + (0.05f + 4.0e-7f * fabsf(z)), g.oz, g.inv_cell_z, g.nz);
     for (int zz = z0; zz <= z1; ++zz)
         for (int yy = y0; yy <= y1; ++yy) {
-            u32 c0 = (u32)((zz * g.ny + yy) * g.nx + x0), c1 = c0 + (u32)(x1 - x0);
-            u32 first = lower_bound_keys(keys, n, c0), last = lower_bound_keys(keys, n, c1 + 1);
+            const u32 c0 = (u32)((zz * g.ny + yy) * g.nx + x0), c1 = c0 + (u32)(x1 - x0);
+            const u32 first = cell_begin[c0], last = cell_begin[c1 + 1u];
             for (u32 s = first + lane; s < last; s += 32) {
                 float4 b = P0[s];
                 float dx = b.x - x, dy = b.y - y, dz = b.z - z;

@@ -22,8 +22,8 @@ PAT_STATIONARY, PAT_CONSTANT_VELOCITY, PAT_ACCELERATING, PAT_NO_HISTORY = 0, 1, 
 FLAG_PROFILE = 1
 FLAG_COUNT_PREDICT_CANDIDATES = 2
 FLAG_GRAPH = 4
-NUM_STAGES = 9
-STAGE_NAMES = ("upload", "keys", "sort", "reorder", "pairs", "sample", "exact", "download", "total")
+NUM_STAGES = 10
+STAGE_NAMES = ("upload", "keys", "sort", "reorder", "pairs", "narrow", "exact", "download", "total", "qorder")
 HALO_RECORD_WORDS = 13
 
 # every symbol include/rcd.h declares (tests/test_abi.py checks the export table against this
