@@ -76,8 +76,11 @@ struct rcd_handle_s {
     uint2 *qa = nullptr;        // pair queue k_pairs -> k_narrow
     u32 *qa_fill = nullptr;
     u32 qa_blocks_cap = 0;
-    uint4 *ovf = nullptr;       // tiles (or rests of tiles) left to the overflow pass of k_pairs
+    uint4 *ovf = nullptr;       // work items (or rests of them) left to the overflow pass of k_pairs
     u32 ovf_cap = 0;
+    uint4 *items = nullptr;     // work items of k_pairs (k_tile_plan)
+    u32 items_cap = 0;
+    int4 *tile_box = nullptr;   // [2 * tiles]
     int stage_blocks = 0, stage_blocks_sms = 148;
     int narrow_blocks[5] = {0, 0, 0, 0, 0};
     int pair_blocks[5] = {0, 0, 0, 0, 0};  // resident blocks per SM x SMs, per kernel variant
@@ -421,10 +424,14 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->q3, (size_t)h->qcap));
     // the S1 filter forwards ~60 (predict) / ~20 (detect) pairs per object at the density of the bench frame;
     // the pair queue is handed out in blocks of QA_BLOCK entries, one per warp at a time
-    h->qa_blocks_cap = (u32)std::max<u64>(h->qcap / QA_BLOCK, 1);
+    // (+ one partly filled block per resident warp of k_pairs)
+    h->qa_blocks_cap = (u32)(h->qcap / QA_BLOCK + 148 * 8 * PAIR_WARPS);
     CREATE_TRY(dev_alloc(&h->qa, (size_t)h->qa_blocks_cap * QA_BLOCK));
     CREATE_TRY(dev_alloc(&h->qa_fill, (size_t)h->qa_blocks_cap));
-    h->ovf_cap = (u32)(cap / TQ + 65536);  // >= work items of a frame (tiles x splits)
+    h->items_cap = (u32)((cap / TQ + 1) * ITEMS_PER_TILE_CAP);  // k_tile_plan never makes more
+    CREATE_TRY(dev_alloc(&h->items, (size_t)h->items_cap));
+    CREATE_TRY(dev_alloc(&h->tile_box, 2 * (cap / TQ + 1)));
+    h->ovf_cap = h->items_cap;  // every work item is handed over at most once
     CREATE_TRY(dev_alloc(&h->ovf, (size_t)h->ovf_cap));
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) {
@@ -449,7 +456,7 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->U);
     cudaFree(h->cell_begin); cudaFree(h->bbox_dev);
     for (int k = 0; k < 2; ++k) { cudaFree(h->qkeys[k]); cudaFree(h->qvals[k]); }
-    cudaFree(h->qa); cudaFree(h->qa_fill); cudaFree(h->ovf);
+    cudaFree(h->qa); cudaFree(h->qa_fill); cudaFree(h->ovf); cudaFree(h->items); cudaFree(h->tile_box);
     if (h->bbox_host) cudaFreeHost(h->bbox_host);
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
     cudaFree(h->q3);
@@ -610,9 +617,13 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         P.tile_counter = h->pair_tile_counter;
         P.qa = h->qa; P.qa_fill = h->qa_fill; P.qa_blocks_cap = h->qa_blocks_cap;
         P.ovf = h->ovf; P.ovf_cap = h->ovf_cap;
+        P.items = h->items; P.items_cap = h->items_cap; P.tile_box = h->tile_box;
+        // work items of about 16 chunks (16 k pair tests per lane-pass); small frames get smaller items so that
+        // every resident warp finds work
+        P.item_chunks = P.ntiles >= 16384 ? 16u : P.ntiles >= 4096 ? 8u : P.ntiles >= 1024 ? 4u : P.ntiles >= 256 ? 2u : 1u;
         P.q3 = h->q3; P.qcap = h->qcap;
         CUDA_TRY(h, cudaMemsetAsync(h->pair_tile_counter, 0, 2 * sizeof(u32), h->stream));
-        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_qa_blocks, 0, 3 * sizeof(unsigned long long), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_qa_blocks, 0, 4 * sizeof(unsigned long long), h->stream));
         const bool count = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) != 0;
         // persistent launch: as many blocks as can be resident, warps pull tiles from a counter
         const int variant = fused ? 4 : mode == RCD_MODE_DETECT ? 0 : (mode == RCD_MODE_COMPUTE_NODE ? 3 : (count ? 2 : 1));
@@ -635,10 +646,15 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
             CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn2, STAGE_THREADS, 0));
             h->narrow_blocks[variant] = std::max(1, per_sm) * std::max(1, sms);
         }
-        // small frames: share each tile between several warps until the resident warps are used
-        P.splits = 1;
-        while (P.splits < 16 && (u64)P.ntiles * P.splits * 2 <= (u64)h->pair_blocks[variant] * PAIR_WARPS) P.splits *= 2;
-        const u64 items = (u64)P.ntiles * P.splits;
+        // plan: the tiles' cell boxes and work items of even size; then the persistent pair kernel
+        {
+            const unsigned pb = (unsigned)std::min<u64>((P.ntiles + 3) / 4, (u64)h->stage_blocks_sms * 8);
+            if (variant == 0) k_tile_plan<RCD_MODE_DETECT><<<pb, 128, 0, h->stream>>>(P);
+            else if (variant == 3) k_tile_plan<RCD_MODE_COMPUTE_NODE><<<pb, 128, 0, h->stream>>>(P);
+            else k_tile_plan<RCD_MODE_PREDICT><<<pb, 128, 0, h->stream>>>(P);
+            KERNEL_CHECK(h);
+        }
+        const u64 items = (u64)P.ntiles * PLAN_ITEMS_PER_TILE;  // (upper estimate: the grid is capped by residency)
         const unsigned blocks = (unsigned)std::min<u64>((items + PAIR_WARPS - 1) / PAIR_WARPS, (u64)h->pair_blocks[variant]);
         // the regular pass, then the overflow pass (returns at once unless the pair queue ran out)
         const unsigned oblocks = std::min(blocks, (unsigned)h->stage_blocks_sms * 4u);
@@ -669,7 +685,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         }
         stage_begin(h, RCD_STAGE_NARROW);
         {
-            const unsigned nb = (unsigned)std::min<u64>((u64)h->narrow_blocks[variant], items * 2 / STAGE_WARPS + 1);
+            const unsigned nb = (unsigned)std::min<u64>((u64)h->narrow_blocks[variant], (u64)P.ntiles * 8 / STAGE_WARPS + 1);
             if (variant == 0) k_narrow<RCD_MODE_DETECT, false><<<nb, STAGE_THREADS, 0, h->stream>>>(P);
             else if (variant == 1) k_narrow<RCD_MODE_PREDICT, false><<<nb, STAGE_THREADS, 0, h->stream>>>(P);
             else if (variant == 2) k_narrow<RCD_MODE_PREDICT, true><<<nb, STAGE_THREADS, 0, h->stream>>>(P);

@@ -72,6 +72,7 @@ struct Counters {
     // (reset before every step)
     unsigned long long n_qa_blocks, n_q3;
     unsigned long long n_overflow;  // parts of tiles k_pairs left to its overflow pass (pair queue full)
+    unsigned long long n_items;     // work items of k_pairs (k_tile_plan)
     unsigned long long n_fallback;  // resolved entries the exact stage had to redo in full (expected 0)
 };
 

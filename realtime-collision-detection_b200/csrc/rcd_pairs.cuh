@@ -51,7 +51,7 @@ constexpr int TQ = 32;            // queries per tile = one warp
 constexpr int PAIR_WARPS = 4;     // warps (independent tiles) per block
 constexpr int PAIR_THREADS = PAIR_WARPS * 32;
 constexpr int CH = 32;            // neighbours staged per chunk (1 per lane)
-constexpr int QA_BLOCK = 2048;    // entries of the pair queue a warp reserves at a time (>= TQ * CH)
+constexpr int QA_BLOCK = 256;     // entries of the pair queue a warp reserves at a time
 constexpr u32 QA_INR = 1u << 30;  // entry flag: certainly within the radius (and counted as a candidate)
 constexpr u32 QA_UND = 1u << 31;  // entry flag: inside the fp32 guard band of the radius: k_exact decides and counts
 constexpr u32 QA_SI_MASK = (1u << 30) - 1u;
@@ -66,7 +66,10 @@ struct PairParams {
     u32 n;                   // objects (owned + halo)
     u32 n_owned;             // queries
     u32 ntiles;
-    u32 splits;              // work items per tile (power of two): small frames split a tile's chunks over warps
+    u32 item_chunks;         // smallest work item of k_pairs, in chunks (k_tile_plan)
+    uint4 *items;            // work items of k_pairs
+    u32 items_cap;
+    int4 *tile_box;          // [2 * ntiles] cell box of every tile: {x0, x1, y0, y1}, {z0, z1, -, -}
     GridParams g;
     const float4 *P0, *P1, *P2;
     const u32 *qorder;       // query order -> position in cell order
@@ -528,8 +531,9 @@ __device__ __forceinline__ bool predict_window(const WindowCoef &c, int &m_lo, i
         t_hi = fminf(t_hi, tm + us + w);
         if (t_lo > t_hi) return false;
     }
-    m_lo = max((int)floorf(2.0f * t_lo), 0);
-    m_hi = min((int)ceilf(2.0f * t_hi), PREDICT_OFFSETS - 1);
+    // the offsets are the times 0.5 m inside the window (2e-3: fp32 rounding of 2 t, and then some)
+    m_lo = max((int)ceilf(2.0f * t_lo - 2.0e-3f), 0);
+    m_hi = min((int)floorf(2.0f * t_hi + 2.0e-3f), PREDICT_OFFSETS - 1);
     return m_lo <= m_hi;
 }
 
@@ -722,6 +726,148 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     return r;
 }
 
+// Volume a neighbour must lie in to matter for one query: a ball of radius Rq for radius queries; for
+// predict queries the capsule of radius 100 (+ slack) about the chord of the centre path
+// c(t) = uv t + ua t^2/2, t in [0, 9.5] (:728-741): the path leaves its chord by at most |ua| 9.5^2 / 8.
+// w is the chord, rad the radius.
+struct QueryVolume {
+    float wx, wy, wz, inv_w2, rad;
+    float fv, fa;  // which parts of the motion the centre path follows (radius queries: all of it)
+    float an;      // |a_i|, rounded up
+    bool radius_query;
+};
+template <int MODE>
+__device__ __forceinline__ QueryVolume query_volume(const float4 &p1, const float4 &p2, u32 pattern, float Rq) {
+    QueryVolume v;
+    // queries that take the radius-R test (detect-like); the others are predict queries
+    v.radius_query = !is_predict(MODE) || pattern == RCD_PAT_NO_HISTORY;
+    v.fv = v.radius_query ? 1.0f : ((pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f);
+    v.fa = v.radius_query ? 1.0f : ((pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f);
+    v.an = sqrt_ub(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z);
+    v.wx = v.wy = v.wz = v.inv_w2 = 0.0f;
+    if (!v.radius_query) {
+        v.wx = p1.x * v.fv * 9.5f + p2.x * v.fa * 45.125f;
+        v.wy = p1.y * v.fv * 9.5f + p2.y * v.fa * 45.125f;
+        v.wz = p1.z * v.fv * 9.5f + p2.z * v.fa * 45.125f;
+        float w2 = v.wx * v.wx + v.wy * v.wy + v.wz * v.wz;
+        v.rad = (PREDICT_RADIUS + 11.28125f * v.an * v.fa) * (1.0f + 1.0e-5f) + 2.0e-2f + 1.0e-5f * sqrtf(w2);
+        if (!(w2 < 1.0e30f) || !(v.rad < 1.0e30f)) {  // non-finite motion: scan everything
+            v.wx = v.wy = v.wz = w2 = 0.0f;
+            v.rad = 1.0e18f;
+        }
+        v.inv_w2 = w2 > 1.0e-12f ? 1.0f / w2 : 0.0f;
+    } else {
+        v.rad = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
+    }
+    return v;
+}
+
+// objects of the cell row `rr` of a tile's box: position of the first one in cell order, and how many
+struct TileBox { int x0, x1, y0, y1, z0, z1; };
+__device__ __forceinline__ void row_span(const PairParams &P, const TileBox &b, int rr, u32 &lo, u32 &cnt) {
+    const int ny_span = b.y1 - b.y0 + 1;
+    const int yy = b.y0 + rr % ny_span, zz = b.z0 + rr / ny_span;
+    const u32 c0 = (u32)((zz * P.g.ny + yy) * P.g.nx + b.x0);
+    const u32 first = P.cell_begin[c0], last = P.cell_begin[c0 + (u32)(b.x1 - b.x0) + 1u];
+    lo = first;
+    cnt = last - first;
+}
+
+// work items of k_pairs: {tile, row batch | flags, first chunk, last chunk + 1}
+constexpr u32 ITEM_MULTI = 1u << 31;  // ... and every later row batch of the tile (boxes with very many rows)
+constexpr u32 ITEM_FIRST = 1u << 30;  // the item that subtracts the query's hit on itself from the candidate count
+constexpr u32 ITEM_RBASE_MASK = (1u << 30) - 1u;
+constexpr int PLAN_MAX_BATCHES = 8;   // tiles with more row batches than this become one ITEM_MULTI item
+constexpr int PLAN_ITEMS_PER_TILE = 32;
+constexpr int ITEMS_PER_TILE_CAP = PLAN_ITEMS_PER_TILE + PLAN_MAX_BATCHES;
+
+// -------------------------------------------------------------------------------------------------
+// k_tile_plan: one warp per tile.  The cost of a tile is the number of objects under its box, which spans
+// four orders of magnitude on clustered frames (hotspot density ~ 1/r): the plan cuts every tile into work
+// items of about the same size -- a run of chunks of one row batch -- so that the persistent warps of k_pairs
+// stay busy to the end.  Also stores the tile's cell box (computed once, here).
+// -------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
+    __shared__ u32 s_nch[4][PLAN_MAX_BATCHES + 1];
+    u32 *nch = s_nch[threadIdx.x >> 5];
+    const u32 lane = threadIdx.x & 31u;
+    const GridParams g = P.g;
+    const float Rq = is_predict(MODE) ? PREDICT_RADIUS : P.R;
+    const u32 nwarps = gridDim.x * (blockDim.x >> 5);
+    for (u32 tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); tile < P.ntiles; tile += nwarps) {
+        const u32 qi = tile * TQ + lane;
+        const bool valid = qi < P.n_owned;
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0, p2 = p0;
+        if (valid) {
+            const u32 s = P.qorder[qi];
+            p0 = P.P0[s];
+            p1 = P.P1[s];
+            p2 = P.P2[s];
+        }
+        const QueryVolume v = query_volume<MODE>(p1, p2, meta_pattern(__float_as_uint(p2.w)), Rq);
+        // cells of the bounding box of the tile's query volumes (cell_coord is monotone, so a
+        // neighbour inside the box in space is inside it in cells; 0.05 m + 1 ulp covers the fp32 sums)
+        const float big = 3.0e38f;
+        const float lox = warp_minf(valid ? fminf(p0.x, p0.x + v.wx) - v.rad : big);
+        const float hix = warp_maxf(valid ? fmaxf(p0.x, p0.x + v.wx) + v.rad : -big);
+        const float loy = warp_minf(valid ? fminf(p0.y, p0.y + v.wy) - v.rad : big);
+        const float hiy = warp_maxf(valid ? fmaxf(p0.y, p0.y + v.wy) + v.rad : -big);
+        const float loz = warp_minf(valid ? fminf(p0.z, p0.z + v.wz) - v.rad : big);
+        const float hiz = warp_maxf(valid ? fmaxf(p0.z, p0.z + v.wz) + v.rad : -big);
+        TileBox b;
+        b.x0 = cell_coord(lox - (0.05f + 4.0e-7f * fabsf(lox)), g.ox, g.inv_cell, g.nx);
+        b.x1 = cell_coord(hix + (0.05f + 4.0e-7f * fabsf(hix)), g.ox, g.inv_cell, g.nx);
+        b.y0 = cell_coord(loy - (0.05f + 4.0e-7f * fabsf(loy)), g.oy, g.inv_cell, g.ny);
+        b.y1 = cell_coord(hiy + (0.05f + 4.0e-7f * fabsf(hiy)), g.oy, g.inv_cell, g.ny);
+        b.z0 = cell_coord(loz - (0.05f + 4.0e-7f * fabsf(loz)), g.oz, g.inv_cell_z, g.nz);
+        b.z1 = cell_coord(hiz + (0.05f + 4.0e-7f * fabsf(hiz)), g.oz, g.inv_cell_z, g.nz);
+        if (lane == 0) {
+            P.tile_box[2 * (size_t)tile] = make_int4(b.x0, b.x1, b.y0, b.y1);
+            P.tile_box[2 * (size_t)tile + 1] = make_int4(b.z0, b.z1, 0, 0);
+        }
+        const int nrows = (b.y1 - b.y0 + 1) * (b.z1 - b.z0 + 1);
+        const int nbatches = (nrows + TQ - 1) / TQ;
+        if (nbatches > PLAN_MAX_BATCHES) {
+            if (lane == 0) {
+                const unsigned long long at = atomicAdd(&P.counters->n_items, 1ULL);
+                if (at < P.items_cap) P.items[at] = make_uint4(tile, ITEM_MULTI | ITEM_FIRST, 0u, 0xffffffffu);
+            }
+            continue;
+        }
+        u32 tot_chunks = 0;
+        __syncwarp();
+        for (int bt = 0; bt < nbatches; ++bt) {
+            u32 lo = 0, cnt = 0;
+            const int rr = bt * TQ + (int)lane;
+            if (rr < nrows) row_span(P, b, rr, lo, cnt);
+            const u32 total = warp_sum(cnt);
+            const u32 c = (total + CH - 1) / CH;
+            if (lane == 0) nch[bt] = c;
+            tot_chunks += c;
+        }
+        __syncwarp();
+        const u32 K = max(P.item_chunks, (tot_chunks + PLAN_ITEMS_PER_TILE - 1) / PLAN_ITEMS_PER_TILE);
+        u32 n_it = 0;
+        for (int bt = 0; bt < nbatches; ++bt) n_it += (nch[bt] + K - 1) / K;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&P.counters->n_items, (unsigned long long)n_it);
+        base = __shfl_sync(FULL_MASK, base, 0);
+        for (u32 j = lane; j < n_it; j += 32) {
+            u32 k = j;
+            int bt = 0;
+            for (; bt < nbatches; ++bt) {
+                const u32 nb = (nch[bt] + K - 1) / K;
+                if (k < nb) break;
+                k -= nb;
+            }
+            if (base + j < P.items_cap)
+                P.items[base + j] = make_uint4(tile, (u32)(bt * TQ) | (j == 0 ? ITEM_FIRST : 0u), k * K, min((k + 1u) * K, nch[bt]));
+        }
+        __syncwarp();
+    }
+}
+
 // -------------------------------------------------------------------------------------------------
 // k_pairs: the S1 filter (see the head of this file).
 // -------------------------------------------------------------------------------------------------
@@ -750,27 +896,21 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
     u32 n_pot = 0;                                // per-lane statistics, flushed once at the end
     u32 qa_block = QA_NO_BLOCK, qa_used = 0;      // this warp's block of the pair queue (uniform)
     bool qa_full = false;                         // (uniform) the pair queue has no block left
-    const u32 n_redo = SLOW ? (u32)min(P.counters->n_overflow, (unsigned long long)P.ovf_cap) : 0u;
+
+    const u32 n_work = SLOW ? (u32)min(P.counters->n_overflow, (unsigned long long)P.ovf_cap)
+                            : (u32)min(P.counters->n_items, (unsigned long long)P.items_cap);
 
     for (;;) {
-        u32 tile = 0;
-        if (lane == 0) tile = atomicAdd(P.tile_counter + (SLOW ? 1 : 0), 1u);
-        tile = __shfl_sync(FULL_MASK, tile, 0);
-        int rbase0 = 0;        // where to start: the beginning, or (overflow pass) where the regular pass stopped
-        u32 c_first = 0xffffffffu;
-        if (SLOW) {
-            if (tile >= n_redo) break;
-            const uint4 rec = P.ovf[tile];
-            tile = rec.x;
-            rbase0 = (int)rec.y;
-            c_first = rec.z;
-        }
-        if (tile >= P.ntiles * P.splits) break;
-        const u32 item = tile;
-        // with few tiles (small frames) each tile is shared by `splits` warps: warp `split` takes the
-        // chunks split, split + splits, ... of every row batch
-        const u32 split = tile % P.splits;
-        tile /= P.splits;
+        u32 idx = 0;
+        if (lane == 0) idx = atomicAdd(P.tile_counter + (SLOW ? 1 : 0), 1u);
+        idx = __shfl_sync(FULL_MASK, idx, 0);
+        if (idx >= n_work) break;
+        // a work item: chunks [c_lo, c_hi) of one row batch of one tile (k_tile_plan), or -- overflow pass --
+        // what the regular pass left of an item when the pair queue ran out
+        const uint4 it = SLOW ? P.ovf[idx] : P.items[idx];
+        const u32 tile = it.x;
+        const int rbase0 = (int)(it.y & ITEM_RBASE_MASK);
+        const bool multi = (it.y & ITEM_MULTI) != 0, first_item = (it.y & ITEM_FIRST) != 0;
 
         const u32 qi = tile * TQ + lane;
         const bool valid = qi < P.n_owned;
@@ -783,31 +923,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
             p2 = P.P2[s];
         }
         const u32 pattern = meta_pattern(__float_as_uint(p2.w));
-        // queries that take the radius-R test (detect-like); the others are predict queries
-        const bool radius_query = !PRED || pattern == RCD_PAT_NO_HISTORY;
+        const QueryVolume vol = query_volume<MODE>(p1, p2, pattern, Rq);
+        const bool radius_query = vol.radius_query;
         const bool counts = valid && (radius_query || FUSED);  // in-radius neighbours are candidates of this query
-        // Volume a neighbour must lie in to matter: a ball of radius Rq for radius queries; for predict
-        // queries the capsule of radius 100 (+ slack) about the chord of the centre path
-        // c(t) = uv t + ua t^2/2, t in [0, 9.5] (:728-741): the path leaves its chord by at most
-        // |ua| 9.5^2 / 8.  w is the chord, rad the radius.
-        float wx = 0.0f, wy = 0.0f, wz = 0.0f, inv_w2 = 0.0f, rad;
-        const float fv = radius_query ? 1.0f : ((pattern >= RCD_PAT_CONSTANT_VELOCITY) ? 1.0f : 0.0f);
-        const float fa = radius_query ? 1.0f : ((pattern == RCD_PAT_ACCELERATING) ? 1.0f : 0.0f);
-        const float an = sqrt_ub(p2.x * p2.x + p2.y * p2.y + p2.z * p2.z);  // |a_i|, rounded up
-        if (!radius_query) {
-            wx = p1.x * fv * 9.5f + p2.x * fa * 45.125f;
-            wy = p1.y * fv * 9.5f + p2.y * fa * 45.125f;
-            wz = p1.z * fv * 9.5f + p2.z * fa * 45.125f;
-            float w2 = wx * wx + wy * wy + wz * wz;
-            rad = (PREDICT_RADIUS + 11.28125f * an * fa) * (1.0f + 1.0e-5f) + 2.0e-2f + 1.0e-5f * sqrtf(w2);
-            if (!(w2 < 1.0e30f) || !(rad < 1.0e30f)) {  // non-finite motion: scan everything
-                wx = wy = wz = w2 = 0.0f;
-                rad = 1.0e18f;
-            }
-            inv_w2 = w2 > 1.0e-12f ? 1.0f / w2 : 0.0f;
-        } else {
-            rad = Rq * (1.0f + 1.0e-5f) + 1.0e-3f;
-        }
+        const float wx = vol.wx, wy = vol.wy, wz = vol.wz, inv_w2 = vol.inv_w2, rad = vol.rad;
+        const float fv = vol.fv, fa = vol.fa, an = vol.an;
         // T1: this query's half.  Radius queries follow their true motion (the detect trajectory, :229-294),
         // predict queries the motion of their pattern (:728-741): M = centre at tm, MV = its velocity there.
         const float uvx = p1.x * fv, uvy = p1.y * fv, uvz = p1.z * fv;
@@ -850,43 +970,26 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
         const float rad2 = rad * rad;
         u32 ncand = 0;  // candidates decided by the filter itself
 
-        // cells of the bounding box of the tile's query volumes (cell_coord is monotone, so a
-        // neighbour inside the box in space is inside it in cells; 0.05 m + 1 ulp covers the fp32 sums)
-        const float big = 3.0e38f;
-        const float lox = warp_minf(valid ? fminf(p0.x, p0.x + wx) - rad : big);
-        const float hix = warp_maxf(valid ? fmaxf(p0.x, p0.x + wx) + rad : -big);
-        const float loy = warp_minf(valid ? fminf(p0.y, p0.y + wy) - rad : big);
-        const float hiy = warp_maxf(valid ? fmaxf(p0.y, p0.y + wy) + rad : -big);
-        const float loz = warp_minf(valid ? fminf(p0.z, p0.z + wz) - rad : big);
-        const float hiz = warp_maxf(valid ? fmaxf(p0.z, p0.z + wz) + rad : -big);
-        const int x0 = cell_coord(lox - (0.05f + 4.0e-7f * fabsf(lox)), g.ox, g.inv_cell, g.nx);
-        const int x1 = cell_coord(hix + (0.05f + 4.0e-7f * fabsf(hix)), g.ox, g.inv_cell, g.nx);
-        const int y0 = cell_coord(loy - (0.05f + 4.0e-7f * fabsf(loy)), g.oy, g.inv_cell, g.ny);
-        const int y1 = cell_coord(hiy + (0.05f + 4.0e-7f * fabsf(hiy)), g.oy, g.inv_cell, g.ny);
-        const int z0 = cell_coord(loz - (0.05f + 4.0e-7f * fabsf(loz)), g.oz, g.inv_cell_z, g.nz);
-        const int z1 = cell_coord(hiz + (0.05f + 4.0e-7f * fabsf(hiz)), g.oz, g.inv_cell_z, g.nz);
-        const int ny_span = y1 - y0 + 1;
-        const int nrows = ny_span * (z1 - z0 + 1);
+        // the tile's cell box (k_tile_plan)
+        TileBox box;
+        {
+            const int4 bxy = P.tile_box[2 * (size_t)tile], bz = P.tile_box[2 * (size_t)tile + 1];
+            box.x0 = bxy.x; box.x1 = bxy.y; box.y0 = bxy.z; box.y1 = bxy.w; box.z0 = bz.x; box.z1 = bz.y;
+        }
+        const int nrows = (box.y1 - box.y0 + 1) * (box.z1 - box.z0 + 1);
 
-        bool stopped = false;  // (uniform) regular pass: the pair queue ran out in this tile
-        if (!SLOW && qa_full) {  // nothing can be queued any more: hand the whole tile to the overflow pass
+        bool stopped = false;  // (uniform) regular pass: the pair queue ran out in this item
+        if (!SLOW && qa_full) {  // nothing can be queued any more: hand the whole item to the overflow pass
             if (lane == 0) {
                 const unsigned long long k = atomicAdd(&P.counters->n_overflow, 1ULL);
-                if (k < P.ovf_cap) P.ovf[k] = make_uint4(item, 0u, split, 0u);
+                if (k < P.ovf_cap) P.ovf[k] = make_uint4(tile, it.y & ~ITEM_FIRST, it.z, it.w);
             }
             stopped = true;
         }
         for (int rbase = rbase0; rbase < nrows && !stopped; rbase += TQ) {
             // ---- span of one cell row per lane: two loads from the dense cell table ------------------
             u32 lo = 0, rcnt = 0;
-            if ((int)lane + rbase < nrows) {
-                const int rr = rbase + (int)lane;
-                const int yy = y0 + rr % ny_span, zz = z0 + rr / ny_span;
-                const u32 c0 = (u32)((zz * g.ny + yy) * g.nx + x0);
-                const u32 first = P.cell_begin[c0], last = P.cell_begin[c0 + (u32)(x1 - x0) + 1u];
-                lo = first;
-                rcnt = last - first;
-            }
+            if ((int)lane + rbase < nrows) row_span(P, box, rbase + (int)lane, lo, rcnt);
             u32 incl = rcnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -960,21 +1063,23 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
             };
 
             u32 kbuf = 0;
-            const u32 c_begin = (SLOW && rbase == rbase0) ? c_first : split;
-            if (c_begin < nchunks) {
+            const u32 c_begin = (rbase == rbase0) ? it.z : 0u;
+            const u32 c_end = min(nchunks, (rbase == rbase0) ? it.w : 0xffffffffu);
+            if (c_begin < c_end) {
                 stage(c_begin, ws.buf[0]);
                 cp_async_wait<0>();
                 relayout(c_begin, ws.buf[0]);
             }
             __syncwarp();
-            for (u32 c = c_begin; c < nchunks; c += P.splits, kbuf ^= 1u) {
+            for (u32 c = c_begin; c < c_end; ++c, kbuf ^= 1u) {
                 StagePacked &b = ws.buf[kbuf];
-                const bool more = c + P.splits < nchunks;
-                if (more) stage(c + P.splits, ws.buf[kbuf ^ 1u]);  // in flight while this chunk is filtered
+                const bool more = c + 1u < c_end;
+                if (more) stage(c + 1u, ws.buf[kbuf ^ 1u]);  // in flight while this chunk is filtered
                 const u32 m = min((u32)CH, total - c * CH);
                 // ---- S1: one query per lane against every staged neighbour, two per packed instruction -----
                 // Each lane appends what passes to a private list in shared memory (no warp vote per test).
-                u32 cnt = 0, nc = 0;
+                u32 nc = 0;
+                unsigned char *pl = &ws.plist[0][lane];
                 const u32 npair = (m + 1u) >> 1;
                 for (u32 u = 0; u < npair; ++u) {
                     const float4 xy = b.xy[u];
@@ -1021,25 +1126,22 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         ta = l2.x <= L2.x;
                         tb = l2.y <= L2.y;
                     }
-                    {
+                    {   // (always stored at the end of the lane's list; the list only grows when the pair passed)
                         const bool inr = d2.x < R2lo_l;
                         const bool und = !inr && d2.x <= R2hi_l;
-                        if ((ta && d2.x < dmaxA) || d2.x < dmaxB || und) {
-                            ws.plist[cnt][lane] = (unsigned char)((2u * u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
-                            ++cnt;
-                        }
+                        *pl = (unsigned char)((2u * u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
+                        pl += ((ta && d2.x < dmaxA) || d2.x < dmaxB || und) ? TQ : 0;
                         nc += inr ? 1u : 0u;
                     }
                     {
                         const bool inr = d2.y < R2lo_l;
                         const bool und = !inr && d2.y <= R2hi_l;
-                        if ((tb && d2.y < dmaxA) || d2.y < dmaxB || und) {
-                            ws.plist[cnt][lane] = (unsigned char)((2u * u + 1u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
-                            ++cnt;
-                        }
+                        *pl = (unsigned char)((2u * u + 1u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
+                        pl += ((tb && d2.y < dmaxA) || d2.y < dmaxB || und) ? TQ : 0;
                         nc += inr ? 1u : 0u;
                     }
                 }
+                const u32 cnt = (u32)(pl - &ws.plist[0][lane]) / TQ;
                 // ---- survivors -> pair queue (the warp's private block; a new one when this one is full) -------
                 u32 off = cnt;
 #pragma unroll
@@ -1056,57 +1158,66 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                             P, s | ((code & PL_INR) ? QA_INR : 0u) | ((code & PL_UND) ? QA_UND : 0u), b.pos[code & 31u]);
                     }
                 } else if (total_pairs) {
-                    if (qa_block == QA_NO_BLOCK || qa_used + total_pairs > (u32)QA_BLOCK) {
-                        u32 nb = 0;
-                        if (lane == 0) {
-                            if (qa_block < P.qa_blocks_cap) P.qa_fill[qa_block] = qa_used;
-                            nb = (u32)min(atomicAdd(&P.counters->n_qa_blocks, 1ULL), 0xfffffffeULL);
+                    // room left in the warp's block; what does not fit goes to new blocks, taken with ONE atomic so that
+                    // they are adjacent: the survivors of a chunk stay one contiguous run of the queue
+                    const u32 room = qa_block == QA_NO_BLOCK ? 0u : (u32)QA_BLOCK - qa_used;
+                    u32 nnew = 0, nb = 0;
+                    if (total_pairs > room) {
+                        nnew = (total_pairs - room + QA_BLOCK - 1) / QA_BLOCK;
+                        if (lane == 0) nb = (u32)min(atomicAdd(&P.counters->n_qa_blocks, (unsigned long long)nnew), 0xf0000000ULL);
+                        nb = __shfl_sync(FULL_MASK, nb, 0);
+                        if (nb + nnew > P.qa_blocks_cap) {  // queue full: the overflow pass redoes the item from this chunk on
+                            if (lane == 0) {
+                                const unsigned long long k = atomicAdd(&P.counters->n_overflow, 1ULL);
+                                if (k < P.ovf_cap)
+                                    P.ovf[k] = make_uint4(tile, (u32)rbase | (multi ? ITEM_MULTI : 0u), c, (rbase == rbase0) ? it.w : 0xffffffffu);
+                            }
+                            for (u32 k = nb + lane; k < min(nb + nnew, P.qa_blocks_cap); k += 32) P.qa_fill[k] = 0u;  // taken, unused
+                            qa_full = true;
+                            stopped = true;
+                            if (more) cp_async_wait<0>();
+                            __syncwarp();
+                            break;
                         }
-                        qa_block = __shfl_sync(FULL_MASK, nb, 0);
-                        qa_used = 0;
                     }
-                    if (qa_block >= P.qa_blocks_cap) {  // queue full: the overflow pass redoes the tile from this chunk on
-                        if (lane == 0) {
-                            const unsigned long long k = atomicAdd(&P.counters->n_overflow, 1ULL);
-                            if (k < P.ovf_cap) P.ovf[k] = make_uint4(item, (u32)rbase, c, 0u);
-                        }
-                        qa_full = true;
-                        stopped = true;
-                        qa_block = QA_NO_BLOCK;
-                        if (more) cp_async_wait<0>();
-                        __syncwarp();
-                        break;
-                    }
-                    uint2 *dst = P.qa + ((size_t)qa_block * QA_BLOCK + qa_used + off);
+                    uint2 *dst_cur = P.qa + ((size_t)(qa_block == QA_NO_BLOCK ? 0u : qa_block) * QA_BLOCK + qa_used);
+                    uint2 *dst_new = P.qa + (size_t)nb * QA_BLOCK;
                     for (u32 k = 0; __any_sync(FULL_MASK, k < cnt); ++k) {
                         if (k < cnt) {
                             const u32 code = ws.plist[k][lane];
-                            dst[k] = make_uint2(s | ((code & PL_INR) ? QA_INR : 0u) | ((code & PL_UND) ? QA_UND : 0u),
-                                                b.pos[code & 31u]);
+                            const uint2 e = make_uint2(s | ((code & PL_INR) ? QA_INR : 0u) | ((code & PL_UND) ? QA_UND : 0u), b.pos[code & 31u]);
+                            const u32 at = off + k;
+                            if (at < room) dst_cur[at] = e; else dst_new[at - room] = e;
                         }
                     }
-                    qa_used += total_pairs;
+                    if (nnew) {  // the old block and all new ones but the last are full now
+                        const u32 rest = total_pairs - room - (nnew - 1u) * QA_BLOCK;  // 1 .. QA_BLOCK
+                        if (lane == 0 && qa_block != QA_NO_BLOCK) P.qa_fill[qa_block] = QA_BLOCK;
+                        for (u32 k = lane; k + 1u < nnew; k += 32) P.qa_fill[nb + k] = QA_BLOCK;
+                        qa_block = nb + nnew - 1u;
+                        qa_used = rest;
+                    } else {
+                        qa_used += total_pairs;
+                    }
                 }
                 ncand += nc;  // (a chunk handed to the overflow pass is counted there)
                 if (more) {
                     cp_async_wait<0>();
-                    relayout(c + P.splits, ws.buf[kbuf ^ 1u]);
+                    relayout(c + 1u, ws.buf[kbuf ^ 1u]);
                 }
                 __syncwarp();
             }
+            if (!multi) break;  // (an ordinary item is one row batch)
         }
         // ---- end of tile ------------------------------------------------------------------------------
         // the filter counted the query itself (distance 0); only the compute-node index returns self (quirk Q8).
-        // (with split tiles the self hit is seen by one of the warps, so split 0 subtracts it and the partial
-        // counts are combined with wrapping adds).  Objects without history owe every candidate twice in the
+        // (the hit is seen by one of the tile's items, so the first one subtracts it and the partial counts are
+        // combined with wrapping adds).  Objects without history owe every candidate twice in the
         // fused frame: once as detect_collisions, once as the fall-back of predict_collisions (:590-592).
         const bool self_seen = (p0.x - p0.x) == 0.0f && (p0.y - p0.y) == 0.0f && (p0.z - p0.z) == 0.0f;  // finite position
-        if (!SLOW && MODE != RCD_MODE_COMPUTE_NODE && counts && split == 0 && self_seen) ncand -= 1u;
+        if (!SLOW && MODE != RCD_MODE_COMPUTE_NODE && counts && first_item && self_seen) ncand -= 1u;
         if (FUSED && pattern == RCD_PAT_NO_HISTORY) ncand *= 2u;
-        if (counts && P.cand_count) {
-            if (!SLOW && P.splits == 1) P.cand_count[P.sorted_slot[s]] = ncand;
-            else if (ncand) atomicAdd(&P.cand_count[P.sorted_slot[s]], ncand);
-        }
+        if (counts && P.cand_count && ncand) atomicAdd(&P.cand_count[P.sorted_slot[s]], ncand);
         long long csum = warp_sum((long long)(counts ? (int)ncand : 0));
         if (lane == 0 && csum) atomicAdd(&P.counters->n_candidates, (unsigned long long)csum);
     }
