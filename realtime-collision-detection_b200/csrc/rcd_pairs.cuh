@@ -773,13 +773,12 @@ __device__ __forceinline__ void row_span(const PairParams &P, const TileBox &b, 
     cnt = last - first;
 }
 
-// work items of k_pairs: {tile, row batch | flags, first chunk, last chunk + 1}
-constexpr u32 ITEM_MULTI = 1u << 31;  // ... and every later row batch of the tile (boxes with very many rows)
+// work items of k_pairs: {tile, row batch | flags, first chunk in that batch, number of chunks}: a run of
+// chunks in the tile's sequence of (row batch, chunk), which may continue into the following row batches
 constexpr u32 ITEM_FIRST = 1u << 30;  // the item that subtracts the query's hit on itself from the candidate count
 constexpr u32 ITEM_RBASE_MASK = (1u << 30) - 1u;
-constexpr int PLAN_MAX_BATCHES = 8;   // tiles with more row batches than this become one ITEM_MULTI item
 constexpr int PLAN_ITEMS_PER_TILE = 32;
-constexpr int ITEMS_PER_TILE_CAP = PLAN_ITEMS_PER_TILE + PLAN_MAX_BATCHES;
+constexpr int ITEMS_PER_TILE_CAP = PLAN_ITEMS_PER_TILE;
 
 // -------------------------------------------------------------------------------------------------
 // k_tile_plan: one warp per tile.  The cost of a tile is the number of objects under its box, which spans
@@ -789,8 +788,6 @@ constexpr int ITEMS_PER_TILE_CAP = PLAN_ITEMS_PER_TILE + PLAN_MAX_BATCHES;
 // -------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
-    __shared__ u32 s_nch[4][PLAN_MAX_BATCHES + 1];
-    u32 *nch = s_nch[threadIdx.x >> 5];
     const u32 lane = threadIdx.x & 31u;
     const GridParams g = P.g;
     const float Rq = is_predict(MODE) ? PREDICT_RADIUS : P.R;
@@ -828,43 +825,33 @@ __global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
         }
         const int nrows = (b.y1 - b.y0 + 1) * (b.z1 - b.z0 + 1);
         const int nbatches = (nrows + TQ - 1) / TQ;
-        if (nbatches > PLAN_MAX_BATCHES) {
-            if (lane == 0) {
-                const unsigned long long at = atomicAdd(&P.counters->n_items, 1ULL);
-                if (at < P.items_cap) P.items[at] = make_uint4(tile, ITEM_MULTI | ITEM_FIRST, 0u, 0xffffffffu);
-            }
-            continue;
-        }
         u32 tot_chunks = 0;
-        __syncwarp();
         for (int bt = 0; bt < nbatches; ++bt) {
             u32 lo = 0, cnt = 0;
             const int rr = bt * TQ + (int)lane;
             if (rr < nrows) row_span(P, b, rr, lo, cnt);
-            const u32 total = warp_sum(cnt);
-            const u32 c = (total + CH - 1) / CH;
-            if (lane == 0) nch[bt] = c;
-            tot_chunks += c;
+            tot_chunks += (warp_sum(cnt) + CH - 1) / CH;
         }
-        __syncwarp();
+        if (tot_chunks == 0) continue;
+        // at most PLAN_ITEMS_PER_TILE items of K chunks each; item j starts at chunk j K of the tile's sequence
         const u32 K = max(P.item_chunks, (tot_chunks + PLAN_ITEMS_PER_TILE - 1) / PLAN_ITEMS_PER_TILE);
-        u32 n_it = 0;
-        for (int bt = 0; bt < nbatches; ++bt) n_it += (nch[bt] + K - 1) / K;
+        const u32 n_it = (tot_chunks + K - 1) / K;
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(&P.counters->n_items, (unsigned long long)n_it);
         base = __shfl_sync(FULL_MASK, base, 0);
-        for (u32 j = lane; j < n_it; j += 32) {
-            u32 k = j;
-            int bt = 0;
-            for (; bt < nbatches; ++bt) {
-                const u32 nb = (nch[bt] + K - 1) / K;
-                if (k < nb) break;
-                k -= nb;
-            }
-            if (base + j < P.items_cap)
-                P.items[base + j] = make_uint4(tile, (u32)(bt * TQ) | (j == 0 ? ITEM_FIRST : 0u), k * K, min((k + 1u) * K, nch[bt]));
+        u32 cum = 0;
+        for (int bt = 0; bt < nbatches; ++bt) {
+            u32 lo = 0, cnt = 0;
+            const int rr = bt * TQ + (int)lane;
+            if (rr < nrows) row_span(P, b, rr, lo, cnt);
+            const u32 nch = (warp_sum(cnt) + CH - 1) / CH;
+            // the items that start inside this batch's chunks [cum, cum + nch)
+            const u32 j0 = (cum + K - 1) / K, j1 = min((cum + nch + K - 1) / K, n_it);
+            for (u32 j = j0 + lane; j < j1; j += 32)
+                if (base + j < P.items_cap)
+                    P.items[base + j] = make_uint4(tile, (u32)(bt * TQ) | (j == 0 ? ITEM_FIRST : 0u), j * K - cum, min(K, tot_chunks - j * K));
+            cum += nch;
         }
-        __syncwarp();
     }
 }
 
@@ -910,7 +897,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
         const uint4 it = SLOW ? P.ovf[idx] : P.items[idx];
         const u32 tile = it.x;
         const int rbase0 = (int)(it.y & ITEM_RBASE_MASK);
-        const bool multi = (it.y & ITEM_MULTI) != 0, first_item = (it.y & ITEM_FIRST) != 0;
+        const bool first_item = (it.y & ITEM_FIRST) != 0;
+        u32 remaining = it.w;  // chunks left to do
 
         const u32 qi = tile * TQ + lane;
         const bool valid = qi < P.n_owned;
@@ -986,7 +974,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
             }
             stopped = true;
         }
-        for (int rbase = rbase0; rbase < nrows && !stopped; rbase += TQ) {
+        for (int rbase = rbase0; rbase < nrows && remaining && !stopped; rbase += TQ) {
             // ---- span of one cell row per lane: two loads from the dense cell table ------------------
             u32 lo = 0, rcnt = 0;
             if ((int)lane + rbase < nrows) row_span(P, box, rbase + (int)lane, lo, rcnt);
@@ -1063,8 +1051,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
             };
 
             u32 kbuf = 0;
-            const u32 c_begin = (rbase == rbase0) ? it.z : 0u;
-            const u32 c_end = min(nchunks, (rbase == rbase0) ? it.w : 0xffffffffu);
+            const u32 c_begin = min(nchunks, (rbase == rbase0) ? it.z : 0u);
+            const u32 c_end = c_begin + min(nchunks - c_begin, remaining);
             if (c_begin < c_end) {
                 stage(c_begin, ws.buf[0]);
                 cp_async_wait<0>();
@@ -1170,7 +1158,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                             if (lane == 0) {
                                 const unsigned long long k = atomicAdd(&P.counters->n_overflow, 1ULL);
                                 if (k < P.ovf_cap)
-                                    P.ovf[k] = make_uint4(tile, (u32)rbase | (multi ? ITEM_MULTI : 0u), c, (rbase == rbase0) ? it.w : 0xffffffffu);
+                                    P.ovf[k] = make_uint4(tile, (u32)rbase, c, remaining - (c - c_begin));
                             }
                             for (u32 k = nb + lane; k < min(nb + nnew, P.qa_blocks_cap); k += 32) P.qa_fill[k] = 0u;  // taken, unused
                             qa_full = true;
@@ -1207,7 +1195,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                 }
                 __syncwarp();
             }
-            if (!multi) break;  // (an ordinary item is one row batch)
+            remaining -= c_end - c_begin;
         }
         // ---- end of tile ------------------------------------------------------------------------------
         // the filter counted the query itself (distance 0); only the compute-node index returns self (quirk Q8).
