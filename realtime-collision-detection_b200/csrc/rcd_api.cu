@@ -622,8 +622,9 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         // every resident warp finds work
         P.item_chunks = P.ntiles >= 16384 ? 16u : P.ntiles >= 4096 ? 8u : P.ntiles >= 1024 ? 4u : P.ntiles >= 256 ? 2u : 1u;
         P.q3 = h->q3; P.qcap = h->qcap;
+        P.q3_split = mode == RCD_MODE_PREDICT ? h->qcap / 4 : h->qcap;
         CUDA_TRY(h, cudaMemsetAsync(h->pair_tile_counter, 0, 2 * sizeof(u32), h->stream));
-        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_qa_blocks, 0, 4 * sizeof(unsigned long long), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_qa_blocks, 0, 5 * sizeof(unsigned long long), h->stream));
         const bool count = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) != 0;
         // persistent launch: as many blocks as can be resident, warps pull tiles from a counter
         const int variant = fused ? 4 : mode == RCD_MODE_DETECT ? 0 : (mode == RCD_MODE_COMPUTE_NODE ? 3 : (count ? 2 : 1));

@@ -94,6 +94,7 @@ struct PairParams {
     u32 ovf_cap;
     QEntry *q3;              // k_narrow -> k_exact
     u32 qcap;
+    u32 q3_split;            // detect entries: [0, q3_split); predict entries: [q3_split, qcap)
 };
 
 // relative guard band of the fp32 radius test (fp32 error of d2 is < 1e-6 relative)
@@ -865,7 +866,7 @@ __global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
 // no call in its loops.
 template <int MODE, bool COUNT_CAND, bool SLOW>
 #ifndef RCD_PAIR_MIN_BLOCKS
-#define RCD_PAIR_MIN_BLOCKS 8
+#define RCD_PAIR_MIN_BLOCKS 6
 #endif
 __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) k_pairs(PairParams P) {
     __shared__ WarpShared shared[PAIR_WARPS];
@@ -1230,22 +1231,37 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
 // -------------------------------------------------------------------------------------------------
 constexpr int STAGE_THREADS = 128;
 constexpr int STAGE_WARPS = STAGE_THREADS / 32;
-constexpr int SC = 25;  // coefficients per pair (odd stride: conflict-free)
+constexpr int SC = 27;  // coefficients per pair (odd stride: conflict-free)
 enum { SC_D = 0, SC_CV = 3, SC_CA = 6, SC_RV = 9, SC_RA = 12, SC_UV = 15, SC_UA = 18, SC_HR2 = 21, SC_INVRV2 = 22,
-       SC_LIM2 = 23, SC_SAFEB2 = 24 };
+       SC_LIM2 = 23, SC_SAFEB2 = 24, SC_SAFEIN2 = 25, SC_INVSAFE = 26 };
 struct SampleShared {
     float coef[32][SC];
-    float r2first[32][PREDICT_OFFSETS];
-    unsigned char first[32][PREDICT_OFFSETS];  // first sample within safe + band (valid where hit_mask is set)
+    float part[32][PREDICT_OFFSETS];           // offset-dependent part of the risk of a certain hit (< 0: undecided in
+                                               // fp32), with the index of the first sample in the 4 lowest mantissa bits
     u32 hit_mask[32];                          // offsets with a sample within safe + band
     u32 si[32], sj[32];
     unsigned short items[64];                  // pair | offset << 5
 };
 constexpr int QA_BATCHES_PER_BLOCK = QA_BLOCK / 32;
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Q3 holds two kinds of entries, kept apart so that the warps of k_exact run one code path: detect entries grow
+// from the front, predict entries fill [q3_split, qcap) (the predict modes; other modes: q3_split = qcap).
+__device__ __forceinline__ bool push_detect(const PairParams &P, bool flag, u32 si, u32 sj, u32 word) {
+    return global_push(P.q3, P.q3_split, &P.counters->n_q3, flag, si, sj, word);
+}
+__device__ __forceinline__ bool push_predict(const PairParams &P, bool flag, u32 si, u32 sj, u32 word) {
+    return global_push(P.q3 + P.q3_split, P.qcap - P.q3_split, &P.counters->n_q3p, flag, si, sj, word);
+}
+
 template <int MODE, bool COUNT_CAND>
 #ifndef RCD_NARROW_MIN_BLOCKS
-#define RCD_NARROW_MIN_BLOCKS 6
+#define RCD_NARROW_MIN_BLOCKS 8
 #endif
 __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow(PairParams P) {
     __shared__ SampleShared shared[STAGE_WARPS];
@@ -1258,17 +1274,25 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
     const unsigned long long wstride = (unsigned long long)gridDim.x * STAGE_WARPS;
     const float R2 = PREDICT_RADIUS * PREDICT_RADIUS;
     u32 n_exact = 0, n_pot = 0;
-    for (unsigned long long batch = (unsigned long long)blockIdx.x * STAGE_WARPS + (threadIdx.x >> 5); batch < nbatch;
-         batch += wstride) {
-        const u32 blk = (u32)(batch / QA_BATCHES_PER_BLOCK), within = (u32)(batch % QA_BATCHES_PER_BLOCK) * 32u;
-        const u32 fill = P.qa_fill[blk];
-        if (within >= fill) continue;  // (uniform) the warp that owned the block stopped before this batch
+    // the queue entry of a batch (loaded one batch ahead of its use); x = 0xffffffff: none
+    auto fetch = [&](unsigned long long batch) {
+        uint2 e = make_uint2(0xffffffffu, 0u);
+        if (batch < nbatch) {
+            const u32 blk = (u32)(batch / QA_BATCHES_PER_BLOCK), within = (u32)(batch % QA_BATCHES_PER_BLOCK) * 32u;
+            if (within + lane < P.qa_fill[blk]) e = __ldcs(P.qa + (size_t)blk * QA_BLOCK + within + lane);
+        }
+        return e;
+    };
+    unsigned long long batch = (unsigned long long)blockIdx.x * STAGE_WARPS + (threadIdx.x >> 5);
+    uint2 e_next = fetch(batch);
+    for (; batch < nbatch; batch += wstride) {
+        const uint2 e = e_next;
+        e_next = fetch(batch + wstride);
+        if (!__any_sync(FULL_MASK, e.x != 0xffffffffu)) continue;  // the warp that owned the block stopped before this batch
         // ---- 1. lane = pair ------------------------------------------------------------------------
         u32 si = 0, sj = 0, mask = 0, det_word = 0;
         bool det_keep = false;
-        float safe = 5.0f, band = 0.0f;
-        if (within + lane < fill) {
-            const uint2 e = P.qa[(size_t)blk * QA_BLOCK + within + lane];
+        if (e.x != 0xffffffffu) {
             si = e.x & QA_SI_MASK;
             sj = e.y;
             const bool inr = (e.x & QA_INR) != 0, und = (e.x & QA_UND) != 0;
@@ -1290,9 +1314,24 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                         det_word = (und ? RADIUS_UNDECIDED : 0u) | (twice ? ENTRY_TWICE : 0u);
                     }
                     if (!nohist) {
-                        mask = predict_mask<COUNT_CAND>(P, a0, a1, a2, b0, b1, b2, si, sj, pat, n_exact);
+                        const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
+                        if (COUNT_CAND) {
+                            mask = predict_mask<true>(P, a0, a1, a2, b0, b1, b2, si, sj, pat, n_exact);
+                        } else {
+                            // the offsets whose state g(t_m) = centre_i(t_m) - predicted_j(t_m) is within reach of the 10
+                            // samples (|g| <= hr, the first half of offset_may_hit), two offsets per packed instruction
+#pragma unroll
+                            for (int m = 0; m < PREDICT_OFFSETS; m += 2) {
+                                const float2 t2 = make_float2(0.5f * (float)m, 0.5f * (float)(m + 1));
+                                const float2 h2 = make_float2(0.125f * (float)(m * m), 0.125f * (float)((m + 1) * (m + 1)));
+                                const float2 gx = fma2(splat2(c.cvx), t2, fma2(splat2(c.cax), h2, splat2(-c.dx)));
+                                const float2 gy = fma2(splat2(c.cvy), t2, fma2(splat2(c.cay), h2, splat2(-c.dy)));
+                                const float2 gz = fma2(splat2(c.cvz), t2, fma2(splat2(c.caz), h2, splat2(-c.dz)));
+                                const float2 g2 = fma2(gz, gz, fma2(gy, gy, mul2(gx, gx)));
+                                mask |= (g2.x <= c.hr2 ? (1u << m) : 0u) | (g2.y <= c.hr2 ? (2u << m) : 0u);
+                            }
+                        }
                         if (mask) {
-                            const PredictCoef c = predict_coef(a0, a1, a2, b0, b1, b2, pat);
                             float *o = sh.coef[lane];
                             o[SC_D] = c.dx; o[SC_D + 1] = c.dy; o[SC_D + 2] = c.dz;
                             o[SC_CV] = c.cvx; o[SC_CV + 1] = c.cvy; o[SC_CV + 2] = c.cvz;
@@ -1302,14 +1341,17 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                             o[SC_UV] = c.uvx; o[SC_UV + 1] = c.uvy; o[SC_UV + 2] = c.uvz;
                             o[SC_UA] = c.uax; o[SC_UA + 1] = c.uay; o[SC_UA + 2] = c.uaz;
                             o[SC_HR2] = c.hr2; o[SC_INVRV2] = c.inv_rv2; o[SC_LIM2] = c.lim2; o[SC_SAFEB2] = c.safe_b2;
-                            safe = (a0.w + b0.w) * 0.5f + 5.0f;
-                            band = sqrtf(c.safe_b2) - safe;  // the guard band of predict_coef
+                            const float safe = (a0.w + b0.w) * 0.5f + 5.0f;
+                            const float band = sqrtf(c.safe_b2) - safe;  // the guard band of predict_coef
+                            const float safe_in = fmaxf(safe - band, 0.0f);
+                            o[SC_SAFEIN2] = safe_in * safe_in;
+                            o[SC_INVSAFE] = 1.0f / safe;
                         }
                     }
                 }
             }
         }
-        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, det_keep, si, sj, det_word))
+        if (!push_detect(P, det_keep, si, sj, det_word))
             n_pot += finish_entry_inline<MODE>(P, si, sj, det_word);  // queue full: decide here
         if (!PRED) continue;
         mask &= (1u << PREDICT_OFFSETS) - 1u;
@@ -1351,8 +1393,13 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                     if (r2 <= safe_b2) { first = kk; r2first = r2; }
                 }
                 if (first >= 0) {
-                    sh.first[pr][m] = (unsigned char)first;
-                    sh.r2first[pr][m] = r2first;
+                    // a first sample inside the guard band: fp64 decides (-1).  Otherwise a certain hit at sample `first`,
+                    // every earlier sample certainly outside: the parts of the risk that differ between the offsets of
+                    // a pair (collision_detection.py:371-374) decide the merge (fp32 error of `part` ~1e-5)
+                    float part = -1.0f;
+                    if (r2first <= c[SC_SAFEIN2])
+                        part = 0.3f * (1.0f - sqrt_approx(r2first) * c[SC_INVSAFE]) + 0.3f * (1.0f - 0.01f * (float)first);
+                    sh.part[pr][m] = __uint_as_float((__float_as_uint(part) & ~15u) | (u32)first);  // (15 ulp << 1e-4)
                     atomicOr(&sh.hit_mask[pr], 1u << m);
                 }
             }
@@ -1371,27 +1418,20 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                 if (cand < 32u && v <= f) pr = cand;
             }
             const u32 pr_off = __shfl_sync(FULL_MASK, off, pr);
-            u32 pr_mask = __shfl_sync(FULL_MASK, mask, pr);
+            const u32 pr_mask = __shfl_sync(FULL_MASK, mask, pr);
             bool pass = false;
             u32 m = 0;
             if (f < total) {
-                if (COUNT_CAND) {  // sparse mask: r-th set bit
-                    for (u32 r = f - pr_off; r > 0; --r) pr_mask &= pr_mask - 1;
-                    m = (u32)__ffs(pr_mask) - 1u;
-                } else {           // phase 1 queues whole windows: consecutive offsets
-                    m = (u32)__ffs(pr_mask) - 1u + (f - pr_off);
-                }
+                m = __fns(pr_mask, 0u, (int)(f - pr_off) + 1);  // (f - pr_off)-th offset of the pair's mask
                 pass = true;
                 if (!COUNT_CAND) {  // with COUNT_CAND both tests were already taken in phase 1
                     const float *c = sh.coef[pr];
                     const float t = 0.5f * (float)m, h = 0.5f * t * t;
                     const float dx = c[SC_D], dy = c[SC_D + 1], dz = c[SC_D + 2];
-                    // offset_may_hit(): none of the 10 samples can come within the safe distance otherwise
                     const float gx = c[SC_CV] * t + c[SC_CA] * h - dx, gy = c[SC_CV + 1] * t + c[SC_CA + 1] * h - dy,
                                 gz = c[SC_CV + 2] * t + c[SC_CA + 2] * h - dz;
                     const float rvx = c[SC_RV], rvy = c[SC_RV + 1], rvz = c[SC_RV + 2];
-                    pass = gx * gx + gy * gy + gz * gz <= c[SC_HR2];
-                    if (pass) {
+                    {   // (|g| <= hr was taken in phase 1) the samples move along g + rv tau + ra tau^2 / 2
                         const float tau = fminf(fmaxf(-(gx * rvx + gy * rvy + gz * rvz) * c[SC_INVRV2], 0.0f), 0.9f);
                         const float ex = gx + rvx * tau, ey = gy + rvy * tau, ez = gz + rvz * tau;
                         pass = ex * ex + ey * ey + ez * ez <= c[SC_LIM2];
@@ -1421,32 +1461,26 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
         __syncwarp();
 
         // ---- 4. lane = pair: merge over the offsets ------------------------------------------------------
-        const float safe_in = fmaxf(safe - band, 0.0f), safe_in2 = safe_in * safe_in;
-        const float inv_safe = 1.0f / safe;
-        u32 maybe_mask = 0;      // offsets with a sample inside safe + band
+        const u32 maybe_mask = sh.hit_mask[lane];  // the other offsets have no sample within safe + band: certainly no hit
         bool doubt = false;      // some decisive sample lies inside the band
         float best = -1.0f, second = -1.0f;
-        int best_m = -1, best_k = 0;
-        u32 rest = sh.hit_mask[lane];  // the other offsets have no sample within safe + band: certainly no hit
+        int best_m = -1;
+        u32 rest = maybe_mask;
         while (rest) {
             const int m = __ffs(rest) - 1;
             rest &= rest - 1;
-            const u32 first = sh.first[lane][m];
-            const float r2first = sh.r2first[lane][m];
-            maybe_mask |= 1u << m;
-            if (r2first > safe_in2) { doubt = true; continue; }  // the first candidate sample is inside the band
-            // certain hit at sample `first`, and every earlier sample is certainly outside: the parts of the
-            // risk that differ between offsets (collision_detection.py:371-374) decide the merge
-            const float part = 0.3f * (1.0f - sqrtf(r2first) * inv_safe) + 0.3f * (1.0f - 0.01f * (float)first);
-            if (part > best) { second = best; best = part; best_m = m; best_k = (int)first; }
+            const float part = sh.part[lane][m];
+            doubt = doubt || part < 0.0f;
+            if (part > best) { second = best; best = part; best_m = m; }
             else if (part > second) second = part;
         }
         u32 word = 0;
         if (maybe_mask) {
-            // a runner-up within 1e-4 (fp32 error of `part` is ~1e-5) or any sample in the band: fp64 decides
-            word = (doubt || best_m < 0 || best - second <= 1.0e-4f) ? maybe_mask : (RESOLVED | (u32)best_m | ((u32)best_k << 8));
+            // a runner-up within 1e-4 or any sample in the band: fp64 decides
+            word = (doubt || best_m < 0 || best - second <= 1.0e-4f)
+                       ? maybe_mask : (RESOLVED | (u32)best_m | ((__float_as_uint(best) & 15u) << 8));
         }
-        if (!global_push(P.q3, P.qcap, &P.counters->n_q3, word != 0, si, sj, word))
+        if (!push_predict(P, word != 0, si, sj, word))
             finish_entry_inline<RCD_MODE_PREDICT>(P, si, sj, word);
         __syncwarp();  // the next batch overwrites this warp's shared memory
     }
@@ -1458,13 +1492,17 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
     }
 }
 
-// k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp
+// k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp.
+// Detect entries (front of Q3) and predict entries (from q3_split on) are mapped to different warps.
 #ifndef RCD_EXACT_MIN_BLOCKS
 #define RCD_EXACT_MIN_BLOCKS 4
 #endif
 template <int MODE>
 __global__ void __launch_bounds__(STAGE_THREADS, RCD_EXACT_MIN_BLOCKS) k_exact(PairParams P) {
-    const unsigned long long n = min(P.counters->n_q3, (unsigned long long)P.qcap);
+    const unsigned long long nd = min(P.counters->n_q3, (unsigned long long)P.q3_split);
+    const unsigned long long np = min(P.counters->n_q3p, (unsigned long long)(P.qcap - P.q3_split));
+    const unsigned long long nd_pad = (nd + 31ULL) & ~31ULL;
+    const unsigned long long n = nd_pad + np;
     const unsigned long long stride = (unsigned long long)gridDim.x * STAGE_THREADS;
     const unsigned long long rounds = (n + stride - 1) / stride;
     const u32 lane = threadIdx.x & 31u;
@@ -1472,8 +1510,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_EXACT_MIN_BLOCKS) k_exact(P
     for (unsigned long long r = 0; r < rounds; ++r) {  // uniform trip count: the emission is warp-wide
         const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
         EmitRec e = no_rec();
-        if (k < n) {
-            const QEntry q = P.q3[k];
+        if (k < nd || (k >= nd_pad && k < n)) {
+            const QEntry q = k < nd ? P.q3[k] : P.q3[P.q3_split + (k - nd_pad)];
             e = exact_entry<MODE>(P, q.si, q.sj, q.mask);
             n_pot += e.potential;
             n_exact += (is_predict(MODE) && (q.mask & 0xfffffu) && !(q.mask & RESOLVED)) ? (u32)__popc(q.mask & 0xfffffu) : 1u;
