@@ -227,6 +227,30 @@ int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n);
 int rcd_query_radius(rcd_handle h, uint64_t nq, const float *qx, const float *qy, const float *qz,
                      float radius, uint64_t *offsets, uint32_t *ids, uint64_t cap);
 
+/* ---- the per-pair helpers of the detector ----------------------------------------------------------
+ * CollisionPredictionModel calls two semi-private methods of the detector for every pair it examines
+ * (collision_detection.py:821-830): _precise_collision_detection (:296-342) and _risk_assessment (:344-389).
+ * Inside a frame their work is fused into the pair kernels; these entry points evaluate them for explicit
+ * pairs, in float64 on the device, in the reference's operation order (the same device functions the
+ * frame kernels use: rcd_exact.cuh), so that callers of the helpers -- and unit tests -- get the same bits. */
+typedef struct {
+    float px, py, pz, vx, vy, vz, ax, ay, az, size, heading;
+    uint32_t type;
+} rcd_object;  /* one vehicle, 48 bytes */
+typedef struct {
+    int32_t hit;    /* 0: no sample within the safe distance (the reference returns None) */
+    int32_t step;   /* index of the first such sample */
+    double collision_time, distance, safe_distance, relative_speed;
+    double cx, cy, cz;  /* collision_position (midpoint) */
+    double risk;        /* _risk_assessment of that collision_info */
+} rcd_pair_exact_result;  /* 72 bytes */
+/* _precise_collision_detection(a[k], b[k], time_window, time_step) + _risk_assessment for n pairs (host arrays). */
+int rcd_pair_exact(rcd_handle h, uint64_t n, const rcd_object *a, const rcd_object *b, double time_window,
+                   double time_step, rcd_pair_exact_result *out);
+/* _risk_assessment for n explicit collision_info records: in[k] = {heading_i, heading_j, same type ? 1 : 0,
+ * collision_time, distance, safe_distance, relative_speed} (7 doubles each) -> risk_out[k]. */
+int rcd_risk_assessment(rcd_handle h, uint64_t n, const double *in, double *risk_out);
+
 /* Trajectory-pattern classifier (collision_detection.py:623-711) for n objects with up to
  * `stride` (x, y, z, t) float64 samples each, already in timestamp order; count[i] samples are
  * valid.  Writes RCD_PAT_* codes to pattern_out (host). */
@@ -276,12 +300,20 @@ const char *rcd_ingest_last_error(rcd_ingest g);
  * (and len >= 1 MiB) the buffer is cut at newlines, so a message must not contain a raw newline
  * (json.dumps never emits one).  Messages that are malformed or lack a field the reference reads are
  * skipped and counted in *n_bad (the reference logs and drops them, warning_system.py:677-678).
- * *n_out = messages decoded (RCD_ECAPACITY if > cap), *max_seq = largest rcd_record.seq of the batch.
- * Limits of the record format: at most 255 distinct type strings per rcd_ingest and at most 255 messages
- * for one vehicle in one call (RCD_ECAPACITY beyond).  Needs no CUDA device. */
+ * *n_out = messages decoded, *max_seq = largest rcd_record.seq of the batch.  If the buffer holds more than
+ * `cap` well-formed messages nothing is decoded, *n_out = how many there are and the call returns RCD_ECAPACITY
+ * (no state has changed: call again with a larger buffer).  Every message is taken or dropped on its own, like
+ * in the reference's handler: the limits of the record format never fail a batch -- the 256th and later
+ * messages of one vehicle in one call are dropped (counted in *n_bad), type strings beyond the first 255
+ * distinct ones share code 255, and once rcd_ingest_set_limit's id limit is reached messages of unknown
+ * vehicles are dropped (counted in *n_bad) while known vehicles keep being served.  Needs no CUDA device. */
 int rcd_ingest_decode_json(rcd_ingest g, const char *buf, uint64_t len, int32_t threads, rcd_record *out,
                            uint64_t cap, uint64_t *n_out, uint64_t *n_bad, uint32_t *max_seq);
 int rcd_ingest_counts(rcd_ingest g, uint64_t *n_ids, uint64_t *n_types);
+/* At most max_ids distinct vehicle ids are interned (= the frame capacity the records are applied to). */
+int rcd_ingest_set_limit(rcd_ingest g, uint64_t max_ids);
+/* Messages dropped since creation because of the id limit or the 255-messages-per-vehicle-per-call limit. */
+int rcd_ingest_rejected(rcd_ingest g, uint64_t *n);
 /* interned strings (UTF-8, not NUL-terminated; valid until the next decode call) */
 int rcd_ingest_id_name(rcd_ingest g, uint32_t slot, const char **name, uint32_t *len);
 int rcd_ingest_type_name(rcd_ingest g, uint32_t code, const char **name, uint32_t *len);
@@ -310,12 +342,14 @@ typedef struct {
     uint32_t i, j;        /* caller ids: vehicle_id, other_vehicle_id */
     uint32_t alert_id;    /* running number given at creation (the reference draws a uuid) */
     float risk, ttc;      /* risk_level, time_to_collision after the update */
+    float distance;       /* CollisionRisk.distance of that risk (the alert message quotes it, :313-329) */
     int8_t priority;      /* after the update */
     int8_t old_priority;  /* before it (-1: none) */
     uint8_t kind;         /* RCD_ALERT_* */
     uint8_t acknowledged;
+    uint32_t reserved;
     double timestamp;     /* AlertInfo.timestamp: `now` of the last update */
-} rcd_alert_event;        /* 32 bytes */
+} rcd_alert_event;        /* 40 bytes */
 typedef struct {
     uint64_t n_events;    /* events produced by the call (only min(n_events, cap) were stored) */
     uint64_t n_created, n_changed, n_refreshed, n_expired;
@@ -329,7 +363,7 @@ int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts);
  * PRIORITY_CHANGED events, plus the REFRESHED ones if report_refreshed != 0; order is not deterministic. */
 int rcd_alerts_update(rcd_handle h, double now, int32_t report_refreshed, rcd_alert_event *events, uint64_t cap,
                       rcd_alert_stats *stats);
-/* The same for an explicit list of risks (host array of rcd_pair; i, j, ttc, risk, priority and predicted
+/* The same for an explicit list of risks (host array of rcd_pair; i, j, ttc, risk, distance, priority and predicted
  * are read; a pair with priority < 0 is skipped).  If (i, j) occurs more than once, a non-predicted entry
  * is applied before a predicted one; other duplicates are the caller's to split into separate calls. */
 int rcd_alerts_update_pairs(rcd_handle h, const rcd_pair *pairs, uint64_t n, double now, int32_t report_refreshed,

@@ -302,6 +302,22 @@ static int precise_hit(double pix, double piy, double piz, double vix, double vi
     return -1;
 }
 
+/* CollisionDetector._precise_collision_detection (collision_detection.py:296-342) for one pair of vehicles:
+ * a, b = {px, py, pz, vx, vy, vz, ax, ay, az, size}.  Returns the index of the first sample inside the safe
+ * distance (-1: None); out = {collision_time, distance, safe_distance, relative_speed, mid x, y, z}. */
+int32_t orc_precise(const double *a, const double *b, double time_window, double *out) {
+    const double safe = safe_dist(a[9], b[9]);
+    double dist = 0.0, mid[3] = {0.0, 0.0, 0.0};
+    const int k = precise_hit(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], b[0], b[1], b[2], b[3], b[4], b[5],
+                              b[6], b[7], b[8], safe, time_window, &dist, mid);
+    out[0] = k * 0.1;
+    out[1] = dist;
+    out[2] = safe;
+    out[3] = mag3(a[3] - b[3], a[4] - b[4], a[5] - b[5]);
+    out[4] = mid[0]; out[5] = mid[1]; out[6] = mid[2];
+    return k;
+}
+
 /* ------------------------------------------------------------------------------------------
  * detect(i) for one vehicle: collision_detection.py:110-191 (stages :208-389).
  * ---------------------------------------------------------------------------------------- */

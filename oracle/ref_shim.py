@@ -283,6 +283,36 @@ def run_priority_A(risk_ttc: Sequence[Tuple[float, float]]) -> List[int]:
     return out
 
 
+def run_alert_messages_A(cases: Sequence[Tuple[float, str, float, float]]) -> List[str]:
+    """``AlertManager._generate_alert_message`` (warning_system.py:313-329) for (risk_level, other_vehicle_id,
+    time_to_collision, distance) tuples."""
+    ref = load_reference()
+    ws = ref.warning_system
+    mgr = ws.AlertManager.__new__(ws.AlertManager)
+    out = []
+    for risk, other, ttc, dist in cases:
+        r = types.SimpleNamespace(risk_level=risk, other_vehicle_id=other, time_to_collision=ttc, distance=dist)
+        out.append(mgr._generate_alert_message(r))
+    return out
+
+
+def run_pair_helpers_A(frame, pairs: Sequence[Tuple[int, int]], time_window: float) -> List[Any]:
+    """``CollisionDetector._precise_collision_detection`` (:296-342) and ``_risk_assessment`` (:344-389) for the
+    listed pairs of a frame: per pair None, or (collision_time, distance, safe_distance, relative_speed,
+    mid x, y, z, risk)."""
+    ref, _index, det, vehicles = build_detector_A(frame)
+    out = []
+    for i, j in pairs:
+        info = det._precise_collision_detection(vehicles[i], vehicles[j], time_window)
+        if info is None:
+            out.append(None)
+            continue
+        risk = det._risk_assessment(vehicles[i], vehicles[j], info)
+        m = info["collision_position"]
+        out.append((info["collision_time"], info["distance"], info["safe_distance"], info["relative_speed"], m.x, m.y, m.z, risk))
+    return out
+
+
 def run_nearby_A(frame, queries: Sequence[Tuple[float, float, float]], radius: float) -> List[List[int]]:
     """Reference ``SpatialIndex.get_nearby_vehicles`` (spatial_index.py:229-271) for explicit
     query points (self is NOT stripped: Q8)."""

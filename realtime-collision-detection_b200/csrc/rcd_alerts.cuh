@@ -7,7 +7,7 @@
 // Here the table is an open-addressing hash table in HBM keyed by (i << 32 | j); a frame's emitted
 // pairs are folded into it where they lie (the pair buffer never leaves the device) and only the
 // CHANGES -- created alerts, priority changes, expiries -- are handed to the host.
-//   entry = 32 bytes: key, timestamp (float64 like time.time()), risk, ttc, alert number, priority, acknowledged
+//   entry = 40 bytes: key, timestamp (float64 like time.time()), risk, ttc, distance, alert number, priority, acknowledged
 // Expiry rebuilds the table into its twin (no tombstones).
 #pragma once
 #include "rcd_common.cuh"
@@ -17,15 +17,17 @@ namespace rcd {
 struct AlertEntry {
     unsigned long long key;  // i << 32 | j; ALERT_EMPTY = free
     double ts;
-    float risk, ttc;
+    float risk, ttc, distance;
     u32 alert_id;
     int8_t priority;
     uint8_t acked;
     uint16_t pad;
+    u32 pad2;
 };
-static_assert(sizeof(AlertEntry) == 32, "AlertEntry is 32 bytes");
-static_assert(sizeof(rcd_alert_event) == 32, "rcd_alert_event is 32 bytes");
+static_assert(sizeof(AlertEntry) == 40, "AlertEntry is 40 bytes");
+static_assert(sizeof(rcd_alert_event) == 40, "rcd_alert_event is 40 bytes");
 constexpr unsigned long long ALERT_EMPTY = ~0ull;
+constexpr u32 ALERT_ID_NONE = 0xffffffffu;  // an entry whose creator has not published it yet
 
 struct AlertCounters {
     unsigned long long n_events;     // events appended (may exceed the buffer; only the first cap are stored)
@@ -92,11 +94,21 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
     const unsigned long long stride = (unsigned long long)gridDim.x * ALERT_THREADS;
     const unsigned long long rounds = (n + stride - 1) / stride;
     u32 created = 0, changed = 0, refreshed = 0, dropped = 0;
+    // A key can occur twice in one pass (a vehicle without history owes the same risk as detect_collisions and as
+    // the fall-back of predict_collisions): the thread that loses the insertion may arrive before the winner has
+    // filled the entry in.  The winner publishes the entry by writing alert_id LAST (the table is initialised to
+    // 0xff.., so an unpublished entry reads ALERT_ID_NONE); a loser that finds it unpublished counts a silent
+    // refresh (what the reference's loop does with the second copy: update_alert with the same priority) and,
+    // if refreshes are reported, fetches the number after its other work.
+    constexpr int MAX_DEFERRED = 2;
+    rcd_alert_event deferred[MAX_DEFERRED];
+    volatile u32 *deferred_id[MAX_DEFERRED];
+    int n_deferred = 0;
     for (unsigned long long r = 0; r < rounds; ++r) {  // uniform trip count: the emission is warp-wide
         const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * ALERT_THREADS + threadIdx.x;
         bool emit = false;
         rcd_alert_event e;
-        e.i = e.j = e.alert_id = 0; e.risk = e.ttc = 0.0f; e.priority = e.old_priority = -1; e.kind = 0; e.acknowledged = 0;
+        e.i = e.j = e.alert_id = 0; e.reserved = 0; e.risk = e.ttc = e.distance = 0.0f; e.priority = e.old_priority = -1; e.kind = 0; e.acknowledged = 0;
         e.timestamp = now;
         if (k < n) {
             const rcd_pair p = pairs[k];
@@ -107,26 +119,44 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
                 if (!a) {
                     ++dropped;
                 } else {
-                    e.i = p.i; e.j = p.j; e.risk = p.risk; e.ttc = p.ttc; e.priority = p.priority;
+                    e.i = p.i; e.j = p.j; e.risk = p.risk; e.ttc = p.ttc; e.distance = p.distance; e.priority = p.priority;
+                    volatile u32 *idp = &a->alert_id;
                     if (inserted) {  // create_alert (:120-160)
-                        a->alert_id = atomicAdd(&c->next_id, 1u);
-                        a->acked = 0;
+                        a->acked = 0; a->pad = 0; a->pad2 = 0;
+                        a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->priority = p.priority; a->ts = now;
+                        e.alert_id = atomicAdd(&c->next_id, 1u);
+                        __threadfence();
+                        *idp = e.alert_id;  // publishes the entry
                         e.kind = RCD_ALERT_CREATED;
                         e.old_priority = -1;
                         ++created;
                         emit = true;
+                    } else if ((e.alert_id = *idp) == ALERT_ID_NONE) {  // being created by another thread of this pass
+                        e.kind = RCD_ALERT_REFRESHED;
+                        e.old_priority = p.priority;
+                        ++refreshed;
+                        if (emit_refreshed) {
+                            if (n_deferred < MAX_DEFERRED) { deferred[n_deferred] = e; deferred_id[n_deferred] = idp; ++n_deferred; }
+                            else emit = true;
+                        }
                     } else {         // update_alert (:162-197): the priority queue only hears of priority changes
+                        __threadfence();
                         e.old_priority = a->priority;
                         e.acknowledged = a->acked;
                         if (a->priority != p.priority) { e.kind = RCD_ALERT_PRIORITY_CHANGED; ++changed; emit = true; }
                         else { e.kind = RCD_ALERT_REFRESHED; ++refreshed; emit = emit_refreshed != 0; }
+                        a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->priority = p.priority; a->ts = now;
                     }
-                    e.alert_id = a->alert_id;
-                    a->risk = p.risk; a->ttc = p.ttc; a->priority = p.priority; a->ts = now;
                 }
             }
         }
         alert_emit(emit, e, ev, ev_cap, c);
+    }
+    const int max_deferred = __reduce_max_sync(FULL_MASK, n_deferred);
+    for (int d = 0; d < max_deferred; ++d) {
+        rcd_alert_event e = deferred[d < n_deferred ? d : 0];
+        if (d < n_deferred) e.alert_id = *deferred_id[d];
+        alert_emit(d < n_deferred, e, ev, ev_cap, c);
     }
     unsigned long long v[4] = {created, changed, refreshed, dropped};
 #pragma unroll
@@ -151,22 +181,22 @@ k_alert_expire(const AlertEntry *__restrict__ src, unsigned long long cap, doubl
         const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * ALERT_THREADS + threadIdx.x;
         bool emit = false;
         rcd_alert_event e;
-        e.i = e.j = e.alert_id = 0; e.risk = e.ttc = 0.0f; e.priority = e.old_priority = -1; e.kind = RCD_ALERT_EXPIRED;
+        e.i = e.j = e.alert_id = 0; e.reserved = 0; e.risk = e.ttc = e.distance = 0.0f; e.priority = e.old_priority = -1; e.kind = RCD_ALERT_EXPIRED;
         e.acknowledged = 0; e.timestamp = 0.0;
         if (k < cap) {
             const AlertEntry a = src[k];
             if (a.key != ALERT_EMPTY) {
                 if (a.acked || __dsub_rn(now, a.ts) > max_age) {
                     e.i = (u32)(a.key >> 32); e.j = (u32)(a.key & 0xffffffffu); e.alert_id = a.alert_id;
-                    e.risk = a.risk; e.ttc = a.ttc; e.priority = e.old_priority = a.priority; e.acknowledged = a.acked;
+                    e.risk = a.risk; e.ttc = a.ttc; e.distance = a.distance; e.priority = e.old_priority = a.priority; e.acknowledged = a.acked;
                     e.timestamp = a.ts;
                     emit = true;
                     ++expired;
                 } else {
                     bool inserted = false;
                     AlertEntry *d = alert_find_or_insert(dst, cap - 1, a.key, inserted);  // same capacity: always fits
-                    d->ts = a.ts; d->risk = a.risk; d->ttc = a.ttc; d->alert_id = a.alert_id;
-                    d->priority = a.priority; d->acked = a.acked; d->pad = 0;
+                    d->ts = a.ts; d->risk = a.risk; d->ttc = a.ttc; d->distance = a.distance; d->alert_id = a.alert_id;
+                    d->priority = a.priority; d->acked = a.acked; d->pad = 0; d->pad2 = 0;
                     ++live;
                 }
             }
@@ -199,13 +229,13 @@ k_alert_dump(const AlertEntry *__restrict__ tab, unsigned long long cap, rcd_ale
         const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * ALERT_THREADS + threadIdx.x;
         bool emit = false;
         rcd_alert_event e;
-        e.i = e.j = e.alert_id = 0; e.risk = e.ttc = 0.0f; e.priority = e.old_priority = -1; e.kind = RCD_ALERT_REFRESHED;
+        e.i = e.j = e.alert_id = 0; e.reserved = 0; e.risk = e.ttc = e.distance = 0.0f; e.priority = e.old_priority = -1; e.kind = RCD_ALERT_REFRESHED;
         e.acknowledged = 0; e.timestamp = 0.0;
         if (k < cap) {
             const AlertEntry a = tab[k];
             if (a.key != ALERT_EMPTY) {
                 e.i = (u32)(a.key >> 32); e.j = (u32)(a.key & 0xffffffffu); e.alert_id = a.alert_id;
-                e.risk = a.risk; e.ttc = a.ttc; e.priority = e.old_priority = a.priority; e.acknowledged = a.acked;
+                e.risk = a.risk; e.ttc = a.ttc; e.distance = a.distance; e.priority = e.old_priority = a.priority; e.acknowledged = a.acked;
                 e.timestamp = a.ts;
                 emit = true;
             }

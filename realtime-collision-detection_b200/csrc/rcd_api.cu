@@ -1061,6 +1061,58 @@ int rcd_classify_patterns(rcd_handle h, uint64_t n, uint32_t stride, const doubl
     return RCD_OK;
 }
 
+int rcd_pair_exact(rcd_handle h, uint64_t n, const rcd_object *a, const rcd_object *b, double time_window, double time_step,
+                   rcd_pair_exact_result *out) {
+    if (!h || (n && (!a || !b || !out))) return RCD_EINVAL;
+    if (!(time_step > 0.0) || !std::isfinite(time_step) || !(time_window >= 0.0) || !std::isfinite(time_window))
+        return fail(h, RCD_EINVAL, "rcd_pair_exact: bad time_window / time_step");
+    if (n == 0) return RCD_OK;
+    if (n > 0x7fffffffull) return fail(h, RCD_ECAPACITY, "rcd_pair_exact: too many pairs");
+    const double nsteps = std::floor(time_window / time_step);  // int(time_window / time_step), :322
+    const int steps = nsteps > 1.0e9 ? 1000000000 : (int)nsteps;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    rcd_object *da = nullptr, *db = nullptr;
+    rcd_pair_exact_result *dout = nullptr;
+    cudaError_t e = dev_alloc(&da, (size_t)n);
+    if (e == cudaSuccess) e = dev_alloc(&db, (size_t)n);
+    if (e == cudaSuccess) e = dev_alloc(&dout, (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(da, a, (size_t)n * sizeof(rcd_object), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(db, b, (size_t)n * sizeof(rcd_object), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_pair_exact<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>((u32)n, da, db, steps, time_step, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)n * sizeof(rcd_pair_exact_result), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    if (e != cudaSuccess) return fail(h, e == cudaErrorMemoryAllocation ? RCD_ENOMEM : RCD_ECUDA,
+                                      std::string("rcd_pair_exact: ") + cudaGetErrorString(e));
+    ++h->launches;
+    return RCD_OK;
+}
+
+int rcd_risk_assessment(rcd_handle h, uint64_t n, const double *in, double *risk_out) {
+    if (!h || (n && (!in || !risk_out))) return RCD_EINVAL;
+    if (n == 0) return RCD_OK;
+    if (n > 0x7fffffffull) return fail(h, RCD_ECAPACITY, "rcd_risk_assessment: too many records");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    double *din = nullptr, *dout = nullptr;
+    cudaError_t e = dev_alloc(&din, 7 * (size_t)n);
+    if (e == cudaSuccess) e = dev_alloc(&dout, (size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(din, in, 7 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        k_risk_assessment<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>((u32)n, din, dout);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(risk_out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(din); cudaFree(dout);
+    if (e != cudaSuccess) return fail(h, e == cudaErrorMemoryAllocation ? RCD_ENOMEM : RCD_ECUDA,
+                                      std::string("rcd_risk_assessment: ") + cudaGetErrorString(e));
+    ++h->launches;
+    return RCD_OK;
+}
+
 int rcd_history_configure(rcd_handle h, uint32_t max_history) {
     if (!h) return RCD_EINVAL;
     if (max_history < 2 || max_history > 4096) return fail(h, RCD_EINVAL, "rcd_history_configure: max_history must be in [2, 4096]");

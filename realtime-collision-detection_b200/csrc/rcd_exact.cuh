@@ -87,12 +87,12 @@ struct HitD {
 // (pi*, vi*, ai*) / (pj*, vj*, aj*) are the two start states.
 __device__ __noinline__ HitD precise_hit_d(double pix, double piy, double piz, double pjx, double pjy,
                                            double pjz, const ObjD &a, const ObjD &b, double safe,
-                                           int steps) {
+                                           int steps, double time_step = 0.1) {
     HitD h;
     h.k = -1;
     h.dist = 0; h.mx = 0; h.my = 0; h.mz = 0;
     for (int k = 0; k < steps; ++k) {
-        double t = dmul((double)k, 0.1);
+        double t = dmul((double)k, time_step);
         double xi = pos1_d(pix, a.vx, a.ax, t), yi = pos1_d(piy, a.vy, a.ay, t), zi = pos1_d(piz, a.vz, a.az, t);
         double xj = pos1_d(pjx, b.vx, b.ax, t), yj = pos1_d(pjy, b.vy, b.ay, t), zj = pos1_d(pjz, b.vz, b.az, t);
         double d = dist3_d(xi, yi, zi, xj, yj, zj);

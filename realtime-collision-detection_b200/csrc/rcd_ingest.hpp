@@ -282,8 +282,12 @@ struct Ingest {
     std::vector<uint32_t> batch_stamp;  // per slot: batch number of the last message
     std::vector<uint8_t> batch_seq;     // per slot: messages seen in that batch
     uint32_t batch = 0;
+    uint64_t max_ids = ~0ull;           // new ids beyond this are rejected (rcd_ingest_set_limit)
+    uint64_t n_rejected = 0;            // messages dropped since creation: unknown id with the table full,
+                                        // or more than 255 messages of one vehicle in one call
     std::string err;
 };
+constexpr uint32_t TYPE_CODE_OTHER = 255;  // every type string beyond the first 255 distinct ones
 
 }  // namespace rcd_ingest_impl
 
@@ -329,16 +333,33 @@ int rcd_ingest_decode_json(rcd_ingest g, const char *buf, uint64_t len, int32_t 
                 pool.emplace_back([&, k] { parse_range(cut[k], cut[k + 1], parts[k], bad[k]); });
             for (auto &t : pool) t.join();
         }
-        // ---- intern + fill records (serial: slots are assigned in arrival order) ----
+        // ---- capacity is checked before any state changes: a caller that retries with a larger buffer sees the
+        // same slots and sequence numbers as if the first call had never happened
+        uint64_t n_parsed = 0, n_bad = 0;
+        for (int k = 0; k < T; ++k) { n_parsed += parts[k].size(); n_bad += bad[k]; }
+        if (n_parsed > cap) {
+            *n_out = n_parsed;
+            if (n_bad_out) *n_bad_out = n_bad;
+            if (max_seq_out) *max_seq_out = 0;
+            g->err = "record buffer too small";
+            return RCD_ECAPACITY;
+        }
+        // ---- intern + fill records (serial: slots are assigned in arrival order).  Every message stands on its
+        // own, like in the reference's handler (warning_system.py:638-678): one that cannot be taken is dropped
+        // and counted, the rest of the batch is applied.
         ++g->batch;
-        uint64_t n = 0, n_bad = 0;
+        uint64_t n = 0;
         uint32_t max_seq = 0;
         for (int k = 0; k < T; ++k) {
-            n_bad += bad[k];
             for (const Msg &m : parts[k]) {
                 auto it = g->ids.find(m.id);
                 uint32_t slot;
                 if (it == g->ids.end()) {
+                    if (g->id_names.size() >= g->max_ids) {  // table full: known vehicles keep being served
+                        ++n_bad;
+                        ++g->n_rejected;
+                        continue;
+                    }
                     slot = (uint32_t)g->id_names.size();
                     g->ids.emplace(m.id, slot);
                     g->id_names.push_back(m.id);
@@ -348,14 +369,23 @@ int rcd_ingest_decode_json(rcd_ingest g, const char *buf, uint64_t len, int32_t 
                 auto tt = g->types.find(m.type);
                 uint32_t code;
                 if (tt == g->types.end()) {
-                    if (g->type_names.size() >= 255) { g->err = "more than 255 distinct vehicle types"; return RCD_ECAPACITY; }
-                    code = (uint32_t)g->type_names.size();
-                    g->types.emplace(m.type, code);
-                    g->type_names.push_back(m.type);
+                    if (g->type_names.size() >= TYPE_CODE_OTHER) {
+                        // the record format has 8 bits: the types beyond the first 255 share one code (only equality
+                        // of types is ever used, collision_detection.py:498-513; they compare equal to each other)
+                        code = TYPE_CODE_OTHER;
+                    } else {
+                        code = (uint32_t)g->type_names.size();
+                        g->types.emplace(m.type, code);
+                        g->type_names.push_back(m.type);
+                    }
                 } else code = tt->second;
                 if (g->batch_stamp[slot] != g->batch) { g->batch_stamp[slot] = g->batch; g->batch_seq[slot] = 0; }
                 const uint32_t seq = g->batch_seq[slot];
-                if (seq >= 255) { g->err = "more than 255 messages for one vehicle in one batch"; return RCD_ECAPACITY; }
+                if (seq >= 255) {  // 8-bit sequence numbers: the 256th message of one vehicle in one call is dropped
+                    ++n_bad;
+                    ++g->n_rejected;
+                    continue;
+                }
                 g->batch_seq[slot] = (uint8_t)(seq + 1);
                 if (seq > max_seq) max_seq = seq;
                 if (n < cap) {
@@ -376,7 +406,6 @@ int rcd_ingest_decode_json(rcd_ingest g, const char *buf, uint64_t len, int32_t 
         *n_out = n;
         if (n_bad_out) *n_bad_out = n_bad;
         if (max_seq_out) *max_seq_out = max_seq;
-        if (n > cap) { g->err = "record buffer too small"; return RCD_ECAPACITY; }
         return RCD_OK;
     } catch (const std::bad_alloc &) {
         g->err = "out of host memory";
@@ -387,6 +416,16 @@ int rcd_ingest_decode_json(rcd_ingest g, const char *buf, uint64_t len, int32_t 
     }
 }
 
+int rcd_ingest_set_limit(rcd_ingest g, uint64_t max_ids) {
+    if (!g) return RCD_EINVAL;
+    g->max_ids = max_ids;
+    return RCD_OK;
+}
+int rcd_ingest_rejected(rcd_ingest g, uint64_t *n) {
+    if (!g || !n) return RCD_EINVAL;
+    *n = g->n_rejected;
+    return RCD_OK;
+}
 int rcd_ingest_counts(rcd_ingest g, uint64_t *n_ids, uint64_t *n_types) {
     if (!g) return RCD_EINVAL;
     if (n_ids) *n_ids = g->id_names.size();
@@ -400,7 +439,13 @@ int rcd_ingest_id_name(rcd_ingest g, uint32_t slot, const char **name, uint32_t 
     return RCD_OK;
 }
 int rcd_ingest_type_name(rcd_ingest g, uint32_t code, const char **name, uint32_t *len) {
-    if (!g || !name || !len || code >= g->type_names.size()) return RCD_EINVAL;
+    if (!g || !name || !len) return RCD_EINVAL;
+    if (code == rcd_ingest_impl::TYPE_CODE_OTHER && g->type_names.size() <= code) {
+        *name = "";
+        *len = 0;
+        return RCD_OK;
+    }
+    if (code >= g->type_names.size()) return RCD_EINVAL;
     *name = g->type_names[code].data();
     *len = (uint32_t)g->type_names[code].size();
     return RCD_OK;

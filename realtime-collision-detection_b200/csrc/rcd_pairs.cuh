@@ -313,6 +313,9 @@ __device__ __noinline__ EmitRec exact_predict_resolved(const PairParams &P, u32 
 }
 
 __device__ __noinline__ EmitRec exact_compute_node(const PairParams &P, u32 si, u32 sj) {
+    // predict_position needs >= 2 samples of both vehicles (compute_node.py:202-203, 269-270): pairs that came here
+    // for the radius decision have not passed the fp32 narrow phase, which checks this
+    if (meta_pattern(__float_as_uint(P.P2[si].w)) == 0u || meta_pattern(__float_as_uint(P.P2[sj].w)) == 0u) return no_rec();
     ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
     ComputeNodeResultD r = compute_node_pair_d(A, B, (double)P.pt, (double)P.threshold);
     if (!r.hit) return no_rec();
@@ -1597,6 +1600,43 @@ k_query_radius(u32 nq, const float *__restrict__ qx, const float *__restrict__ q
                 }
             }
         }
+}
+
+// -------------------------------------------------------------------------------------------------
+// The per-pair helpers for explicit pairs (rcd_pair_exact / rcd_risk_assessment): one thread per pair,
+// the same fp64 device functions the frame kernels decide with.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ ObjD widen_object(const rcd_object &o) {
+    ObjD d;
+    d.px = o.px; d.py = o.py; d.pz = o.pz; d.vx = o.vx; d.vy = o.vy; d.vz = o.vz;
+    d.ax = o.ax; d.ay = o.ay; d.az = o.az; d.size = o.size; d.heading = o.heading;
+    d.type = o.type;
+    return d;
+}
+__global__ void __launch_bounds__(128)
+k_pair_exact(u32 n, const rcd_object *__restrict__ a, const rcd_object *__restrict__ b, int steps, double time_step,
+             rcd_pair_exact_result *__restrict__ out) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const ObjD A = widen_object(a[k]), B = widen_object(b[k]);
+    const double safe = safe_d(A.size, B.size);
+    const HitD h = precise_hit_d(A.px, A.py, A.pz, B.px, B.py, B.pz, A, B, safe, steps, time_step);
+    rcd_pair_exact_result r;
+    r.hit = h.k >= 0 ? 1 : 0;
+    r.step = h.k;
+    r.collision_time = h.k >= 0 ? dmul((double)h.k, time_step) : 0.0;
+    r.distance = h.dist;
+    r.safe_distance = safe;
+    r.relative_speed = mag3_d(dsub(A.vx, B.vx), dsub(A.vy, B.vy), dsub(A.vz, B.vz));
+    r.cx = h.mx; r.cy = h.my; r.cz = h.mz;
+    r.risk = h.k >= 0 ? risk_level_d(A.heading, B.heading, A.type, B.type, r.collision_time, h.dist, safe, r.relative_speed) : 0.0;
+    out[k] = r;
+}
+__global__ void __launch_bounds__(128) k_risk_assessment(u32 n, const double *__restrict__ in, double *__restrict__ out) {
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double *v = in + 7 * (size_t)k;
+    out[k] = risk_level_d(v[0], v[1], v[2] != 0.0 ? 1u : 0u, 1u, v[3], v[4], v[5], v[6]);
 }
 
 // -------------------------------------------------------------------------------------------------

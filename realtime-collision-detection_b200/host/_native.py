@@ -35,9 +35,9 @@ SYMBOLS = (
     "rcd_halo_append", "rcd_history_configure", "rcd_history_append", "rcd_history_reset", "rcd_history_move",
     "rcd_history_classify", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_sync",
     "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
-    "rcd_ingest_counts", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
+    "rcd_ingest_counts", "rcd_ingest_set_limit", "rcd_ingest_rejected", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
     "rcd_alerts_configure", "rcd_alerts_update", "rcd_alerts_update_pairs", "rcd_alerts_expire",
-    "rcd_alerts_acknowledge", "rcd_alerts_download", "rcd_download_begin", "rcd_download_finish", "rcd_graph_replays",
+    "rcd_alerts_acknowledge", "rcd_alerts_download", "rcd_download_begin", "rcd_download_finish", "rcd_graph_replays", "rcd_pair_exact", "rcd_risk_assessment",
 )
 
 
@@ -61,12 +61,20 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("ttc", "<f4"), ("distance", 
                        ("reserved", "u1")])
 assert PAIR_DTYPE.itemsize == 48
 
-# numpy mirror of rcd_alert_event (32 bytes)
+# numpy mirrors of rcd_object (48 bytes) and rcd_pair_exact_result (72 bytes)
+OBJECT_DTYPE = np.dtype([(k, "<f4") for k in ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "size", "heading")] +
+                        [("type", "<u4")])
+assert OBJECT_DTYPE.itemsize == 48
+PAIR_EXACT_DTYPE = np.dtype([("hit", "<i4"), ("step", "<i4")] + [(k, "<f8") for k in (
+    "collision_time", "distance", "safe_distance", "relative_speed", "cx", "cy", "cz", "risk")])
+assert PAIR_EXACT_DTYPE.itemsize == 72
+
+# numpy mirror of rcd_alert_event (40 bytes)
 ALERT_REFRESHED, ALERT_CREATED, ALERT_PRIORITY_CHANGED, ALERT_EXPIRED = 0, 1, 2, 3
 ALERT_EVENT_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("alert_id", "<u4"), ("risk", "<f4"), ("ttc", "<f4"),
-                              ("priority", "i1"), ("old_priority", "i1"), ("kind", "u1"), ("acknowledged", "u1"),
-                              ("timestamp", "<f8")])
-assert ALERT_EVENT_DTYPE.itemsize == 32
+                              ("distance", "<f4"), ("priority", "i1"), ("old_priority", "i1"), ("kind", "u1"),
+                              ("acknowledged", "u1"), ("reserved", "<u4"), ("timestamp", "<f8")])
+assert ALERT_EVENT_DTYPE.itemsize == 40
 
 
 class RcdAlertStats(ctypes.Structure):
@@ -137,6 +145,9 @@ def load() -> ctypes.CDLL:
     if hasattr(L, "rcd_graph_replays"):
         L.rcd_graph_replays.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_sync.argtypes = [vp]
+    if hasattr(L, "rcd_pair_exact"):
+        L.rcd_pair_exact.argtypes = [vp, u64, vp, vp, ctypes.c_double, ctypes.c_double, vp]
+        L.rcd_risk_assessment.argtypes = [vp, u64, vp, vp]
     if not hasattr(L, "rcd_ingest_create") and os.environ.get("RCD_B200_LIB"):
         _lib = L
         return L
@@ -147,6 +158,8 @@ def load() -> ctypes.CDLL:
     L.rcd_ingest_decode_json.argtypes = [vp, vp, u64, i32, vp, u64, ctypes.POINTER(u64), ctypes.POINTER(u64),
                                          ctypes.POINTER(u32)]
     L.rcd_ingest_counts.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.rcd_ingest_set_limit.argtypes = [vp, u64]
+    L.rcd_ingest_rejected.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_ingest_id_name.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(u32)]
     L.rcd_ingest_type_name.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(u32)]
     L.rcd_ingest_lookup.argtypes = [vp, ctypes.c_char_p, u32, ctypes.POINTER(u32)]

@@ -125,6 +125,38 @@ class CollisionDetector:
     def _calculate_safe_distance(self, vehicle1: Vehicle, vehicle2: Vehicle) -> float:
         return (vehicle1.size + vehicle2.size) / 2 + SAFE_DISTANCE_DEFAULT
 
+    # -- the per-pair helpers the prediction model calls on the detector (collision_detection.py:821-830) ----
+    def _object_record(self, vehicle: Vehicle) -> np.ndarray:
+        o = np.zeros(1, dtype=N.OBJECT_DTYPE)
+        p, v, a = vehicle.position, vehicle.velocity, vehicle.acceleration
+        o[0] = (p.x, p.y, p.z, v.x, v.y, v.z, a.x, a.y, a.z, vehicle.size, vehicle.heading,
+                self.spatial_index._table.type_code(vehicle.type))
+        return o
+
+    def _engine(self):
+        frames = self.spatial_index._frames
+        frames._ensure_engine()
+        return frames.engine
+
+    def _precise_collision_detection(self, vehicle: Vehicle, other_vehicle: Vehicle, time_window: float,
+                                     time_step: float = 0.1) -> Optional[Dict[str, Any]]:
+        """:296-342 for one pair, evaluated by the device function the frame kernels use (rcd_pair_exact): first
+        sample t = k * time_step, k < int(time_window / time_step), with distance <= safe distance."""
+        r = self._engine().pair_exact(self._object_record(vehicle), self._object_record(other_vehicle), time_window, time_step)[0]
+        if not r["hit"]:
+            return None
+        return {"collision_time": float(r["collision_time"]),
+                "collision_position": Position(float(r["cx"]), float(r["cy"]), float(r["cz"])),
+                "distance": float(r["distance"]), "safe_distance": float(r["safe_distance"]),
+                "relative_speed": float(r["relative_speed"])}
+
+    def _risk_assessment(self, vehicle: Vehicle, other_vehicle: Vehicle, collision_info: Dict[str, Any]) -> float:
+        """:344-389 (+ _get_type_factor :498-513) for one collision_info, on the device (rcd_risk_assessment)."""
+        rec = np.array([[vehicle.heading, other_vehicle.heading, 1.0 if vehicle.type == other_vehicle.type else 0.0,
+                         collision_info["collision_time"], collision_info["distance"], collision_info["safe_distance"],
+                         collision_info.get("relative_speed", 0.0)]], np.float64)
+        return float(self._engine().risk_assessment(rec)[0])
+
     def get_stats(self) -> Dict[str, Any]:
         return self.stats
 
@@ -193,8 +225,13 @@ class CollisionPredictionModel:
         reseed = set()
         for ev in table.events[self._events_seen:]:
             if ev[0] == "move":
-                engine.history_move(ev[1], ev[2])
-                reseed.discard(ev[2])
+                dst, src = ev[1], ev[2]
+                if src in reseed:  # the moved vehicle is itself new: its ring is rebuilt at the new slot, never copied
+                    reseed.discard(src)
+                    reseed.add(dst)
+                else:
+                    engine.history_move(dst, src)
+                    reseed.discard(dst)  # whatever was pending for the slot's previous occupant is void
             else:  # a (possibly recycled) slot got a new vehicle
                 reseed.add(ev[1])
         self._events_seen = len(table.events)

@@ -234,6 +234,23 @@ class FrameEngine:
         N.check(self._lib.rcd_classify_patterns(self._h, n, stride, _vp(s), _vp(c), _vp(out)), self._h)
         return out
 
+    # -- the detector's per-pair helpers (collision_detection.py:296-389) ------------------------------------
+    def pair_exact(self, a: np.ndarray, b: np.ndarray, time_window: float = 10.0, time_step: float = 0.1) -> np.ndarray:
+        """_precise_collision_detection + _risk_assessment for explicit pairs (OBJECT_DTYPE arrays) -> PAIR_EXACT_DTYPE."""
+        aa, bb = np.ascontiguousarray(a, dtype=N.OBJECT_DTYPE), np.ascontiguousarray(b, dtype=N.OBJECT_DTYPE)
+        out = np.zeros(aa.shape[0], dtype=N.PAIR_EXACT_DTYPE)
+        N.check(self._lib.rcd_pair_exact(self._h, aa.shape[0], _vp(aa), _vp(bb), float(time_window), float(time_step), _vp(out)),
+                self._h)
+        return out
+
+    def risk_assessment(self, records: np.ndarray) -> np.ndarray:
+        """records: float64 [n, 7] = heading_i, heading_j, same type (1 / 0), collision_time, distance, safe_distance,
+        relative_speed -> risk level (collision_detection.py:344-389)."""
+        r = _as(records, np.float64).reshape(-1, 7)
+        out = np.zeros(r.shape[0], np.float64)
+        N.check(self._lib.rcd_risk_assessment(self._h, r.shape[0], _vp(r), _vp(out)), self._h)
+        return out
+
     # -- device-resident trajectory history ---------------------------------------------------------
     def history_configure(self, max_history: int = 100) -> None:
         N.check(self._lib.rcd_history_configure(self._h, int(max_history)), self._h)

@@ -67,13 +67,30 @@ class VehicleIngest:
         rec = np.empty(cap, dtype=N.RECORD_DTYPE) if out is None else out
         n, bad, mseq = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint32()
         ptr = ctypes.cast(buf, ctypes.c_void_p) if isinstance(buf, bytes) else ctypes.cast(ctypes.addressof(buf), ctypes.c_void_p)
-        self._check(self._lib.rcd_ingest_decode_json(self._g, ptr, n_bytes, self.threads,
-                                                     rec.ctypes.data_as(ctypes.c_void_p), cap, ctypes.byref(n),
-                                                     ctypes.byref(bad), ctypes.byref(mseq)))
+        rc = self._lib.rcd_ingest_decode_json(self._g, ptr, n_bytes, self.threads, rec.ctypes.data_as(ctypes.c_void_p), cap,
+                                              ctypes.byref(n), ctypes.byref(bad), ctypes.byref(mseq))
+        if rc == N.RCD_ECAPACITY and out is None and int(n.value) > cap:
+            # more (tiny) messages than the estimate: nothing was decoded and no state changed -- once more, with room
+            cap = int(n.value)
+            rec = np.empty(cap, dtype=N.RECORD_DTYPE)
+            rc = self._lib.rcd_ingest_decode_json(self._g, ptr, n_bytes, self.threads, rec.ctypes.data_as(ctypes.c_void_p),
+                                                  cap, ctypes.byref(n), ctypes.byref(bad), ctypes.byref(mseq))
+        self._check(rc)
         self.bad_messages += int(bad.value)
         return rec[: int(n.value)], int(mseq.value)
 
     # -- id / type tables -------------------------------------------------------------------
+    def set_limit(self, max_ids: int) -> None:
+        """At most ``max_ids`` distinct vehicles: messages of further (unknown) vehicles are dropped and counted
+        (``bad_messages``, ``rejected``) while the known ones keep being served."""
+        self._check(self._lib.rcd_ingest_set_limit(self._g, int(max_ids)))
+
+    @property
+    def rejected(self) -> int:
+        n = ctypes.c_uint64()
+        self._check(self._lib.rcd_ingest_rejected(self._g, ctypes.byref(n)))
+        return int(n.value)
+
     @property
     def n_objects(self) -> int:
         n = ctypes.c_uint64()
@@ -121,6 +138,7 @@ class VehiclePositionStream:
         self.engine = FrameEngine(max_objects, max_pairs, device=device, world_bounds=world_bounds)
         self.engine.history_configure(max_history)
         self.ingest = VehicleIngest(threads=threads)
+        self.ingest.set_limit(max_objects)  # a full frame rejects new vehicles, it does not fail every later batch
         self.messages_applied = 0
 
     def close(self) -> None:

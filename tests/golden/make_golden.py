@@ -139,6 +139,34 @@ def alerts_fixture(name):
     print(name, len(rows), "ops,", sum(len(r["events"]) for r in rows), "events, final table", len(rows[-1]["table"]))
 
 
+def helpers_fixture(name):
+    """The per-pair helpers the reference's prediction model calls on the detector (collision_detection.py:296-389)
+    and the alert message tiers (warning_system.py:313-329)."""
+    import json
+    frame = W.uniform_frame(500, 107, map_size=260.0, drone_fraction=0.3)
+    rng = np.random.default_rng(5)
+    f64 = W.frame_to_f64(frame)
+    # pairs at every distance: neighbours within 30 m (most of them hit within the window) and random ones
+    pos = np.stack([f64["px"], f64["py"], f64["pz"]], 1)
+    pairs = []
+    for i in range(0, 500, 3):
+        d = np.linalg.norm(pos - pos[i], axis=1)
+        near = [int(j) for j in np.argsort(d)[1:7]]
+        pairs += [(i, j) for j in near] + [(i, int(j)) for j in rng.integers(0, 500, 2) if int(j) != i]
+    out = {"frame": {k: v.tolist() for k, v in _frame_arrays(frame).items()}, "cases": []}
+    for T in (10.0, 1.0, 0.35):
+        res = S.run_pair_helpers_A(f64, pairs, T)
+        out["cases"].append({"T": T, "pairs": pairs, "results": res})
+        print(name, T, sum(r is not None for r in res), "hits of", len(res))
+    msg_cases = [(float(r), f"vehicle-{k}", float(t), float(d)) for k, (r, t, d) in enumerate(
+        (r, t, d) for r in (0.3, 0.45, 0.59999, 0.6, 0.79999, 0.8, 0.95, 1.0) for t in (0.0, 0.05, 0.14999, 2.25, 9.95, 19.4)
+        for d in (0.0, 0.05, 0.25, 3.349999, 7.5, 12.25))]
+    msg_cases.append((0.9, "车-7 \"x\"", 1.0, 2.0))
+    out["messages"] = {"cases": msg_cases, "texts": S.run_alert_messages_A(msg_cases)}
+    with open(os.path.join(HERE, name), "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False)
+
+
 def main():
     if not S.reference_available():
         raise SystemExit("needs /root/reference")
@@ -162,6 +190,7 @@ def main():
     scalars_fixture("scalars.npz")
     ingest_fixture("ingest_messages.json")
     alerts_fixture("alert_scenario.json.gz")
+    helpers_fixture("pair_helpers.json")
 
 
 if __name__ == "__main__":

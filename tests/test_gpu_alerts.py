@@ -137,3 +137,36 @@ def test_messages_to_alerts_end_to_end():
         assert len(seen) > 100
         gone = am.cleanup_expired(now=200.0)
         assert set(gone) == set(seen) and am.get_stats()["active_alerts"] == 0
+
+
+def test_the_same_risk_twice_in_one_pass_is_create_then_silent_refresh():
+    """A vehicle without history owes every risk twice (detect_collisions + the fall-back of predict_collisions,
+    collision_detection.py:590-592): the copies sit next to each other in the pair buffer.  The reference's loop
+    creates the alert with the first copy and refreshes it with the second (warning_system.py:259-285) -- never a
+    priority change, never a half-written entry."""
+    from rcd_b200.host import _native as N
+    from rcd_b200.host.engine import FrameEngine
+    rng = np.random.default_rng(5)
+    n = 4000
+    base = np.zeros(n, dtype=N.PAIR_DTYPE)
+    base["i"] = rng.permutation(50_000)[:n].astype(np.uint32)
+    base["j"] = base["i"] + 1 + rng.integers(0, 1000, n).astype(np.uint32)
+    base["risk"] = rng.uniform(0.3, 1.0, n).astype(np.float32)
+    base["ttc"] = rng.uniform(0.0, 10.0, n).astype(np.float32)
+    base["priority"] = rng.integers(0, 4, n).astype(np.int8)
+    twice = np.repeat(base, 2)  # adjacent copies: same warp (31 of 32 times) or neighbouring warps
+    with FrameEngine(64, 64) as e:
+        e.alerts_configure(16384)
+        ev, st = e.alerts_update_pairs(twice, 100.0, report_refreshed=True)
+        assert st["n_created"] == n and st["n_refreshed"] == n and st["n_changed"] == 0 and st["n_live"] == n
+        created = ev[ev["kind"] == N.ALERT_CREATED]
+        refreshed = ev[ev["kind"] == N.ALERT_REFRESHED]
+        assert len(created) == n and len(refreshed) == n and len(ev) == 2 * n
+        ids = {(int(r["i"]), int(r["j"])): int(r["alert_id"]) for r in created}
+        assert len(set(ids.values())) == n
+        for r in refreshed:  # the refresh reports the number and the priority the creation gave the alert
+            assert int(r["alert_id"]) == ids[(int(r["i"]), int(r["j"]))]
+            assert int(r["old_priority"]) == int(r["priority"])
+        # the next frame sees complete entries
+        ev, st = e.alerts_update_pairs(base, 101.0)
+        assert st["n_refreshed"] == n and st["n_created"] == 0 and st["n_changed"] == 0 and len(ev) == 0

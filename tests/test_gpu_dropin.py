@@ -221,3 +221,94 @@ def test_device_trajectory_rings_follow_the_host_histories():
     model.update_trajectory(v.id, v.position, t - 3.0)
     assert not model._ordered
     assert np.array_equal(model.trajectory_patterns(), _oracle_patterns(model, table))
+
+
+def test_new_vehicle_in_a_recycled_slot_that_is_moved_in_the_same_tick_keeps_its_own_history():
+    """The last vehicle is removed (its ring stays behind), a new vehicle takes that slot, and before the next
+    frame another removal swap-moves the new vehicle into the hole: the ring must be rebuilt from the new
+    vehicle's own samples at its final slot, not copied from the slot's previous occupant."""
+    from rcd_b200.host.collision_detection import CollisionDetector, CollisionPredictionModel
+    from rcd_b200.host.models import Position, Vector, Vehicle
+    from rcd_b200.host.spatial_index import SpatialIndex
+    det = CollisionDetector(SpatialIndex())
+    model = CollisionPredictionModel(det)
+    table = det.spatial_index._table
+
+    def put(vid, x, vx, ax, t):
+        v = Vehicle(id=vid, position=Position(x + vx * t + 0.5 * ax * t * t, 0.0, 0.0), velocity=Vector(vx + ax * t, 0.0, 0.0),
+                    acceleration=Vector(ax, 0.0, 0.0), heading=0.0, size=2.0, type="car", timestamp=t)
+        det.update_vehicle(v)
+        model.update_trajectory(vid, v.position, t)
+
+    for k in range(12):  # five accelerating vehicles with long histories; "x" sits in the last slot
+        for j, vid in enumerate(("a", "b", "c", "d", "x")):
+            put(vid, 100.0 * j, 3.0, 1.5, 0.5 * k)
+    assert np.array_equal(model.trajectory_patterns(), _oracle_patterns(model, table))
+    assert model.trajectory_patterns()[table.slot_of["x"]] == 2
+    # one tick: x leaves, the parked newcomer takes its slot, b leaves -> the newcomer is swap-moved into b's hole
+    det.remove_vehicle("x")
+    for k in range(3):
+        put("new", 900.0, 0.0, 0.0, 6.0 + 0.5 * k)
+    det.remove_vehicle("b")
+    assert table.slot_of["new"] == 1
+    got = model.trajectory_patterns()
+    assert np.array_equal(got, _oracle_patterns(model, table))
+    assert got[table.slot_of["new"]] == 0  # stationary: x's accelerating history is gone
+
+
+def test_pair_helpers_match_the_reference_golden():
+    """CollisionDetector._precise_collision_detection / _risk_assessment (collision_detection.py:296-389): the same
+    hits, float64 values within a few ulp of the reference's own results (x * x vs pow(x, 2.0), CUDA sin vs
+    glibc sin: INTEGRATION.md, "last-ulp deviations"), through rcd_pair_exact / rcd_risk_assessment and through
+    the drop-in methods."""
+    import json
+    import os
+    from rcd_b200.host import _native as N
+    from rcd_b200.host.collision_detection import CollisionDetector
+    from rcd_b200.host.engine import FrameEngine
+    from rcd_b200.host.models import Position, Vector, Vehicle
+    from rcd_b200.host.spatial_index import SpatialIndex
+    from tests.helpers import GOLDEN
+    d = json.load(open(os.path.join(GOLDEN, "pair_helpers.json"), encoding="utf-8"))
+    f = {k[len("frame_"):]: np.asarray(v) for k, v in d["frame"].items()}
+    n = len(f["px"])
+    objs = np.zeros(n, dtype=N.OBJECT_DTYPE)
+    for k in ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "size", "heading"):
+        objs[k] = f[k]
+    objs["type"] = f["type"]
+    cols = ("collision_time", "distance", "safe_distance", "relative_speed", "cx", "cy", "cz", "risk")
+    with FrameEngine(16, 16) as e:
+        for case in d["cases"]:
+            ii = np.array([p[0] for p in case["pairs"]]); jj = np.array([p[1] for p in case["pairs"]])
+            got = e.pair_exact(objs[ii], objs[jj], case["T"])
+            want_hit = np.array([r is not None for r in case["results"]])
+            assert np.array_equal(got["hit"].astype(bool), want_hit)
+            want = np.array([r for r in case["results"] if r is not None], np.float64)
+            g = got[want_hit]
+            assert np.array_equal(g["collision_time"], want[:, 0])  # k * 0.1: the same float64 product
+            for c, name in enumerate(cols):
+                assert_close(g[name], want[:, c], name, 1e-13, 1e-13)
+        # _risk_assessment on collision_info records that did not come from the scan
+        rng = np.random.default_rng(3)
+        rec = np.stack([rng.uniform(-7, 7, 500), rng.uniform(-7, 7, 500), rng.integers(0, 2, 500).astype(float),
+                        rng.uniform(0, 15, 500), rng.uniform(0, 12, 500), rng.uniform(5.5, 10, 500), rng.uniform(0, 80, 500)], 1)
+        from oracle import oracle as O
+        want = np.array([O.risk_level(r[0], r[1], 0, 0 if r[2] else 1, r[3], r[4], r[5], r[6]) for r in rec])
+        assert_close(e.risk_assessment(rec), want, "risk", 1e-13, 1e-15)
+    # the drop-in methods (what CollisionPredictionModel._detect_at_position calls, :821-830)
+    det = CollisionDetector(SpatialIndex())
+    vehicles = [Vehicle(id=f"v{i}", position=Position(float(f["px"][i]), float(f["py"][i]), float(f["pz"][i])),
+                        velocity=Vector(float(f["vx"][i]), float(f["vy"][i]), float(f["vz"][i])),
+                        acceleration=Vector(float(f["ax"][i]), float(f["ay"][i]), float(f["az"][i])), heading=float(f["heading"][i]),
+                        size=float(f["size"][i]), type=f"type{int(f['type'][i])}", timestamp=0.0) for i in range(n)]
+    case = d["cases"][1]  # time_window = 1.0: the prediction model's call
+    seen = 0
+    for (i, j), want in list(zip(case["pairs"], case["results"]))[:150]:
+        info = det._precise_collision_detection(vehicles[i], vehicles[j], case["T"])
+        assert (info is None) == (want is None)
+        if info is None:
+            continue
+        seen += 1
+        assert info["collision_time"] == want[0] and abs(info["distance"] - want[1]) <= 1e-12
+        assert abs(det._risk_assessment(vehicles[i], vehicles[j], info) - want[7]) <= 1e-13
+    assert seen > 10

@@ -128,6 +128,54 @@ def test_record_buffer_too_small_is_an_error():
         assert e.value.code == N.RCD_ECAPACITY
 
 
+def test_record_buffer_too_small_changes_no_state():
+    """ECAPACITY is reported before ids are interned or sequence numbers advance: the retry with a larger buffer
+    returns what a first call would have returned."""
+    from rcd_b200.host import _native as N
+    from rcd_b200.host.ingest import VehicleIngest
+    text = "\n".join(C.seeded_messages(40, 11))
+    with VehicleIngest(threads=1) as g, VehicleIngest(threads=1) as fresh:
+        with pytest.raises(N.NativeError):
+            g.decode(text, out=np.empty(4, dtype=N.RECORD_DTYPE))
+        assert g.n_objects == 0
+        ra, sa = g.decode(text)
+        rb, sb = fresh.decode(text)
+        assert ra.tobytes() == rb.tobytes() and sa == sb and g.ids() == fresh.ids()
+
+
+def test_one_misbehaving_producer_does_not_discard_the_batch():
+    """Limits of the record format degrade per message (the reference handles every message on its own,
+    warning_system.py:638-678): the 256th message of one vehicle in a call is dropped, type strings beyond 255
+    share a code, and a full id table rejects new vehicles while known ones keep being served."""
+    from rcd_b200.host.ingest import VehicleIngest
+    rng = random.Random(3)
+    good = [C.reference_message(rng, k, 10.0 + k, vid=f"car-{k}") for k in range(20)]
+    flood = [C.reference_message(rng, 100 + k, 50.0 + k, vid="chatty") for k in range(300)]
+    with VehicleIngest(threads=1) as g:
+        rec, max_seq = g.decode("\n".join(good[:10] + flood + good[10:]))
+        assert len(rec) == 20 + 255 and max_seq == 254
+        assert g.bad_messages == 45 and g.rejected == 45
+        assert sorted(set(rec["slot"].tolist())) == list(range(21))  # every other vehicle was applied
+        # the next call starts new sequence numbers: the chatty vehicle is served again
+        rec2, _ = g.decode(flood[0])
+        assert len(rec2) == 1 and rec2["seq"][0] == 0
+    with VehicleIngest(threads=1) as g:
+        msgs = []
+        for k in range(300):
+            m = json.loads(C.reference_message(rng, k, 1.0 + k, vid=f"v{k}"))
+            m["type"] = f"kind-{k}"
+            msgs.append(json.dumps(m))
+        rec, _ = g.decode("\n".join(msgs))
+        assert len(rec) == 300 and g.bad_messages == 0 and g.n_types == 255
+        assert rec["type"][:255].tolist() == list(range(255)) and set(rec["type"][255:].tolist()) == {255}
+    with VehicleIngest(threads=1) as g:
+        g.set_limit(5)
+        rec, _ = g.decode("\n".join(good))
+        assert len(rec) == 5 and g.n_objects == 5 and g.rejected == 15
+        rec, _ = g.decode("\n".join(good))  # known vehicles keep being served, forever
+        assert len(rec) == 5 and rec["slot"].tolist() == list(range(5)) and g.rejected == 30
+
+
 @pytest.mark.needs_reference
 def test_fresh_messages_against_the_live_reference():
     from oracle import ref_shim as S

@@ -92,3 +92,31 @@ def test_empty_and_single_object_frames():
             o = O.frame_A(f, mode)
             assert o["counts"].tolist() == [0, 0, 0, 0] and len(o["risks"]) == 0
         assert O.frame_B(f)["counts"][0] == n  # a lone vehicle finds itself
+
+
+def test_pair_helpers_and_alert_messages_match_the_reference_golden():
+    """_precise_collision_detection / _risk_assessment (collision_detection.py:296-389) of the oracle against the
+    reference's own bytecode, bit for bit in float64; and the alert message tiers (warning_system.py:313-329),
+    byte for byte, of the host mirror."""
+    import json
+    from oracle import oracle as O
+    from rcd_b200.host.warning_system import alert_message
+    d = json.load(open(os.path.join(GOLDEN, "pair_helpers.json"), encoding="utf-8"))
+    f = {k[len("frame_"):]: np.asarray(v, np.float32).astype(np.float64) for k, v in d["frame"].items()}
+    obj = lambda i: [f[k][i] for k in ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "size")]
+    for case in d["cases"]:
+        hits = 0
+        for (i, j), want in zip(case["pairs"], case["results"]):
+            got = O.precise(obj(i), obj(j), case["T"])
+            assert (got is None) == (want is None)
+            if want is None:
+                continue
+            hits += 1
+            assert list(got) == want[:7]
+            risk = O.risk_level(f["heading"][i], f["heading"][j], int(f["type"][i]), int(f["type"][j]), want[0], want[1], want[2], want[3])
+            assert risk == want[7]
+        assert hits > 100
+    for (risk, other, ttc, dist), text in zip(d["messages"]["cases"], d["messages"]["texts"]):
+        assert alert_message(risk, other, ttc, dist) == text
+        assert alert_message(risk, other, ttc, dist).encode("utf-8") == text.encode("utf-8")
+    assert len(d["messages"]["texts"]) > 200
