@@ -217,6 +217,24 @@ int rcd_download_unsorted(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n
 int rcd_download_begin(rcd_handle h, rcd_pair *out, uint64_t cap);
 int rcd_download_finish(rcd_handle h, rcd_counts_t *counts, uint64_t *n_out);
 
+/* Compact pair record for consumers that do not need the collision position or the stage-2 values: the fields
+ * AlertManager.process_collision_risks reads (warning_system.py:259-285, 313-329) plus the relative speed.  32 bytes. */
+typedef struct {
+    uint32_t i, j;
+    float ttc, distance, rel_speed, risk;
+    float t_closest;    /* detect: time_to_closest; predict: winning offset time t_m */
+    int8_t priority;
+    uint8_t offset;
+    uint8_t predicted;
+    uint8_t reserved;
+} rcd_pair_compact;
+/* Like rcd_download_begin / rcd_download_finish with compact records: the frame's pairs are narrowed to 32 bytes on
+ * the device (one pass over the pair buffer) before they cross the bus.  rcd_download_finish serves both kinds. */
+int rcd_download_begin_compact(rcd_handle h, rcd_pair_compact *out, uint64_t cap);
+
+/* Risks emitted for every object of the last frame (as the querying vehicle), upload order, n entries. */
+int rcd_download_risk_counts(rcd_handle h, uint32_t *out, uint64_t n);
+
 /* Per-object broad-phase candidate counts of the last frame, in upload order (n entries). */
 int rcd_download_candidate_counts(rcd_handle h, uint32_t *out, uint64_t n);
 
@@ -377,6 +395,16 @@ int rcd_alerts_acknowledge(rcd_handle h, uint64_t n, const uint32_t *i, const ui
 /* Every live alert, sorted by (i, j), as event records with kind = RCD_ALERT_REFRESHED. */
 int rcd_alerts_download(rcd_handle h, rcd_alert_event *out, uint64_t cap, uint64_t *n_out);
 
+/* Summary delivery: what the reference's consumer acts on -- the alert changes of the frame
+ * (process_collision_risks folded into the device alert table: created alerts and priority changes, plus the
+ * refreshed ones on request) and how many risks every object has -- while the pair records stay on the device.
+ * Pipelined like rcd_download_begin / _finish: `begin` returns at once and the next rcd_upload / rcd_step may be
+ * issued; `finish` waits for that frame, copies min(n_events, cap) events, the per-object risk counts (upload
+ * order, n entries; NULL / 0 to skip) and the frame's totals.  Needs rcd_alerts_configure.  One delivery
+ * (download or summary) in flight at a time. */
+int rcd_summary_begin(rcd_handle h, double now, int32_t report_refreshed);
+int rcd_summary_finish(rcd_handle h, rcd_alert_event *events, uint64_t cap, uint64_t *n_events, rcd_alert_stats *stats,
+                       uint32_t *risk_counts, uint64_t n, rcd_counts_t *counts);
 /* Spatial-slab support: pack every owned object whose x lies within `halo` of
  * peer p's slab [slab_lo[p], slab_hi[p]) -- p != self -- into 52-byte records
  * (11 floats, meta u32 = type | pattern << 8, id u32), grouped by peer.  out_records is a DEVICE

@@ -51,6 +51,12 @@ struct rcd_handle_s {
     float4 *P0 = nullptr, *P1 = nullptr, *P2 = nullptr;
     float4 *U = nullptr;  // packed 48-byte records in upload order
     u32 *sorted_slot = nullptr;
+    u32 *sorted_id = nullptr;   // caller ids in cell order (the frame kernels never touch the upload buffers)
+    // uploads from host memory run on their own stream and overlap the previous frame: the upload buffers are
+    // free again as soon as that frame's index is built (k_pack_keys + k_reorder have consumed them)
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t ev_upload_done = nullptr, ev_inputs_free = nullptr;
+    bool upload_pending = false, inputs_busy = false, capturing = false;
     u32 *cell_begin = nullptr;  // [cells_cap + 1] dense cell table
     u32 cells_cap = 0;
     float cell_scale = 0.5f;    // grid cell edge (x, y) as a fraction of the query radius
@@ -70,6 +76,7 @@ struct rcd_handle_s {
     Counters *counters = nullptr;
     Counters *counters_host = nullptr;  // pinned
     u32 *cand_count = nullptr;
+    u32 *risk_count = nullptr, *risk_count_alt = nullptr;
     u32 *pair_tile_counter = nullptr;
     QEntry *q3 = nullptr;
     u32 qcap = 0;
@@ -130,11 +137,17 @@ struct rcd_handle_s {
     bool flip_pending = false, download_pending = false;
     rcd_pair *pend_dev = nullptr, *pend_out = nullptr;
     u64 pend_cap = 0, pend_n = 0, pend_n_owned = 0;
+    int pend_kind = 0;                       // 0 pairs, 1 compact pairs, 2 summary (alert events + risk counts)
+    rcd_pair_compact *compact_dev = nullptr; // scratch of rcd_download_begin_compact
+    rcd_pair_compact *pend_out_compact = nullptr;
+    u32 *pend_risk = nullptr;
+    rcd_alert_event *pend_ev = nullptr;
+    AlertCounters *pend_alert_counters_host = nullptr;  // pinned
     // alert table (rcd_alerts.cuh)
     AlertEntry *alert_tab[2] = {nullptr, nullptr};
     int alert_cur = 0;
     u64 alert_cap = 0, alert_ev_cap = 0;
-    rcd_alert_event *alert_ev = nullptr;
+    rcd_alert_event *alert_ev = nullptr, *alert_ev_alt = nullptr;  // (twin: summary deliveries in flight)
     AlertCounters *alert_counters = nullptr;
     AlertCounters *alert_counters_host = nullptr;  // pinned
     std::string err;
@@ -168,14 +181,31 @@ cudaError_t dev_alloc(T **p, size_t count) {
     return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T));
 }
 
-void stage_begin(rcd_handle h, int s) {
+void stage_begin(rcd_handle h, int s, cudaStream_t on = nullptr) {
     if (h->flags & RCD_FLAG_PROFILE) {
-        cudaEventRecord(h->stages[h->stage_mode][s].begin, h->stream);
+        cudaEventRecord(h->stages[h->stage_mode][s].begin, on ? on : h->stream);
         h->stages[h->stage_mode][s].used = true;
     }
 }
-void stage_end(rcd_handle h, int s) {
-    if (h->flags & RCD_FLAG_PROFILE) cudaEventRecord(h->stages[h->stage_mode][s].end, h->stream);
+void stage_end(rcd_handle h, int s, cudaStream_t on = nullptr) {
+    if (h->flags & RCD_FLAG_PROFILE) cudaEventRecord(h->stages[h->stage_mode][s].end, on ? on : h->stream);
+}
+
+// Order the handle's stream after an upload that is still running on the upload stream.
+int wait_upload(rcd_handle h) {
+    if (h->upload_pending && !h->capturing) {
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_upload_done, 0));
+        h->upload_pending = false;
+    }
+    return RCD_OK;
+}
+// The frame no longer reads the upload buffers: the next upload may overwrite them.
+int release_inputs(rcd_handle h) {
+    if (!h->capturing) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_inputs_free, h->stream));
+        h->inputs_busy = true;
+    }
+    return RCD_OK;
 }
 
 InputState input_state(rcd_handle h) {
@@ -233,6 +263,10 @@ int build_index(rcd_handle h, float cell_req) {
     if (h->index_valid && h->index_cell_req == cell_req) return RCD_OK;
     h->index_valid = false;
     h->qorder_kind = 0;
+    {
+        int rcw = wait_upload(h);
+        if (rcw) return rcw;
+    }
     if (n == 0) {
         float z[3] = {0, 0, 0};
         h->grid = make_grid(z, z, cell_req, h->cell_scale, h->cells_cap);
@@ -288,8 +322,12 @@ int build_index(rcd_handle h, float cell_req) {
 
     stage_begin(h, RCD_STAGE_REORDER);
     k_reorder<<<(n + REORDER_THREADS - 1) / REORDER_THREADS, REORDER_THREADS, 0, h->stream>>>(
-        h->vals[cur], n, h->U, h->P0, h->P1, h->P2, h->sorted_slot);
+        h->vals[cur], n, h->U, h->in_id, h->P0, h->P1, h->P2, h->sorted_slot, h->sorted_id);
     KERNEL_CHECK(h);
+    {
+        int rcr = release_inputs(h);
+        if (rcr) return rcr;
+    }
     k_cell_table<<<(g.ncells + CT_CELLS - 1) / CT_CELLS, CT_THREADS, 0, h->stream>>>(h->keys[cur], n, g.ncells, h->cell_begin);
     KERNEL_CHECK(h);
     stage_end(h, RCD_STAGE_REORDER);
@@ -334,10 +372,34 @@ int build_query_order(rcd_handle h, int kind) {
     return RCD_OK;
 }
 
-int copy_in(rcd_handle h, void *dst, const void *src, size_t bytes, int32_t srckind) {
-    CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, srckind == RCD_SRC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                h->stream));
+int copy_in(rcd_handle h, void *dst, const void *src, size_t bytes, int32_t srckind, cudaStream_t on) {
+    CUDA_TRY(h, cudaMemcpyAsync(dst, src, bytes, srckind == RCD_SRC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, on));
     return RCD_OK;
+}
+
+// The stream an upload of kind `src` runs on.  Host memory: the upload stream, after the previous frame has
+// released the upload buffers.  Device memory: the handle's stream (ordered after a pending host upload).
+int upload_stream(rcd_handle h, int32_t src, cudaStream_t *on) {
+    if (src == RCD_SRC_DEVICE) {
+        int rc = wait_upload(h);
+        if (rc) return rc;
+        *on = h->stream;
+        return RCD_OK;
+    }
+    if (h->inputs_busy) {
+        CUDA_TRY(h, cudaStreamWaitEvent(h->up_stream, h->ev_inputs_free, 0));
+        h->inputs_busy = false;
+    }
+    *on = h->up_stream;
+    return RCD_OK;
+}
+int upload_issued(rcd_handle h, cudaStream_t on) {
+    if (on == h->up_stream) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_upload_done, h->up_stream));
+        h->upload_pending = true;
+        return RCD_OK;
+    }
+    return release_inputs(h);  // written on the handle's stream: a later host upload must come after it
 }
 
 }  // namespace
@@ -381,6 +443,9 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
 
     CREATE_TRY(cudaSetDevice(h->device));
     CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_upload_done, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&h->ev_inputs_free, cudaEventDisableTiming));
     const size_t cap = (size_t)h->cap;
     for (int k = 0; k < 11; ++k) {
         CREATE_TRY(dev_alloc(&h->in_f[k], cap));
@@ -402,6 +467,7 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->P2, cap));
     CREATE_TRY(dev_alloc(&h->U, 3 * (cap + 4)));
     CREATE_TRY(dev_alloc(&h->sorted_slot, cap));
+    CREATE_TRY(dev_alloc(&h->sorted_id, cap));
     CREATE_TRY(dev_alloc(&h->cell_begin, (size_t)h->cells_cap + 1));
     for (int k = 0; k < 2; ++k) {
         CREATE_TRY(dev_alloc(&h->qkeys[k], cap + 4));
@@ -417,6 +483,7 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->counters, 1));
     CREATE_TRY(cudaMallocHost(reinterpret_cast<void **>(&h->counters_host), sizeof(Counters)));
     CREATE_TRY(dev_alloc(&h->cand_count, cap));
+    CREATE_TRY(dev_alloc(&h->risk_count, cap));
     CREATE_TRY(dev_alloc(&h->pair_tile_counter, 2));
     // the fp32 stages forward about 5 candidate entries per emitted pair on clustered frames; a full
     // queue is not an error (the pair is then finished in place) but it is slower
@@ -447,8 +514,13 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
 int rcd_destroy(rcd_handle h) {
     if (!h) return RCD_OK;
     cudaSetDevice(h->device);
+    if (h->up_stream) cudaStreamSynchronize(h->up_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (int k = 0; k < 11; ++k) cudaFree(h->in_f[k]);
+    cudaFree(h->sorted_id);
+    if (h->ev_upload_done) cudaEventDestroy(h->ev_upload_done);
+    if (h->ev_inputs_free) cudaEventDestroy(h->ev_inputs_free);
+    if (h->up_stream) cudaStreamDestroy(h->up_stream);
     cudaFree(h->in_type); cudaFree(h->in_pattern); cudaFree(h->in_id);
     for (int k = 0; k < 2; ++k) { cudaFree(h->keys[k]); cudaFree(h->vals[k]); }
     cudaFree(h->hist); cudaFree(h->tile_status); cudaFree(h->tile_counter);
@@ -463,7 +535,9 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->traj); cudaFree(h->traj_count);
     for (auto &g : h->graphs)
         if (g.exec) cudaGraphExecDestroy(g.exec);
-    cudaFree(h->out_alt); cudaFree(h->counters_alt);
+    cudaFree(h->out_alt); cudaFree(h->counters_alt); cudaFree(h->risk_count); cudaFree(h->risk_count_alt);
+    cudaFree(h->compact_dev); cudaFree(h->alert_ev_alt);
+    if (h->pend_alert_counters_host) cudaFreeHost(h->pend_alert_counters_host);
     if (h->pend_counters_host) cudaFreeHost(h->pend_counters_host);
     if (h->pend_event) cudaEventDestroy(h->pend_event);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -491,28 +565,37 @@ int rcd_upload(rcd_handle h, uint64_t n, const float *px, const float *py, const
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) h->stages[m][s].used = false;
     h->stage_mode = 0;
-    stage_begin(h, RCD_STAGE_UPLOAD);
+    cudaStream_t on = nullptr;
+    {
+        int rc = upload_stream(h, src, &on);
+        if (rc) return rc;
+    }
+    stage_begin(h, RCD_STAGE_UPLOAD, on);
     const float *f[11] = {px, py, pz, vx, vy, vz, ax, ay, az, size, heading};
     const size_t bytes = (size_t)n * sizeof(float);
     for (int k = 0; k < 11 && n; ++k) {
         if (f[k]) {
-            int rc = copy_in(h, h->in_f[k], f[k], bytes, src);
+            int rc = copy_in(h, h->in_f[k], f[k], bytes, src, on);
             if (rc) return rc;
         } else {
-            CUDA_TRY(h, cudaMemsetAsync(h->in_f[k], 0, bytes, h->stream));
+            CUDA_TRY(h, cudaMemsetAsync(h->in_f[k], 0, bytes, on));
         }
     }
     if (n) {
-        if (type) { int rc = copy_in(h, h->in_type, type, (size_t)n, src); if (rc) return rc; }
-        else CUDA_TRY(h, cudaMemsetAsync(h->in_type, 0, (size_t)n, h->stream));
-        CUDA_TRY(h, cudaMemsetAsync(h->in_pattern, RCD_PAT_ACCELERATING, (size_t)n, h->stream));
-        if (id) { int rc = copy_in(h, h->in_id, id, (size_t)n * sizeof(u32), src); if (rc) return rc; }
+        if (type) { int rc = copy_in(h, h->in_type, type, (size_t)n, src, on); if (rc) return rc; }
+        else CUDA_TRY(h, cudaMemsetAsync(h->in_type, 0, (size_t)n, on));
+        CUDA_TRY(h, cudaMemsetAsync(h->in_pattern, RCD_PAT_ACCELERATING, (size_t)n, on));
+        if (id) { int rc = copy_in(h, h->in_id, id, (size_t)n * sizeof(u32), src, on); if (rc) return rc; }
         else {
-            k_iota<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->in_id, (u32)n);
+            k_iota<<<(unsigned)((n + 255) / 256), 256, 0, on>>>(h->in_id, (u32)n);
             KERNEL_CHECK(h);
         }
     }
-    stage_end(h, RCD_STAGE_UPLOAD);
+    stage_end(h, RCD_STAGE_UPLOAD, on);
+    {
+        int rc = upload_issued(h, on);
+        if (rc) return rc;
+    }
     h->n = n;
     h->n_owned = n;
     h->index_valid = false;
@@ -525,8 +608,13 @@ int rcd_set_patterns(rcd_handle h, uint64_t n, const uint8_t *pattern, int32_t s
     if (n > h->n) return fail(h, RCD_EINVAL, "rcd_set_patterns: n exceeds the uploaded object count");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (n) {
-        if (pattern) { int rc = copy_in(h, h->in_pattern, pattern, (size_t)n, src); if (rc) return rc; }
-        else CUDA_TRY(h, cudaMemsetAsync(h->in_pattern, RCD_PAT_ACCELERATING, (size_t)n, h->stream));
+        cudaStream_t on = nullptr;
+        int rc = upload_stream(h, pattern ? src : RCD_SRC_HOST, &on);
+        if (rc) return rc;
+        if (pattern) { rc = copy_in(h, h->in_pattern, pattern, (size_t)n, src, on); if (rc) return rc; }
+        else CUDA_TRY(h, cudaMemsetAsync(h->in_pattern, RCD_PAT_ACCELERATING, (size_t)n, on));
+        rc = upload_issued(h, on);
+        if (rc) return rc;
     }
     h->index_valid = false;  // the pattern is packed into the cell-ordered state
     h->frame_done = false;
@@ -566,6 +654,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
     if (!append && h->flip_pending) {  // the previous frame is being delivered: write into the twin buffers
         std::swap(h->out, h->out_alt);
         std::swap(h->counters, h->counters_alt);
+        std::swap(h->risk_count, h->risk_count_alt);
         h->flip_pending = false;
     }
     h->frame_done = false;
@@ -584,6 +673,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
     stage_begin(h, RCD_STAGE_PAIRS);
     if (!append) CUDA_TRY(h, cudaMemsetAsync(h->counters, 0, sizeof(Counters), h->stream));
     if (h->n) CUDA_TRY(h, cudaMemsetAsync(h->cand_count, 0, (size_t)h->n * sizeof(u32), h->stream));
+    if (h->n && !append) CUDA_TRY(h, cudaMemsetAsync(h->risk_count, 0, (size_t)h->n * sizeof(u32), h->stream));
     if (h->n && h->n_owned) {
         PairParams P;
         P.n = (u32)h->n;
@@ -592,7 +682,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         P.P0 = h->P0; P.P1 = h->P1; P.P2 = h->P2;
         P.qorder = h->qvals[h->q_sorted_buf];
         P.sorted_slot = h->sorted_slot;
-        P.in_id = h->in_id;
+        P.sorted_id = h->sorted_id;
         P.cell_begin = h->cell_begin;
         P.R = search_radius;
         P.T = time_window;
@@ -613,6 +703,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         P.out_cap = h->max_pairs;
         P.counters = h->counters;
         P.cand_count = h->cand_count;
+        P.risk_count = h->risk_count;
         P.ntiles = (u32)((h->n_owned + TQ - 1) / TQ);
         P.tile_counter = h->pair_tile_counter;
         P.qa = h->qa; P.qa_fill = h->qa_fill; P.qa_blocks_cap = h->qa_blocks_cap;
@@ -723,6 +814,11 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     if (!want) return step_impl(h, mode, search_radius, time_window);
     const bool append = (mode & RCD_STEP_APPEND) != 0;
     const bool flip = !append && h->flip_pending;
+    {   // (events of other streams stay outside the graph: order the stream before the launch / the capture)
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        int rcw = wait_upload(h);
+        if (rcw) return rcw;
+    }
     rcd_handle_s::StepKey key;
     key.mode = mode; key.R = search_radius; key.T = time_window;
     key.pt = h->cn_prediction_time; key.thr = h->cn_risk_threshold;
@@ -741,10 +837,15 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         if (flip) {
             std::swap(h->out, h->out_alt);
             std::swap(h->counters, h->counters_alt);
+            std::swap(h->risk_count, h->risk_count_alt);
             h->flip_pending = false;
         }
         h->frame_done = false;
         CUDA_TRY(h, cudaGraphLaunch(g.exec, h->stream));
+        {
+            int rcr = release_inputs(h);  // (at the end of the step: a graph has no events inside)
+            if (rcr) return rcr;
+        }
         h->launches = (append ? h->launches : 0) + g.launches;
         h->grid = g.grid;
         h->index_valid = true;
@@ -768,12 +869,13 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     // ---- second sighting: capture ----
     CUDA_TRY(h, cudaSetDevice(h->device));
     struct Saved {
-        rcd_pair *out, *out_alt; Counters *counters, *counters_alt; bool flip_pending, frame_done, index_valid;
+        rcd_pair *out, *out_alt; Counters *counters, *counters_alt; u32 *risk_count, *risk_count_alt; bool flip_pending, frame_done, index_valid;
         float index_cell_req; int sorted_buf, last_mode, stage_mode; GridParams grid; u64 launches; int qorder_kind, q_sorted_buf;
-    } pre = {h->out, h->out_alt, h->counters, h->counters_alt, h->flip_pending, h->frame_done, h->index_valid,
+    } pre = {h->out, h->out_alt, h->counters, h->counters_alt, h->risk_count, h->risk_count_alt, h->flip_pending, h->frame_done, h->index_valid,
              h->index_cell_req, h->sorted_buf, h->last_mode, h->stage_mode, h->grid, h->launches, h->qorder_kind, h->q_sorted_buf};
     auto restore = [&]() {
         h->out = pre.out; h->out_alt = pre.out_alt; h->counters = pre.counters; h->counters_alt = pre.counters_alt;
+        h->risk_count = pre.risk_count; h->risk_count_alt = pre.risk_count_alt;
         h->flip_pending = pre.flip_pending; h->frame_done = pre.frame_done; h->index_valid = pre.index_valid;
         h->index_cell_req = pre.index_cell_req; h->sorted_buf = pre.sorted_buf; h->last_mode = pre.last_mode;
         h->stage_mode = pre.stage_mode; h->grid = pre.grid; h->launches = pre.launches;
@@ -784,7 +886,9 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
     cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
     int rc = RCD_OK;
     if (e == cudaSuccess) {
+        h->capturing = true;
         rc = step_impl(h, mode, search_radius, time_window);
+        h->capturing = false;
         cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
         if (e2 != cudaSuccess) e = e2;
     }
@@ -803,6 +907,10 @@ int rcd_step(rcd_handle h, int32_t mode, float search_radius, float time_window)
         restore();
         h->graph_broken = true;
         return step_impl(h, mode, search_radius, time_window);
+    }
+    {
+        int rcr = release_inputs(h);
+        if (rcr) return rcr;
     }
     rcd_handle_s::StepGraph &slot = h->graphs[h->graph_next];
     h->graph_next = (h->graph_next + 1) % 4;
@@ -921,23 +1029,43 @@ int rcd_download_unsorted(rcd_handle h, rcd_pair *out, uint64_t cap, uint64_t *n
     return download_impl(h, out, cap, n_out, false);
 }
 
-int rcd_download_begin(rcd_handle h, rcd_pair *out, uint64_t cap) {
-    if (!h || (cap && !out)) return RCD_EINVAL;
-    if (!h->frame_done) return fail(h, RCD_ESTATE, "rcd_download_begin: no frame has been stepped");
-    if (h->download_pending) return fail(h, RCD_ESTATE, "rcd_download_begin: a download is already in flight");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+// twin buffers + copy stream of the pipelined deliveries (allocated at the first use)
+static int delivery_ready(rcd_handle h) {
     if (!h->out_alt) {
         CUDA_TRY(h, dev_alloc(&h->out_alt, (size_t)h->max_pairs));
         CUDA_TRY(h, dev_alloc(&h->counters_alt, 1));
+        CUDA_TRY(h, dev_alloc(&h->risk_count_alt, (size_t)h->cap));
         CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void **>(&h->pend_counters_host), sizeof(Counters)));
+        CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void **>(&h->pend_alert_counters_host), sizeof(AlertCounters)));
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->pend_event, cudaEventDisableTiming));
     }
+    return RCD_OK;
+}
+static void counts_out(rcd_handle h, const Counters &c, rcd_counts_t *counts) {
+    if (!counts) return;
+    counts->n_objects = h->pend_n;
+    counts->n_owned = h->pend_n_owned;
+    counts->n_candidates = c.n_candidates;
+    counts->n_potential = c.n_potential;
+    counts->n_pairs = c.n_pairs;
+    counts->n_high_risk = c.n_high_risk;
+    counts->n_written = std::min<u64>(c.n_pairs, h->max_pairs);
+    for (int k = 0; k < 4; ++k) counts->n_alerts[k] = c.n_alerts[k];
+    counts->n_exact = c.n_exact;
+    counts->n_fallback = c.n_fallback;
+}
+static int delivery_begin(rcd_handle h, const char *who) {
+    if (!h->frame_done) return fail(h, RCD_ESTATE, std::string(who) + ": no frame has been stepped");
+    if (h->download_pending) return fail(h, RCD_ESTATE, std::string(who) + ": a delivery is already in flight");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    return delivery_ready(h);
+}
+static int delivery_issued(rcd_handle h) {  // the frame's totals ride along; later work goes to the twin buffers
     CUDA_TRY(h, cudaMemcpyAsync(h->pend_counters_host, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaEventRecord(h->pend_event, h->stream));
     h->pend_dev = h->out;
-    h->pend_out = out;
-    h->pend_cap = cap;
+    h->pend_risk = h->risk_count;
     h->pend_n = h->n;
     h->pend_n_owned = h->n_owned;
     h->download_pending = true;
@@ -945,31 +1073,59 @@ int rcd_download_begin(rcd_handle h, rcd_pair *out, uint64_t cap) {
     return RCD_OK;
 }
 
+int rcd_download_begin(rcd_handle h, rcd_pair *out, uint64_t cap) {
+    if (!h || (cap && !out)) return RCD_EINVAL;
+    int rc = delivery_begin(h, "rcd_download_begin");
+    if (rc) return rc;
+    h->pend_kind = 0;
+    h->pend_out = out;
+    h->pend_cap = cap;
+    return delivery_issued(h);
+}
+
+int rcd_download_begin_compact(rcd_handle h, rcd_pair_compact *out, uint64_t cap) {
+    if (!h || (cap && !out)) return RCD_EINVAL;
+    int rc = delivery_begin(h, "rcd_download_begin_compact");
+    if (rc) return rc;
+    if (!h->compact_dev) CUDA_TRY(h, dev_alloc(&h->compact_dev, (size_t)h->max_pairs));
+    // (one scratch buffer: the narrowing of frame k + 1 runs on the handle's stream after frame k's copy was issued
+    // and waited for by rcd_download_finish -- one delivery in flight at a time)
+    k_compact_pairs<<<(unsigned)h->stage_blocks_sms * 8, 256, 0, h->stream>>>(h->out, h->max_pairs, &h->counters->n_pairs, h->compact_dev);
+    KERNEL_CHECK(h);
+    h->pend_kind = 1;
+    h->pend_out_compact = out;
+    h->pend_cap = cap;
+    return delivery_issued(h);
+}
+
 int rcd_download_finish(rcd_handle h, rcd_counts_t *counts, uint64_t *n_out) {
     if (!h || !n_out) return RCD_EINVAL;
-    if (!h->download_pending) return fail(h, RCD_ESTATE, "rcd_download_finish: no download in flight");
+    if (!h->download_pending || h->pend_kind == 2) return fail(h, RCD_ESTATE, "rcd_download_finish: no download in flight");
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaEventSynchronize(h->pend_event));  // the frame is complete; later work keeps running
     const Counters &c = *h->pend_counters_host;
     const u64 m = std::min<u64>(std::min<u64>(c.n_pairs, h->max_pairs), h->pend_cap);
     if (m) {
-        CUDA_TRY(h, cudaMemcpyAsync(h->pend_out, h->pend_dev, (size_t)m * sizeof(rcd_pair), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (h->pend_kind == 0)
+            CUDA_TRY(h, cudaMemcpyAsync(h->pend_out, h->pend_dev, (size_t)m * sizeof(rcd_pair), cudaMemcpyDeviceToHost, h->copy_stream));
+        else
+            CUDA_TRY(h, cudaMemcpyAsync(h->pend_out_compact, h->compact_dev, (size_t)m * sizeof(rcd_pair_compact),
+                                        cudaMemcpyDeviceToHost, h->copy_stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
     }
-    if (counts) {
-        counts->n_objects = h->pend_n;
-        counts->n_owned = h->pend_n_owned;
-        counts->n_candidates = c.n_candidates;
-        counts->n_potential = c.n_potential;
-        counts->n_pairs = c.n_pairs;
-        counts->n_high_risk = c.n_high_risk;
-        counts->n_written = std::min<u64>(c.n_pairs, h->max_pairs);
-        for (int k = 0; k < 4; ++k) counts->n_alerts[k] = c.n_alerts[k];
-        counts->n_exact = c.n_exact;
-        counts->n_fallback = c.n_fallback;
-    }
+    counts_out(h, c, counts);
     *n_out = m;
     h->download_pending = false;
+    return RCD_OK;
+}
+
+int rcd_download_risk_counts(rcd_handle h, uint32_t *out, uint64_t n) {
+    if (!h || (n && !out)) return RCD_EINVAL;
+    if (!h->frame_done) return fail(h, RCD_ESTATE, "rcd_download_risk_counts: no frame has been stepped");
+    if (n > h->n) return fail(h, RCD_EINVAL, "rcd_download_risk_counts: n exceeds the object count");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (n) CUDA_TRY(h, cudaMemcpyAsync(out, h->risk_count, (size_t)n * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return RCD_OK;
 }
 
@@ -990,6 +1146,10 @@ int rcd_query_radius(rcd_handle h, uint64_t nq, const float *qx, const float *qy
     for (u64 q = 0; q <= nq; ++q) offsets[q] = 0;
     if (nq == 0 || h->n == 0) return RCD_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    {
+        int rcw = wait_upload(h);
+        if (rcw) return rcw;
+    }
     // reuse the index of the last frame if there is one, else build one with the default cell
     int rc = build_index(h, h->index_valid ? h->index_cell_req : std::max(radius, 1.0f));
     if (rc) return rc;
@@ -1200,6 +1360,8 @@ int rcd_history_classify(rcd_handle h, uint8_t *pattern_out) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc = history_ready(h, "rcd_history_classify");
     if (rc) return rc;
+    rc = wait_upload(h);
+    if (rc) return rc;
     if (h->n) {
         k_history_classify<<<(unsigned)((h->n + 127) / 128), 128, 0, h->stream>>>((u32)h->n, h->traj, h->traj_count,
                                                                                   (u32)h->cap, h->traj_len, h->in_pattern);
@@ -1226,6 +1388,10 @@ int rcd_apply_records(rcd_handle h, uint64_t n, const rcd_record *records, uint3
         if (rc) return rc;
     }
     const bool hist = append_history && h->traj;
+    {
+        int rcw = wait_upload(h);
+        if (rcw) return rcw;
+    }
     for (int m = 0; m < 3; ++m)
         for (int s = 0; s < RCD_NUM_STAGES; ++s) h->stages[m][s].used = false;
     h->stage_mode = 0;
@@ -1254,6 +1420,10 @@ int rcd_apply_records(rcd_handle h, uint64_t n, const rcd_record *records, uint3
         ++h->launches;
     }
     stage_end(h, RCD_STAGE_UPLOAD);
+    if (e == cudaSuccess) {
+        int rcr = release_inputs(h);
+        if (rcr) return rcr;
+    }
     if (staged) {
         if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);  // the staging buffer is freed below
         cudaFree(staged);
@@ -1300,9 +1470,9 @@ int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts) {
     if (!h || max_alerts == 0 || max_alerts > (1ull << 31)) return h ? fail(h, RCD_EINVAL, "rcd_alerts_configure: max_alerts must be in [1, 2^31]") : RCD_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(h->alert_tab[0]); cudaFree(h->alert_tab[1]); cudaFree(h->alert_ev); cudaFree(h->alert_counters);
+    cudaFree(h->alert_tab[0]); cudaFree(h->alert_tab[1]); cudaFree(h->alert_ev); cudaFree(h->alert_ev_alt); cudaFree(h->alert_counters);
     if (h->alert_counters_host) cudaFreeHost(h->alert_counters_host);
-    h->alert_tab[0] = h->alert_tab[1] = nullptr; h->alert_ev = nullptr; h->alert_counters = nullptr; h->alert_counters_host = nullptr;
+    h->alert_tab[0] = h->alert_tab[1] = nullptr; h->alert_ev = h->alert_ev_alt = nullptr; h->alert_counters = nullptr; h->alert_counters_host = nullptr;
     h->alert_cap = 0;
     u64 cap = 1024;
     while (cap < 2 * max_alerts) cap <<= 1;  // load factor <= 0.5
@@ -1319,21 +1489,64 @@ int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts) {
     return RCD_OK;
 }
 
+// fold pairs into the table (both passes), events -> h->alert_ev
+static int alerts_enqueue_update(rcd_handle h, const rcd_pair *dev_pairs, u64 n_max, const unsigned long long *n_dev, double now,
+                                 int32_t report_refreshed) {
+    if (n_max == 0) return RCD_OK;
+    int sms = 0;
+    CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    const unsigned blocks = (unsigned)std::min<u64>((n_max + ALERT_THREADS - 1) / ALERT_THREADS, (u64)std::max(1, sms) * 8);
+    for (int pass = 0; pass < 2; ++pass) {
+        k_alert_update<<<blocks, ALERT_THREADS, 0, h->stream>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
+                                                                h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
+                                                                h->alert_counters, report_refreshed);
+        KERNEL_CHECK(h);
+    }
+    return RCD_OK;
+}
 static int alerts_update_impl(rcd_handle h, const rcd_pair *dev_pairs, u64 n_max, const unsigned long long *n_dev, double now,
                               int32_t report_refreshed, rcd_alert_event *events, uint64_t cap, rcd_alert_stats *stats) {
-    return alerts_call(h, events, cap, stats, false, [&]() -> int {
-        if (n_max == 0) return RCD_OK;
-        int sms = 0;
-        CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-        const unsigned blocks = (unsigned)std::min<u64>((n_max + ALERT_THREADS - 1) / ALERT_THREADS, (u64)std::max(1, sms) * 8);
-        for (int pass = 0; pass < 2; ++pass) {
-            k_alert_update<<<blocks, ALERT_THREADS, 0, h->stream>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
-                                                                    h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
-                                                                    h->alert_counters, report_refreshed);
-            KERNEL_CHECK(h);
-        }
-        return RCD_OK;
-    });
+    return alerts_call(h, events, cap, stats, false,
+                       [&]() -> int { return alerts_enqueue_update(h, dev_pairs, n_max, n_dev, now, report_refreshed); });
+}
+
+int rcd_summary_begin(rcd_handle h, double now, int32_t report_refreshed) {
+    if (!h) return RCD_EINVAL;
+    int rc = alerts_ready(h, "rcd_summary_begin");
+    if (rc) return rc;
+    rc = delivery_begin(h, "rcd_summary_begin");
+    if (rc) return rc;
+    if (!h->alert_ev_alt) CUDA_TRY(h, dev_alloc(&h->alert_ev_alt, (size_t)h->alert_ev_cap));
+    std::swap(h->alert_ev, h->alert_ev_alt);  // the events of the previous summary may still be on their way to the host
+    CUDA_TRY(h, cudaMemsetAsync(h->alert_counters, 0, offsetof(AlertCounters, n_live), h->stream));
+    rc = alerts_enqueue_update(h, h->out, h->max_pairs, &h->counters->n_pairs, now, report_refreshed);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->pend_alert_counters_host, h->alert_counters, sizeof(AlertCounters), cudaMemcpyDeviceToHost, h->stream));
+    h->pend_kind = 2;
+    h->pend_ev = h->alert_ev;
+    return delivery_issued(h);
+}
+
+int rcd_summary_finish(rcd_handle h, rcd_alert_event *events, uint64_t cap, uint64_t *n_events, rcd_alert_stats *stats,
+                       uint32_t *risk_counts, uint64_t n, rcd_counts_t *counts) {
+    if (!h || (cap && !events) || (n && !risk_counts)) return RCD_EINVAL;
+    if (!h->download_pending || h->pend_kind != 2) return fail(h, RCD_ESTATE, "rcd_summary_finish: no summary in flight");
+    if (n > h->pend_n) return fail(h, RCD_EINVAL, "rcd_summary_finish: n exceeds the frame's object count");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventSynchronize(h->pend_event));
+    const AlertCounters &ac = *h->pend_alert_counters_host;
+    const u64 n_ev = std::min<u64>(std::min<u64>(ac.n_events, h->alert_ev_cap), cap);
+    if (n_ev) CUDA_TRY(h, cudaMemcpyAsync(events, h->pend_ev, (size_t)n_ev * sizeof(rcd_alert_event), cudaMemcpyDeviceToHost, h->copy_stream));
+    if (n) CUDA_TRY(h, cudaMemcpyAsync(risk_counts, h->pend_risk, (size_t)n * sizeof(u32), cudaMemcpyDeviceToHost, h->copy_stream));
+    if (n_ev || n) CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+    if (n_events) *n_events = n_ev;
+    if (stats) {
+        stats->n_events = ac.n_events; stats->n_created = ac.n_created; stats->n_changed = ac.n_changed;
+        stats->n_refreshed = ac.n_refreshed; stats->n_expired = ac.n_expired; stats->n_live = ac.n_live; stats->n_dropped = ac.n_dropped;
+    }
+    counts_out(h, *h->pend_counters_host, counts);
+    h->download_pending = false;
+    return RCD_OK;
 }
 
 int rcd_alerts_update(rcd_handle h, double now, int32_t report_refreshed, rcd_alert_event *events, uint64_t cap,
@@ -1436,6 +1649,10 @@ int rcd_halo_pack(rcd_handle h, int32_t n_peers, int32_t self, const float *slab
     if (!h || !slab_lo || !slab_hi || !counts || n_peers < 1 || n_peers > MAX_PEERS || self < 0 || self >= n_peers)
         return fail(h, RCD_EINVAL, "rcd_halo_pack: bad arguments");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    {
+        int rcw = wait_upload(h);
+        if (rcw) return rcw;
+    }
     for (int p = 0; p < n_peers; ++p) counts[p] = 0;
     if (h->n_owned == 0) return RCD_OK;
     SlabParams sp;
@@ -1481,12 +1698,20 @@ int rcd_halo_append(rcd_handle h, const void *records, uint64_t n_records) {
     if (h->n + n_records > h->cap) return fail(h, RCD_ECAPACITY, "rcd_halo_append: exceeds max_objects");
     if (n_records == 0) return RCD_OK;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    {
+        int rcw = wait_upload(h);
+        if (rcw) return rcw;
+    }
     MutableState st;
     for (int k = 0; k < 11; ++k) st.f[k] = h->in_f[k];
     st.type = h->in_type; st.pattern = h->in_pattern; st.id = h->in_id;
     k_halo_append<<<(unsigned)((n_records + 255) / 256), 256, 0, h->stream>>>(static_cast<const u32 *>(records),
                                                                              (u32)n_records, (u32)h->n, st);
     KERNEL_CHECK(h);
+    {
+        int rcr = release_inputs(h);
+        if (rcr) return rcr;
+    }
     h->n += n_records;
     h->index_valid = false;
     h->frame_done = false;
@@ -1503,6 +1728,7 @@ int rcd_stage_ms(rcd_handle h, int32_t mode, float *ms) {
     if (!h || !ms || mode < 0 || mode > 2) return RCD_EINVAL;
     if (!(h->flags & RCD_FLAG_PROFILE)) return fail(h, RCD_ESTATE, "rcd_stage_ms: handle was created without RCD_FLAG_PROFILE");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->up_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (int s = 0; s < RCD_NUM_STAGES; ++s) {
         ms[s] = 0.0f;
@@ -1525,6 +1751,7 @@ int rcd_launch_count(rcd_handle h, uint64_t *n) {
 int rcd_sync(rcd_handle h) {
     if (!h) return RCD_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->up_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return RCD_OK;
 }

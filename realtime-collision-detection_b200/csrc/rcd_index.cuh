@@ -275,17 +275,19 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
 
 // -------------------------------------------------------------------------------------------------
 // K4: gather the packed planes into cell order.
-// Algorithmic bytes: 8 N (key + perm) + 48 N gathered + 52 N written = 108 N;
+// Algorithmic bytes: 4 N (perm) + 52 N gathered (record + caller id) + 56 N written = 112 N;
 // a 48-byte record spans exactly two 32-byte sectors, so DRAM traffic is about 124 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int REORDER_THREADS = 256;
 
 __global__ void __launch_bounds__(REORDER_THREADS)
-k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U, float4 *__restrict__ P0,
-          float4 *__restrict__ P1, float4 *__restrict__ P2, u32 *__restrict__ sorted_slot) {
+k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U, const u32 *__restrict__ in_id,
+          float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2, u32 *__restrict__ sorted_slot,
+          u32 *__restrict__ sorted_id) {
     u32 s = blockIdx.x * REORDER_THREADS + threadIdx.x;
     if (s >= n) return;
     const u32 src = __ldcs(perm + s);
+    sorted_id[s] = __ldg(in_id + src);
     const float4 *rec = U + 3 * (size_t)src;
     const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
     P0[s] = a;

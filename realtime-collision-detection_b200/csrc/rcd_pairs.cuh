@@ -74,7 +74,7 @@ struct PairParams {
     const float4 *P0, *P1, *P2;
     const u32 *qorder;       // query order -> position in cell order
     const u32 *sorted_slot;  // cell order -> upload slot
-    const u32 *in_id;        // upload slot -> caller id
+    const u32 *sorted_id;    // cell order -> caller id
     const u32 *cell_begin;   // [ncells + 1]
     float R, T;              // search radius / time window (detect)
     int steps;               // int(T / 0.1)
@@ -87,6 +87,7 @@ struct PairParams {
     Counters *counters;
     u32 *tile_counter;
     u32 *cand_count;         // per upload slot
+    u32 *risk_count;         // per upload slot: risks emitted for the object as the querying vehicle
     uint2 *qa;               // pair queue k_pairs -> k_narrow: {si | flags, sj}
     u32 *qa_fill;            // entries used in every QA block
     u32 qa_blocks_cap;
@@ -199,10 +200,11 @@ __device__ __forceinline__ EmitRec no_rec() {
 
 // store one pair at `pos` (three 16-byte stores; rcd_pair is 48 bytes)
 __device__ __forceinline__ void store_pair(const PairParams &P, unsigned long long pos, const EmitRec &e) {
+    atomicAdd(&P.risk_count[P.sorted_slot[e.si]], 1u);
     if (pos >= P.out_cap) return;
     rcd_pair r;
-    r.i = P.in_id[P.sorted_slot[e.si]];
-    r.j = P.in_id[P.sorted_slot[e.sj]];
+    r.i = P.sorted_id[e.si];
+    r.j = P.sorted_id[e.sj];
     r.ttc = e.ttc; r.distance = e.dist; r.rel_speed = e.rs; r.risk = e.risk;
     r.cx = e.cx; r.cy = e.cy; r.cz = e.cz;
     r.t_closest = e.tcl; r.d_closest = e.dcl;
@@ -1600,6 +1602,23 @@ k_query_radius(u32 nq, const float *__restrict__ qx, const float *__restrict__ q
                 }
             }
         }
+}
+
+// rcd_pair (48 bytes) -> rcd_pair_compact (32 bytes), before the records cross the bus
+__global__ void __launch_bounds__(256)
+k_compact_pairs(const rcd_pair *__restrict__ in, unsigned long long n_max, const unsigned long long *__restrict__ n_dev,
+                rcd_pair_compact *__restrict__ out) {
+    const unsigned long long n = min(*n_dev, n_max);
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        const rcd_pair p = in[k];
+        rcd_pair_compact c;
+        c.i = p.i; c.j = p.j; c.ttc = p.ttc; c.distance = p.distance; c.rel_speed = p.rel_speed; c.risk = p.risk;
+        c.t_closest = p.t_closest; c.priority = p.priority; c.offset = p.offset; c.predicted = p.predicted; c.reserved = 0;
+        const uint4 *src = reinterpret_cast<const uint4 *>(&c);
+        uint4 *dst = reinterpret_cast<uint4 *>(out + k);
+        dst[0] = src[0]; dst[1] = src[1];
+    }
 }
 
 // -------------------------------------------------------------------------------------------------

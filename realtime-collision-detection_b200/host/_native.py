@@ -37,7 +37,8 @@ SYMBOLS = (
     "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
     "rcd_ingest_counts", "rcd_ingest_set_limit", "rcd_ingest_rejected", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
     "rcd_alerts_configure", "rcd_alerts_update", "rcd_alerts_update_pairs", "rcd_alerts_expire",
-    "rcd_alerts_acknowledge", "rcd_alerts_download", "rcd_download_begin", "rcd_download_finish", "rcd_graph_replays", "rcd_pair_exact", "rcd_risk_assessment",
+    "rcd_alerts_acknowledge", "rcd_alerts_download", "rcd_download_begin", "rcd_download_finish", "rcd_graph_replays", "rcd_pair_exact", "rcd_risk_assessment", "rcd_download_begin_compact", "rcd_summary_begin", "rcd_summary_finish",
+    "rcd_download_risk_counts",
 )
 
 
@@ -60,6 +61,12 @@ PAIR_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("ttc", "<f4"), ("distance", 
                        ("d_closest", "<f4"), ("priority", "i1"), ("offset", "u1"), ("predicted", "u1"),
                        ("reserved", "u1")])
 assert PAIR_DTYPE.itemsize == 48
+
+# numpy mirror of rcd_pair_compact (32 bytes)
+PAIR_COMPACT_DTYPE = np.dtype([("i", "<u4"), ("j", "<u4"), ("ttc", "<f4"), ("distance", "<f4"), ("rel_speed", "<f4"),
+                               ("risk", "<f4"), ("t_closest", "<f4"), ("priority", "i1"), ("offset", "u1"),
+                               ("predicted", "u1"), ("reserved", "u1")])
+assert PAIR_COMPACT_DTYPE.itemsize == 32
 
 # numpy mirrors of rcd_object (48 bytes) and rcd_pair_exact_result (72 bytes)
 OBJECT_DTYPE = np.dtype([(k, "<f4") for k in ("px", "py", "pz", "vx", "vy", "vz", "ax", "ay", "az", "size", "heading")] +
@@ -145,6 +152,11 @@ def load() -> ctypes.CDLL:
     if hasattr(L, "rcd_graph_replays"):
         L.rcd_graph_replays.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_sync.argtypes = [vp]
+    if hasattr(L, "rcd_summary_begin"):
+        L.rcd_download_begin_compact.argtypes = [vp, vp, u64]
+        L.rcd_summary_begin.argtypes = [vp, ctypes.c_double, i32]
+        L.rcd_summary_finish.argtypes = [vp, vp, u64, ctypes.POINTER(u64), vp, vp, u64, vp]
+        L.rcd_download_risk_counts.argtypes = [vp, vp, u64]
     if hasattr(L, "rcd_pair_exact"):
         L.rcd_pair_exact.argtypes = [vp, u64, vp, vp, ctypes.c_double, ctypes.c_double, vp]
         L.rcd_risk_assessment.argtypes = [vp, u64, vp, vp]

@@ -187,6 +187,33 @@ class FrameEngine:
         d["n_alerts"] = [int(v) for v in c.n_alerts]
         return out[: int(n.value)], d
 
+    def download_begin_compact(self, out: np.ndarray) -> None:
+        """Like download_begin with 32-byte records (``PAIR_COMPACT_DTYPE``): narrowed on the device first."""
+        self._pending_out = out
+        N.check(self._lib.rcd_download_begin_compact(self._h, _vp(out), int(out.shape[0])), self._h)
+
+    def summary_begin(self, now: float, report_refreshed: bool = False) -> None:
+        """Start the summary delivery of the frame just stepped (alert changes + per-object risk counts) and
+        return at once; needs alerts_configure."""
+        N.check(self._lib.rcd_summary_begin(self._h, float(now), 1 if report_refreshed else 0), self._h)
+
+    def summary_finish(self, events: Optional[np.ndarray] = None, risk_counts: Optional[np.ndarray] = None):
+        """Wait for the pending summary: (events, alert stats, risk counts or None, frame totals)."""
+        ev = self._alert_events(None) if events is None else events
+        st, c, n_ev = N.RcdAlertStats(), N.RcdCounts(), ctypes.c_uint64()
+        nrc = 0 if risk_counts is None else int(risk_counts.shape[0])
+        N.check(self._lib.rcd_summary_finish(self._h, _vp(ev), ev.shape[0], ctypes.byref(n_ev), ctypes.byref(st),
+                                             _vp(risk_counts) if nrc else None, nrc, ctypes.byref(c)), self._h)
+        d = {k: int(getattr(c, k)) for k, _ in N.RcdCounts._fields_ if k != "n_alerts"}
+        d["n_alerts"] = [int(v) for v in c.n_alerts]
+        return ev[: int(n_ev.value)], self._alert_stats(st), risk_counts, d
+
+    def risk_counts(self) -> np.ndarray:
+        """Risks emitted per object (as the querying vehicle) in the last frame, upload order."""
+        out = np.zeros(self.n, np.uint32)
+        N.check(self._lib.rcd_download_risk_counts(self._h, _vp(out), out.shape[0]), self._h)
+        return out
+
     def candidate_counts(self) -> np.ndarray:
         out = np.zeros(int(self.counts()["n_objects"]), np.uint32)
         N.check(self._lib.rcd_download_candidate_counts(self._h, _vp(out), out.shape[0]), self._h)

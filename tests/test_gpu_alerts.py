@@ -170,3 +170,52 @@ def test_the_same_risk_twice_in_one_pass_is_create_then_silent_refresh():
         # the next frame sees complete entries
         ev, st = e.alerts_update_pairs(base, 101.0)
         assert st["n_refreshed"] == n and st["n_created"] == 0 and st["n_changed"] == 0 and len(ev) == 0
+
+
+def test_summary_delivery_equals_the_synchronous_calls_frame_by_frame():
+    """rcd_summary_begin / _finish: frame k's alert changes, per-object risk counts and totals arrive complete
+    although frame k + 1 was uploaded and stepped in between; they equal rcd_alerts_update + the pair list of a
+    second engine that runs the same frames one at a time.  Compact pair records equal the narrowed full records."""
+    from rcd_b200.host import _native as N, workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    n = 6000
+    rng = np.random.default_rng(3)
+    frames = [W.uniform_frame(n, 201, map_size=1000.0, drone_fraction=0.3)]
+    for _ in range(4):
+        frames.append(W.advance(frames[-1], 0.3, rng, map_size=(1000.0, 1000.0)))
+    pat = W.random_patterns(n, 202)
+    key = lambda ev: sorted((int(e["i"]), int(e["j"]), int(e["kind"]), int(e["priority"]), int(e["old_priority"]),
+                             float(e["risk"]), float(e["ttc"]), float(e["distance"]), float(e["timestamp"])) for e in ev)
+    with FrameEngine(n, 1 << 20) as ref, FrameEngine(n, 1 << 20) as e:
+        ref.alerts_configure(1 << 18)
+        e.alerts_configure(1 << 18)
+        want, got = [], []
+        for k, f in enumerate(frames):
+            ref.upload(f); ref.set_patterns(pat); ref.step(N.MODE_PREDICT, with_detect=True)
+            pairs = ref.download()
+            ev, st = ref.alerts_update(100.0 + k)
+            assert np.array_equal(ref.risk_counts(), np.bincount(pairs["i"], minlength=n))
+            want.append((key(ev), st, np.bincount(pairs["i"], minlength=n).astype(np.uint32), ref.counts()))
+            e.upload(f); e.set_patterns(pat); e.step(N.MODE_PREDICT, with_detect=True)
+            if k:
+                got.append(e.summary_finish(risk_counts=np.zeros(n, np.uint32)))
+            e.summary_begin(100.0 + k)
+            with pytest.raises(N.NativeError):
+                e.download_begin(np.zeros(16, N.PAIR_DTYPE))  # one delivery at a time
+        got.append(e.summary_finish(risk_counts=np.zeros(n, np.uint32)))
+        assert sum(len(w[0]) for w in want) > 1000
+        for (w_ev, w_st, w_rc, w_c), (g_ev, g_st, g_rc, g_c) in zip(want, got):
+            assert key(g_ev) == w_ev
+            assert g_st == w_st
+            assert np.array_equal(g_rc, w_rc)
+            for name in ("n_pairs", "n_candidates", "n_potential", "n_high_risk", "n_alerts", "n_objects"):
+                assert g_c[name] == w_c[name], name
+        # compact records
+        full = ref.download()
+        buf = np.zeros(len(full) + 8, dtype=N.PAIR_COMPACT_DTYPE)
+        ref.download_begin_compact(buf)
+        compact, counts = ref.download_finish()
+        assert counts["n_pairs"] == len(full) == len(compact)
+        compact = np.sort(compact, order=["i", "j", "predicted"], kind="stable")
+        for name in ("i", "j", "ttc", "distance", "rel_speed", "risk", "t_closest", "priority", "offset", "predicted"):
+            assert np.array_equal(compact[name], full[name]), name
