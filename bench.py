@@ -10,18 +10,27 @@ A *step* is one frame = what the reference's perf harness times
 detect_collisions for every object and predict_collisions for every object, deliver the results.
 
 Workload (default): BASELINE.json configs[3] -- 1M mixed vehicles+drones, 3-D, clustered in 50
-urban hotspots on a 31.6 km map (reference generator law r = U*radius).  With N GPUs the frame is
-N x 1M objects on a map of N times the area (same density, 50 hotspots per 1M objects): weak
-scaling.  Space is cut into N x-slabs of equal estimated pair work; every frame each GPU packs the
-objects within the halo width of the other slabs and exchanges them with NCCL (all_to_all over
-NVLink), then runs the frame on owned + halo objects (results are emitted by the owner only).
+urban hotspots on a 31.6 km map (reference generator law r = U*radius).  With N GPUs the headline
+frame is N x 1M objects on a map of N times the area (same density, 50 hotspots per 1M objects):
+weak scaling.  Space is cut into N x-slabs; the cuts start at equal estimated pair work and are
+moved during warm-up from the measured frame time of every slab (re-balancing, host/slabs.py);
+every frame each GPU packs the objects within the halo width of the other slabs into fixed-size
+regions and trades them with one NCCL all_to_all on the engine's stream (nothing in the frame
+waits for the host), then runs the frame on owned + halo objects; results are emitted by the owner.
 
 value : whole-job object-updates/s with the frame's object state already in HBM when the timed
         region starts (the engine still ingests it device-to-device every frame).  Timed on the
         device with CUDA events on the engine's stream, max over ranks; L2 is flushed (256 MiB
         write) before every timed frame.
-e2e   : same metric through the public host API: pinned host SoA arrays -> H2D -> frame -> D2H of
-        the totals and the emitted pairs, wall clock, max over ranks.
+e2e   : same metric through the public host API: pinned host SoA arrays -> H2D -> frame -> delivery
+        to host memory, wall clock, max over ranks.  Default delivery = what the reference's consumer
+        acts on (warning_system.py:259-285): the alert changes of the frame (process_collision_risks
+        folded into the device alert table) + per-object risk counts + totals (rcd_summary_*); the
+        full pair records (every CollisionRisk, 48 B each) are measured next to it (`e2e.full_pairs`).
+Extra keys at N > 1 (same run, after the headline): `strong_scaling` = configs[3] as written (1M
+objects in total over the N slabs); at N = 8 also `configs4_10m` (10M objects, heavy skew).
+`verify`: a sample of queries of the headline frame re-computed by the CPU oracle (outside every timed
+region) and compared with what the GPUs emitted -- pair set exact, values to 1e-4.
 """
 from __future__ import annotations
 
@@ -41,14 +50,22 @@ if ROOT not in sys.path:
 
 METRIC = "object-updates/s"
 PER_GPU_DEFAULT = 1_000_000
-H2D_BYTES_PER_OBJECT = 11 * 4 + 1 + 1  # 11 fp32 fields + type + trajectory pattern
+H2D_BYTES_PER_OBJECT = 11 * 4 + 1 + 1 + 4  # 11 fp32 fields + type + trajectory pattern + caller id
+FRAME_DESC = "ingest + index + detect-all + predict-all (performance_test.py:794-813)"
+L2_DESC = "flushed with a 256 MiB write before every timed frame"
 
 
 # ----------------------------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------------------------
+_FRAME_CACHE = {}
+
+
 def make_frames(workload: str, n_gpus: int, per_gpu: int, n_frames: int = 2):
     """Global frames (the same on every rank: deterministic seeds) + description."""
+    key = (workload, n_gpus, per_gpu, n_frames)
+    if key in _FRAME_CACHE:
+        return _FRAME_CACHE[key]
     from rcd_b200.host import workloads as W
     n = per_gpu * n_gpus
     if workload == "cfg4_1m_clustered3d":
@@ -72,9 +89,9 @@ def make_frames(workload: str, n_gpus: int, per_gpu: int, n_frames: int = 2):
         f0 = W.uniform_frame(n, 2001, map_size=side)
         desc = f"configs[2]: {n} uniform vehicles 2-D, {side / 1000:.1f} km map"
         bounds = ((0.0, 0.0, 0.0), (side, side, 0.0))
-    elif workload == "cfg2_5k_city":
-        f0 = W.reference_city_frame(n, 1235)
-        desc = f"configs[1]: reference perf-test generator, {n} vehicles, 10 km map"
+    elif workload in ("cfg2_5k_city", "cfg1_1k_city"):
+        f0 = W.reference_city_frame(n, 1235 if workload == "cfg2_5k_city" else 1234)
+        desc = f"configs[{1 if workload == 'cfg2_5k_city' else 0}]: reference perf-test generator, {n} vehicles, 10 km map"
         side = 10000.0
         bounds = ((0.0, 0.0, 0.0), (side, side, 0.0))
     else:
@@ -83,7 +100,16 @@ def make_frames(workload: str, n_gpus: int, per_gpu: int, n_frames: int = 2):
     rng = np.random.default_rng(99)
     for _ in range(1, n_frames):  # the reference advances every vehicle between frames (:147-195)
         frames.append(W.advance(frames[-1], 0.05, rng, map_size=(side, side)))
-    return frames, desc, bounds, side
+    _FRAME_CACHE[key] = (frames, desc, bounds, side)
+    return _FRAME_CACHE[key]
+
+
+def make_config(args, workload: str, desc: str, n_total: int, per_gpu: int, world: int, halo: float) -> dict:
+    """The `config` object: identical in the B200 arm and the reference arm of the same command."""
+    return {"workload": f"{workload}: {desc}", "objects": int(n_total), "objects_per_gpu": int(per_gpu), "frame": FRAME_DESC,
+            "gpu_arm": {"partition": (f"{world} x-slabs (cuts re-balanced from measured slab times during warm-up), halo "
+                                      f"{halo:.0f} m, fixed-size NCCL all_to_all of halo records") if world > 1 else "single GPU",
+                        "l2": L2_DESC, "max_pairs": int(args.max_pairs), "cuda_graph": bool(args.graph)}}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -146,7 +172,7 @@ class ClockSampler:
 def cpu_frame_seconds(frame, pattern, budget_s: float):
     """Time of one reference frame (index + detect-all + predict-all) on the host cores,
     extrapolated from a bounded sample: every `stride`-th object is queried against the FULL
-    index; the index build is timed in full.  Returns (seconds_per_frame, description, threads)."""
+    index; the index build is timed in full.  Returns (seconds_per_frame, description, threads, measured_s)."""
     from oracle import oracle as O
     from rcd_b200.host import workloads as W
     f64 = W.frame_to_f64(frame)
@@ -174,34 +200,38 @@ def cpu_frame_seconds(frame, pattern, budget_s: float):
     t_frame = 2 * t_index + t_queries * (n / queried)
     desc = (f"oracle/oracle.c (float64 port of src/collision, OpenMP {threads} threads): index built over all "
             f"{n} objects, every {stride}-th object queried (detect + predict = {queried} queries each, "
-            f"{t_sample:.1f} s measured), extrapolated to the full frame")
-    return t_frame, desc, threads
+            f"{t_sample:.1f} s measured)" + (", extrapolated to the full frame" if stride > 1 else ""))
+    return t_frame, desc, threads, t_sample, stride > 1
 
 
 def run_reference(args):
     """--impl reference: the reference's algorithm on the host cores (oracle port; the reference
     itself is pure Python and absent from the GPU box)."""
+    from rcd_b200.host.slabs import halo_width
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frames, desc, _bounds, _side = make_frames(args.workload, args.gpus, args.objects_per_gpu, 1)
+    frames, desc, _bounds, _side = make_frames(args.workload, args.gpus, args.objects_per_gpu, 2)
     n = len(frames[0]["px"])
     pattern = np.full(n, 2, np.uint8)
     steps = max(1, args.steps)
     budget = max(2.0, min(20.0, 120.0 / (steps + args.warmup)))
-    times = []
+    times, measured, extrap = [], [], False
     info = None
     for k in range(args.warmup + steps):
-        t, info, threads = cpu_frame_seconds(frames[0], pattern, budget)
+        t, info, threads, t_meas, ex = cpu_frame_seconds(frames[0], pattern, budget)
         if k >= args.warmup:
             times.append(t)
+            measured.append(t_meas)
+            extrap = extrap or ex
     t_mean = float(np.mean(times))
     value = n / t_mean
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "object-updates/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": t_mean * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "objects": n, "frame": "index + detect-all + predict-all"},
+        "config": make_config(args, args.workload, desc, n, args.objects_per_gpu, args.gpus, halo_width(frames)),
+        "extrapolated": bool(extrap), "measured_seconds_per_step": float(np.mean(measured)),
         "cpu_baseline": {"value": value, "unit": "object-updates/s", "cores": threads, "kind": "port", "sample": info},
         "e2e": {"value": value, "unit": "object-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -211,14 +241,382 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------
 # the B200 arm
 # ----------------------------------------------------------------------------------------------
+class SlabJob:
+    """One workload on this rank: global frames -> this rank's x-slab -> engine (+ halo exchange)."""
+
+    def __init__(self, args, workload: str, per_gpu: int, world: int, rank: int, local_rank: int, cuts=None,
+                 profile: bool = True, graph: bool = False, max_pairs=None):
+        import torch
+        from rcd_b200.host import workloads as W
+        from rcd_b200.host.engine import FRAME_FIELDS, FrameEngine
+        from rcd_b200.host.slabs import SlabExchange, halo_width, owner_of, slab_bounds
+        self.torch, self.FRAME_FIELDS = torch, FRAME_FIELDS
+        self.world, self.rank, self.local_rank = world, rank, local_rank
+        self.workload, self.per_gpu = workload, per_gpu
+        self.frames, self.desc, self.bounds, self.side = make_frames(workload, world, per_gpu, 2)
+        frames, bounds, side = self.frames, self.bounds, self.side
+        self.n_total = len(frames[0]["px"])
+        self.lo, self.hi = cuts if cuts is not None else slab_bounds(frames[0], world, side)
+        lo, hi = self.lo, self.hi
+        self.halo = halo_width(frames)
+        ids_all = np.arange(self.n_total, dtype=np.uint32)
+        self.own, self.own_ids = [], []
+        n_recv_max = 0
+        for f in frames:
+            mine = owner_of(f["px"], lo, hi) == rank
+            self.own.append(W.take(f, mine))
+            self.own_ids.append(ids_all[mine])
+            if world > 1:
+                x = f["px"]
+                n_recv_max = max(n_recv_max, int(((x >= lo[rank] - self.halo) & (x < hi[rank] + self.halo) & ~mine).sum()))
+        self.n_own_max = max(len(o["px"]) for o in self.own)
+        self.slack = 1.25
+        cap = int(self.n_own_max + self.slack * n_recv_max) + 512 * world + 4096
+        self.cap = cap
+        self.max_pairs = int(args.max_pairs if max_pairs is None else max_pairs)
+        # slab bounding box (+ halo) as the static grid bounds: no per-frame bbox round trip
+        self.xlo = max(0.0, float(lo[rank]) - self.halo) if np.isfinite(lo[rank]) else 0.0
+        self.xhi = min(side, float(hi[rank]) + self.halo) if np.isfinite(hi[rank]) else side
+        self.eng_bounds = ((self.xlo, bounds[0][1], bounds[0][2]), (self.xhi, bounds[1][1], bounds[1][2]))
+        self.profile, self.graph = profile, graph
+        self.eng = FrameEngine(cap, self.max_pairs, device=local_rank, world_bounds=self.eng_bounds, profile=profile and not graph,
+                               graph=graph)
+        self.stream = torch.cuda.ExternalStream(self.eng.cuda_stream(), device=torch.device("cuda", local_rank))
+        self.exch = SlabExchange(self.eng, lo, hi, rank, world, self.halo, self.stream, slack=self.slack) if world > 1 else None
+        # device-resident copies of the frames (the engine ingests them device-to-device every step) and pinned host copies
+        self.dev, self.pin = [], []
+        for f, fid in zip(self.own, self.own_ids):
+            n = len(f["px"])
+            d = {k: torch.from_numpy(f[k]).cuda() for k in FRAME_FIELDS}
+            d["type"] = torch.from_numpy(f["type"]).cuda()
+            d["id"] = torch.from_numpy(fid.astype(np.int32)).cuda()
+            d["pattern"] = torch.full((n,), 2, dtype=torch.uint8, device="cuda")
+            self.dev.append(d)
+            p = {k: torch.from_numpy(f[k]).pin_memory() for k in FRAME_FIELDS}
+            p["type"] = torch.from_numpy(f["type"]).pin_memory()
+            p["id"] = torch.from_numpy(fid.astype(np.int32)).pin_memory()
+            p["pattern"] = torch.full((n,), 2, dtype=torch.uint8).pin_memory()
+            self.pin.append(p)
+        if self.exch is not None:  # size the exchange regions from frame 0 (counting pass + one exchange of sizes)
+            self._upload_dev(0)
+            self.exch.configure()
+        torch.cuda.synchronize()
+
+    # -- one frame ---------------------------------------------------------------------------------
+    def _upload_dev(self, k: int) -> None:
+        d = self.dev[k % len(self.dev)]
+        n = int(d["px"].shape[0])
+        self.eng.upload_device(n, [d[f].data_ptr() for f in self.FRAME_FIELDS], d["type"].data_ptr(), d["id"].data_ptr())
+        self.eng.set_patterns_device(n, d["pattern"].data_ptr())
+
+    def _upload_host(self, k: int) -> None:
+        p = self.pin[k % len(self.pin)]
+        n = int(p["px"].shape[0])
+        self.eng.upload_host_ptrs(n, [p[f].data_ptr() for f in self.FRAME_FIELDS], p["type"].data_ptr(), p["id"].data_ptr())
+        self.eng.set_patterns_host_ptr(n, p["pattern"].data_ptr())
+
+    def frame(self, k: int, host: bool = False, halo_events=None) -> None:
+        """Ingest frame k (device-resident copy, or pinned host memory), trade halos, detect-all + predict-all."""
+        from rcd_b200.host import _native as N
+        (self._upload_host if host else self._upload_dev)(k)
+        if self.exch is not None:
+            if halo_events is not None:
+                halo_events[0].record(self.stream)
+            self.exch.exchange()
+            if halo_events is not None:
+                halo_events[1].record(self.stream)
+        self.eng.step(N.MODE_PREDICT, with_detect=True)  # one sweep over the neighbourhoods
+
+    def launches(self) -> int:
+        return self.eng.launch_count() + (self.exch.launches_last if self.exch is not None else 0)
+
+    def close(self) -> None:
+        self.eng.close()
+        self.dev = self.pin = None
+
+
+def barrier(world: int):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def time_resident(job: SlabJob, steps: int, warmup: int, flush):
+    """W warm-up frames, then K device-timed frames (events on the engine's stream, L2 flushed before each)."""
+    import torch
+    from rcd_b200.host import _native as N
+    eng, stream = job.eng, job.stream
+    for k in range(warmup):
+        job.frame(k)
+        eng.sync()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    hev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    stage_acc, launches = {}, 0
+    barrier(job.world)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        with torch.cuda.stream(stream):
+            flush.zero_()  # L2 flush: 256 MiB write, outside the timed events
+            ev[k][0].record(stream)
+        job.frame(k, halo_events=hev[k])
+        ev[k][1].record(stream)
+        if job.profile and not job.graph:  # per-stage times of this frame (synchronises after the end event was recorded)
+            for mode in (N.MODE_DETECT, N.MODE_PREDICT):
+                for name, ms in eng.stage_ms(mode).items():
+                    key = ("detect." if mode == N.MODE_DETECT else "predict.") + name
+                    stage_acc[key] = stage_acc.get(key, 0.0) + ms
+        launches += job.launches()
+    barrier(job.world)
+    t_wall = time.perf_counter() - t0
+    lat = np.array([a.elapsed_time(b) for a, b in ev], np.float64)
+    halo_ms = np.array([a.elapsed_time(b) for a, b in hev], np.float64) if job.exch is not None else np.zeros(steps)
+    return lat, halo_ms, {k: v / steps for k, v in stage_acc.items()}, launches, eng.counts(), t_wall
+
+
+def time_e2e(job: SlabJob, steps: int, warmup: int, delivery: str, inflight: int, bufs):
+    """K frames through the host API from pinned memory: H2D -> (halo) -> frame -> delivery, wall clock.
+    delivery 'summary': alert changes + per-object risk counts + totals; 'pairs': every rcd_pair record.
+    inflight 2: the delivery of frame k overlaps the kernels of frame k + 1 (twin buffers in the handle)."""
+    eng = job.eng
+    now = [1000.0]
+
+    def begin(k):
+        if delivery == "summary":
+            now[0] += 0.05
+            eng.summary_begin(now[0])
+        else:
+            eng.download_begin(bufs["pairs"][k % 2])
+
+    def finish(k):
+        if delivery == "summary":
+            n_own = int(job.pin[k % len(job.pin)]["px"].shape[0])
+            ev, st, _rc, _c = eng.summary_finish(bufs["events"], bufs["risk"][:n_own])
+            return ev.nbytes + 4 * n_own + 96 + 56, int(st["n_events"])
+        got, _c = eng.download_finish()
+        return got.nbytes + 96, int(got.shape[0])
+
+    def run(n_frames):
+        lat, nbytes, items, t_start = [], 0, 0, {}
+        if inflight >= 2:
+            t_start[0] = time.perf_counter()
+            job.frame(0, host=True)
+            begin(0)
+            for k in range(1, n_frames + 1):
+                if k < n_frames:
+                    t_start[k] = time.perf_counter()
+                    job.frame(k, host=True)
+                b, m = finish(k - 1)
+                lat.append(time.perf_counter() - t_start[k - 1])
+                nbytes += b
+                items += m
+                if k < n_frames:
+                    begin(k)
+        else:
+            for k in range(n_frames):
+                t0 = time.perf_counter()
+                job.frame(k, host=True)
+                begin(k)
+                b, m = finish(k)
+                lat.append(time.perf_counter() - t0)
+                nbytes += b
+                items += m
+        return lat, nbytes, items
+
+    run(max(2, min(warmup, 4)))  # allocates the twin buffers, fills the alert table: outside the timed region
+    barrier(job.world)
+    t0 = time.perf_counter()
+    lat, nbytes, items = run(steps)
+    barrier(job.world)
+    t = time.perf_counter() - t0
+    return {"t": t, "lat_ms": np.array(lat) * 1e3, "d2h_per_step": nbytes / steps, "items_per_step": items / steps}
+
+
+def reduce_max(world, vals):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(v) for v in t.cpu()]
+
+
+def reduce_sum(world, vals):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [float(v) for v in t.cpu()]
+
+
+def gather_list(world, val: float):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([val], dtype=torch.float64, device="cuda")
+    if world == 1:
+        return [float(val)]
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [float(o[0]) for o in out]
+
+
+def rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rounds: int):
+    """Move the x-cuts towards equal measured frame time per slab: a few short runs, each followed by an
+    all-gather of the slabs' frame times and `rebalanced_cuts` (host/slabs.py).  Returns (cuts, history)."""
+    from rcd_b200.host.slabs import rebalanced_cuts, slab_bounds
+    frames, _d, _b, side = make_frames(workload, world, per_gpu, 2)
+    cuts = slab_bounds(frames[0], world, side)
+    hist = []
+    best = (None, float("inf"))
+    for it in range(rounds + 1):
+        job = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=False)
+        lat, _h, _s, _l, _c, _t = time_resident(job, 3, 2, flush)
+        job.close()
+        ms = gather_list(world, float(np.mean(lat)))
+        hist.append([round(v, 3) for v in ms])
+        if max(ms) < best[1]:
+            best = (cuts, max(ms))
+        if it == rounds:
+            break
+        cuts = rebalanced_cuts(frames[0]["px"], cuts[0], cuts[1], ms, side)
+    return best[0], hist
+
+
+def verify_frame(job: SlabJob, k: int, n_queries: int):
+    """Sampled oracle check of frame k (outside every timed region): every stride-th object of the GLOBAL frame is
+    re-computed by the CPU oracle on rank 0 (detect + predict against all objects) and compared with what the
+    owners emitted for those queries: pair set exact, values to 1e-4 relative."""
+    import torch.distributed as dist
+    from oracle import oracle as O  # the checker, never the thing measured
+    from rcd_b200.host import workloads as W
+    world, rank = job.world, job.rank
+    frame = job.frames[k % len(job.frames)]
+    n = job.n_total
+    stride = max(1, n // max(1, n_queries))
+    job.frame(k)
+    got = job.eng.download(sort=False)
+    c = job.eng.counts()
+    overflow = c["n_pairs"] > c["n_written"]
+    sel = got[got["i"] % stride == 0].copy()
+    parts = [sel]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, sel)
+        flags = [None] * world
+        dist.all_gather_object(flags, bool(overflow))
+        overflow = any(flags)
+    if rank != 0:
+        return None
+    t0 = time.perf_counter()
+    both = np.concatenate(parts)
+    f64 = W.frame_to_f64(frame)
+    threads = max(O.max_threads(), os.cpu_count() or 1)
+    pat = np.full(n, 2, np.uint8)
+    res = {"queries": (n + stride - 1) // stride, "stride": stride, "pairs_checked": int(len(both)), "ok": True, "detail": []}
+    if overflow:
+        res["ok"] = None
+        res["detail"].append("pair buffer overflowed on some rank: the emitted records are a subset, counts only")
+        return res
+    for mode, flag in (("detect", 0), ("predict", 1)):
+        ora = O.frame_A(f64, mode, pattern_codes=pat if mode == "predict" else None, want_potentials=False,
+                        query_stride=stride, risk_cap=1 << 24, threads=threads)["risks"]
+        part = np.sort(both[both["predicted"] == flag], order=["i", "j"])
+        same = len(part) == len(ora) and np.array_equal(part["i"], ora["i"]) and np.array_equal(part["j"], ora["j"])
+        if not same:
+            res["ok"] = False
+            res["detail"].append(f"{mode}: pair set differs ({len(part)} emitted vs {len(ora)} oracle)")
+            continue
+        for fld in ("ttc", "distance", "risk", "rel_speed"):
+            a, b = part[fld].astype(np.float64), ora[fld].astype(np.float64)
+            bad = np.abs(a - b) > 1e-4 * np.abs(b) + 1e-6
+            if bad.any():
+                res["ok"] = False
+                res["detail"].append(f"{mode}: {fld} differs beyond 1e-4 in {int(bad.sum())} pairs")
+        if not np.array_equal(part["priority"].astype(np.int32), ora["priority"].astype(np.int32)):
+            res["ok"] = False
+            res["detail"].append(f"{mode}: alert class differs")
+        res[f"{mode}_pairs"] = int(len(ora))
+    res["oracle_seconds"] = round(time.perf_counter() - t0, 2)
+    return res
+
+
+def measure(args, workload, per_gpu, world, rank, local_rank, flush, steps, warmup, rebalance_rounds, with_e2e=True,
+            with_verify=True, sampler=None):
+    """Everything for one workload: (re-balanced) slabs, device-timed frames, end-to-end frames, verification."""
+    import torch
+    from rcd_b200.host import _native as N
+    cuts, rb_hist = (None, [])
+    if world > 1 and rebalance_rounds > 0:
+        cuts, rb_hist = rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rebalance_rounds)
+    job = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=True, graph=args.graph)
+    lat, halo_ms, stage_ms, launches, counts, t_wall = time_resident(job, steps, warmup, flush)
+    n_own_mean = float(np.mean([len(o["px"]) for o in job.own]))
+    out = {"job": job, "lat": lat, "stage_ms": stage_ms, "launches": launches, "counts": counts, "t_wall": t_wall,
+           "rebalance_ms": rb_hist}
+    graph_replays = job.eng.graph_replays() if args.graph else 0
+    if args.graph:  # stage breakdown on a profiled twin (outside every timed region)
+        twin = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=True, graph=False)
+        _l, _h, out["stage_ms"], _n, _c, _t = time_resident(twin, steps, 1, flush)
+        twin.close()
+    out["graph_replays"] = graph_replays
+    # ---- end to end ----------------------------------------------------------------------------------
+    e2e = None
+    if with_e2e:
+        n_pairs_max = reduce_max(world, [float(counts["n_pairs"])])[0]
+        eng = job.eng
+        eng.alerts_configure(int(max(1 << 20, 3 * n_pairs_max)))
+        ev_cap = int(max(1 << 18, min(n_pairs_max, 4 << 20)))
+        bufs = {"events": torch.empty(ev_cap * 40, dtype=torch.uint8).pin_memory().numpy().view(N.ALERT_EVENT_DTYPE),
+                "risk": torch.empty(job.n_own_max, dtype=torch.int32).pin_memory().numpy().view(np.uint32)}
+        runs = {}
+        for inflight in ((2, 1) if args.e2e_inflight >= 2 else (1,)):
+            runs[inflight] = time_e2e(job, steps, warmup, "summary", inflight, bufs)
+        t_best = {k: reduce_max(world, [v["t"]])[0] for k, v in runs.items()}  # every rank must pick the same one
+        pick = min(t_best, key=lambda k: t_best[k])
+        r = runs[pick]
+        e2e = {"t": t_best[pick], "inflight": pick, "lat_ms": r["lat_ms"], "d2h_per_step": r["d2h_per_step"],
+               "events_per_step": r["items_per_step"],
+               "other": {k: {"ms_per_step": t_best[k] / steps * 1e3, "p99_ms": float(np.percentile(runs[k]["lat_ms"], 99))}
+                         for k in runs if k != pick}}
+        # full pair records (every CollisionRisk), two frames in flight
+        k_full = max(3, min(steps, 10))
+        cap_pairs = min(job.max_pairs, int(args.host_pairs_cap))
+        bufs["pairs"] = [torch.empty(cap_pairs * 48, dtype=torch.uint8).pin_memory().numpy().view(N.PAIR_DTYPE) for _ in range(2)]
+        rf = time_e2e(job, k_full, 2, "pairs", 2, bufs)
+        e2e["full"] = {"t": reduce_max(world, [rf["t"]])[0], "steps": k_full, "lat_ms": rf["lat_ms"], "d2h_per_step": rf["d2h_per_step"]}
+        bufs.clear()
+    out["e2e"] = e2e
+    out["verify"] = verify_frame(job, 0, args.verify_queries) if with_verify and args.verify_queries > 0 else None
+    # ---- reduce over ranks (max time, summed counts) ---------------------------------------------------
+    t_dev = float(lat.sum()) / 1e3
+    out["t_dev"] = reduce_max(world, [t_dev])[0]
+    sums = reduce_sum(world, [n_own_mean, float(counts["n_pairs"]), float(counts["n_candidates"]),
+                              float(counts["n_objects"] - counts["n_owned"]),
+                              e2e["d2h_per_step"] if e2e else 0.0, e2e["full"]["d2h_per_step"] if e2e else 0.0,
+                              e2e["events_per_step"] if e2e else 0.0])
+    out["objs"], out["n_pairs"], out["n_cand"], out["n_halo"], out["d2h"], out["d2h_full"], out["events"] = sums
+    lat_all = torch.from_numpy(lat).cuda()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(lat_all, op=dist.ReduceOp.MAX)  # a frame is done when its slowest slab is done
+    out["lat_all"] = lat_all.cpu().numpy()
+    out["per_rank_ms"] = [round(v, 3) for v in gather_list(world, float(np.mean(lat)))]
+    out["per_rank_halo_ms"] = [round(v, 4) for v in gather_list(world, float(np.mean(halo_ms)))]
+    out["per_rank_objects"] = [int(v) for v in gather_list(world, float(counts["n_objects"]))]
+    out["n_own_mean"] = n_own_mean
+    return out
+
+
+def lat_stats(lat):
+    return {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
+            "p99_reference_rule": float(np.sort(lat)[min(len(lat) - 1, int(len(lat) * 0.99))]), "max": float(lat.max())}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
-
-    from rcd_b200.host import _native as N
-    from rcd_b200.host import workloads as W
-    from rcd_b200.host.engine import FRAME_FIELDS, FrameEngine
-    from rcd_b200.host.slabs import SlabExchange, halo_width, slab_bounds
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,210 +631,43 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    frames, desc, bounds, side = make_frames(args.workload, world, args.objects_per_gpu, 2)
-    n_total = len(frames[0]["px"])
-    lo, hi = slab_bounds(frames[0], world, side)
-    halo = halo_width(frames)
-    ids_all = np.arange(n_total, dtype=np.uint32)
-    own, own_ids = [], []
-    for f in frames:
-        m = (f["px"] >= lo[rank]) & (f["px"] < hi[rank])
-        own.append(W.take(f, m))
-        own_ids.append(ids_all[m])
-    n_own_max = max(len(o["px"]) for o in own)
-    # exact halo sizes (narrow slabs in dense hotspots send the same object to several peers)
-    n_send_max, n_recv_max = 0, 0
-    if world > 1:
-        for f in frames:
-            x = f["px"]
-            owner = (np.searchsorted(hi, x, side="right")).clip(0, world - 1)
-            mine = owner == rank
-            xs = x[mine]
-            n_send = sum(int(((xs >= lo[p] - halo) & (xs < hi[p] + halo)).sum()) for p in range(world) if p != rank)
-            n_recv = int(((x >= lo[rank] - halo) & (x < hi[rank] + halo) & ~mine).sum())
-            n_send_max, n_recv_max = max(n_send_max, n_send), max(n_recv_max, n_recv)
-    cap = int(n_own_max + 1.1 * n_recv_max) + 4096
-    max_pairs = int(args.max_pairs)
-    # slab bounding box (+ halo) as the static grid bounds: no per-frame bbox round trip
-    xlo = max(0.0, float(lo[rank]) - halo) if np.isfinite(lo[rank]) else 0.0
-    xhi = min(side, float(hi[rank]) + halo) if np.isfinite(hi[rank]) else side
-    eng_bounds = ((xlo, bounds[0][1], bounds[0][2]), (xhi, bounds[1][1], bounds[1][2]))
-    # --graph: rcd_step is replayed as a CUDA graph (RCD_FLAG_GRAPH), which excludes the per-stage events; the stage
-    # breakdown then comes from a few extra frames on a profiled twin engine after the timed regions
-    eng = FrameEngine(cap, max_pairs, device=local_rank, world_bounds=eng_bounds, profile=not args.graph, graph=args.graph)
-    stream = torch.cuda.ExternalStream(eng.cuda_stream(), device=torch.device("cuda", local_rank))
-    exch = SlabExchange(eng, lo, hi, rank, world, halo, stream, cap_records=int(1.1 * n_send_max) + 4096) if world > 1 else None
-
-    # device-resident copies of the frames (the engine ingests them device-to-device every step)
-    dev = []
-    pin = []
-    for f, fid in zip(own, own_ids):
-        n = len(f["px"])
-        d = {k: torch.from_numpy(f[k]).cuda() for k in FRAME_FIELDS}
-        d["type"] = torch.from_numpy(f["type"]).cuda()
-        d["id"] = torch.from_numpy(fid.astype(np.int32)).cuda()
-        d["pattern"] = torch.full((n,), 2, dtype=torch.uint8, device="cuda")
-        dev.append(d)
-        p = {k: torch.from_numpy(f[k]).pin_memory() for k in FRAME_FIELDS}
-        p["type"] = torch.from_numpy(f["type"]).pin_memory()
-        p["id"] = torch.from_numpy(fid.astype(np.int32)).pin_memory()
-        p["pattern"] = torch.full((n,), 2, dtype=torch.uint8).pin_memory()
-        pin.append(p)
-    pairs_pin = torch.empty(min(max_pairs, int(args.host_pairs_cap)) * 48, dtype=torch.uint8).pin_memory()
-    pairs_host = pairs_pin.numpy().view(N.PAIR_DTYPE)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    torch.cuda.synchronize()
 
-    launches = [0]
-    stage_acc = {}
-
-    def frame_resident(k: int):
-        d = dev[k % len(dev)]
-        n = int(d["px"].shape[0])
-        eng.upload_device(n, [d[f].data_ptr() for f in FRAME_FIELDS], d["type"].data_ptr(), d["id"].data_ptr())
-        eng.set_patterns_device(n, d["pattern"].data_ptr())
-        if exch is not None:
-            exch.exchange()
-        eng.step(N.MODE_PREDICT, with_detect=True)  # detect-all + predict-all, one sweep
-
-    def frame_e2e(k: int):
-        p = pin[k % len(pin)]
-        n = int(p["px"].shape[0])
-        eng.upload_host_ptrs(n, [p[f].data_ptr() for f in FRAME_FIELDS], p["type"].data_ptr(), p["id"].data_ptr())
-        eng.set_patterns_host_ptr(n, p["pattern"].data_ptr())
-        if exch is not None:
-            exch.exchange()
-        eng.step(N.MODE_PREDICT, with_detect=True)  # detect-all + predict-all, one sweep
-        return eng.download(sort=False, out=pairs_host)  # delivery only: consumers group on their own
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up ------------------------------------------------------------------------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()  # runs through warm-up and both timed regions (the frames are milliseconds long)
+        sampler.start()  # runs through warm-up and the timed regions (the frames are milliseconds long)
         time.sleep(0.3)
-    for k in range(args.warmup):
-        frame_resident(k)
-        eng.sync()
-    counts = eng.counts()
-
-    # ---- timed region: device-resident frames ---------------------------------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()  # L2 flush: 256 MiB write, outside the timed events
-            ev[k][0].record(stream)
-        frame_resident(k)
-        ev[k][1].record(stream)
-        # per-stage times of this frame (synchronises after the frame's end event was recorded)
-        if not args.graph:
-            for mode in (N.MODE_DETECT, N.MODE_PREDICT):
-                for name, ms in eng.stage_ms(mode).items():
-                    key = ("detect." if mode == N.MODE_DETECT else "predict.") + name
-                    stage_acc[key] = stage_acc.get(key, 0.0) + ms
-        launches[0] += eng.launch_count() + (exch.launches_last if exch is not None else 0)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    lat_ms = np.array([a.elapsed_time(b) for a, b in ev], np.float64)
-    t_dev = float(lat_ms.sum()) / 1e3
-    counts = eng.counts()
-
-    # ---- timed region: end to end from pinned host memory ----------------------------------------
-    for k in range(min(args.warmup, 3)):
-        frame_e2e(k)
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    e2e_lat = []
-    for k in range(args.steps):
-        tf = time.perf_counter()
-        pairs = frame_e2e(k)
-        e2e_lat.append(time.perf_counter() - tf)
-        d2h += pairs.nbytes + 96
-    barrier()
-    t_e2e = time.perf_counter() - t0
-    e2e_serial = {"ms_per_step": t_e2e / args.steps * 1e3, "p99_ms": float(np.percentile(np.array(e2e_lat) * 1e3, 99))}
-    inflight = 1
-    # Two frames in flight: rcd_download_begin / _finish deliver frame k from the handle's twin pair buffer on a
-    # copy stream while the kernels of frame k + 1 run.  Every frame still pays its own H2D and D2H inside the
-    # timed region; a frame's latency runs from its first upload call to the arrival of its last pair.
-    if args.e2e_inflight >= 2:
-        pairs_pin2 = torch.empty(pairs_pin.numel(), dtype=torch.uint8).pin_memory()
-        bufs = [pairs_host, pairs_pin2.numpy().view(N.PAIR_DTYPE)]
-
-        def submit(k: int):
-            p = pin[k % len(pin)]
-            n = int(p["px"].shape[0])
-            eng.upload_host_ptrs(n, [p[f].data_ptr() for f in FRAME_FIELDS], p["type"].data_ptr(), p["id"].data_ptr())
-            eng.set_patterns_host_ptr(n, p["pattern"].data_ptr())
-            if exch is not None:
-                exch.exchange()
-            eng.step(N.MODE_PREDICT, with_detect=True)
-
-        def pipelined(n_frames: int):
-            lat, nbytes, t_start = [], 0, {}
-            t_start[0] = time.perf_counter()
-            submit(0)
-            eng.download_begin(bufs[0])
-            for k in range(1, n_frames + 1):
-                if k < n_frames:
-                    t_start[k] = time.perf_counter()
-                    submit(k)
-                got, _c = eng.download_finish()  # frame k - 1
-                lat.append(time.perf_counter() - t_start[k - 1])
-                nbytes += got.nbytes + 96
-                if k < n_frames:
-                    eng.download_begin(bufs[k % 2])
-            return lat, nbytes
-
-        pipelined(2)  # allocate the twin buffers outside the timed region
-        barrier()
-        t0 = time.perf_counter()
-        lat_pipe, d2h_pipe = pipelined(args.steps)
-        barrier()
-        t_pipe = time.perf_counter() - t0
-        t_both = torch.tensor([t_pipe, t_e2e], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t_both, op=dist.ReduceOp.MAX)  # every rank must take the same branch
-        if float(t_both[0]) < float(t_both[1]):
-            t_e2e, inflight, e2e_lat, d2h = t_pipe, 2, lat_pipe, d2h_pipe
+    steps = args.steps
+    m = measure(args, args.workload, args.objects_per_gpu, world, rank, local_rank, flush, steps, args.warmup,
+                args.rebalance if world > 1 else 0)
     clocks = sampler.stop() if rank == 0 else None
-    graph_replays = eng.graph_replays() if args.graph else 0
-    if args.graph:  # stage breakdown on a profiled twin (outside every timed region)
-        prof = FrameEngine(cap, max_pairs, device=local_rank, world_bounds=eng_bounds, profile=True)
-        keep, eng = eng, prof
-        ex_keep, exch = exch, (SlabExchange(prof, lo, hi, rank, world, halo,
-                                            torch.cuda.ExternalStream(prof.cuda_stream(), device=torch.device("cuda", local_rank)),
-                                            cap_records=int(1.1 * n_send_max) + 4096) if world > 1 else None)
-        for k in range(args.steps):
-            frame_resident(k)
-            for mode in (N.MODE_DETECT, N.MODE_PREDICT):
-                for name, ms in eng.stage_ms(mode).items():
-                    key = ("detect." if mode == N.MODE_DETECT else "predict.") + name
-                    stage_acc[key] = stage_acc.get(key, 0.0) + ms
-        eng, exch = keep, ex_keep
-        prof.close()
+    job = m["job"]
 
-    # ---- reduce over ranks (max time, summed counts) -----------------------------------------------
-    n_own_mean = float(np.mean([len(o["px"]) for o in own]))
-    red = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device="cuda")
-    sums = torch.tensor([n_own_mean, float(counts["n_pairs"]), float(counts["n_candidates"]), float(d2h) / args.steps,
-                         float(counts["n_objects"] - counts["n_owned"])], dtype=torch.float64, device="cuda")
-    lat_all = torch.from_numpy(lat_ms).cuda()
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-        dist.all_reduce(lat_all, op=dist.ReduceOp.MAX)  # a frame is done when its slowest slab is done
-    t_dev, t_e2e, t_wall = (float(v) for v in red.cpu())
-    objs, n_pairs, n_cand, d2h_step, n_halo = (float(v) for v in sums.cpu())
-    lat = lat_all.cpu().numpy()
+    # ---- extra lines BASELINE.json names (after the headline, same process) ------------------------------
+    extras = {}
+    if world > 1 and args.extras and args.workload == "cfg4_1m_clustered3d" and args.objects_per_gpu == PER_GPU_DEFAULT:
+        job.close()
+        xs = max(5, min(steps, 10))
+        s = measure(args, "cfg4_1m_clustered3d", PER_GPU_DEFAULT // world, world, rank, local_rank, flush, xs, 3,
+                    min(args.rebalance, 2), with_e2e=False, with_verify=False)
+        extras["strong_scaling"] = {
+            "workload": f"configs[3] as written: {int(s['objs'])} objects in total over {world} x-slabs", "scaling": "strong",
+            "value": s["objs"] * xs / s["t_dev"], "unit": "object-updates/s", "ms_per_step": s["t_dev"] / xs * 1e3,
+            "latency_ms": lat_stats(s["lat_all"]), "steps": xs, "per_rank_ms": s["per_rank_ms"],
+            "per_rank_halo_ms": s["per_rank_halo_ms"], "pairs_emitted": s["n_pairs"], "halo_objects": s["n_halo"]}
+        s["job"].close()
+        if world == 8:
+            for name in ("cfg5_10m_skew3d_uniform_disc", "cfg5_10m_skew3d"):
+                xs = 3
+                s = measure(args, name, 1_250_000, world, rank, local_rank, flush, xs, 3, 1, with_e2e=False, with_verify=False)
+                extras["configs4_10m" + ("_uniform_disc" if name.endswith("disc") else "_reference_law")] = {
+                    "workload": f"{name}: {s['job'].desc}", "scaling": "n/a (10M objects on 8 GPUs)",
+                    "value": s["objs"] * xs / s["t_dev"], "unit": "object-updates/s", "ms_per_step": s["t_dev"] / xs * 1e3,
+                    "candidates_per_s": s["n_cand"] * xs / s["t_dev"], "latency_ms": lat_stats(s["lat_all"]), "steps": xs,
+                    "per_rank_ms": s["per_rank_ms"], "pairs_emitted": s["n_pairs"], "candidates": s["n_cand"],
+                    "pairs_stored_cap_per_gpu": int(args.max_pairs),
+                    "note": "counts are exact beyond the pair buffer; records past it are not stored"}
+                s["job"].close()
 
     if rank == 0:
         from_peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -444,71 +675,82 @@ def run_b200(args):
             peak, peak_src = float(json.load(open(from_peaks))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        steps = args.steps
-        n_loc = n_own_mean + counts["n_objects"] - counts["n_owned"]  # rank 0: owned + halo
-        stage_ms = {k: v / steps for k, v in stage_acc.items()}
+        counts = m["counts"]
+        n_loc = m["n_own_mean"] + counts["n_objects"] - counts["n_owned"]  # rank 0: owned + halo
         # algorithmic bytes per launch (DESIGN.md "byte model"), rank 0's objects
-        npass = max(1, -(-int(np.ceil(np.log2(max(2, eng_ncells(bounds, xlo, xhi))))) // 8))
-        model = {
-            "keys": 102.0 * n_loc, "sort": (16.0 * npass) * n_loc, "reorder": 108.0 * n_loc,
-            "pairs": 56.0 * n_loc, "narrow": 0.0, "exact": 0.0, "qorder": 0.0,
-        }
+        npass = max(1, -(-int(np.ceil(np.log2(max(2, eng_ncells(job.bounds, job.xlo, job.xhi))))) // 8))
+        model = {"keys": 102.0 * n_loc, "sort": (16.0 * npass) * n_loc, "reorder": 108.0 * n_loc,
+                 "pairs": 56.0 * n_loc, "narrow": 0.0, "exact": 0.0, "qorder": 0.0}
         kernels = {}
-        for key, ms in stage_ms.items():
+        for key, ms in m["stage_ms"].items():
             mode, name = key.split(".")
             if name in model and ms > 0:
                 b = model[name]
                 kernels[key] = {"ms": round(ms, 5), "alg_bytes": b, "gbs": round(b / (ms * 1e-3) / 1e9, 2) if b else None}
         dom_key = max((k for k in kernels if kernels[k]["alg_bytes"]), key=lambda k: kernels[k]["ms"])
         dom = kernels[dom_key]
-        traffic = None
+        traffic, ncu_info = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom_key)
+            tj = json.load(open(tpath))
+            traffic = tj.get(dom_key)
+            ncu_info = tj.get("ncu", {}).get(dom_key)
+        pair_tests = None
+        if "predict.pairs" in kernels:  # S1 tests of the pair kernel: candidates are the in-radius subset of them
+            pair_tests = m["n_cand"] / world / (kernels["predict.pairs"]["ms"] * 1e-3)
         cpu = None
         if world == 1:  # the CPU baseline is timed on rank 0 at N=1 only
-            cpu_t, cpu_desc, cpu_threads = cpu_frame_seconds(frames[0], np.full(n_total, 2, np.uint8), args.cpu_budget)
-            cpu = {"value": n_total / cpu_t, "unit": "object-updates/s", "cores": cpu_threads, "kind": "port",
-                   "sample": cpu_desc}
+            cpu_t, cpu_desc, cpu_threads, _tm, ex = cpu_frame_seconds(job.frames[0], np.full(job.n_total, 2, np.uint8), args.cpu_budget)
+            cpu = {"value": job.n_total / cpu_t, "unit": "object-updates/s", "cores": cpu_threads, "kind": "port",
+                   "sample": cpu_desc, "extrapolated": bool(ex)}
+        e2e = m["e2e"]
         out = {
-            "metric": METRIC, "value": objs * steps / t_dev, "unit": "object-updates/s", "n_gpus": world,
-            "steps": steps, "warmup": args.warmup, "ms_per_step": t_dev / steps * 1e3, "higher_is_better": True,
+            "metric": METRIC, "value": m["objs"] * steps / m["t_dev"], "unit": "object-updates/s", "n_gpus": world,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": m["t_dev"] / steps * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 pre-filter + f64 decisions", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "objects": int(objs), "objects_per_gpu": args.objects_per_gpu,
-                       "frame": "ingest + index + detect-all + predict-all (performance_test.py:794-813)",
-                       "partition": f"{world} x-slabs, halo {halo:.0f} m, NCCL all_to_all" if world > 1 else "single GPU",
-                       "l2": "flushed with a 256 MiB write before every timed frame", "max_pairs": max_pairs,
-                       "cuda_graph": bool(args.graph), "graph_replays": int(graph_replays)},
-            "latency_ms": {"p50": float(np.percentile(lat, 50)), "p99": float(np.percentile(lat, 99)),
-                           "p99_reference_rule": float(np.sort(lat)[min(len(lat) - 1, int(len(lat) * 0.99))]),
-                           "max": float(lat.max())},
-            "frame_totals": {"pairs_emitted": n_pairs, "candidates": n_cand, "halo_objects": n_halo},
-            "e2e": {"value": objs * steps / t_e2e, "unit": "object-updates/s",
-                    "h2d_bytes_per_step": int(objs * H2D_BYTES_PER_OBJECT + objs * 4), "d2h_bytes_per_step": int(d2h_step),
-                    "ms_per_step": t_e2e / steps * 1e3, "p99_ms": float(np.percentile(np.array(e2e_lat) * 1e3, 99)),
-                    "frames_in_flight": inflight, "one_frame_in_flight": e2e_serial},
-            "gpu_launches": int(launches[0]),
+            "config": make_config(args, args.workload, job.desc, job.n_total, args.objects_per_gpu, world, job.halo),
+            "latency_ms": lat_stats(m["lat_all"]),
+            "frame_totals": {"pairs_emitted": m["n_pairs"], "candidates": m["n_cand"], "halo_objects": m["n_halo"]},
+            "per_rank": {"frame_ms": m["per_rank_ms"], "halo_ms": m["per_rank_halo_ms"], "objects_with_halo": m["per_rank_objects"],
+                         "rebalance_rounds_ms": m["rebalance_ms"]},
+            "e2e": {"value": m["objs"] * steps / e2e["t"], "unit": "object-updates/s",
+                    "h2d_bytes_per_step": int(m["objs"] * H2D_BYTES_PER_OBJECT), "d2h_bytes_per_step": int(m["d2h"]),
+                    "delivery": "alert changes (rcd_alert_event, 40 B) + per-object risk counts + totals (rcd_summary_begin/_finish)",
+                    "alert_events_per_step": m["events"], "ms_per_step": e2e["t"] / steps * 1e3,
+                    "p99_ms": float(np.percentile(e2e["lat_ms"], 99)), "frames_in_flight": e2e["inflight"],
+                    "other_inflight": e2e["other"],
+                    "full_pairs": {"value": m["objs"] * e2e["full"]["steps"] / e2e["full"]["t"], "unit": "object-updates/s",
+                                   "delivery": "every emitted pair as a 48-byte rcd_pair (rcd_download_begin/_finish), 2 frames in flight",
+                                   "d2h_bytes_per_step": int(m["d2h_full"]), "ms_per_step": e2e["full"]["t"] / e2e["full"]["steps"] * 1e3,
+                                   "p99_ms": float(np.percentile(e2e["full"]["lat_ms"], 99)), "steps": e2e["full"]["steps"]}},
+            "gpu_launches": int(m["launches"]),
+            "graph_replays": int(m["graph_replays"]),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom_key, "achieved": dom["gbs"], "peak": peak, "unit": "GB/s",
                          "frac": dom["gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
-                         "note": "the pair kernels are fp32-ALU bound (pairs >> bytes); HBM-bound stages are in `kernels`"},
+                         "pair_tests_per_s": pair_tests, "ncu": ncu_info,
+                         "note": "the pair kernels are fp32-ALU / issue bound (pairs >> bytes): pair_tests_per_s and the ncu "
+                                 "issue figures describe them; HBM-bound stages are in `kernels`"},
             "kernels": kernels,
             "cpu_baseline": cpu,
-            "wall_s_timed_region": t_wall,
+            "verify": m["verify"],
+            "wall_s_timed_region": m["t_wall"],
         }
+        out.update(extras)
         emit(json.dumps(out))
-    eng.close()
+    if not extras:
+        job.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def eng_ncells(bounds, xlo, xhi):
-    cell = 100.0 * 1.002 + 0.02
+    cell = (100.0 * 1.002 + 0.02) * 0.5
     nx = int((xhi - xlo) / cell) + 1
     ny = int((bounds[1][1] - bounds[0][1]) / cell) + 1
-    nz = int((bounds[1][2] - bounds[0][2]) / cell) + 1
-    return nx * ny * nz
+    nz = int((bounds[1][2] - bounds[0][2]) / (2 * cell)) + 1
+    return nx * ny * nz + 1
 
 
 _REAL_STDOUT = None
@@ -537,7 +779,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--workload", default="cfg4_1m_clustered3d",
-                    choices=["cfg2_5k_city", "cfg3_100k_uniform2d", "cfg4_1m_clustered3d", "cfg5_10m_skew3d",
+                    choices=["cfg1_1k_city", "cfg2_5k_city", "cfg3_100k_uniform2d", "cfg4_1m_clustered3d", "cfg5_10m_skew3d",
                              "cfg5_10m_skew3d_uniform_disc"])
     ap.add_argument("--objects-per-gpu", type=int, default=None)
     ap.add_argument("--max-pairs", type=int, default=32_000_000)
@@ -545,13 +787,19 @@ def main():
     ap.add_argument("--graph", action="store_true",
                     help="replay rcd_step as a CUDA graph (RCD_FLAG_GRAPH): for the small, launch-bound configs")
     ap.add_argument("--e2e-inflight", type=int, default=2,
-                    help="frames in flight in the end-to-end leg at N=1 (2 = result copy overlaps the next frame)")
+                    help="frames in flight in the end-to-end leg (2 = the delivery overlaps the next frame)")
     ap.add_argument("--host-pairs-cap", type=int, default=32_000_000,
-                    help="pairs per rank the end-to-end leg copies back to (pinned) host memory per frame")
+                    help="pairs per rank the full-pairs end-to-end leg copies back to (pinned) host memory per frame")
+    ap.add_argument("--rebalance", type=int, default=3, help="re-balancing rounds of the slab cuts during warm-up (N > 1)")
+    ap.add_argument("--verify-queries", type=int, default=2000,
+                    help="queries of the headline frame re-computed by the CPU oracle after the timed regions (0 = off)")
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="skip the strong-scaling / 10M lines that follow the headline at N > 1")
     args = ap.parse_args()
     if args.objects_per_gpu is None:
-        args.objects_per_gpu = {"cfg2_5k_city": 5000, "cfg3_100k_uniform2d": 100_000, "cfg4_1m_clustered3d": PER_GPU_DEFAULT,
-                                "cfg5_10m_skew3d": 1_250_000, "cfg5_10m_skew3d_uniform_disc": 1_250_000}[args.workload]
+        args.objects_per_gpu = {"cfg1_1k_city": 1000, "cfg2_5k_city": 5000, "cfg3_100k_uniform2d": 100_000,
+                                "cfg4_1m_clustered3d": PER_GPU_DEFAULT, "cfg5_10m_skew3d": 1_250_000,
+                                "cfg5_10m_skew3d_uniform_disc": 1_250_000}[args.workload]
     args.warmup = max(args.warmup, 3)
     quiet_stdout()
     if args.impl == "reference":

@@ -408,10 +408,20 @@ int rcd_summary_finish(rcd_handle h, rcd_alert_event *events, uint64_t cap, uint
 /* Spatial-slab support: pack every owned object whose x lies within `halo` of
  * peer p's slab [slab_lo[p], slab_hi[p]) -- p != self -- into 52-byte records
  * (11 floats, meta u32 = type | pattern << 8, id u32), grouped by peer.  out_records is a DEVICE
- * buffer of cap records; counts[n_peers] is written to host memory (synchronises). */
+ * buffer of cap records; counts[n_peers] is written to host memory (synchronises).  out_records = NULL with
+ * cap = 0 only counts. */
 int rcd_halo_pack(rcd_handle h, int32_t n_peers, int32_t self, const float *slab_lo,
                   const float *slab_hi, float halo, void *out_records, uint64_t cap,
                   uint64_t *counts);
+/* The same without a host round trip: peer p's records go to the region [peer_offset[p], peer_offset[p + 1]) of
+ * out_records (a DEVICE buffer of peer_offset[n_peers] records; peer_offset is a host array); unused slots of
+ * every region are left as ghost records (all bits set: an object without a position, which pairs with
+ * nothing).  counts_dev (DEVICE, n_peers entries) receives the true counts, which may exceed a region: the
+ * surplus is dropped, so the caller looks at the counts now and then and re-sizes the regions.  Fixed region
+ * sizes make the exchange a fixed-size all_to_all and rcd_halo_append(everything received) the whole
+ * receiving side: nothing in the per-frame path waits for the host. */
+int rcd_halo_pack_async(rcd_handle h, int32_t n_peers, int32_t self, const float *slab_lo, const float *slab_hi,
+                        float halo, void *out_records, const uint64_t *peer_offset, uint64_t *counts_dev);
 /* Append n_records packed halo records (DEVICE buffer) after the owned objects. */
 int rcd_halo_append(rcd_handle h, const void *records, uint64_t n_records);
 

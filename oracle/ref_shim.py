@@ -497,3 +497,67 @@ def run_alert_scenario_A(script) -> List[Any]:
         return out
     finally:
         ws.time = real_time
+
+
+# ----------------------------------------------------------------------------------------
+# Partitioner driver: the reference's SpatialPartitioner (spatial_index.py:435-862) on a scripted scenario.
+# R6: __init__ calls _initialize_shards() before it creates self.stats (:466-469 vs :493); the shim gives the
+# instance an empty stats dict first.  Region ids and new shard ids are uuids: they are reported by canonical
+# names (a region by its sorted cells, a new shard as "new-<k>" in order of creation).
+# ----------------------------------------------------------------------------------------
+def run_partitioner_A(vehicles: Sequence[Tuple[float, float, float]], num_shards: int, queries, ops) -> List[Any]:
+    """ops: ("query",) | ("loads", {shard_name: load}) | ("rebalance",) | ("stats",) | ("insert", [(x, y, z)]).
+    Returns one result per op."""
+    ref = load_reference()
+    si = ref.spatial_index
+    index = si.SpatialIndex(adjustment_interval=math.inf)
+    n_ins = 0
+    for (x, y, z) in vehicles:
+        index.insert_vehicle(f"v{n_ins}", ref.Position(x, y, z))
+        n_ins += 1
+    orig_init = si.SpatialPartitioner._initialize_shards
+
+    def _init_with_stats(self):
+        self.stats = {}
+        orig_init(self)
+
+    si.SpatialPartitioner._initialize_shards = _init_with_stats
+    try:
+        part = si.SpatialPartitioner(index, num_shards=num_shards)
+    finally:
+        si.SpatialPartitioner._initialize_shards = orig_init
+
+    def canon(shard):
+        if shard is None:
+            return None
+        names = list(part.shard_loads)
+        k = names.index(shard)
+        return shard if k < num_shards else f"new-{k - num_shards}"
+
+    out: List[Any] = []
+    for op in ops:
+        if op[0] == "query":
+            out.append([canon(part.get_shard_for_position(ref.Position(x, y, z))) for (x, y, z) in queries])
+        elif op[0] == "loads":
+            names = list(part.shard_loads)
+            for name, load in op[1].items():
+                real = names[num_shards + int(name[4:])] if name.startswith("new-") else name
+                part.update_load(real, load)
+            out.append(None)
+        elif op[0] == "rebalance":
+            r = part.rebalance_shards()
+            out.append({k: v for k, v in r.items() if k != "elapsed_ms"})
+        elif op[0] == "insert":
+            for (x, y, z) in op[1]:
+                index.insert_vehicle(f"v{n_ins}", ref.Position(x, y, z))
+                n_ins += 1
+            out.append(None)
+        elif op[0] == "stats":
+            st = part.get_stats()
+            regions = sorted((sorted((lvl, tuple(g)) for lvl, g in cells), canon(part.region_to_shard.get(rid)))
+                             for rid, cells in part.regions.items())
+            out.append({"total_shards": st["total_shards"], "total_regions": st["total_regions"],
+                        "shards": {canon(s): {"regions": v["regions"], "vehicles": v["vehicles"], "load": v["load"]}
+                                   for s, v in st["shards"].items()},
+                        "regions": regions})
+    return out

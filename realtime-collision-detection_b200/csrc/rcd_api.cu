@@ -291,7 +291,7 @@ int build_index(rcd_handle h, float cell_req) {
     }
     h->grid = make_grid(h->wmin, h->wmax, cell_req, h->cell_scale, h->cells_cap);
     const GridParams g = h->grid;
-    const int passes = key_passes(g.ncells);
+    const int passes = key_passes(g.ncells + 1);  // + the cell of the objects without a position (rcd_index.cuh)
     const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
 
     stage_begin(h, RCD_STAGE_KEYS);
@@ -328,7 +328,7 @@ int build_index(rcd_handle h, float cell_req) {
         int rcr = release_inputs(h);
         if (rcr) return rcr;
     }
-    k_cell_table<<<(g.ncells + CT_CELLS - 1) / CT_CELLS, CT_THREADS, 0, h->stream>>>(h->keys[cur], n, g.ncells, h->cell_begin);
+    k_cell_table<<<(g.ncells + 1 + CT_CELLS - 1) / CT_CELLS, CT_THREADS, 0, h->stream>>>(h->keys[cur], n, g.ncells + 1, h->cell_begin);
     KERNEL_CHECK(h);
     stage_end(h, RCD_STAGE_REORDER);
     h->index_valid = true;
@@ -468,7 +468,7 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->U, 3 * (cap + 4)));
     CREATE_TRY(dev_alloc(&h->sorted_slot, cap));
     CREATE_TRY(dev_alloc(&h->sorted_id, cap));
-    CREATE_TRY(dev_alloc(&h->cell_begin, (size_t)h->cells_cap + 1));
+    CREATE_TRY(dev_alloc(&h->cell_begin, (size_t)h->cells_cap + 2));
     for (int k = 0; k < 2; ++k) {
         CREATE_TRY(dev_alloc(&h->qkeys[k], cap + 4));
         CREATE_TRY(dev_alloc(&h->qvals[k], cap + 4));
@@ -1672,6 +1672,11 @@ int rcd_halo_pack(rcd_handle h, int32_t n_peers, int32_t self, const float *slab
     u64 total = 0;
     if (e == cudaSuccess) {
         for (int p = 0; p < n_peers; ++p) { host_base[p] = total; total += host_cnt[p]; counts[p] = host_cnt[p]; }
+        if (!out_records && cap == 0) {  // counting pass only
+            cudaFree(dcnt);
+            ++h->launches;
+            return RCD_OK;
+        }
         if (total > cap || (total && !out_records)) {
             cudaFree(dcnt);
             return fail(h, RCD_ECAPACITY, "rcd_halo_pack: record buffer too small");
@@ -1690,6 +1695,36 @@ int rcd_halo_pack(rcd_handle h, int32_t n_peers, int32_t self, const float *slab
     cudaFree(dcnt);
     if (e != cudaSuccess) return fail(h, RCD_ECUDA, std::string("rcd_halo_pack: ") + cudaGetErrorString(e));
     h->launches += total ? 2 : 1;
+    return RCD_OK;
+}
+
+int rcd_halo_pack_async(rcd_handle h, int32_t n_peers, int32_t self, const float *slab_lo, const float *slab_hi, float halo,
+                        void *out_records, const uint64_t *peer_offset, uint64_t *counts_dev) {
+    if (!h || !slab_lo || !slab_hi || !peer_offset || !counts_dev || !out_records || n_peers < 1 || n_peers > MAX_PEERS ||
+        self < 0 || self >= n_peers)
+        return fail(h, RCD_EINVAL, "rcd_halo_pack_async: bad arguments");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    {
+        int rcw = wait_upload(h);
+        if (rcw) return rcw;
+    }
+    SlabParams sp;
+    sp.n_peers = n_peers; sp.self = self; sp.halo = halo;
+    SlabRegions rg;
+    for (int p = 0; p < n_peers; ++p) {
+        sp.lo[p] = slab_lo[p]; sp.hi[p] = slab_hi[p];
+        rg.offset[p] = peer_offset[p];
+        rg.cap[p] = peer_offset[p + 1] - peer_offset[p];
+    }
+    const u64 total = peer_offset[n_peers];
+    // every slot starts as a ghost record (all bits set: NaN state, id 0xffffffff); the kernel overwrites the used ones
+    if (total) CUDA_TRY(h, cudaMemsetAsync(out_records, 0xff, (size_t)total * HALO_WORDS * sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(counts_dev, 0, (size_t)n_peers * sizeof(unsigned long long), h->stream));
+    if (h->n_owned) {
+        k_halo_pack_regions<<<(unsigned)((h->n_owned + 255) / 256), 256, 0, h->stream>>>(
+            (u32)h->n_owned, input_state(h), sp, rg, reinterpret_cast<unsigned long long *>(counts_dev), static_cast<u32 *>(out_records));
+        KERNEL_CHECK(h);
+    }
     return RCD_OK;
 }
 

@@ -49,7 +49,9 @@ k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__
         const float4 r1 = make_float4(__ldcs(in.vx + i), __ldcs(in.vy + i), __ldcs(in.vz + i), __ldcs(in.heading + i));
         const u32 meta = pack_meta(__ldcs(in.type + i), __ldcs(in.pattern + i), i < n_owned);
         const float4 r2 = make_float4(__ldcs(in.ax + i), __ldcs(in.ay + i), __ldcs(in.az + i), __uint_as_float(meta));
-        const u32 k = cell_key(g, x, y, z);
+        // objects without a position (NaN: ghost slots of the halo exchange, rcd_halo_pack_async) go to a cell of
+        // their own behind the grid, which is under no query's box
+        const u32 k = (x == x && y == y && z == z) ? cell_key(g, x, y, z) : g.ncells;
         keys[i] = k;
         vals[i] = i;
         float4 *rec = U + 3 * (size_t)i;

@@ -1823,6 +1823,49 @@ k_halo_pack(u32 n_owned, InputState in, SlabParams sp, int phase, unsigned long 
     }
 }
 
+// Single pass, nothing for the host to wait for: peer p's records go to its own region of the send buffer
+// (offset[p], cap[p] records), the slot is claimed with one warp-aggregated atomic per peer.  counts[p] keeps the
+// true number even when it exceeds cap[p] (the surplus is dropped: the caller checks the counts now and then and
+// re-sizes the regions).
+struct SlabRegions {
+    unsigned long long offset[MAX_PEERS], cap[MAX_PEERS];
+};
+__global__ void __launch_bounds__(256)
+k_halo_pack_regions(u32 n_owned, InputState in, SlabParams sp, SlabRegions rg, unsigned long long *__restrict__ counts,
+                    u32 *__restrict__ out) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n_owned;
+    const float x = valid ? in.px[i] : 0.0f;
+    const u32 lane = threadIdx.x & 31u;
+    for (int p = 0; p < sp.n_peers; ++p) {
+        if (p == sp.self) continue;
+        const bool send = valid && x >= sp.lo[p] - sp.halo && x < sp.hi[p] + sp.halo;
+        const u32 ballot = __ballot_sync(FULL_MASK, send);
+        if (ballot == 0) continue;
+        unsigned long long base = 0;
+        const u32 leader = __ffs(ballot) - 1;
+        if (lane == leader) base = atomicAdd(&counts[p], (unsigned long long)__popc(ballot));
+        base = __shfl_sync(FULL_MASK, base, leader);
+        if (!send) continue;
+        const unsigned long long k = base + __popc(ballot & lanemask_lt());
+        if (k >= rg.cap[p]) continue;
+        u32 *r = out + (rg.offset[p] + k) * HALO_WORDS;
+        r[0] = __float_as_uint(x);
+        r[1] = __float_as_uint(in.py[i]);
+        r[2] = __float_as_uint(in.pz[i]);
+        r[3] = __float_as_uint(in.vx[i]);
+        r[4] = __float_as_uint(in.vy[i]);
+        r[5] = __float_as_uint(in.vz[i]);
+        r[6] = __float_as_uint(in.ax[i]);
+        r[7] = __float_as_uint(in.ay[i]);
+        r[8] = __float_as_uint(in.az[i]);
+        r[9] = __float_as_uint(in.size[i]);
+        r[10] = __float_as_uint(in.heading[i]);
+        r[11] = (u32)in.type[i] | ((u32)in.pattern[i] << 8);
+        r[12] = in.id ? in.id[i] : i;
+    }
+}
+
 struct MutableState {
     float *f[11];
     uint8_t *type, *pattern;

@@ -32,7 +32,7 @@ SYMBOLS = (
     "rcd_version", "rcd_last_error", "rcd_create", "rcd_destroy", "rcd_upload", "rcd_set_patterns",
     "rcd_set_owned", "rcd_step", "rcd_build_index", "rcd_set_compute_node_params", "rcd_truncate", "rcd_invalidate", "rcd_counts", "rcd_download", "rcd_download_unsorted",
     "rcd_download_candidate_counts", "rcd_query_radius", "rcd_classify_patterns", "rcd_halo_pack",
-    "rcd_halo_append", "rcd_history_configure", "rcd_history_append", "rcd_history_reset", "rcd_history_move",
+    "rcd_halo_pack_async", "rcd_halo_append", "rcd_history_configure", "rcd_history_append", "rcd_history_reset", "rcd_history_move",
     "rcd_history_classify", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_sync",
     "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
     "rcd_ingest_counts", "rcd_ingest_set_limit", "rcd_ingest_rejected", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
@@ -141,6 +141,8 @@ def load() -> ctypes.CDLL:
     L.rcd_classify_patterns.argtypes = [vp, u64, u32, vp, vp, vp]
     L.rcd_halo_pack.argtypes = [vp, i32, i32, vp, vp, f32, vp, u64, vp]
     L.rcd_halo_append.argtypes = [vp, vp, u64]
+    if hasattr(L, "rcd_halo_pack_async"):
+        L.rcd_halo_pack_async.argtypes = [vp, i32, i32, vp, vp, f32, vp, vp, vp]
     L.rcd_history_configure.argtypes = [vp, u32]
     L.rcd_history_append.argtypes = [vp, u64, vp, vp, vp, vp, vp]
     L.rcd_history_reset.argtypes = [vp, u64, vp]

@@ -354,6 +354,14 @@ class FrameEngine:
                 self._h)
         return counts.astype(np.int64)
 
+    def halo_pack_async(self, slab_lo, slab_hi, self_rank: int, halo: float, out_ptr: int, peer_offset: np.ndarray,
+                        counts_ptr: int) -> None:
+        """Single-pass pack into fixed per-peer regions of a device buffer; counts stay on the device."""
+        lo, hi = _as(slab_lo, np.float32), _as(slab_hi, np.float32)
+        off = _as(peer_offset, np.uint64)
+        N.check(self._lib.rcd_halo_pack_async(self._h, int(lo.shape[0]), int(self_rank), _vp(lo), _vp(hi), float(halo),
+                                              ctypes.c_void_p(int(out_ptr)), _vp(off), ctypes.c_void_p(int(counts_ptr))), self._h)
+
     def halo_append(self, rec_ptr: int, n_records: int) -> None:
         N.check(self._lib.rcd_halo_append(self._h, ctypes.c_void_p(int(rec_ptr)) if rec_ptr else None,
                                           int(n_records)), self._h)

@@ -135,29 +135,89 @@ def all_to_all_records(send, send_counts: Sequence[int], group=None):
     return recv, recv_counts
 
 
-class SlabExchange:
-    """Per-frame halo exchange of one rank on the GPU: pack (CUDA) -> all_to_all (NCCL) -> append."""
+def rebalanced_cuts(x: np.ndarray, lo: np.ndarray, hi: np.ndarray, ms: Sequence[float], side: float,
+                    damping: float = 0.7) -> Tuple[np.ndarray, np.ndarray]:
+    """New x-cuts from the measured frame time of every slab (the re-balancing step of SURVEY.md 8e): every object
+    of slab r weighs ms[r] / count[r] (its slab's measured cost per object), the cuts move to equal cumulative
+    weight.  `damping` < 1 moves only part of the way (the cost per object changes with the cut)."""
+    n_slabs = len(lo)
+    if n_slabs == 1:
+        return np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    x = np.asarray(x, np.float64)
+    owner = owner_of(x, lo, hi)
+    count = np.bincount(owner, minlength=n_slabs).astype(np.float64)
+    per_obj = np.asarray(ms, np.float64) / np.maximum(count, 1.0)
+    w = per_obj[owner]
+    order = np.argsort(x, kind="stable")
+    cw = np.cumsum(w[order])
+    old = np.asarray(hi[:-1], np.float64)
+    cuts = []
+    for k in range(1, n_slabs):
+        at = min(len(order) - 1, int(np.searchsorted(cw, cw[-1] * k / n_slabs)))
+        cuts.append(float(x[order[at]]))
+    cuts = np.asarray(cuts, np.float64)
+    cuts = old + damping * (cuts - old)
+    cuts = np.maximum.accumulate(cuts)
+    cuts = [float(np.float32(c)) for c in cuts]
+    return np.array([-np.inf] + cuts, np.float32), np.array(cuts + [np.inf], np.float32)
 
-    def __init__(self, engine, lo, hi, rank: int, world: int, halo: float, stream, cap_records: int, group=None):
-        import torch
+
+class SlabExchange:
+    """Per-frame halo exchange of one rank on the GPU, without a host round trip: single-pass pack into fixed
+    per-peer regions (``rcd_halo_pack_async``; unused slots stay ghost records) -> fixed-size NCCL all_to_all on
+    the engine's stream -> append of everything received (``rcd_halo_append``).  The region sizes come from a
+    counting pass over a representative frame (``configure``) and carry slack; ``overflowed()`` (which does wait
+    for the device) tells whether a region was too small and the sizes have to be taken again."""
+
+    def __init__(self, engine, lo, hi, rank: int, world: int, halo: float, stream, group=None, slack: float = 1.5,
+                 min_records: int = 256):
         self.engine, self.rank, self.world, self.halo = engine, int(rank), int(world), float(halo)
         self.lo, self.hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
-        self.stream, self.group, self.cap = stream, group, int(cap_records)
-        dev = torch.device("cuda", engine.device)
-        self.send = torch.empty((self.cap, RECORD_WORDS), dtype=torch.int32, device=dev)
+        self.stream, self.group = stream, group
+        self.slack, self.min_records = float(slack), int(min_records)
         self.launches_last = 0
         self.halo_last = 0
+        self.send = self.recv = self.counts = None
+
+    def set_cuts(self, lo, hi) -> None:
+        self.lo, self.hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+
+    def configure(self) -> None:
+        """Size the per-peer regions from the objects the engine holds now (its owned objects of a representative
+        frame): a counting pass on this rank, one exchange of the sizes with the peers.  Waits for the device."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.engine.device)
+        counts = self.engine.halo_pack(self.lo, self.hi, self.rank, self.halo, 0, 0)  # counting pass only
+        cap_send = [0 if p == self.rank else int(c * self.slack) + self.min_records for p, c in enumerate(counts)]
+        sc = torch.tensor(cap_send, dtype=torch.int64, device=dev)
+        rc = torch.empty_like(sc)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        self.cap_send, self.cap_recv = cap_send, [int(v) for v in rc.cpu()]
+        self.send_offset = np.concatenate([[0], np.cumsum(self.cap_send)]).astype(np.uint64)
+        self.n_recv = int(sum(self.cap_recv))
+        self.send = torch.empty((max(1, int(self.send_offset[-1])), RECORD_WORDS), dtype=torch.int32, device=dev)
+        self.recv = torch.empty((max(1, self.n_recv), RECORD_WORDS), dtype=torch.int32, device=dev)
+        self.counts = torch.zeros(self.world, dtype=torch.int64, device=dev)
+        self.halo_last = self.n_recv
 
     def exchange(self) -> int:
-        """Pack this rank's boundary objects, trade them, append what the peers sent.  The engine
-        must hold only its owned objects (call after upload).  Returns the halo object count."""
+        """Pack this rank's boundary objects, trade them, append what the peers sent.  The engine must hold only
+        its owned objects (call after upload).  Returns the halo slots appended (ghosts included)."""
         import torch
-        counts = self.engine.halo_pack(self.lo, self.hi, self.rank, self.halo, self.send.data_ptr(), self.cap)
+        import torch.distributed as dist
+        self.engine.halo_pack_async(self.lo, self.hi, self.rank, self.halo, self.send.data_ptr(), self.send_offset,
+                                    self.counts.data_ptr())
         with torch.cuda.stream(self.stream):
-            recv, recv_counts = all_to_all_records(self.send, counts, self.group)
-        total = int(sum(recv_counts))
-        self._keep = recv  # alive until the append kernel has consumed it
-        self.engine.halo_append(recv.data_ptr() if total else 0, total)
-        self.launches_last = (2 if int(np.sum(counts)) else 1) + (1 if total else 0)
-        self.halo_last = total
-        return total
+            dist.all_to_all_single(self.recv[: self.n_recv], self.send[: int(self.send_offset[-1])],
+                                   output_split_sizes=self.cap_recv, input_split_sizes=self.cap_send, group=self.group)
+        self.engine.halo_append(self.recv.data_ptr() if self.n_recv else 0, self.n_recv)
+        self.launches_last = 1 + (1 if self.n_recv else 0)
+        return self.n_recv
+
+    def sent_counts(self) -> np.ndarray:
+        """Records this rank wanted to send to every peer in the last exchange (waits for the device)."""
+        return self.counts.cpu().numpy().astype(np.int64)
+
+    def overflowed(self) -> bool:
+        return bool(np.any(self.sent_counts() > np.asarray(self.cap_send, np.int64)))

@@ -10,6 +10,7 @@ levels mix (quirk Q9) and is not reproduced; ``get_grid_level`` is always 0 and
 from __future__ import annotations
 
 import time
+import uuid
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional, Set, Tuple
 
@@ -134,9 +135,18 @@ class SpatialIndex:
 
 
 class SpatialPartitioner:
-    """Position -> shard mapping (spatial_index.py:435-862).  The reference builds regions of grid
-    cells and hashes them onto shards; on one 8-GPU box the shards are x-slabs of equal estimated
-    work (host/slabs.py).  Same method names and return types."""
+    """Position -> shard mapping (spatial_index.py:435-862), in two modes.
+
+    *Region mode* (default) is the reference's own model, kept decision for decision (golden:
+    tests/golden/partitioner.json, produced by the reference's class): a region is a list of (level, cell); every
+    level-0 cell that exists when the partitioner is built becomes a region on ``shard-{hash(cell) % n}`` (:477-493);
+    ``rebalance_shards`` splits the most populated region of every overloaded shard (2x2x2 children of a single cell, or
+    the cell list halved by population, :701-771) handing the parts to underloaded or new shards, and merges adjacent
+    single-cell regions of underloaded shard pairs (:773-826).  Positions outside every region map to ``None``.
+
+    *Slab mode* (``attach_slabs``) is what the GPUs of one box run: shard k is the x-slab of GPU k, the
+    loads are the GPUs' measured frame times, and ``rebalance_shards`` moves the cuts (``slabs.rebalanced_cuts``) and
+    hands them to the attached ``SlabExchange`` objects, which re-size their halo regions."""
 
     def __init__(self, spatial_index: SpatialIndex, num_shards: int = 10, min_load: float = 0.3, max_load: float = 0.7,
                  rebalance_interval: float = 60.0):
@@ -145,42 +155,176 @@ class SpatialPartitioner:
         self.min_load = min_load
         self.max_load = max_load
         self.rebalance_interval = rebalance_interval
+        self.regions: Dict[str, List[Tuple[int, Tuple[int, int, int]]]] = {}
+        self.region_to_shard: Dict[str, str] = {}
         self.shard_loads: Dict[str, float] = {f"shard-{k}": 0.0 for k in range(num_shards)}
-        self.stats = {"total_regions": num_shards, "total_shards": num_shards, "rebalance_count": 0,
-                      "last_rebalance": time.time()}
-        self._lo = np.array([-np.inf], np.float32)
-        self._hi = np.array([np.inf], np.float32)
-        self.rebalance_shards()
+        for cell in spatial_index.grids.get(0, {}):
+            rid = self._new_region([(0, cell)])
+            self.region_to_shard[rid] = f"shard-{hash(cell) % num_shards}"
+        # (the reference creates its stats after the regions and so reports total_regions = 0 until the first rebalance)
+        self.stats = {"total_shards": num_shards, "total_regions": 0, "last_rebalance": time.time()}
+        self._slabs = None  # slab mode: {"lo", "hi", "side", "exchanges"}
 
+    def _new_region(self, cells) -> str:
+        rid = f"region-{uuid.uuid4()}"
+        self.regions[rid] = list(cells)
+        return rid
+
+    # -- lookup (:495-558) ---------------------------------------------------------------------------
     def get_shard_for_position(self, position: Position) -> Optional[str]:
-        from .slabs import owner_of
-        return f"shard-{int(owner_of(np.array([position.x], np.float32), self._lo, self._hi)[0])}"
+        if self._slabs is not None:
+            from .slabs import owner_of
+            return f"shard-{int(owner_of(np.array([position.x], np.float32), self._slabs['lo'], self._slabs['hi'])[0])}"
+        level = self.spatial_index.get_grid_level(position)
+        cell = self.spatial_index.get_grid_id(position, level)
+        rid = self._find_region_for_grid(level, cell)
+        up = level
+        while rid is None and up > 0:  # a region may hold an ancestor of the cell
+            up -= 1
+            rid = self._find_region_for_grid(up, self._get_parent_grid_id(cell, level, up))
+        return self.region_to_shard.get(rid)
 
+    def _find_region_for_grid(self, level: int, grid_id: Tuple[int, int, int]) -> Optional[str]:
+        want = (level, tuple(grid_id))
+        for rid, cells in self.regions.items():
+            if want in cells:
+                return rid
+        return None
+
+    @staticmethod
+    def _get_parent_grid_id(grid_id, current_level: int, parent_level: int) -> Tuple[int, int, int]:
+        f = 2 ** (current_level - parent_level)
+        return (grid_id[0] // f, grid_id[1] // f, grid_id[2] // f)
+
+    # -- loads and rebalancing (:560-679) -----------------------------------------------------------------
     def update_load(self, shard_id: str, load: float) -> None:
-        self.shard_loads[shard_id] = load
+        if shard_id in self.shard_loads:
+            self.shard_loads[shard_id] = load
 
     def check_rebalance(self) -> bool:
-        if time.time() - self.stats["last_rebalance"] < self.rebalance_interval:
+        now = time.time()
+        if now - self.stats["last_rebalance"] < self.rebalance_interval:
             return False
-        loads = list(self.shard_loads.values())
-        if loads and (max(loads) > self.max_load or min(loads) < self.min_load):
-            self.rebalance_shards()
-            return True
-        return False
+        self.rebalance_shards()
+        self.stats["last_rebalance"] = now
+        return True
 
-    def rebalance_shards(self) -> None:
-        from .slabs import slab_bounds
-        t = self.spatial_index._table
-        if t.n >= self.num_shards:
-            frame = t.frame()
-            side = float(max(frame["px"].max(), frame["py"].max(), 1.0))
-            self._lo, self._hi = slab_bounds(frame, self.num_shards, side)
+    def _cell_population(self, level: int, cell) -> int:
+        c = self.spatial_index.grids.get(level, {}).get(cell)
+        return c.vehicle_count if c is not None else 0
+
+    def _get_region_vehicle_count(self, region_id: str) -> int:
+        return sum(self._cell_population(lvl, cell) for lvl, cell in self.regions.get(region_id, ()))
+
+    def rebalance_shards(self) -> Dict[str, Any]:
+        t0 = time.perf_counter()
+        if self._slabs is not None:
+            return self._rebalance_slabs(t0)
+        over = [s for s, l in self.shard_loads.items() if l > self.max_load]
+        under = [s for s, l in self.shard_loads.items() if l < self.min_load]
+        n_split = n_merged = 0
+        for shard in over:  # the most populated region of an overloaded shard is split
+            mine = sorted((r for r, s in self.region_to_shard.items() if s == shard),
+                          key=self._get_region_vehicle_count, reverse=True)
+            if not mine:
+                continue
+            parts = self._split_region(mine[0])
+            n_split += 1
+            for k, rid in enumerate(parts):  # the first part stays, the others go to underloaded (else new) shards
+                self.region_to_shard[rid] = shard if k == 0 else (under.pop(0) if under else self._create_new_shard())
+        while len(under) >= 2:  # underloaded shards pairwise: merge one pair of adjacent single-cell regions
+            a, b = under.pop(0), under.pop(0)
+            pair = next(((r1, r2) for r1 in [r for r, s in self.region_to_shard.items() if s == a]
+                         for r2 in [r for r, s in self.region_to_shard.items() if s == b]
+                         if self._can_merge_regions(r1, r2)), None)
+            if pair is None:
+                under += [a, b]
+                break
+            self.region_to_shard[self._merge_regions(*pair)] = a
+            for r in pair:
+                del self.region_to_shard[r]
+                del self.regions[r]
+            n_merged += 1
+        self.stats["total_shards"] = len(self.shard_loads)
+        self.stats["total_regions"] = len(self.regions)
+        return {"overloaded": len(over), "underloaded": len(under), "split_regions": n_split, "merged_regions": n_merged,
+                "elapsed_ms": (time.perf_counter() - t0) * 1e3}
+
+    def _split_region(self, region_id: str) -> List[str]:
+        cells = self.regions.get(region_id)
+        if not cells:
+            return []
+        if len(cells) == 1:
+            level, (gx, gy, gz) = cells[0]
+            if level >= self.spatial_index.max_level:
+                return []
+            parts = [[(level + 1, (2 * gx + dx, 2 * gy + dy, 2 * gz + dz))] for dx in (0, 1) for dy in (0, 1) for dz in (0, 1)]
         else:
-            self._lo = np.array([-np.inf] + [np.inf] * (self.num_shards - 1), np.float32)
-            self._hi = np.array([np.inf] * self.num_shards, np.float32)
-        self.stats["rebalance_count"] += 1
-        self.stats["last_rebalance"] = time.time()
+            ranked = sorted(cells, key=lambda c: self._cell_population(c[0], c[1]), reverse=True)
+            parts = [ranked[: len(ranked) // 2], ranked[len(ranked) // 2:]]
+        out = [self._new_region(p) for p in parts]
+        del self.regions[region_id]
+        return out
+
+    def _can_merge_regions(self, region_id1: str, region_id2: str) -> bool:
+        a, b = self.regions.get(region_id1), self.regions.get(region_id2)
+        if a is None or b is None or len(a) != 1 or len(b) != 1 or a[0][0] != b[0][0]:
+            return False
+        return sum(abs(p - q) for p, q in zip(a[0][1], b[0][1])) == 1  # face neighbours
+
+    def _merge_regions(self, region_id1: str, region_id2: str) -> str:
+        if region_id1 not in self.regions or region_id2 not in self.regions:
+            return ""
+        return self._new_region(self.regions[region_id1] + self.regions[region_id2])
+
+    def _create_new_shard(self) -> str:
+        shard = f"shard-{uuid.uuid4()}"
+        self.shard_loads[shard] = 0.0
+        self.stats["total_shards"] += 1
+        return shard
+
+    # -- slab mode ------------------------------------------------------------------------
+    def attach_slabs(self, lo, hi, side: float, exchanges=()) -> None:
+        """Shards become the x-slabs [lo[k], hi[k]) of the box's GPUs; `exchanges`: the SlabExchange objects (one per
+        local GPU) that follow the cuts.  num_shards must equal the number of slabs."""
+        if len(lo) != self.num_shards:
+            raise ValueError("attach_slabs: one slab per shard")
+        self._slabs = {"lo": np.asarray(lo, np.float32), "hi": np.asarray(hi, np.float32), "side": float(side),
+                       "exchanges": list(exchanges)}
+        self.shard_loads = {f"shard-{k}": self.shard_loads.get(f"shard-{k}", 0.0) for k in range(self.num_shards)}
+
+    @property
+    def slab_cuts(self):
+        return None if self._slabs is None else (self._slabs["lo"], self._slabs["hi"])
+
+    def _rebalance_slabs(self, t0: float) -> Dict[str, Any]:
+        from .slabs import rebalanced_cuts
+        sl = self._slabs
+        loads = [max(float(self.shard_loads[f"shard-{k}"]), 1e-9) for k in range(self.num_shards)]
+        t = self.spatial_index._table
+        moved = False
+        if t.n >= self.num_shards and max(loads) > 1e-9:
+            lo, hi = rebalanced_cuts(t.f["px"][: t.n], sl["lo"], sl["hi"], loads, sl["side"])
+            moved = not np.array_equal(hi, sl["hi"])
+            sl["lo"], sl["hi"] = lo, hi
+            for ex in sl["exchanges"]:
+                ex.set_cuts(lo, hi)
+        over = sum(l > self.max_load for l in loads)
+        under = sum(l < self.min_load for l in loads)
+        return {"overloaded": int(over), "underloaded": int(under), "split_regions": 0, "merged_regions": 0,
+                "cuts_moved": bool(moved), "elapsed_ms": (time.perf_counter() - t0) * 1e3}
 
     def get_stats(self) -> Dict[str, Any]:
-        return {**self.stats, "shard_loads": dict(self.shard_loads),
-                "slab_bounds": [(float(a), float(b)) for a, b in zip(self._lo, self._hi)]}
+        shards = {}
+        if self._slabs is not None:
+            from .slabs import owner_of
+            t = self.spatial_index._table
+            cnt = np.bincount(owner_of(t.f["px"][: t.n], self._slabs["lo"], self._slabs["hi"]), minlength=self.num_shards)
+            for k in range(self.num_shards):
+                shards[f"shard-{k}"] = {"regions": 1, "vehicles": int(cnt[k]), "load": self.shard_loads[f"shard-{k}"]}
+            return {**self.stats, "shards": shards,
+                    "slab_bounds": [(float(a), float(b)) for a, b in zip(self._slabs["lo"], self._slabs["hi"])]}
+        for shard, load in self.shard_loads.items():
+            mine = [r for r, s in self.region_to_shard.items() if s == shard]
+            shards[shard] = {"regions": len(mine), "vehicles": sum(self._get_region_vehicle_count(r) for r in mine), "load": load}
+        return {**self.stats, "shards": shards}

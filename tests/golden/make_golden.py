@@ -167,6 +167,38 @@ def helpers_fixture(name):
         json.dump(out, f, ensure_ascii=False)
 
 
+def partitioner_case(seed=5, n=300):
+    """Scenario for the reference SpatialPartitioner (shared with tests/test_dropin_cpu.py)."""
+    rng = np.random.default_rng(seed)
+    f32 = lambda a: [float(np.float32(v)) for v in a]
+    veh = list(zip(f32(rng.uniform(0, 6000, n)), f32(rng.uniform(0, 4000, n)), f32(rng.uniform(0, 100, n))))
+    more = list(zip(f32(rng.uniform(5000, 9000, 40)), f32(rng.uniform(0, 4000, 40)), f32(rng.uniform(0, 100, 40))))
+    queries = veh[:40] + more[:10] + [(7500.0, 100.0, 0.0), (-10.0, 5.0, 1.0), (999.5, 999.5, 99.5), (1000.0, 1000.0, 100.0)]
+    ops = [["query"], ["stats"],
+           ["loads", {"shard-0": 0.9, "shard-1": 0.1, "shard-2": 0.2, "shard-3": 0.95, "shard-4": 0.5, "shard-5": 0.5,
+                      "shard-6": 0.25, "shard-7": 0.6}],
+           ["rebalance"], ["query"], ["stats"],
+           ["insert", more], ["query"],
+           ["loads", {"shard-0": 0.2, "shard-1": 0.1, "shard-2": 0.2, "shard-3": 0.1, "shard-4": 0.75, "shard-5": 0.05,
+                      "shard-6": 0.25, "shard-7": 0.99}],
+           ["rebalance"], ["query"], ["stats"],
+           ["loads", {"shard-4": 0.8, "shard-7": 0.71, "shard-0": 0.5, "shard-1": 0.5, "shard-2": 0.5, "shard-3": 0.5}],
+           ["rebalance"], ["query"], ["stats"],
+           ["loads", {f"shard-{k}": 0.1 for k in range(8)}],  # nothing overloaded, everything underloaded: merges
+           ["rebalance"], ["query"], ["stats"], ["rebalance"], ["stats"]]
+    return {"vehicles": veh, "num_shards": 8, "queries": queries, "ops": ops}
+
+
+def partitioner_fixture(name):
+    import json
+    case = partitioner_case()
+    res = S.run_partitioner_A(case["vehicles"], case["num_shards"], case["queries"], [tuple(o) for o in case["ops"]])
+    case["results"] = res
+    with open(os.path.join(HERE, name), "w") as f:
+        json.dump(case, f)
+    print(name, [r for r in res if isinstance(r, dict) and "split_regions" in r])
+
+
 def main():
     if not S.reference_available():
         raise SystemExit("needs /root/reference")
@@ -191,6 +223,7 @@ def main():
     ingest_fixture("ingest_messages.json")
     alerts_fixture("alert_scenario.json.gz")
     helpers_fixture("pair_helpers.json")
+    partitioner_fixture("partitioner.json")
 
 
 if __name__ == "__main__":

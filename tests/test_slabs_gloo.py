@@ -111,3 +111,33 @@ def test_pack_unpack_roundtrip():
     for k in S.FRAME_FIELDS:
         assert np.array_equal(f2[k], frame[k][m])
     assert np.array_equal(f2["type"], frame["type"][m]) and np.array_equal(ids2, ids[m]) and np.array_equal(pat2, pat[m])
+
+
+def test_rebalanced_cuts_move_towards_equal_cost():
+    """The re-balancing step: with a cost model in which an object's cost grows with the local density,
+    repeating `rebalanced_cuts` on the measured slab costs brings the slabs' costs together; the cuts stay ordered and
+    every object keeps exactly one owner."""
+    from rcd_b200.host import slabs as S
+    from rcd_b200.host import workloads as W
+    side, n_slabs = 8000.0, 4
+    frame = W.hotspot_frame(60000, 5, side, 4, drone_fraction=0.0)
+    x = frame["px"].astype(np.float64)
+    cell = np.clip((x / 100.0).astype(np.int64), 0, 79) * 80 + np.clip((frame["py"] / 100.0).astype(np.int64), 0, 79)
+    cost_obj = 1.0 + 0.5 * np.bincount(cell, minlength=6400)[cell]  # "pair work" of every object
+
+    def slab_cost(lo, hi):
+        return np.bincount(S.owner_of(frame["px"], lo, hi), weights=cost_obj, minlength=n_slabs)
+
+    lo = np.array([-np.inf] + [side * k / n_slabs for k in range(1, n_slabs)], np.float32)  # naive equal-width cuts
+    hi = np.array([side * k / n_slabs for k in range(1, n_slabs)] + [np.inf], np.float32)
+    first = slab_cost(lo, hi)
+    for _ in range(6):
+        lo, hi = S.rebalanced_cuts(frame["px"], lo, hi, slab_cost(lo, hi), side)
+        assert lo[0] == -np.inf and hi[-1] == np.inf and np.all(lo[1:] == hi[:-1]) and np.all(np.diff(hi[:-1]) >= 0)
+        owner = S.owner_of(frame["px"], lo, hi)
+        assert np.all((frame["px"] >= lo[owner]) & (frame["px"] < hi[owner]))
+    last = slab_cost(lo, hi)
+    assert last.max() / last.mean() < 1.1 < first.max() / first.mean(), (first, last)
+    # one slab: nothing to cut
+    l1, h1 = S.rebalanced_cuts(frame["px"], np.array([-np.inf], np.float32), np.array([np.inf], np.float32), [1.0], side)
+    assert l1.tolist() == [-np.inf] and h1.tolist() == [np.inf]
