@@ -7,9 +7,11 @@
 // Here the table is an open-addressing hash table in HBM keyed by (i << 32 | j); a frame's emitted
 // pairs are folded into it where they lie (the pair buffer never leaves the device) and only the
 // CHANGES -- created alerts, priority changes, expiries -- are handed to the host.
-//   entry = 40 bytes: key, timestamp (float64 like time.time()), risk, ttc, distance, alert number, priority, acknowledged
+//   entry = 40 bytes: key, timestamp (float64 like time.time()), risk, ttc, distance, and one 64-bit state word
+//   {alert number, priority, acknowledged} that is read and written whole (an update never needs a fence)
 // Expiry rebuilds the table into its twin (no tombstones).
 #pragma once
+#include <cstddef>
 #include "rcd_common.cuh"
 
 namespace rcd {
@@ -18,16 +20,25 @@ struct AlertEntry {
     unsigned long long key;  // i << 32 | j; ALERT_EMPTY = free
     double ts;
     float risk, ttc, distance;
+    u32 pad2;
+    // the state word (offset 32, 8-byte aligned): everything an update has to READ.  The creator of an entry writes it
+    // LAST, whole; the table is initialised to 0xff.., so an unpublished entry reads alert_id = ALERT_ID_NONE
     u32 alert_id;
     int8_t priority;
     uint8_t acked;
     uint16_t pad;
-    u32 pad2;
 };
-static_assert(sizeof(AlertEntry) == 40, "AlertEntry is 40 bytes");
+static_assert(sizeof(AlertEntry) == 40 && offsetof(AlertEntry, alert_id) == 32, "AlertEntry: 40 bytes, state word at 32");
 static_assert(sizeof(rcd_alert_event) == 40, "rcd_alert_event is 40 bytes");
 constexpr unsigned long long ALERT_EMPTY = ~0ull;
 constexpr u32 ALERT_ID_NONE = 0xffffffffu;  // an entry whose creator has not published it yet
+
+__device__ __forceinline__ unsigned long long alert_state(u32 id, int priority, u32 acked) {
+    return (unsigned long long)id | ((unsigned long long)(uint8_t)priority << 32) | ((unsigned long long)(acked & 0xffu) << 40);
+}
+__device__ __forceinline__ volatile unsigned long long *alert_state_ptr(AlertEntry *a) {
+    return reinterpret_cast<volatile unsigned long long *>(&a->alert_id);
+}
 
 struct AlertCounters {
     unsigned long long n_events;     // events appended (may exceed the buffer; only the first cap are stored)
@@ -96,10 +107,10 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
     u32 created = 0, changed = 0, refreshed = 0, dropped = 0;
     // A key can occur twice in one pass (a vehicle without history owes the same risk as detect_collisions and as
     // the fall-back of predict_collisions): the thread that loses the insertion may arrive before the winner has
-    // filled the entry in.  The winner publishes the entry by writing alert_id LAST (the table is initialised to
-    // 0xff.., so an unpublished entry reads ALERT_ID_NONE); a loser that finds it unpublished counts a silent
-    // refresh (what the reference's loop does with the second copy: update_alert with the same priority) and,
-    // if refreshes are reported, fetches the number after its other work.
+    // filled the entry in.  The winner publishes the entry by writing its state word LAST; a loser that finds it
+    // unpublished counts a silent refresh (what the reference's loop does with the second copy: update_alert with
+    // the same priority) and, if refreshes are reported, fetches the number after its other work.  Updates of
+    // published entries read the state word whole and need no fence: the rest of the entry is only ever written here.
     constexpr int MAX_DEFERRED = 2;
     rcd_alert_event deferred[MAX_DEFERRED];
     volatile u32 *deferred_id[MAX_DEFERRED];
@@ -120,32 +131,40 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
                     ++dropped;
                 } else {
                     e.i = p.i; e.j = p.j; e.risk = p.risk; e.ttc = p.ttc; e.distance = p.distance; e.priority = p.priority;
+                    volatile unsigned long long *sp = alert_state_ptr(a);
                     volatile u32 *idp = &a->alert_id;
                     if (inserted) {  // create_alert (:120-160)
-                        a->acked = 0; a->pad = 0; a->pad2 = 0;
-                        a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->priority = p.priority; a->ts = now;
+                        a->pad2 = 0;
+                        a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->ts = now;
                         e.alert_id = atomicAdd(&c->next_id, 1u);
                         __threadfence();
-                        *idp = e.alert_id;  // publishes the entry
+                        *sp = alert_state(e.alert_id, p.priority, 0u);  // publishes the entry
                         e.kind = RCD_ALERT_CREATED;
                         e.old_priority = -1;
                         ++created;
                         emit = true;
-                    } else if ((e.alert_id = *idp) == ALERT_ID_NONE) {  // being created by another thread of this pass
-                        e.kind = RCD_ALERT_REFRESHED;
-                        e.old_priority = p.priority;
-                        ++refreshed;
-                        if (emit_refreshed) {
-                            if (n_deferred < MAX_DEFERRED) { deferred[n_deferred] = e; deferred_id[n_deferred] = idp; ++n_deferred; }
-                            else emit = true;
+                    } else {
+                        const unsigned long long st = *sp;
+                        e.alert_id = (u32)st;
+                        if (e.alert_id == ALERT_ID_NONE) {  // being created by another thread of this pass
+                            e.kind = RCD_ALERT_REFRESHED;
+                            e.old_priority = p.priority;
+                            ++refreshed;
+                            if (emit_refreshed) {
+                                if (n_deferred < MAX_DEFERRED) { deferred[n_deferred] = e; deferred_id[n_deferred] = idp; ++n_deferred; }
+                                else emit = true;
+                            }
+                        } else {     // update_alert (:162-197): the priority queue only hears of priority changes
+                            const int old_priority = (int)(int8_t)((st >> 32) & 0xffu);
+                            const u32 acked = (u32)((st >> 40) & 0xffu);
+                            e.old_priority = (int8_t)old_priority;
+                            e.acknowledged = (uint8_t)acked;
+                            a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->ts = now;
+                            if (old_priority != (int)p.priority) {
+                                *sp = alert_state(e.alert_id, p.priority, acked);
+                                e.kind = RCD_ALERT_PRIORITY_CHANGED; ++changed; emit = true;
+                            } else { e.kind = RCD_ALERT_REFRESHED; ++refreshed; emit = emit_refreshed != 0; }
                         }
-                    } else {         // update_alert (:162-197): the priority queue only hears of priority changes
-                        __threadfence();
-                        e.old_priority = a->priority;
-                        e.acknowledged = a->acked;
-                        if (a->priority != p.priority) { e.kind = RCD_ALERT_PRIORITY_CHANGED; ++changed; emit = true; }
-                        else { e.kind = RCD_ALERT_REFRESHED; ++refreshed; emit = emit_refreshed != 0; }
-                        a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->priority = p.priority; a->ts = now;
                     }
                 }
             }

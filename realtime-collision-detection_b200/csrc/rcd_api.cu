@@ -134,6 +134,11 @@ struct rcd_handle_s {
     Counters *pend_counters_host = nullptr;  // pinned snapshot of the pending frame's totals
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t pend_event = nullptr;
+    // summary deliveries fold the frame into the alert table on a stream of their own, next to the kernels of the
+    // following frame (random 40-byte accesses beside ALU-bound pair kernels)
+    cudaStream_t alert_stream = nullptr;
+    cudaEvent_t ev_frame_done = nullptr, ev_alert_done = nullptr;
+    bool alert_async = false;  // work on alert_stream the handle's stream has not been ordered after yet
     bool flip_pending = false, download_pending = false;
     rcd_pair *pend_dev = nullptr, *pend_out = nullptr;
     u64 pend_cap = 0, pend_n = 0, pend_n_owned = 0;
@@ -516,6 +521,8 @@ int rcd_destroy(rcd_handle h) {
     cudaSetDevice(h->device);
     if (h->up_stream) cudaStreamSynchronize(h->up_stream);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->alert_stream) cudaStreamSynchronize(h->alert_stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (int k = 0; k < 11; ++k) cudaFree(h->in_f[k]);
     cudaFree(h->sorted_id);
     if (h->ev_upload_done) cudaEventDestroy(h->ev_upload_done);
@@ -541,6 +548,9 @@ int rcd_destroy(rcd_handle h) {
     if (h->pend_counters_host) cudaFreeHost(h->pend_counters_host);
     if (h->pend_event) cudaEventDestroy(h->pend_event);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->alert_stream) { cudaStreamSynchronize(h->alert_stream); cudaStreamDestroy(h->alert_stream); }
+    if (h->ev_frame_done) cudaEventDestroy(h->ev_frame_done);
+    if (h->ev_alert_done) cudaEventDestroy(h->ev_alert_done);
     cudaFree(h->alert_tab[0]); cudaFree(h->alert_tab[1]); cudaFree(h->alert_ev); cudaFree(h->alert_counters);
     if (h->alert_counters_host) cudaFreeHost(h->alert_counters_host);
     if (h->counters_host) cudaFreeHost(h->counters_host);
@@ -1039,6 +1049,17 @@ static int delivery_ready(rcd_handle h) {
         CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void **>(&h->pend_alert_counters_host), sizeof(AlertCounters)));
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->pend_event, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->alert_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_frame_done, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_alert_done, cudaEventDisableTiming));
+    }
+    return RCD_OK;
+}
+// Order the handle's stream after the alert-table work a summary delivery left on alert_stream.
+static int alerts_join(rcd_handle h) {
+    if (h->alert_async) {
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_alert_done, 0));
+        h->alert_async = false;
     }
     return RCD_OK;
 }
@@ -1061,9 +1082,10 @@ static int delivery_begin(rcd_handle h, const char *who) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     return delivery_ready(h);
 }
-static int delivery_issued(rcd_handle h) {  // the frame's totals ride along; later work goes to the twin buffers
-    CUDA_TRY(h, cudaMemcpyAsync(h->pend_counters_host, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaEventRecord(h->pend_event, h->stream));
+static int delivery_issued(rcd_handle h, cudaStream_t on = nullptr) {  // the frame's totals ride along; later work goes to the twin buffers
+    if (!on) on = h->stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->pend_counters_host, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, on));
+    CUDA_TRY(h, cudaEventRecord(h->pend_event, on));
     h->pend_dev = h->out;
     h->pend_risk = h->risk_count;
     h->pend_n = h->n;
@@ -1452,6 +1474,10 @@ extern "C++" {
 template <typename F>
 static int alerts_call(rcd_handle h, rcd_alert_event *events, uint64_t cap, rcd_alert_stats *stats, bool reset_live, F launch) {
     CUDA_TRY(h, cudaSetDevice(h->device));
+    {
+        int rcj = alerts_join(h);
+        if (rcj) return rcj;
+    }
     CUDA_TRY(h, cudaMemsetAsync(h->alert_counters, 0, offsetof(AlertCounters, n_live), h->stream));
     if (reset_live) CUDA_TRY(h, cudaMemsetAsync(&h->alert_counters->n_live, 0, sizeof(unsigned long long), h->stream));
     int rc = launch();
@@ -1469,6 +1495,8 @@ static int alerts_call(rcd_handle h, rcd_alert_event *events, uint64_t cap, rcd_
 int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts) {
     if (!h || max_alerts == 0 || max_alerts > (1ull << 31)) return h ? fail(h, RCD_EINVAL, "rcd_alerts_configure: max_alerts must be in [1, 2^31]") : RCD_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->alert_stream) CUDA_TRY(h, cudaStreamSynchronize(h->alert_stream));
+    h->alert_async = false;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(h->alert_tab[0]); cudaFree(h->alert_tab[1]); cudaFree(h->alert_ev); cudaFree(h->alert_ev_alt); cudaFree(h->alert_counters);
     if (h->alert_counters_host) cudaFreeHost(h->alert_counters_host);
@@ -1491,13 +1519,14 @@ int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts) {
 
 // fold pairs into the table (both passes), events -> h->alert_ev
 static int alerts_enqueue_update(rcd_handle h, const rcd_pair *dev_pairs, u64 n_max, const unsigned long long *n_dev, double now,
-                                 int32_t report_refreshed) {
+                                 int32_t report_refreshed, cudaStream_t on = nullptr) {
     if (n_max == 0) return RCD_OK;
+    if (!on) on = h->stream;
     int sms = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
     const unsigned blocks = (unsigned)std::min<u64>((n_max + ALERT_THREADS - 1) / ALERT_THREADS, (u64)std::max(1, sms) * 8);
     for (int pass = 0; pass < 2; ++pass) {
-        k_alert_update<<<blocks, ALERT_THREADS, 0, h->stream>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
+        k_alert_update<<<blocks, ALERT_THREADS, 0, on>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
                                                                 h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
                                                                 h->alert_counters, report_refreshed);
         KERNEL_CHECK(h);
@@ -1518,13 +1547,22 @@ int rcd_summary_begin(rcd_handle h, double now, int32_t report_refreshed) {
     if (rc) return rc;
     if (!h->alert_ev_alt) CUDA_TRY(h, dev_alloc(&h->alert_ev_alt, (size_t)h->alert_ev_cap));
     std::swap(h->alert_ev, h->alert_ev_alt);  // the events of the previous summary may still be on their way to the host
-    CUDA_TRY(h, cudaMemsetAsync(h->alert_counters, 0, offsetof(AlertCounters, n_live), h->stream));
-    rc = alerts_enqueue_update(h, h->out, h->max_pairs, &h->counters->n_pairs, now, report_refreshed);
+    // the fold runs on alert_stream, after the frame and beside whatever the handle's stream does next (the next
+    // frame writes the twin pair buffer and twin totals; other alert calls join alert_stream first)
+    cudaStream_t as = h->alert_stream;
+    CUDA_TRY(h, cudaEventRecord(h->ev_frame_done, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(as, h->ev_frame_done, 0));
+    CUDA_TRY(h, cudaMemsetAsync(h->alert_counters, 0, offsetof(AlertCounters, n_live), as));
+    rc = alerts_enqueue_update(h, h->out, h->max_pairs, &h->counters->n_pairs, now, report_refreshed, as);
     if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->pend_alert_counters_host, h->alert_counters, sizeof(AlertCounters), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->pend_alert_counters_host, h->alert_counters, sizeof(AlertCounters), cudaMemcpyDeviceToHost, as));
     h->pend_kind = 2;
     h->pend_ev = h->alert_ev;
-    return delivery_issued(h);
+    rc = delivery_issued(h, as);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaEventRecord(h->ev_alert_done, as));
+    h->alert_async = true;
+    return RCD_OK;
 }
 
 int rcd_summary_finish(rcd_handle h, rcd_alert_event *events, uint64_t cap, uint64_t *n_events, rcd_alert_stats *stats,
@@ -1602,6 +1640,8 @@ int rcd_alerts_acknowledge(rcd_handle h, uint64_t n, const uint32_t *i, const ui
     if (n == 0) return RCD_OK;
     if (n > 0xffffffffull) return fail(h, RCD_ECAPACITY, "rcd_alerts_acknowledge: too many pairs");
     CUDA_TRY(h, cudaSetDevice(h->device));
+    rc = alerts_join(h);
+    if (rc) return rc;
     u32 *d = nullptr;
     CUDA_TRY(h, dev_alloc(&d, 2 * (size_t)n + 1));
     cudaError_t e = cudaMemcpyAsync(d, i, (size_t)n * sizeof(u32), cudaMemcpyHostToDevice, h->stream);
@@ -1788,6 +1828,7 @@ int rcd_sync(rcd_handle h) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(h->up_stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->alert_stream) CUDA_TRY(h, cudaStreamSynchronize(h->alert_stream));
     return RCD_OK;
 }
 

@@ -18,8 +18,11 @@
 //                  expanded about the middle tm of the time window, g(tm + u) = g0 + g1 u + ca u^2 / 2 with
 //                  g0 = centre_i(tm) - pos_j(tm) and g1 the relative velocity at tm -- differences of
 //                  per-object quantities, so the neighbour's half is computed once when it is staged --
-//                  and the linear part must come within  L = A_i + B_j + 0.9 |g1|  on |u| <= D, where
-//                  A_i, B_j bound the safe distance, the motion of the 10 samples and |ca| D^2 / 2.
+//                  and the linear part must come within  L = A_i + B_j + kq |ca|  for some u in [-D, D + 0.9]:
+//                  A_i, B_j bound the safe distance and the rounding, kq |ca| the curvature |ca| D^2 / 2 and the
+//                  part of the 10 samples' motion that is not along g1 (the samples of an offset move with the
+//                  pair's CURRENT relative velocity rv = g1 + delta for tau <= 0.9 s: the part along g1 only
+//                  stretches the window by 0.9 s, |delta| <= |v_i - uv_i| + tm |ca| goes into the bound).
 //              Survivors (about 1 in 20) are appended to the pair queue QA, which warps fill in private
 //              2048-entry blocks (one global atomic per block, not per push).
 //   k_narrow : QA -> Q3.  A warp takes 32 queued pairs (lane = pair): detect narrow phase (temporal
@@ -929,23 +932,29 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
         const float Mx = fmaf(uax, h2, fmaf(uvx, tm, p0.x)), My = fmaf(uay, h2, fmaf(uvy, tm, p0.y)),
                     Mz = fmaf(uaz, h2, fmaf(uvz, tm, p0.z));
         const float MVx = fmaf(uax, tm, uvx), MVy = fmaf(uay, tm, uvy), MVz = fmaf(uaz, tm, uvz);
-        // L = A_i + B_j + krv |g1| + kq |Ua_i - a_j| bounds: the safe distance, guard bands, the motion of the 10
-        // samples (0.9 |rv| + 0.405 |ra|, predict only), |ca| D^2 / 2 and the fp32 rounding of M, MV (x4), with
-        // |rv| <= |g1| + |v_i - uv_i| + tm |Ua_i - a_j|,  |ra| <= |Ua_i - a_j| + |a_i - Ua_i|,  |ca| = |Ua_i - a_j|
-        // (Ua_i = ua_i: the acceleration the query's centre path follows).
-        float A, krv, kq;
+        // The linear part of the relative trajectory must come within  L = A_i + B_j + kq |Ua_i - a_j|  of zero for
+        // some u in [-D, Dhi].  Predict queries: a hit at offset t_m = tm + u, sample tau is
+        //   |g(t_m) + rv tau + ra tau^2 / 2| <= safe,   g(tm + u) = g0 + g1 u + ca u^2 / 2  (exact),
+        // and with rv = g1 + delta, delta = (v_i - uv_i) - ca tm, this is
+        //   |g0 + g1 (u + tau)| <= safe + 0.405 |ra| + 0.9 |delta| + |ca| D^2 / 2,   u + tau in [-D, D + 0.9]:
+        // the motion of the samples along g1 only stretches the window (Dhi = D + 0.9); what is left of it,
+        // 0.9 |delta| <= 0.9 |v_i - uv_i| + 0.9 tm |ca|, and |ra| <= |ca| + |a_i - Ua_i| go into A and kq
+        // (ca = Ua_i - a_j: the acceleration the query's centre path follows, minus the neighbour's).  The detect
+        // part of the fused frame follows the same g for accelerating patterns: its samples g(0.1 k), k < 100, lie
+        // inside the stretched window and the curvature up to there, |ca| (D + 0.4)^2 / 2, is below kq |ca|.
+        // Radius queries have no sample motion: Dhi = D, kq = D^2 / 2.  err: fp32 rounding of M, MV (x4).
+        float A, kq, Dhi;
         {
+            Dhi = radius_query ? D : D + 0.9f;
             const float err = 5.0e-7f * (abs3(p0.x, p0.y, p0.z) + tm * abs3(uvx, uvy, uvz) + h2 * abs3(uax, uay, uaz)) +
-                              5.0e-7f * D * (abs3(uvx, uvy, uvz) + tm * abs3(uax, uay, uaz));
+                              5.0e-7f * (D + 0.9f) * (abs3(uvx, uvy, uvz) + tm * abs3(uax, uay, uaz));
             if (radius_query) {
                 A = 0.5f * p0.w + 5.0f + 2.0e-2f + err;
-                krv = 0.0f;
                 kq = 0.5f * D * D * (1.0f + 1.2e-4f);
             } else {
                 const float dvx = p1.x - uvx, dvy = p1.y - uvy, dvz = p1.z - uvz;
                 const float dvn = sqrt_ub(dvx * dvx + dvy * dvy + dvz * dvz);
                 A = 0.5f * p0.w + 5.0f + 2.0e-2f + 0.405f * an * (1.0f - fa) + 0.9f * dvn + err;
-                krv = 0.9f * (1.0f + 1.2e-4f);
                 kq = (0.405f + 0.9f * tm + 0.5f * D * D) * (1.0f + 1.2e-4f);
             }
             A *= 1.0f + 1.0e-4f;
@@ -1033,7 +1042,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         nvy = -fmaf(q2.y, tm, q1.y);
                         nvz = -fmaf(q2.z, tm, q1.z);
                         const float err = 5.0e-7f * (abs3(q0.x, q0.y, q0.z) + tm * abs3(q1.x, q1.y, q1.z) + h2 * abs3(q2.x, q2.y, q2.z)) +
-                                          5.0e-7f * D * (abs3(q1.x, q1.y, q1.z) + tm * abs3(q2.x, q2.y, q2.z));
+                                          5.0e-7f * (D + 0.9f) * (abs3(q1.x, q1.y, q1.z) + tm * abs3(q2.x, q2.y, q2.z));
                         B = (0.5f * q0.w + err) * (1.0f + 1.0e-4f);
                         nax = -q2.x; nay = -q2.y; naz = -q2.z;
                     }
@@ -1101,10 +1110,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         const float2 g12 = fma2(hz, hz, fma2(hy, hy, mul2(hx, hx)));
                         const float2 dot = fma2(gz, hz, fma2(gy, hy, mul2(gx, hx)));
                         const float2 g12c = make_float2(fmaxf(g12.x, 1.0e-12f), fmaxf(g12.y, 1.0e-12f));
-                        const float2 r = make_float2(rsqrt_fast(g12c.x), rsqrt_fast(g12c.y));
-                        const float2 sn = mul2(g12c, r);                 // |g1| (to ~3e-7)
-                        const float2 um = mul2(dot, mul2(r, r));          // -(minimum of the linear part, relative to tm)
-                        const float2 uc = make_float2(fminf(fmaxf(-um.x, -D), D), fminf(fmaxf(-um.y, -D), D));
+                        const float2 um = mul2(dot, make_float2(rcp_fast(g12c.x), rcp_fast(g12c.y)));  // -(minimum of the linear part, relative to tm)
+                        const float2 uc = make_float2(fminf(fmaxf(-um.x, -D), Dhi), fminf(fmaxf(-um.y, -D), Dhi));
                         const float2 lx = fma2(hx, uc, gx), ly = fma2(hy, uc, gy), lz = fma2(hz, uc, gz);
                         const float2 l2 = fma2(lz, lz, fma2(ly, ly, mul2(lx, lx)));
                         const float4 naxy = b.naxy[u];
@@ -1115,7 +1122,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         const float2 q2 = fma2(qz, qz, fma2(qy, qy, mul2(qx, qx)));
                         const float2 q2c = make_float2(fmaxf(q2.x, 1.0e-30f), fmaxf(q2.y, 1.0e-30f));
                         const float2 qn = mul2(q2c, make_float2(rsqrt_fast(q2c.x), rsqrt_fast(q2c.y)));
-                        const float2 L = fma2(splat2(kq), qn, fma2(splat2(krv), sn, add2(make_float2(zb.z, zb.w), splat2(A))));
+                        const float2 L = fma2(splat2(kq), qn, add2(make_float2(zb.z, zb.w), splat2(A)));
                         const float2 L2 = mul2(L, L);
                         ta = l2.x <= L2.x;
                         tb = l2.y <= L2.y;

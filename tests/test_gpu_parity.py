@@ -584,3 +584,65 @@ def test_graph_replay_gives_the_same_frames():
             assert e.download().tobytes() == ref.download().tobytes()
             assert e.counts() == ref.counts()
         assert e.graph_replays() > before
+
+
+@pytest.mark.parametrize("workload,n", [("cfg1_1k_city", 1000), ("cfg2_5k_city", 5000)])
+def test_reference_perf_test_configs_full_oracle(workload, n):
+    """BASELINE configs[0] / configs[1] exactly as bench.py runs them (the reference generator's frame and the frame
+    after one motion step, performance_test.py:82-195): the fused bench frame against the full oracle, with the
+    bench's patterns (all accelerating) and with mixed patterns."""
+    import bench
+    from rcd_b200.host import workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    frames, _desc, bounds, _side = bench.make_frames(workload, 1, n, 2)
+    with FrameEngine(n, 64 * n, world_bounds=bounds) as e:
+        for k, frame in enumerate(frames):
+            got = _check_fused(e, frame, np.full(n, 2, np.uint8))
+            assert len(got) > 100
+            _check_fused(e, frame, W.random_patterns(n, 40 + k))
+
+
+@pytest.mark.parametrize("law", ["reference", "uniform"])
+def test_reduced_configs4_heavy_skew_sampled_oracle_and_overflow(law):
+    """configs[4] (10 M objects, Zipf-weighted hotspots, both radial laws of SURVEY.md 8d) reduced to 150 k objects
+    at the same density law: a hotspot core with thousands of objects inside one search radius.  (a) sampled queries
+    against the full-index oracle, records and per-object risk counts; (b) the same frame through an engine whose
+    pair buffer and queues are far too small: the overflow passes finish the pairs in place, every total stays exact
+    and the records that were stored are real ones."""
+    from rcd_b200.host import _native as N, workloads as W
+    from rcd_b200.host.engine import FrameEngine
+    O = _oracle()
+    n = 150_000
+    side = 100000.0 * np.sqrt(n / 10_000_000)
+    frame = W.hotspot_frame(n, 2003, side, 3, zipf_s=1.0, radial_law=law)
+    pat = np.full(n, 2, np.uint8)
+    f64 = f64_frame(frame)
+    stride = 101
+    bounds = ((0, 0, 0), (side, side, 100))
+    with FrameEngine(n, 8_000_000, world_bounds=bounds) as big, FrameEngine(n, 100_000, world_bounds=bounds) as small:
+        for e in (big, small):
+            e.upload(frame)
+            e.set_patterns(pat)
+            e.step(N.MODE_PREDICT, with_detect=True)
+        cb, cs = big.counts(), small.counts()
+        assert cb["n_written"] == cb["n_pairs"], "the big buffer must hold the frame"
+        if law == "reference":
+            assert cb["n_pairs"] > 1_500_000  # the dense core really is there
+        got = big.download()
+        sel = got[got["i"] % stride == 0]
+        det = O.frame_A(f64, "detect", want_potentials=False, query_stride=stride, risk_cap=1 << 24)["risks"]
+        pred = O.frame_A(f64, "predict", pattern_codes=pat, want_potentials=False, query_stride=stride, risk_cap=1 << 24)["risks"]
+        compare_pairs(sel[sel["predicted"] == 0], det, "detect")
+        compare_pairs(sel[sel["predicted"] == 1], pred, "predict")
+        q = np.arange(0, n, stride)
+        want_counts = np.bincount(np.concatenate([det["i"], pred["i"]]).astype(np.int64), minlength=n)
+        assert np.array_equal(big.risk_counts()[q], want_counts[q])
+        # (b) overflow: totals exact, per-object risk counts exact, stored records are a subset
+        assert cs["n_written"] == 100_000 < cs["n_pairs"]
+        for k in ("n_pairs", "n_candidates", "n_potential", "n_high_risk", "n_alerts"):
+            assert cs[k] == cb[k], k
+        assert cs["n_fallback"] == 0 and cb["n_fallback"] == 0
+        assert np.array_equal(small.risk_counts(), big.risk_counts())
+        part = small.download(sort=False)
+        key = lambda a: (a["i"].astype(np.int64) << 33) | (a["j"].astype(np.int64) << 1) | a["predicted"].astype(np.int64)
+        assert np.isin(key(part), key(got)).all()

@@ -22,7 +22,12 @@ rows = list(csv.reader(csvtxt.splitlines()))
 hi = [k for k, r in enumerate(rows) if "Instructions Executed" in r][0]
 hdr = rows[hi]; ia = hdr.index("Instructions Executed"); iat = hdr.index("Avg. Threads Executed")
 isamp = hdr.index("Warp Stall Sampling (All Samples)") if "Warp Stall Sampling (All Samples)" in hdr else None
-data = [r for r in rows[hi + 1:] if len(r) > ia and r[ia].isdigit()]
+data = []
+for r in rows[hi + 1:]:  # the first launch only (the report repeats the table per launch)
+    if r and r[0] == "Kernel Name":
+        break
+    if len(r) > ia and r[ia].isdigit():
+        data.append(r)
 print("sass rows", len(seq), len(data))
 tot = sum(int(r[ia]) for r in data); print("total warp instr", tot)
 agg, thr, smp = collections.Counter(), collections.Counter(), collections.Counter()
