@@ -41,7 +41,8 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = LIB + ".building"  # (renamed into place when complete: a snapshot never sees half a library)
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     # the host compiler must be one nvcc 12.9 accepts; /usr/bin/g++ (13.x) is
     if os.path.exists("/usr/bin/g++"):
         cmd += ["-ccbin", "/usr/bin/g++"]
@@ -49,7 +50,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose or r.returncode != 0:
         sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building librcd_b200.so")
+    os.replace(tmp, LIB)
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write(r.stdout + r.stderr)
     return LIB

@@ -118,11 +118,9 @@ struct StagePacked {      // a chunk of 32 neighbours, two side by side per entr
 struct WarpShared {
     float4 r0[CH], r1[CH], r2[CH];  // landing zone of the cp.async copies (the chunk after the one being filtered)
     StagePacked buf[2];
-    unsigned char plist[CH][TQ];    // per-lane lists of the staged neighbours that passed: index | flags
     u32 row_lo[TQ];
     u32 row_prefix[TQ + 1];
 };
-constexpr u32 PL_INR = 0x40u, PL_UND = 0x80u;
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -874,7 +872,7 @@ __global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
 // no call in its loops.
 template <int MODE, bool COUNT_CAND, bool SLOW>
 #ifndef RCD_PAIR_MIN_BLOCKS
-#define RCD_PAIR_MIN_BLOCKS 6
+#define RCD_PAIR_MIN_BLOCKS 5
 #endif
 __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) k_pairs(PairParams P) {
     __shared__ WarpShared shared[PAIR_WARPS];
@@ -959,15 +957,21 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
             }
             A *= 1.0f + 1.0e-4f;
         }
-        // what passes, per lane:  (t1 && d2 < dmaxA) || d2 < dmaxB || inside the guard band of the radius
-        float R2lo_l = -1.0f, R2hi_l = -1.0f, dmaxA = -1.0f, dmaxB = -1.0f;
+        // The filter keeps four bit masks per lane and chunk (bit = staged neighbour): im = inside the radius for
+        // certain, nm = inside radius + guard band, tm = passed T1 (or the capsule test), bm = within the compute-node
+        // distance bound.  What passes, per lane:  (tm & useT & (im | ~andI)) | (im & orI) | (bm & orB) | (nm & ~im):
+        //   radius query, T1 on  : in the radius and T1            radius query, T1 off : in the radius
+        //   predict query        : T1 (+ everything in the radius where the fused detect part follows another trajectory)
+        //   compute-node         : within min(radius, 50 m)
+        float R2lo_l = -1.0f, R2hi_l = -1.0f, dmaxB = -1.0f;
+        u32 useT = 0u, andI = 0u, orI = 0u, orB = 0u;
         if (counts) { R2lo_l = R2_lo; R2hi_l = R2_hi; }
         if (valid) {
-            if (MODE == RCD_MODE_COMPUTE_NODE) dmaxB = fminf(R2_lo, 2500.0f * (1.0f + 2.0f * BAND_R2));  // current_distance <= 50
-            else if (radius_query) { if (t1_on) dmaxA = R2_lo; else dmaxB = R2_lo; }
+            if (MODE == RCD_MODE_COMPUTE_NODE) { dmaxB = fminf(R2_lo, 2500.0f * (1.0f + 2.0f * BAND_R2)); orB = ~0u; }  // current_distance <= 50
+            else if (radius_query) { if (t1_on) { useT = ~0u; andI = ~0u; } else orI = ~0u; }
             else {
-                dmaxA = FAR;
-                if (FUSED && pattern != RCD_PAT_ACCELERATING) dmaxB = R2_lo;  // detect follows another trajectory: all of them
+                useT = ~0u;
+                if (FUSED && pattern != RCD_PAT_ACCELERATING) orI = ~0u;  // detect follows another trajectory: all of them
             }
         }
         const float rad2 = rad * rad;
@@ -1080,9 +1084,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                 if (more) stage(c + 1u, ws.buf[kbuf ^ 1u]);  // in flight while this chunk is filtered
                 const u32 m = min((u32)CH, total - c * CH);
                 // ---- S1: one query per lane against every staged neighbour, two per packed instruction -----
-                // Each lane appends what passes to a private list in shared memory (no warp vote per test).
-                u32 nc = 0;
-                unsigned char *pl = &ws.plist[0][lane];
+                // Each lane keeps what passes as bit masks over the staged chunk (no warp vote, no store per test).
+                u32 im = 0, nm = 0, tm = 0, bm = 0, bit = 1u;
                 const u32 npair = (m + 1u) >> 1;
                 for (u32 u = 0; u < npair; ++u) {
                     const float4 xy = b.xy[u];
@@ -1107,9 +1110,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         const float2 hx = add2(make_float2(nzv.z, nzv.w), splat2(MVx));  // g1 = MV_i - NV_j
                         const float2 hy = add2(make_float2(nvyz.x, nvyz.y), splat2(MVy));
                         const float2 hz = add2(make_float2(nvyz.z, nvyz.w), splat2(MVz));
-                        const float2 g12 = fma2(hz, hz, fma2(hy, hy, mul2(hx, hx)));
+                        const float2 g12c = fma2(hz, hz, fma2(hy, hy, fma2(hx, hx, splat2(1.0e-12f))));  // |g1|^2 (+ a floor)
                         const float2 dot = fma2(gz, hz, fma2(gy, hy, mul2(gx, hx)));
-                        const float2 g12c = make_float2(fmaxf(g12.x, 1.0e-12f), fmaxf(g12.y, 1.0e-12f));
                         const float2 um = mul2(dot, make_float2(rcp_fast(g12c.x), rcp_fast(g12c.y)));  // -(minimum of the linear part, relative to tm)
                         const float2 uc = make_float2(fminf(fmaxf(-um.x, -D), Dhi), fminf(fmaxf(-um.y, -D), Dhi));
                         const float2 lx = fma2(hx, uc, gx), ly = fma2(hy, uc, gy), lz = fma2(hz, uc, gz);
@@ -1119,30 +1121,32 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         const float2 qx = add2(make_float2(naxy.x, naxy.y), splat2(uax));  // Ua_i - a_j
                         const float2 qy = add2(make_float2(naxy.z, naxy.w), splat2(uay));
                         const float2 qz = add2(naz, splat2(uaz));
-                        const float2 q2 = fma2(qz, qz, fma2(qy, qy, mul2(qx, qx)));
-                        const float2 q2c = make_float2(fmaxf(q2.x, 1.0e-30f), fmaxf(q2.y, 1.0e-30f));
+                        const float2 q2c = fma2(qz, qz, fma2(qy, qy, fma2(qx, qx, splat2(1.0e-12f))));  // |ca|^2 (+ the same floor)
                         const float2 qn = mul2(q2c, make_float2(rsqrt_fast(q2c.x), rsqrt_fast(q2c.y)));
                         const float2 L = fma2(splat2(kq), qn, add2(make_float2(zb.z, zb.w), splat2(A)));
                         const float2 L2 = mul2(L, L);
                         ta = l2.x <= L2.x;
                         tb = l2.y <= L2.y;
                     }
-                    {   // (always stored at the end of the lane's list; the list only grows when the pair passed)
-                        const bool inr = d2.x < R2lo_l;
-                        const bool und = !inr && d2.x <= R2hi_l;
-                        *pl = (unsigned char)((2u * u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
-                        pl += ((ta && d2.x < dmaxA) || d2.x < dmaxB || und) ? TQ : 0;
-                        nc += inr ? 1u : 0u;
+                    im |= (d2.x < R2lo_l) ? bit : 0u;
+                    nm |= (d2.x <= R2hi_l) ? bit : 0u;
+                    im |= (d2.y < R2lo_l) ? (bit << 1) : 0u;
+                    nm |= (d2.y <= R2hi_l) ? (bit << 1) : 0u;
+                    if (USE_CAPSULE || t1_on) {
+                        tm |= ta ? bit : 0u;
+                        tm |= tb ? (bit << 1) : 0u;
                     }
-                    {
-                        const bool inr = d2.y < R2lo_l;
-                        const bool und = !inr && d2.y <= R2hi_l;
-                        *pl = (unsigned char)((2u * u + 1u) | (inr ? PL_INR : 0u) | (und ? PL_UND : 0u));
-                        pl += ((tb && d2.y < dmaxA) || d2.y < dmaxB || und) ? TQ : 0;
-                        nc += inr ? 1u : 0u;
+                    if (MODE == RCD_MODE_COMPUTE_NODE) {
+                        bm |= (d2.x < dmaxB) ? bit : 0u;
+                        bm |= (d2.y < dmaxB) ? (bit << 1) : 0u;
                     }
+                    bit <<= 2;
                 }
-                const u32 cnt = (u32)(pl - &ws.plist[0][lane]) / TQ;
+                if (!(USE_CAPSULE || t1_on)) tm = ~0u;
+                const u32 um = nm & ~im;   // inside the guard band of the radius: the exact stage decides (and counts)
+                const u32 pm = (tm & useT & (im | ~andI)) | (im & orI) | (bm & orB) | um;
+                const u32 nc = (u32)__popc(im);
+                const u32 cnt = (u32)__popc(pm);
                 // ---- survivors -> pair queue (the warp's private block; a new one when this one is full) -------
                 u32 off = cnt;
 #pragma unroll
@@ -1153,10 +1157,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                 const u32 total_pairs = __shfl_sync(FULL_MASK, off, 31);
                 off -= cnt;
                 if (SLOW) {  // overflow pass: finish every survivor here
-                    for (u32 k = 0; k < cnt; ++k) {
-                        const u32 code = ws.plist[k][lane];
+                    for (u32 rest = pm; rest; rest &= rest - 1u) {
+                        const u32 j = (u32)__ffs(rest) - 1u;
                         n_pot += narrow_entry_inline<MODE, COUNT_CAND>(
-                            P, s | ((code & PL_INR) ? QA_INR : 0u) | ((code & PL_UND) ? QA_UND : 0u), b.pos[code & 31u]);
+                            P, s | (((im >> j) & 1u) ? QA_INR : 0u) | (((um >> j) & 1u) ? QA_UND : 0u), b.pos[j]);
                     }
                 } else if (total_pairs) {
                     // room left in the warp's block; what does not fit goes to new blocks, taken with ONE atomic so that
@@ -1183,11 +1187,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                     }
                     uint2 *dst_cur = P.qa + ((size_t)(qa_block == QA_NO_BLOCK ? 0u : qa_block) * QA_BLOCK + qa_used);
                     uint2 *dst_new = P.qa + (size_t)nb * QA_BLOCK;
-                    for (u32 k = 0; __any_sync(FULL_MASK, k < cnt); ++k) {
-                        if (k < cnt) {
-                            const u32 code = ws.plist[k][lane];
-                            const uint2 e = make_uint2(s | ((code & PL_INR) ? QA_INR : 0u) | ((code & PL_UND) ? QA_UND : 0u), b.pos[code & 31u]);
-                            const u32 at = off + k;
+                    u32 at = off;
+                    for (u32 rest = pm; __any_sync(FULL_MASK, rest != 0u); rest &= rest - 1u, ++at) {
+                        if (rest) {
+                            const u32 j = (u32)__ffs(rest) - 1u;
+                            const uint2 e = make_uint2(s | (((im >> j) & 1u) ? QA_INR : 0u) | (((um >> j) & 1u) ? QA_UND : 0u), b.pos[j]);
                             if (at < room) dst_cur[at] = e; else dst_new[at - room] = e;
                         }
                     }
@@ -1330,8 +1334,12 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                         if (COUNT_CAND) {
                             mask = predict_mask<true>(P, a0, a1, a2, b0, b1, b2, si, sj, pat, n_exact);
                         } else {
-                            // the offsets whose state g(t_m) = centre_i(t_m) - predicted_j(t_m) is within reach of the 10
-                            // samples (|g| <= hr, the first half of offset_may_hit), two offsets per packed instruction
+                            // the offsets whose 10 samples can come within the safe distance at all (offset_may_hit): the
+                            // samples leave the offset state g(t_m) = centre_i(t_m) - predicted_j(t_m) along rv tau (+ at most
+                            // 0.405 |ra|), tau in [0, 0.9] -- closest point of that segment to the origin, two offsets per
+                            // packed instruction
+                            const float nir = -c.inv_rv2 * (1.0f / 0.9f);
+                            const float r9x = 0.9f * c.rvx, r9y = 0.9f * c.rvy, r9z = 0.9f * c.rvz;
 #pragma unroll
                             for (int m = 0; m < PREDICT_OFFSETS; m += 2) {
                                 const float2 t2 = make_float2(0.5f * (float)m, 0.5f * (float)(m + 1));
@@ -1339,8 +1347,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                                 const float2 gx = fma2(splat2(c.cvx), t2, fma2(splat2(c.cax), h2, splat2(-c.dx)));
                                 const float2 gy = fma2(splat2(c.cvy), t2, fma2(splat2(c.cay), h2, splat2(-c.dy)));
                                 const float2 gz = fma2(splat2(c.cvz), t2, fma2(splat2(c.caz), h2, splat2(-c.dz)));
-                                const float2 g2 = fma2(gz, gz, fma2(gy, gy, mul2(gx, gx)));
-                                mask |= (g2.x <= c.hr2 ? (1u << m) : 0u) | (g2.y <= c.hr2 ? (2u << m) : 0u);
+                                const float2 dot = fma2(gz, splat2(c.rvz), fma2(gy, splat2(c.rvy), mul2(gx, splat2(c.rvx))));
+                                const float2 sc = make_float2(__saturatef(dot.x * nir), __saturatef(dot.y * nir));  // tau / 0.9
+                                const float2 ex = fma2(splat2(r9x), sc, gx), ey = fma2(splat2(r9y), sc, gy), ez = fma2(splat2(r9z), sc, gz);
+                                const float2 e2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+                                mask |= (e2.x <= c.lim2 ? (1u << m) : 0u) | (e2.y <= c.lim2 ? (2u << m) : 0u);
                             }
                         }
                         if (mask) {
@@ -1440,15 +1451,8 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                     const float *c = sh.coef[pr];
                     const float t = 0.5f * (float)m, h = 0.5f * t * t;
                     const float dx = c[SC_D], dy = c[SC_D + 1], dz = c[SC_D + 2];
-                    const float gx = c[SC_CV] * t + c[SC_CA] * h - dx, gy = c[SC_CV + 1] * t + c[SC_CA + 1] * h - dy,
-                                gz = c[SC_CV + 2] * t + c[SC_CA + 2] * h - dz;
-                    const float rvx = c[SC_RV], rvy = c[SC_RV + 1], rvz = c[SC_RV + 2];
-                    {   // (|g| <= hr was taken in phase 1) the samples move along g + rv tau + ra tau^2 / 2
-                        const float tau = fminf(fmaxf(-(gx * rvx + gy * rvy + gz * rvz) * c[SC_INVRV2], 0.0f), 0.9f);
-                        const float ex = gx + rvx * tau, ey = gy + rvy * tau, ez = gz + rvz * tau;
-                        pass = ex * ex + ey * ey + ez * ez <= c[SC_LIM2];
-                    }
-                    if (pass) {  // neighbour within 100 m of the predicted centre?
+                    // (that the samples of this offset can reach the safe distance was established in phase 1)
+                    {   // neighbour within 100 m of the predicted centre?
                         const float ux = c[SC_UV] * t + c[SC_UA] * h - dx, uy = c[SC_UV + 1] * t + c[SC_UA + 1] * h - dy,
                                     uz = c[SC_UV + 2] * t + c[SC_UA + 2] * h - dz;
                         const float c2 = ux * ux + uy * uy + uz * uz;
