@@ -552,9 +552,11 @@ def measure(args, workload, per_gpu, world, rank, local_rank, flush, steps, warm
         cuts, rb_hist = rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rebalance_rounds)
     job = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=True, graph=args.graph)
     lat, halo_ms, stage_ms, launches, counts, t_wall = time_resident(job, steps, warmup, flush)
+    # a halo region that was too small would have dropped records: look at the device-side counts once, after the frames
+    halo_overflow = reduce_max(world, [1.0 if (job.exch is not None and job.exch.overflowed()) else 0.0])[0] > 0
     n_own_mean = float(np.mean([len(o["px"]) for o in job.own]))
     out = {"job": job, "lat": lat, "stage_ms": stage_ms, "launches": launches, "counts": counts, "t_wall": t_wall,
-           "rebalance_ms": rb_hist}
+           "rebalance_ms": rb_hist, "halo_overflow": bool(halo_overflow)}
     graph_replays = job.eng.graph_replays() if args.graph else 0
     if args.graph:  # stage breakdown on a profiled twin (outside every timed region)
         twin = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=True, graph=False)
@@ -656,7 +658,19 @@ def run_b200(args):
             "latency_ms": lat_stats(s["lat_all"]), "steps": xs, "per_rank_ms": s["per_rank_ms"],
             "per_rank_halo_ms": s["per_rank_halo_ms"], "pairs_emitted": s["n_pairs"], "halo_objects": s["n_halo"]}
         s["job"].close()
+        _FRAME_CACHE.clear()
         if world == 8:
+            # the north-star size: 10 M objects on the box, at the configs[3] density (1.25 M per GPU)
+            xs = max(5, min(steps, 10))
+            s = measure(args, "cfg4_1m_clustered3d", 1_250_000, world, rank, local_rank, flush, xs, 3, min(args.rebalance, 2),
+                        with_e2e=False, with_verify=False)
+            extras["north_star_10m"] = {
+                "workload": f"cfg4_1m_clustered3d: {s['job'].desc}", "scaling": "weak (1.25 M objects per GPU)",
+                "value": s["objs"] * xs / s["t_dev"], "unit": "object-updates/s", "ms_per_step": s["t_dev"] / xs * 1e3,
+                "latency_ms": lat_stats(s["lat_all"]), "steps": xs, "per_rank_ms": s["per_rank_ms"],
+                "per_rank_halo_ms": s["per_rank_halo_ms"], "pairs_emitted": s["n_pairs"], "halo_objects": s["n_halo"]}
+            s["job"].close()
+            _FRAME_CACHE.clear()
             for name in ("cfg5_10m_skew3d_uniform_disc", "cfg5_10m_skew3d"):
                 xs = 3
                 s = measure(args, name, 1_250_000, world, rank, local_rank, flush, xs, 3, 1, with_e2e=False, with_verify=False)
@@ -668,6 +682,7 @@ def run_b200(args):
                     "pairs_stored_cap_per_gpu": int(args.max_pairs),
                     "note": "counts are exact beyond the pair buffer; records past it are not stored"}
                 s["job"].close()
+                _FRAME_CACHE.clear()
 
     if rank == 0:
         from_peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -712,7 +727,7 @@ def run_b200(args):
             "latency_ms": lat_stats(m["lat_all"]),
             "frame_totals": {"pairs_emitted": m["n_pairs"], "candidates": m["n_cand"], "halo_objects": m["n_halo"]},
             "per_rank": {"frame_ms": m["per_rank_ms"], "halo_ms": m["per_rank_halo_ms"], "objects_with_halo": m["per_rank_objects"],
-                         "rebalance_rounds_ms": m["rebalance_ms"]},
+                         "rebalance_rounds_ms": m["rebalance_ms"], "halo_region_overflow": m["halo_overflow"]},
             "e2e": {"value": m["objs"] * steps / e2e["t"], "unit": "object-updates/s",
                     "h2d_bytes_per_step": int(m["objs"] * H2D_BYTES_PER_OBJECT), "d2h_bytes_per_step": int(m["d2h"]),
                     "delivery": "alert changes (rcd_alert_event, 40 B) + per-object risk counts + totals (rcd_summary_begin/_finish)",

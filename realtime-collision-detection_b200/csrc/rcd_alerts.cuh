@@ -91,7 +91,7 @@ __device__ __forceinline__ void alert_emit(bool flag, const rcd_alert_event &e, 
     if (at < cap) ev[at] = e;
 }
 
-constexpr int ALERT_THREADS = 256;
+constexpr int ALERT_THREADS = 128;
 
 // Fold pairs into the table: every pair with priority >= 0 (risk_level >= RISK_LEVEL_LOW, :273) whose
 // `predicted` flag equals `pass` (a frame that ran detect AND predict can carry one risk of each kind for

@@ -139,6 +139,7 @@ struct rcd_handle_s {
     cudaStream_t alert_stream = nullptr;
     cudaEvent_t ev_frame_done = nullptr, ev_alert_done = nullptr;
     bool alert_async = false;  // work on alert_stream the handle's stream has not been ordered after yet
+    u64 last_n_pairs = 0;      // emitted pairs of the last frame whose totals reached the host (sizes the alert fold's grid)
     bool flip_pending = false, download_pending = false;
     rcd_pair *pend_dev = nullptr, *pend_out = nullptr;
     u64 pend_cap = 0, pend_n = 0, pend_n_owned = 0;
@@ -447,7 +448,11 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     } while (0)
 
     CREATE_TRY(cudaSetDevice(h->device));
-    CREATE_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {   // the frame's stream outranks the alert stream: block slots go to the frame's kernels first
+        int least = 0, greatest = 0;
+        CREATE_TRY(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CREATE_TRY(cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, greatest));
+    }
     CREATE_TRY(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_upload_done, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&h->ev_inputs_free, cudaEventDisableTiming));
@@ -990,6 +995,7 @@ int rcd_counts(rcd_handle h, rcd_counts_t *out) {
     CUDA_TRY(h, cudaMemcpyAsync(h->counters_host, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     const Counters &c = *h->counters_host;
+    h->last_n_pairs = c.n_pairs;
     out->n_objects = h->n;
     out->n_owned = h->n_owned;
     out->n_candidates = c.n_candidates;
@@ -1049,7 +1055,11 @@ static int delivery_ready(rcd_handle h) {
         CUDA_TRY(h, cudaMallocHost(reinterpret_cast<void **>(&h->pend_alert_counters_host), sizeof(AlertCounters)));
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->pend_event, cudaEventDisableTiming));
-        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->alert_stream, cudaStreamNonBlocking));
+        {
+            int least = 0, greatest = 0;
+            CUDA_TRY(h, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            CUDA_TRY(h, cudaStreamCreateWithPriority(&h->alert_stream, cudaStreamNonBlocking, least));
+        }
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_frame_done, cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_alert_done, cudaEventDisableTiming));
     }
@@ -1064,6 +1074,7 @@ static int alerts_join(rcd_handle h) {
     return RCD_OK;
 }
 static void counts_out(rcd_handle h, const Counters &c, rcd_counts_t *counts) {
+    h->last_n_pairs = c.n_pairs;
     if (!counts) return;
     counts->n_objects = h->pend_n;
     counts->n_owned = h->pend_n_owned;
@@ -1521,14 +1532,23 @@ int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts) {
 static int alerts_enqueue_update(rcd_handle h, const rcd_pair *dev_pairs, u64 n_max, const unsigned long long *n_dev, double now,
                                  int32_t report_refreshed, cudaStream_t on = nullptr) {
     if (n_max == 0) return RCD_OK;
-    if (!on) on = h->stream;
     int sms = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
-    const unsigned blocks = (unsigned)std::min<u64>((n_max + ALERT_THREADS - 1) / ALERT_THREADS, (u64)std::max(1, sms) * 8);
+    sms = std::max(1, sms);
+    u64 blocks = std::min<u64>((n_max + ALERT_THREADS - 1) / ALERT_THREADS, (u64)sms * 16);
+    if (on) {
+        // beside the next frame (lower-priority stream): many short-lived blocks -- about one pair per thread, sized from
+        // the last pair count the host has seen; the grid-stride loop covers whatever the estimate misses -- so that
+        // block slots go back to the frame's kernels as soon as they ask for them
+        const u64 est = h->last_n_pairs ? h->last_n_pairs + h->last_n_pairs / 4 : (u64)sms * 16 * ALERT_THREADS;
+        blocks = std::min<u64>((n_max + ALERT_THREADS - 1) / ALERT_THREADS, std::max<u64>((est + ALERT_THREADS - 1) / ALERT_THREADS, (u64)sms));
+    } else {
+        on = h->stream;
+    }
     for (int pass = 0; pass < 2; ++pass) {
-        k_alert_update<<<blocks, ALERT_THREADS, 0, on>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
-                                                                h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
-                                                                h->alert_counters, report_refreshed);
+        k_alert_update<<<(unsigned)blocks, ALERT_THREADS, 0, on>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
+                                                        h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
+                                                        h->alert_counters, report_refreshed);
         KERNEL_CHECK(h);
     }
     return RCD_OK;
