@@ -356,8 +356,16 @@ int build_query_order(rcd_handle h, int kind) {
     QueryKeyParams q;
     q.ox = g.ox; q.oy = g.oy;
     const double ex = std::max((double)g.nx * g.cell, 1e-3), ey = std::max((double)g.ny * g.cell, 1e-3);
-    q.inv_res_x = (float)(2048.0 / ex);
-    q.inv_res_y = (float)(2048.0 / ey);
+    // QKEY_BITS bits for both axes, split so that the lattice cells are as square as they get (x-slabs are long in y)
+    int bits_x = (int)std::floor(0.5 * (QKEY_BITS + std::log2(ex / ey)) + 0.5);
+    bits_x = std::min(16, std::max(QKEY_BITS - 16, bits_x));
+    const int bits_y = QKEY_BITS - bits_x;
+    q.max_x = (float)((1u << bits_x) - 1u);
+    q.max_y = (float)((1u << bits_y) - 1u);
+    q.inv_res_x = (float)((double)(1u << bits_x) / ex);
+    q.inv_res_y = (float)((double)(1u << bits_y) / ey);
+    q.bits_lo = std::min(bits_x, bits_y);
+    q.x_longer = bits_x > bits_y ? 1 : 0;
     q.capsule = kind == 2 ? 1 : 0;
     const int blocks = (int)std::min<u64>(((u64)n + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
     k_query_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(h->P0, h->P1, h->P2, n, q, h->qkeys[0], h->qvals[0], h->hist);

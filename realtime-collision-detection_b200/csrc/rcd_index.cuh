@@ -373,12 +373,12 @@ k_cell_table(const u32 *__restrict__ keys, u32 n, u32 ncells, u32 *__restrict__ 
 // consecutive 32 objects are then a compact tile at any density.  Halo copies (not queried) get the
 // top key and end up behind the last tile.  Bytes: 48 N read + 8 N written, then the sort passes.
 // -------------------------------------------------------------------------------------------------
-constexpr int QKEY_BITS = 11;                       // per axis
-constexpr u32 QKEY_NOT_QUERIED = 1u << (2 * QKEY_BITS);  // bit 22: sorts behind every query
-constexpr int QKEY_PASSES = 3;                      // 23 bits
+constexpr int QKEY_BITS = 23;                       // both axes together, split so that the key lattice is (nearly) square
+constexpr u32 QKEY_NOT_QUERIED = 1u << QKEY_BITS;   // bit 23: sorts behind every query
+constexpr int QKEY_PASSES = 3;                      // 24 bits
 
-__device__ __forceinline__ u32 spread_bits_2d(u32 v) {  // 11 bits -> every other bit
-    v &= 0x7ffu;
+__device__ __forceinline__ u32 spread_bits_2d(u32 v) {  // 16 bits -> every other bit
+    v &= 0xffffu;
     v = (v | (v << 8)) & 0x00ff00ffu;
     v = (v | (v << 4)) & 0x0f0f0f0fu;
     v = (v | (v << 2)) & 0x33333333u;
@@ -389,6 +389,9 @@ __device__ __forceinline__ u32 spread_bits_2d(u32 v) {  // 11 bits -> every othe
 struct QueryKeyParams {
     float ox, oy;          // origin of the key lattice
     float inv_res_x, inv_res_y;
+    float max_x, max_y;    // 2^bits_x - 1, 2^bits_y - 1
+    int bits_lo;           // min(bits_x, bits_y): that many bits of each axis are interleaved; the longer axis keeps
+    int x_longer;          // its remaining high bits on top (a slab is 8 times as long as it is wide: 10 + 13 bits)
     int capsule;           // 1: predict queries are keyed by the middle of their chord
 };
 
@@ -414,9 +417,11 @@ k_query_keys(const float4 *__restrict__ P0, const float4 *__restrict__ P1, const
                 const float mx = x + p1.x * fv + p2.x * fa, my = y + p1.y * fv + p2.y * fa;
                 if (fabsf(mx) < 1.0e30f && fabsf(my) < 1.0e30f) { x = mx; y = my; }
             }
-            const float fx = fminf(fmaxf((x - q.ox) * q.inv_res_x, 0.0f), 2047.0f);  // NaN -> 0
-            const float fy = fminf(fmaxf((y - q.oy) * q.inv_res_y, 0.0f), 2047.0f);
-            key = spread_bits_2d((u32)fx) | (spread_bits_2d((u32)fy) << 1);
+            const u32 ix = (u32)fminf(fmaxf((x - q.ox) * q.inv_res_x, 0.0f), q.max_x);  // NaN -> 0
+            const u32 iy = (u32)fminf(fmaxf((y - q.oy) * q.inv_res_y, 0.0f), q.max_y);
+            const u32 lo_mask = (1u << q.bits_lo) - 1u;
+            key = spread_bits_2d(ix & lo_mask) | (spread_bits_2d(iy & lo_mask) << 1) |
+                  (((q.x_longer ? ix : iy) >> q.bits_lo) << (2 * q.bits_lo));
         }
         keys[s] = key;
         vals[s] = s;

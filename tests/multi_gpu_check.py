@@ -7,7 +7,10 @@ import numpy as np
 import torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rcd_b200.host import workloads as W, _native as N, slabs as S
+from rcd_b200.host.data_sharding import ShardManager
 from rcd_b200.host.engine import FrameEngine
+from rcd_b200.host.models import Position
+from rcd_b200.host.spatial_index import SpatialIndex, SpatialPartitioner
 from tests.gpu_helpers import compare_pairs
 from oracle import oracle as O
 
@@ -87,11 +90,38 @@ def check(lo, hi, label):
 
 lo, hi = S.slab_bounds(frame, world, box)
 check(lo, hi, "initial cuts")
-# move the cuts as the re-balancing step would (pretend the first slab was the slowest by far)
-ms = [3.0] + [1.0] * (world - 1)
-lo2, hi2 = S.rebalanced_cuts(frame["px"], lo, hi, ms, box)
-assert not np.array_equal(hi, hi2)
+# The shard-manager adapter drives the re-balancing: the partitioner holds the cuts (slab mode),
+# the manager routes every vehicle to the slab it lies in and feeds the slabs' loads back; rebalance_shards() moves
+# the cuts (pretend the first slab was the slowest by far) and the halo exchange follows them.
+index = SpatialIndex()
+for k in range(n):
+    index.insert_vehicle(f"v{k}", Position(float(frame["px"][k]), float(frame["py"][k]), float(frame["pz"][k])))
+part = SpatialPartitioner(index, num_shards=world)
+
+
+class _Follower:  # stands for this rank's SlabExchange: receives the cuts the partitioner decides on
+    cuts = None
+
+    def set_cuts(self, lo, hi):
+        self.cuts = (lo, hi)
+
+
+follow = _Follower()
+part.attach_slabs(lo, hi, box, exchanges=[follow])
+mgr = ShardManager(part, initial_shards=world)
+routed = np.array([int(mgr.get_shard_for_vehicle(f"v{k}", index.get_vehicle_position(f"v{k}"))[6:]) for k in range(0, n, 7)])
+assert np.array_equal(routed, S.owner_of(frame["px"][::7], lo, hi)), "ShardManager routes by slab"
+mgr.update_shard_loads([3.0] + [1.0] * (world - 1))
+res = part.rebalance_shards()
+assert res["cuts_moved"] and follow.cuts is not None
+lo2, hi2 = follow.cuts
+assert not np.array_equal(hi, hi2) and float(hi2[0]) < float(hi[0]), "the slow slab must shrink"
+moved = sum(mgr.get_shard_for_vehicle(f"v{k}", index.get_vehicle_position(f"v{k}")) != f"shard-{routed[i]}"
+            for i, k in enumerate(range(0, n, 7)))
+assert moved == mgr.migrations > 0, "vehicles between the old and the new cut migrate"
 check(lo2, hi2, "re-balanced cuts")
 if rank == 0:
+    print(f"shard manager: {moved} of {len(routed)} sampled vehicles migrated after rebalance_shards(); "
+          f"cuts {[round(float(v), 1) for v in hi[:-1]]} -> {[round(float(v), 1) for v in hi2[:-1]]}", flush=True)
     print("MULTI_GPU_CHECK_OK", flush=True)
 dist.destroy_process_group()
