@@ -88,6 +88,7 @@ struct rcd_handle_s {
     uint4 *items = nullptr;     // work items of k_pairs (k_tile_plan)
     u32 items_cap = 0;
     int4 *tile_box = nullptr;   // [2 * tiles]
+    uint2 *tile_rowx = nullptr; // [TILE_ROWS * tiles]
     int stage_blocks = 0, stage_blocks_sms = 148;
     int narrow_blocks[5] = {0, 0, 0, 0, 0};
     int pair_blocks[5] = {0, 0, 0, 0, 0};  // resident blocks per SM x SMs, per kernel variant
@@ -516,6 +517,7 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     h->items_cap = (u32)((cap / TQ + 1) * ITEMS_PER_TILE_CAP);  // k_tile_plan never makes more
     CREATE_TRY(dev_alloc(&h->items, (size_t)h->items_cap));
     CREATE_TRY(dev_alloc(&h->tile_box, 2 * (cap / TQ + 1)));
+    CREATE_TRY(dev_alloc(&h->tile_rowx, (size_t)TILE_ROWS * (cap / TQ + 1)));
     h->ovf_cap = h->items_cap;  // every work item is handed over at most once
     CREATE_TRY(dev_alloc(&h->ovf, (size_t)h->ovf_cap));
     for (int m = 0; m < 3; ++m)
@@ -548,7 +550,7 @@ int rcd_destroy(rcd_handle h) {
     cudaFree(h->U);
     cudaFree(h->cell_begin); cudaFree(h->bbox_dev);
     for (int k = 0; k < 2; ++k) { cudaFree(h->qkeys[k]); cudaFree(h->qvals[k]); }
-    cudaFree(h->qa); cudaFree(h->qa_fill); cudaFree(h->ovf); cudaFree(h->items); cudaFree(h->tile_box);
+    cudaFree(h->qa); cudaFree(h->qa_fill); cudaFree(h->ovf); cudaFree(h->items); cudaFree(h->tile_box); cudaFree(h->tile_rowx);
     if (h->bbox_host) cudaFreeHost(h->bbox_host);
     cudaFree(h->out); cudaFree(h->counters); cudaFree(h->cand_count); cudaFree(h->pair_tile_counter);
     cudaFree(h->q3);
@@ -731,7 +733,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         P.tile_counter = h->pair_tile_counter;
         P.qa = h->qa; P.qa_fill = h->qa_fill; P.qa_blocks_cap = h->qa_blocks_cap;
         P.ovf = h->ovf; P.ovf_cap = h->ovf_cap;
-        P.items = h->items; P.items_cap = h->items_cap; P.tile_box = h->tile_box;
+        P.items = h->items; P.items_cap = h->items_cap; P.tile_box = h->tile_box; P.tile_rowx = h->tile_rowx;
         // work items of about 16 chunks (16 k pair tests per lane-pass); small frames get smaller items so that
         // every resident warp finds work
         P.item_chunks = P.ntiles >= 16384 ? 16u : P.ntiles >= 4096 ? 8u : P.ntiles >= 1024 ? 4u : P.ntiles >= 256 ? 2u : 1u;

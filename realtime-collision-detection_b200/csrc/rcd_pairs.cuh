@@ -73,6 +73,7 @@ struct PairParams {
     uint4 *items;            // work items of k_pairs
     u32 items_cap;
     int4 *tile_box;          // [2 * ntiles] cell box of every tile: {x0, x1, y0, y1}, {z0, z1, -, -}
+    uint2 *tile_rowx;        // [TILE_ROWS * ntiles] x cell range of the first TILE_ROWS cell rows of every tile's box
     GridParams g;
     const float4 *P0, *P1, *P2;
     const u32 *qorder;       // query order -> position in cell order
@@ -769,13 +770,25 @@ __device__ __forceinline__ QueryVolume query_volume(const float4 &p1, const floa
     return v;
 }
 
-// objects of the cell row `rr` of a tile's box: position of the first one in cell order, and how many
+// objects of the cell row `rr` of a tile's box: position of the first one in cell order, and how many.  The first
+// TILE_ROWS rows of a box carry their own x range (k_tile_plan: the box is the bounding box of 32 query volumes --
+// capsules pointing in all directions -- and its corners are empty; a row only spans the cells some volume reaches).
+constexpr int TILE_ROWS = 64;
 struct TileBox { int x0, x1, y0, y1, z0, z1; };
-__device__ __forceinline__ void row_span(const PairParams &P, const TileBox &b, int rr, u32 &lo, u32 &cnt) {
+__device__ __forceinline__ void row_span(const PairParams &P, const TileBox &b, u32 tile, int rr, u32 &lo, u32 &cnt) {
     const int ny_span = b.y1 - b.y0 + 1;
     const int yy = b.y0 + rr % ny_span, zz = b.z0 + rr / ny_span;
-    const u32 c0 = (u32)((zz * P.g.ny + yy) * P.g.nx + b.x0);
-    const u32 first = P.cell_begin[c0], last = P.cell_begin[c0 + (u32)(b.x1 - b.x0) + 1u];
+    int x0 = b.x0, x1 = b.x1;
+    if (rr < TILE_ROWS) {
+        const uint2 rx = P.tile_rowx[(size_t)tile * TILE_ROWS + rr];
+        x0 = (int)rx.x;
+        x1 = (int)rx.y;
+    }
+    lo = 0;
+    cnt = 0;
+    if (x0 > x1) return;  // no query volume reaches this row
+    const u32 c0 = (u32)((zz * P.g.ny + yy) * P.g.nx + x0);
+    const u32 first = P.cell_begin[c0], last = P.cell_begin[c0 + (u32)(x1 - x0) + 1u];
     lo = first;
     cnt = last - first;
 }
@@ -832,11 +845,54 @@ __global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
         }
         const int nrows = (b.y1 - b.y0 + 1) * (b.z1 - b.z0 + 1);
         const int nbatches = (nrows + TQ - 1) / TQ;
+        // x range of every cell row (lane = row): union over the tile's queries of what their volume reaches inside the
+        // row's y band.  A capsule (chord w, radius rad) is covered by 5 discs about the chord points k/4 with radius
+        // sqrt(rad^2 + (|w|/8)^2); everything in the x-y projection (conservative for the 3-D volume).
+        {
+            const int ny_span = b.y1 - b.y0 + 1;
+            const float r2q = v.rad * v.rad + (v.wx * v.wx + v.wy * v.wy) * (1.0f / 64.0f);
+            for (int bt = 0; bt * TQ < min(nrows, TILE_ROWS); ++bt) {
+                const int rr = bt * TQ + (int)lane;
+                const int yy = b.y0 + rr % ny_span;
+                // the row holds the objects with floor((y - oy) / cell) == yy (border rows also what lies beyond the grid)
+                const float eps = 0.01f * g.cell + 2.0e-6f * (fabsf(g.oy) + fabsf((float)(yy + 1) * g.cell));
+                const float ya = (yy <= 0) ? -big : g.oy + (float)yy * g.cell - eps;
+                const float yb = (yy >= g.ny - 1) ? big : g.oy + (float)(yy + 1) * g.cell + eps;
+                float xmin = big, xmax = -big;
+                for (int q = 0; q < TQ; ++q) {
+                    const float qx = __shfl_sync(FULL_MASK, p0.x, q), qy = __shfl_sync(FULL_MASK, p0.y, q);
+                    const float qwx = __shfl_sync(FULL_MASK, v.wx, q), qwy = __shfl_sync(FULL_MASK, v.wy, q);
+                    const float qr2 = __shfl_sync(FULL_MASK, r2q, q);
+                    if (!__shfl_sync(FULL_MASK, (int)valid, q)) continue;  // (uniform)
+                    if (!(qr2 < 1.0e30f)) { xmin = -big; xmax = big; continue; }  // non-finite motion: everything
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        const float cx = fmaf(qwx, 0.25f * (float)k, qx), cy = fmaf(qwy, 0.25f * (float)k, qy);
+                        const float dy = fmaxf(fmaxf(ya - cy, cy - yb), 0.0f);
+                        const float h2 = qr2 - dy * dy;
+                        if (h2 >= 0.0f) {
+                            const float hx = sqrt_ub(h2);
+                            xmin = fminf(xmin, cx - hx);
+                            xmax = fmaxf(xmax, cx + hx);
+                        }
+                    }
+                }
+                if (rr < nrows) {
+                    uint2 rx = make_uint2(1u, 0u);  // empty
+                    if (xmin <= xmax) {
+                        const int cx0 = cell_coord(xmin - (0.05f + 4.0e-7f * fabsf(xmin)), g.ox, g.inv_cell, g.nx);
+                        const int cx1 = cell_coord(xmax + (0.05f + 4.0e-7f * fabsf(xmax)), g.ox, g.inv_cell, g.nx);
+                        rx = make_uint2((u32)max(cx0, b.x0), (u32)min(cx1, b.x1));
+                    }
+                    P.tile_rowx[(size_t)tile * TILE_ROWS + rr] = rx;  // (read back below by the same lane)
+                }
+            }
+        }
         u32 tot_chunks = 0;
         for (int bt = 0; bt < nbatches; ++bt) {
             u32 lo = 0, cnt = 0;
             const int rr = bt * TQ + (int)lane;
-            if (rr < nrows) row_span(P, b, rr, lo, cnt);
+            if (rr < nrows) row_span(P, b, tile, rr, lo, cnt);
             tot_chunks += (warp_sum(cnt) + CH - 1) / CH;
         }
         if (tot_chunks == 0) continue;
@@ -850,7 +906,7 @@ __global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
         for (int bt = 0; bt < nbatches; ++bt) {
             u32 lo = 0, cnt = 0;
             const int rr = bt * TQ + (int)lane;
-            if (rr < nrows) row_span(P, b, rr, lo, cnt);
+            if (rr < nrows) row_span(P, b, tile, rr, lo, cnt);
             const u32 nch = (warp_sum(cnt) + CH - 1) / CH;
             // the items that start inside this batch's chunks [cum, cum + nch)
             const u32 j0 = (cum + K - 1) / K, j1 = min((cum + nch + K - 1) / K, n_it);
@@ -996,7 +1052,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
         for (int rbase = rbase0; rbase < nrows && remaining && !stopped; rbase += TQ) {
             // ---- span of one cell row per lane: two loads from the dense cell table ------------------
             u32 lo = 0, rcnt = 0;
-            if ((int)lane + rbase < nrows) row_span(P, box, rbase + (int)lane, lo, rcnt);
+            if ((int)lane + rbase < nrows) row_span(P, box, tile, rbase + (int)lane, lo, rcnt);
             u32 incl = rcnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
