@@ -169,28 +169,32 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU baseline (oracle port of the reference algorithm, all host threads, bounded sample)
 # ----------------------------------------------------------------------------------------------
-def cpu_frame_seconds(frame, pattern, budget_s: float):
+def cpu_frame_seconds(frame, pattern, budget_s: float, plan=None):
     """Time of one reference frame (index + detect-all + predict-all) on the host cores,
     extrapolated from a bounded sample: every `stride`-th object is queried against the FULL
-    index; the index build is timed in full.  Returns (seconds_per_frame, description, threads, measured_s)."""
+    index; the index build is timed in full.  `plan` = (stride, t_index) of an earlier call skips the sizing runs.
+    Returns (seconds_per_frame, description, threads, measured_s, extrapolated, plan)."""
     from oracle import oracle as O
     from rcd_b200.host import workloads as W
     f64 = W.frame_to_f64(frame)
     n = len(frame["px"])
     threads = max(O.max_threads(), os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1: ask for all cores
-    # index-only cost (stride so large that only object 0 is queried), once per mode
-    t0 = time.perf_counter()
-    O.frame_A(f64, "detect", want_potentials=False, query_stride=max(n, 1), risk_cap=1 << 16, threads=threads)
-    t_index = time.perf_counter() - t0
-    # pilot to size the sample
-    stride = max(1, n // 2000)
-    t0 = time.perf_counter()
-    O.frame_A(f64, "detect", want_potentials=False, query_stride=stride, risk_cap=1 << 22, threads=threads)
-    O.frame_A(f64, "predict", pattern_codes=pattern, want_potentials=False, query_stride=stride, risk_cap=1 << 22, threads=threads)
-    t_pilot = max(time.perf_counter() - t0 - 2 * t_index, 1e-6)
-    per_query = t_pilot / max(1, (n + stride - 1) // stride)
-    want = int(min(n, max(2000, budget_s / per_query)))
-    stride = max(1, n // want)
+    if plan is None:
+        # index-only cost (stride so large that only object 0 is queried), once per mode
+        t0 = time.perf_counter()
+        O.frame_A(f64, "detect", want_potentials=False, query_stride=max(n, 1), risk_cap=1 << 16, threads=threads)
+        t_index = time.perf_counter() - t0
+        # pilot to size the sample
+        stride = max(1, n // 2000)
+        t0 = time.perf_counter()
+        O.frame_A(f64, "detect", want_potentials=False, query_stride=stride, risk_cap=1 << 22, threads=threads)
+        O.frame_A(f64, "predict", pattern_codes=pattern, want_potentials=False, query_stride=stride, risk_cap=1 << 22, threads=threads)
+        t_pilot = max(time.perf_counter() - t0 - 2 * t_index, 1e-6)
+        per_query = t_pilot / max(1, (n + stride - 1) // stride)
+        want = int(min(n, max(2000, budget_s / per_query)))
+        stride = max(1, n // want)
+    else:
+        stride, t_index = plan
     t0 = time.perf_counter()
     O.frame_A(f64, "detect", want_potentials=False, query_stride=stride, risk_cap=1 << 24, threads=threads)
     O.frame_A(f64, "predict", pattern_codes=pattern, want_potentials=False, query_stride=stride, risk_cap=1 << 24, threads=threads)
@@ -201,7 +205,7 @@ def cpu_frame_seconds(frame, pattern, budget_s: float):
     desc = (f"oracle/oracle.c (float64 port of src/collision, OpenMP {threads} threads): index built over all "
             f"{n} objects, every {stride}-th object queried (detect + predict = {queried} queries each, "
             f"{t_sample:.1f} s measured)" + (", extrapolated to the full frame" if stride > 1 else ""))
-    return t_frame, desc, threads, t_sample, stride > 1
+    return t_frame, desc, threads, t_sample, stride > 1, (stride, t_index)
 
 
 def run_reference(args):
@@ -215,11 +219,11 @@ def run_reference(args):
     n = len(frames[0]["px"])
     pattern = np.full(n, 2, np.uint8)
     steps = max(1, args.steps)
-    budget = max(2.0, min(20.0, 120.0 / (steps + args.warmup)))
+    budget = max(1.0, min(20.0, 90.0 / (steps + args.warmup)))  # the whole run stays within a few minutes
     times, measured, extrap = [], [], False
-    info = None
+    info, plan = None, None
     for k in range(args.warmup + steps):
-        t, info, threads, t_meas, ex = cpu_frame_seconds(frames[0], pattern, budget)
+        t, info, threads, t_meas, ex, plan = cpu_frame_seconds(frames[0], pattern, budget, plan)
         if k >= args.warmup:
             times.append(t)
             measured.append(t_meas)
@@ -372,7 +376,9 @@ def time_resident(job: SlabJob, steps: int, warmup: int, flush):
     t_wall = time.perf_counter() - t0
     lat = np.array([a.elapsed_time(b) for a, b in ev], np.float64)
     halo_ms = np.array([a.elapsed_time(b) for a, b in hev], np.float64) if job.exch is not None else np.zeros(steps)
-    return lat, halo_ms, {k: v / steps for k, v in stage_acc.items()}, launches, eng.counts(), t_wall
+    counts = eng.counts()
+    counts["n_tests"] = eng.pair_tests()
+    return lat, halo_ms, {k: v / steps for k, v in stage_acc.items()}, launches, counts, t_wall
 
 
 def time_e2e(job: SlabJob, steps: int, warmup: int, delivery: str, inflight: int, bufs):
@@ -711,11 +717,11 @@ def run_b200(args):
             traffic = tj.get(dom_key)
             ncu_info = tj.get("ncu", {}).get(dom_key)
         pair_tests = None
-        if "predict.pairs" in kernels:  # S1 tests of the pair kernel: candidates are the in-radius subset of them
-            pair_tests = m["n_cand"] / world / (kernels["predict.pairs"]["ms"] * 1e-3)
+        if "predict.pairs" in kernels:  # (query, neighbour) tests of the S1 filter on rank 0 per second of its pair kernel
+            pair_tests = counts["n_tests"] / (kernels["predict.pairs"]["ms"] * 1e-3)
         cpu = None
         if world == 1:  # the CPU baseline is timed on rank 0 at N=1 only
-            cpu_t, cpu_desc, cpu_threads, _tm, ex = cpu_frame_seconds(job.frames[0], np.full(job.n_total, 2, np.uint8), args.cpu_budget)
+            cpu_t, cpu_desc, cpu_threads, _tm, ex, _plan = cpu_frame_seconds(job.frames[0], np.full(job.n_total, 2, np.uint8), args.cpu_budget)
             cpu = {"value": job.n_total / cpu_t, "unit": "object-updates/s", "cores": cpu_threads, "kind": "port",
                    "sample": cpu_desc, "extrapolated": bool(ex)}
         e2e = m["e2e"]
@@ -725,7 +731,8 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 pre-filter + f64 decisions", "data": "synthetic",
             "config": make_config(args, args.workload, job.desc, job.n_total, args.objects_per_gpu, world, job.halo),
             "latency_ms": lat_stats(m["lat_all"]),
-            "frame_totals": {"pairs_emitted": m["n_pairs"], "candidates": m["n_cand"], "halo_objects": m["n_halo"]},
+            "frame_totals": {"pairs_emitted": m["n_pairs"], "candidates": m["n_cand"], "halo_objects": m["n_halo"],
+                             "pair_tests_rank0": int(counts["n_tests"])},
             "per_rank": {"frame_ms": m["per_rank_ms"], "halo_ms": m["per_rank_halo_ms"], "objects_with_halo": m["per_rank_objects"],
                          "rebalance_rounds_ms": m["rebalance_ms"], "halo_region_overflow": m["halo_overflow"]},
             "e2e": {"value": m["objs"] * steps / e2e["t"], "unit": "object-updates/s",

@@ -432,6 +432,9 @@ int rcd_stage_ms(rcd_handle h, int32_t mode, float *ms /* RCD_NUM_STAGES */);
 /* The handle's CUDA stream (a cudaStream_t), so the caller can order its own work -- halo
  * exchange with NCCL, timing events -- with the frame without extra synchronisation. */
 int rcd_get_stream(rcd_handle h, void **stream);
+/* (query, neighbour) tests the fp32 filter of the pair kernel took in the last frame (waits for it): the unit of work
+ * of the kernel that dominates a frame -- it is issue-bound, not HBM-bound -- for bench.py's roofline object. */
+int rcd_pair_tests(rcd_handle h, uint64_t *n);
 /* Kernel launches issued by the last rcd_step (for bench.py's gpu_launches). */
 int rcd_launch_count(rcd_handle h, uint64_t *n);
 /* Steps served by graph replay since the handle was created (RCD_FLAG_GRAPH; diagnostic). */

@@ -718,7 +718,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         // to 9.5 s, and detect_collisions(100, 10) for objects without history / the fused detect pass)
         if (mode == RCD_MODE_DETECT) {
             P.tm = P.D = 0.5f * time_window;
-            P.use_t1 = time_window <= 64.0f ? 1 : 0;  // (longer windows: the quadratic slack passes everything anyway)
+            P.use_t1 = 1;
         } else {
             P.tm = P.D = 5.0f;
             P.use_t1 = mode == RCD_MODE_PREDICT ? 1 : 0;
@@ -1844,6 +1844,16 @@ int rcd_stage_ms(rcd_handle h, int32_t mode, float *ms) {
             else (void)cudaGetLastError();
         }
     }
+    return RCD_OK;
+}
+
+int rcd_pair_tests(rcd_handle h, uint64_t *n) {
+    if (!h || !n) return RCD_EINVAL;
+    if (!h->frame_done) return fail(h, RCD_ESTATE, "rcd_pair_tests: no frame has been stepped");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaMemcpyAsync(h->counters_host, h->counters, sizeof(Counters), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    *n = h->counters_host->n_tests;
     return RCD_OK;
 }
 

@@ -74,6 +74,7 @@ struct Counters {
     unsigned long long n_overflow;  // parts of tiles k_pairs left to its overflow pass (pair queue full)
     unsigned long long n_items;     // work items of k_pairs (k_tile_plan)
     unsigned long long n_fallback;  // resolved entries the exact stage had to redo in full (expected 0)
+    unsigned long long n_tests;     // (query, neighbour) tests of the S1 filter (k_pairs), padding of last chunks included
 };
 
 // ---- warp / block helpers -----------------------------------------------------------------------

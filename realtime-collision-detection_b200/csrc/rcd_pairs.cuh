@@ -151,6 +151,18 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
     return bits_f2(d);
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// mask = mask << 1 | sign bit of t: one funnel shift per test instead of compare + select + or (the difference itself
+// comes out of a packed add on the FMA pipe; NaN results are canonical, sign clear)
+__device__ __forceinline__ u32 shift_in_sign(u32 mask, float t) {
+    u32 r;
+    asm("shf.l.wrap.b32 %0, %1, %2, 1;" : "=r"(r) : "r"(__float_as_uint(t)), "r"(mask));
+    return r;
+}
+// keeps a loop-invariant value in its register (the compiler would otherwise re-derive it inside the hot loop)
+__device__ __forceinline__ float pin_reg(float v) {
+    asm volatile("" : "+f"(v));
+    return v;
+}
 
 // sqrt(x) rounded up a little: only ever used for conservative bounds (MUFU.SQRT, ~1 ulp)
 __device__ __forceinline__ float sqrt_ub(float x) {
@@ -938,12 +950,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
     constexpr bool PRED = is_predict(MODE);
     constexpr bool FUSED = MODE == MODE_PREDICT_WITH_DETECT;
     constexpr bool USE_CAPSULE = PRED && COUNT_CAND;  // diagnostic variant: every neighbour inside the capsule goes on
-    const bool t1_on = MODE != RCD_MODE_COMPUTE_NODE && !USE_CAPSULE && P.use_t1 != 0;  // (uniform)
+    constexpr bool t1_on = MODE != RCD_MODE_COMPUTE_NODE && !USE_CAPSULE;
     const float tm = P.tm, D = P.D, h2 = 0.5f * tm * tm;
     const float Rq = PRED ? PREDICT_RADIUS : P.R;
     const float R2_hi = Rq * Rq * (1.0f + BAND_R2), R2_lo = Rq * Rq * (1.0f - BAND_R2);
     const float FAR = 3.0e38f;
     u32 n_pot = 0;                                // per-lane statistics, flushed once at the end
+    unsigned long long n_chunks = 0;              // (uniform) chunks of 32 neighbours this warp filtered
     u32 qa_block = QA_NO_BLOCK, qa_used = 0;      // this warp's block of the pair queue (uniform)
     bool qa_full = false;                         // (uniform) the pair queue has no block left
 
@@ -1013,15 +1026,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
             }
             A *= 1.0f + 1.0e-4f;
         }
+        // the clamp of the minimiser to [-D, Dhi] as a saturating FMA: uc = -D + span * sat((u + D) / span)
+        const float span = pin_reg(D + Dhi), inv_span = pin_reg(1.0f / (D + Dhi)), off_span = pin_reg(D / (D + Dhi));
         // The filter keeps four bit masks per lane and chunk (bit = staged neighbour): im = inside the radius for
         // certain, nm = inside radius + guard band, tm = passed T1 (or the capsule test), bm = within the compute-node
         // distance bound.  What passes, per lane:  (tm & useT & (im | ~andI)) | (im & orI) | (bm & orB) | (nm & ~im):
         //   radius query, T1 on  : in the radius and T1            radius query, T1 off : in the radius
         //   predict query        : T1 (+ everything in the radius where the fused detect part follows another trajectory)
         //   compute-node         : within min(radius, 50 m)
-        float R2lo_l = -1.0f, R2hi_l = -1.0f, dmaxB = -1.0f;
+        // (the masks are built from sign bits: d2 - R2lo < 0, d2 - next(R2hi) < 0, bound - value < 0)
+        float R2lo_l = -1.0f, R2hi_n = -1.0f, dmaxB = -1.0f;
         u32 useT = 0u, andI = 0u, orI = 0u, orB = 0u;
-        if (counts) { R2lo_l = R2_lo; R2hi_l = R2_hi; }
+        if (counts) { R2lo_l = R2_lo; R2hi_n = __uint_as_float(__float_as_uint(R2_hi) + 1u); }
         if (valid) {
             if (MODE == RCD_MODE_COMPUTE_NODE) { dmaxB = fminf(R2_lo, 2500.0f * (1.0f + 2.0f * BAND_R2)); orB = ~0u; }  // current_distance <= 50
             else if (radius_query) { if (t1_on) { useT = ~0u; andI = ~0u; } else orI = ~0u; }
@@ -1141,7 +1157,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                 const u32 m = min((u32)CH, total - c * CH);
                 // ---- S1: one query per lane against every staged neighbour, two per packed instruction -----
                 // Each lane keeps what passes as bit masks over the staged chunk (no warp vote, no store per test).
-                u32 im = 0, nm = 0, tm = 0, bm = 0, bit = 1u;
+                u32 im = 0, nm = 0, fm = 0, bm = 0;
                 const u32 npair = (m + 1u) >> 1;
                 for (u32 u = 0; u < npair; ++u) {
                     const float4 xy = b.xy[u];
@@ -1150,14 +1166,13 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                     const float2 dy = add2(make_float2(xy.z, xy.w), splat2(-p0.y));
                     const float2 dz = add2(make_float2(zb.x, zb.y), splat2(-p0.z));
                     const float2 d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-                    bool ta = true, tb = true;
+                    float2 tf = make_float2(0.0f, 0.0f);  // sign set: the test failed
                     if (USE_CAPSULE) {  // distance to the chord (w = 0 for radius queries)
                         const float2 dot = fma2(dz, splat2(wz), fma2(dy, splat2(wy), mul2(dx, splat2(wx))));
                         const float2 sc = make_float2(__saturatef(dot.x * inv_w2), __saturatef(dot.y * inv_w2));
                         const float2 ex = fma2(sc, splat2(-wx), dx), ey = fma2(sc, splat2(-wy), dy), ez = fma2(sc, splat2(-wz), dz);
                         const float2 e2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
-                        ta = e2.x <= rad2;
-                        tb = e2.y <= rad2;
+                        tf = fma2(e2, splat2(-1.0f), splat2(rad2));  // < 0 <=> outside the capsule
                     } else if (t1_on) {
                         const float4 nxy = b.nxy[u], nzv = b.nzv[u], nvyz = b.nvyz[u];
                         const float2 gx = add2(make_float2(nxy.x, nxy.y), splat2(Mx));   // g0 = M_i - N_j
@@ -1169,7 +1184,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         const float2 g12c = fma2(hz, hz, fma2(hy, hy, fma2(hx, hx, splat2(1.0e-12f))));  // |g1|^2 (+ a floor)
                         const float2 dot = fma2(gz, hz, fma2(gy, hy, mul2(gx, hx)));
                         const float2 um = mul2(dot, make_float2(rcp_fast(g12c.x), rcp_fast(g12c.y)));  // -(minimum of the linear part, relative to tm)
-                        const float2 uc = make_float2(fminf(fmaxf(-um.x, -D), Dhi), fminf(fmaxf(-um.y, -D), Dhi));
+                        const float2 sc = make_float2(__saturatef(fmaf(-um.x, inv_span, off_span)), __saturatef(fmaf(-um.y, inv_span, off_span)));
+                        const float2 uc = fma2(sc, splat2(span), splat2(-D));
                         const float2 lx = fma2(hx, uc, gx), ly = fma2(hy, uc, gy), lz = fma2(hz, uc, gz);
                         const float2 l2 = fma2(lz, lz, fma2(ly, ly, mul2(lx, lx)));
                         const float4 naxy = b.naxy[u];
@@ -1181,26 +1197,25 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                         const float2 qn = mul2(q2c, make_float2(rsqrt_fast(q2c.x), rsqrt_fast(q2c.y)));
                         const float2 L = fma2(splat2(kq), qn, add2(make_float2(zb.z, zb.w), splat2(A)));
                         const float2 L2 = mul2(L, L);
-                        ta = l2.x <= L2.x;
-                        tb = l2.y <= L2.y;
+                        tf = fma2(l2, splat2(-1.0f), L2);  // < 0 <=> the linear part stays farther away than L
                     }
-                    im |= (d2.x < R2lo_l) ? bit : 0u;
-                    nm |= (d2.x <= R2hi_l) ? bit : 0u;
-                    im |= (d2.y < R2lo_l) ? (bit << 1) : 0u;
-                    nm |= (d2.y <= R2hi_l) ? (bit << 1) : 0u;
-                    if (USE_CAPSULE || t1_on) {
-                        tm |= ta ? bit : 0u;
-                        tm |= tb ? (bit << 1) : 0u;
-                    }
+                    // the masks grow by one sign bit per test (the first test of the chunk ends up in the highest bit)
+                    const float2 ti = add2(d2, splat2(-R2lo_l)), tn = add2(d2, splat2(-R2hi_n));
+                    im = shift_in_sign(shift_in_sign(im, ti.x), ti.y);
+                    nm = shift_in_sign(shift_in_sign(nm, tn.x), tn.y);
+                    if (USE_CAPSULE || t1_on) fm = shift_in_sign(shift_in_sign(fm, tf.x), tf.y);
                     if (MODE == RCD_MODE_COMPUTE_NODE) {
-                        bm |= (d2.x < dmaxB) ? bit : 0u;
-                        bm |= (d2.y < dmaxB) ? (bit << 1) : 0u;
+                        const float2 tb2 = add2(d2, splat2(-dmaxB));
+                        bm = shift_in_sign(shift_in_sign(bm, tb2.x), tb2.y);
                     }
-                    bit <<= 2;
                 }
-                if (!(USE_CAPSULE || t1_on)) tm = ~0u;
-                const u32 um = nm & ~im;   // inside the guard band of the radius: the exact stage decides (and counts)
-                const u32 pm = (tm & useT & (im | ~andI)) | (im & orI) | (bm & orB) | um;
+                // test k of the chunk (neighbour k) sits in bit nbits - 1 - k; the padding of an odd chunk is masked out
+                const u32 nbits = 2u * npair;
+                const u32 vm = (nbits >= 32u ? ~0u : ((1u << nbits) - 1u)) & ~((1u << (nbits - m)) - 1u);
+                const u32 tm = (USE_CAPSULE || t1_on) ? ~fm : ~0u;
+                im &= vm;
+                const u32 um = nm & ~im & vm;   // inside the guard band of the radius: the exact stage decides (and counts)
+                const u32 pm = ((tm & useT & (im | ~andI)) | (im & orI) | (bm & orB) | um) & vm;
                 const u32 nc = (u32)__popc(im);
                 const u32 cnt = (u32)__popc(pm);
                 // ---- survivors -> pair queue (the warp's private block; a new one when this one is full) -------
@@ -1214,9 +1229,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                 off -= cnt;
                 if (SLOW) {  // overflow pass: finish every survivor here
                     for (u32 rest = pm; rest; rest &= rest - 1u) {
-                        const u32 j = (u32)__ffs(rest) - 1u;
+                        const u32 bt = (u32)__ffs(rest) - 1u;
                         n_pot += narrow_entry_inline<MODE, COUNT_CAND>(
-                            P, s | (((im >> j) & 1u) ? QA_INR : 0u) | (((um >> j) & 1u) ? QA_UND : 0u), b.pos[j]);
+                            P, s | (((im >> bt) & 1u) ? QA_INR : 0u) | (((um >> bt) & 1u) ? QA_UND : 0u), b.pos[nbits - 1u - bt]);
                     }
                 } else if (total_pairs) {
                     // room left in the warp's block; what does not fit goes to new blocks, taken with ONE atomic so that
@@ -1246,8 +1261,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                     u32 at = off;
                     for (u32 rest = pm; __any_sync(FULL_MASK, rest != 0u); rest &= rest - 1u, ++at) {
                         if (rest) {
-                            const u32 j = (u32)__ffs(rest) - 1u;
-                            const uint2 e = make_uint2(s | (((im >> j) & 1u) ? QA_INR : 0u) | (((um >> j) & 1u) ? QA_UND : 0u), b.pos[j]);
+                            const u32 bt = (u32)__ffs(rest) - 1u;
+                            const uint2 e = make_uint2(s | (((im >> bt) & 1u) ? QA_INR : 0u) | (((um >> bt) & 1u) ? QA_UND : 0u),
+                                                       b.pos[nbits - 1u - bt]);
                             if (at < room) dst_cur[at] = e; else dst_new[at - room] = e;
                         }
                     }
@@ -1269,6 +1285,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
                 __syncwarp();
             }
             remaining -= c_end - c_begin;
+            n_chunks += c_end - c_begin;
         }
         // ---- end of tile ------------------------------------------------------------------------------
         // the filter counted the query itself (distance 0); only the compute-node index returns self (quirk Q8).
@@ -1285,6 +1302,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, SLOW ? 4 : RCD_PAIR_MIN_BLOCKS) 
     if (!SLOW && lane == 0 && qa_block < P.qa_blocks_cap) P.qa_fill[qa_block] = qa_used;
     unsigned long long p = warp_sum((unsigned long long)n_pot);
     if (lane == 0 && p) atomicAdd(&P.counters->n_potential, p);
+    if (lane == 0 && n_chunks) atomicAdd(&P.counters->n_tests, n_chunks * (unsigned long long)(CH * TQ));
 }
 
 // -------------------------------------------------------------------------------------------------

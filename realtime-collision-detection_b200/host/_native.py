@@ -33,7 +33,7 @@ SYMBOLS = (
     "rcd_set_owned", "rcd_step", "rcd_build_index", "rcd_set_compute_node_params", "rcd_truncate", "rcd_invalidate", "rcd_counts", "rcd_download", "rcd_download_unsorted",
     "rcd_download_candidate_counts", "rcd_query_radius", "rcd_classify_patterns", "rcd_halo_pack",
     "rcd_halo_pack_async", "rcd_halo_append", "rcd_history_configure", "rcd_history_append", "rcd_history_reset", "rcd_history_move",
-    "rcd_history_classify", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_sync",
+    "rcd_history_classify", "rcd_stage_ms", "rcd_get_stream", "rcd_launch_count", "rcd_pair_tests", "rcd_sync",
     "rcd_ingest_create", "rcd_ingest_destroy", "rcd_ingest_last_error", "rcd_ingest_decode_json",
     "rcd_ingest_counts", "rcd_ingest_set_limit", "rcd_ingest_rejected", "rcd_ingest_id_name", "rcd_ingest_type_name", "rcd_ingest_lookup", "rcd_apply_records",
     "rcd_alerts_configure", "rcd_alerts_update", "rcd_alerts_update_pairs", "rcd_alerts_expire",
@@ -151,6 +151,7 @@ def load() -> ctypes.CDLL:
     L.rcd_stage_ms.argtypes = [vp, i32, vp]
     L.rcd_get_stream.argtypes = [vp, ctypes.POINTER(vp)]
     L.rcd_launch_count.argtypes = [vp, ctypes.POINTER(u64)]
+    L.rcd_pair_tests.argtypes = [vp, ctypes.POINTER(u64)]
     if hasattr(L, "rcd_graph_replays"):
         L.rcd_graph_replays.argtypes = [vp, ctypes.POINTER(u64)]
     L.rcd_sync.argtypes = [vp]

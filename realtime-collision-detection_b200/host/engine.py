@@ -384,6 +384,12 @@ class FrameEngine:
         N.check(self._lib.rcd_launch_count(self._h, ctypes.byref(v)), self._h)
         return int(v.value)
 
+    def pair_tests(self) -> int:
+        """(query, neighbour) tests of the pair kernel's fp32 filter in the last frame."""
+        v = ctypes.c_uint64(0)
+        N.check(self._lib.rcd_pair_tests(self._h, ctypes.byref(v)), self._h)
+        return int(v.value)
+
     def graph_replays(self) -> int:
         n = ctypes.c_uint64()
         N.check(self._lib.rcd_graph_replays(self._h, ctypes.byref(n)), self._h)

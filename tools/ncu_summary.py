@@ -14,6 +14,7 @@ M = {"ms": "gpu__time_duration.sum", "rd": "dram__bytes_read.sum", "wr": "dram__
      "inst": "smsp__inst_executed.sum", "lld": "smsp__inst_executed_op_local_ld.sum", "lst": "smsp__inst_executed_op_local_st.sum",
      "l2hit": "lts__t_sector_hit_rate.pct", "dram_pct": "dram__throughput.avg.pct_of_peak_sustained_elapsed",
      "grid": "launch__grid_size", "block": "launch__block_size", "fma": "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+     "alu": "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
      "fp64": "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active"}
 def val(r, k):
     n = M[k]
@@ -44,7 +45,8 @@ for name, ds in per.items():
     summary[name] = {"ms_under_ncu": round(d["ms"], 5), "dram_read_bytes": d["rd"], "dram_write_bytes": d["wr"],
                      "issue_active_pct": round(d["issue"], 2), "threads_per_inst": round(d["thr"], 2), "warps_active_pct": round(d["warps"], 2),
                      "registers": int(d["regs"]), "warp_inst": d["inst"], "local_ldst_inst": (d["lld"] or 0) + (d["lst"] or 0),
-                     "l2_hit_pct": round(d["l2hit"], 2), "launches_in_report": len(ds)}
+                     "l2_hit_pct": round(d["l2hit"], 2), "launches_in_report": len(ds),
+                     "fma_pipe_pct": d.get("fma"), "alu_pipe_pct": d.get("alu"), "fp64_pipe_pct": d.get("fp64")}
 out = "\n".join(lines) + "\n"
 if len(sys.argv) > 2:
     open(sys.argv[2], "w").write(out)
@@ -57,5 +59,6 @@ if len(sys.argv) > 3:
         if name in summary:
             s = summary[name]
             tj[key] = s["dram_read_bytes"] + s["dram_write_bytes"]
-            tj["ncu"][key] = {k: s[k] for k in ("issue_active_pct", "threads_per_inst", "warps_active_pct", "registers", "local_ldst_inst", "warp_inst")}
+            tj["ncu"][key] = {k: s[k] for k in ("issue_active_pct", "threads_per_inst", "warps_active_pct", "registers", "local_ldst_inst", "warp_inst",
+                                               "fma_pipe_pct", "alu_pipe_pct", "fp64_pipe_pct")}
     json.dump(tj, open(sys.argv[3], "w"), indent=1)
