@@ -857,46 +857,59 @@ __global__ void __launch_bounds__(128) k_tile_plan(PairParams P) {
         }
         const int nrows = (b.y1 - b.y0 + 1) * (b.z1 - b.z0 + 1);
         const int nbatches = (nrows + TQ - 1) / TQ;
-        // x range of every cell row (lane = row): union over the tile's queries of what their volume reaches inside the
-        // row's y band.  A capsule (chord w, radius rad) is covered by 5 discs about the chord points k/4 with radius
-        // sqrt(rad^2 + (|w|/8)^2); everything in the x-y projection (conservative for the 3-D volume).
+        // x range of every cell row: union over the tile's queries (lane = query) of what their volume reaches inside
+        // the row's y band, reduced over the warp with two integer REDUX per row.  A capsule (chord w, radius rad) is
+        // covered by 5 discs about the chord points k/4 with radius sqrt(rad^2 + (|w|/8)^2); everything in the x-y
+        // projection (conservative for the 3-D volume).  Row rr's range is kept by lane rr % 32 and stored per batch.
         {
             const int ny_span = b.y1 - b.y0 + 1;
-            const float r2q = v.rad * v.rad + (v.wx * v.wx + v.wy * v.wy) * (1.0f / 64.0f);
-            for (int bt = 0; bt * TQ < min(nrows, TILE_ROWS); ++bt) {
-                const int rr = bt * TQ + (int)lane;
+            float r2q = v.rad * v.rad + (v.wx * v.wx + v.wy * v.wy) * (1.0f / 64.0f);
+            const bool everything = valid && !(r2q < 1.0e30f);  // non-finite motion
+            if (!valid || everything) r2q = -1.0f;              // (no disc of this lane reaches any row)
+            const bool any_everything = __any_sync(FULL_MASK, everything);
+            float dcx[5], dcy[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                dcx[k] = fmaf(v.wx, 0.25f * (float)k, p0.x);
+                dcy[k] = fmaf(v.wy, 0.25f * (float)k, p0.y);
+            }
+            const int nr = min(nrows, TILE_ROWS);
+            int keep_lo = 0x7fffffff, keep_hi = (int)0x80000000;  // ordered-int encodings of this lane's row range
+            for (int rr = 0; rr < nr; ++rr) {
                 const int yy = b.y0 + rr % ny_span;
                 // the row holds the objects with floor((y - oy) / cell) == yy (border rows also what lies beyond the grid)
                 const float eps = 0.01f * g.cell + 2.0e-6f * (fabsf(g.oy) + fabsf((float)(yy + 1) * g.cell));
                 const float ya = (yy <= 0) ? -big : g.oy + (float)yy * g.cell - eps;
                 const float yb = (yy >= g.ny - 1) ? big : g.oy + (float)(yy + 1) * g.cell + eps;
                 float xmin = big, xmax = -big;
-                for (int q = 0; q < TQ; ++q) {
-                    const float qx = __shfl_sync(FULL_MASK, p0.x, q), qy = __shfl_sync(FULL_MASK, p0.y, q);
-                    const float qwx = __shfl_sync(FULL_MASK, v.wx, q), qwy = __shfl_sync(FULL_MASK, v.wy, q);
-                    const float qr2 = __shfl_sync(FULL_MASK, r2q, q);
-                    if (!__shfl_sync(FULL_MASK, (int)valid, q)) continue;  // (uniform)
-                    if (!(qr2 < 1.0e30f)) { xmin = -big; xmax = big; continue; }  // non-finite motion: everything
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        const float cx = fmaf(qwx, 0.25f * (float)k, qx), cy = fmaf(qwy, 0.25f * (float)k, qy);
-                        const float dy = fmaxf(fmaxf(ya - cy, cy - yb), 0.0f);
-                        const float h2 = qr2 - dy * dy;
-                        if (h2 >= 0.0f) {
-                            const float hx = sqrt_ub(h2);
-                            xmin = fminf(xmin, cx - hx);
-                            xmax = fmaxf(xmax, cx + hx);
-                        }
+                for (int k = 0; k < 5; ++k) {
+                    const float dy = fmaxf(fmaxf(ya - dcy[k], dcy[k] - yb), 0.0f);
+                    const float h2 = r2q - dy * dy;
+                    if (h2 >= 0.0f) {
+                        const float hx = sqrt_ub(h2);
+                        xmin = fminf(xmin, dcx[k] - hx);
+                        xmax = fmaxf(xmax, dcx[k] + hx);
                     }
                 }
-                if (rr < nrows) {
-                    uint2 rx = make_uint2(1u, 0u);  // empty
-                    if (xmin <= xmax) {
-                        const int cx0 = cell_coord(xmin - (0.05f + 4.0e-7f * fabsf(xmin)), g.ox, g.inv_cell, g.nx);
-                        const int cx1 = cell_coord(xmax + (0.05f + 4.0e-7f * fabsf(xmax)), g.ox, g.inv_cell, g.nx);
-                        rx = make_uint2((u32)max(cx0, b.x0), (u32)min(cx1, b.x1));
+                if (any_everything) { xmin = -big; xmax = big; }
+                const int lo_all = __reduce_min_sync(FULL_MASK, float_ordered(xmin));
+                const int hi_all = __reduce_max_sync(FULL_MASK, float_ordered(xmax));
+                if ((int)lane == (rr & 31)) { keep_lo = lo_all; keep_hi = hi_all; }
+                if ((rr & 31) == 31 || rr == nr - 1) {  // a batch of rows is complete: lane l stores row (rr & ~31) + l
+                    const int row = (rr & ~31) + (int)lane;
+                    if (row <= rr) {
+                        const float fx0 = ordered_float(keep_lo), fx1 = ordered_float(keep_hi);
+                        uint2 rx = make_uint2(1u, 0u);  // empty
+                        if (fx0 <= fx1) {
+                            const int cx0 = cell_coord(fx0 - (0.05f + 4.0e-7f * fabsf(fx0)), g.ox, g.inv_cell, g.nx);
+                            const int cx1 = cell_coord(fx1 + (0.05f + 4.0e-7f * fabsf(fx1)), g.ox, g.inv_cell, g.nx);
+                            rx = make_uint2((u32)max(cx0, b.x0), (u32)min(cx1, b.x1));
+                        }
+                        P.tile_rowx[(size_t)tile * TILE_ROWS + row] = rx;  // (read back below by the same lane)
                     }
-                    P.tile_rowx[(size_t)tile * TILE_ROWS + rr] = rx;  // (read back below by the same lane)
+                    keep_lo = 0x7fffffff;
+                    keep_hi = (int)0x80000000;
                 }
             }
         }
