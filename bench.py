@@ -468,7 +468,7 @@ def gather_list(world, val: float):
     return [float(o[0]) for o in out]
 
 
-def rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rounds: int):
+def rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rounds: int, max_pairs=None):
     """Move the x-cuts towards equal measured frame time per slab: a few short runs, each followed by an
     all-gather of the slabs' frame times and `rebalanced_cuts` (host/slabs.py).  Returns (cuts, history)."""
     from rcd_b200.host.slabs import rebalanced_cuts, slab_bounds
@@ -477,7 +477,7 @@ def rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rounds: i
     hist = []
     best = (None, float("inf"))
     for it in range(rounds + 1):
-        job = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=False)
+        job = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=False, max_pairs=max_pairs)
         lat, _h, _s, _l, _c, _t = time_resident(job, 3, 2, flush)
         job.close()
         ms = gather_list(world, float(np.mean(lat)))
@@ -549,14 +549,14 @@ def verify_frame(job: SlabJob, k: int, n_queries: int):
 
 
 def measure(args, workload, per_gpu, world, rank, local_rank, flush, steps, warmup, rebalance_rounds, with_e2e=True,
-            with_verify=True, sampler=None):
+            with_verify=True, sampler=None, max_pairs=None):
     """Everything for one workload: (re-balanced) slabs, device-timed frames, end-to-end frames, verification."""
     import torch
     from rcd_b200.host import _native as N
     cuts, rb_hist = (None, [])
     if world > 1 and rebalance_rounds > 0:
-        cuts, rb_hist = rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rebalance_rounds)
-    job = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=True, graph=args.graph)
+        cuts, rb_hist = rebalance(args, workload, per_gpu, world, rank, local_rank, flush, rebalance_rounds, max_pairs)
+    job = SlabJob(args, workload, per_gpu, world, rank, local_rank, cuts=cuts, profile=True, graph=args.graph, max_pairs=max_pairs)
     lat, halo_ms, stage_ms, launches, counts, t_wall = time_resident(job, steps, warmup, flush)
     # a halo region that was too small would have dropped records: look at the device-side counts once, after the frames
     halo_overflow = reduce_max(world, [1.0 if (job.exch is not None and job.exch.overflowed()) else 0.0])[0] > 0
@@ -679,13 +679,17 @@ def run_b200(args):
             _FRAME_CACHE.clear()
             for name in ("cfg5_10m_skew3d_uniform_disc", "cfg5_10m_skew3d"):
                 xs = 3
-                s = measure(args, name, 1_250_000, world, rank, local_rank, flush, xs, 3, 1, with_e2e=False, with_verify=False)
+                # (the queues between the kernels are sized from the pair buffer: 256 M pairs keep this frame out of the
+                # overflow pass -- 1.8e9 risks per frame on the box with the reference's radial law)
+                big = 256_000_000
+                s = measure(args, name, 1_250_000, world, rank, local_rank, flush, xs, 3, 1, with_e2e=False, with_verify=False,
+                            max_pairs=big)
                 extras["configs4_10m" + ("_uniform_disc" if name.endswith("disc") else "_reference_law")] = {
                     "workload": f"{name}: {s['job'].desc}", "scaling": "n/a (10M objects on 8 GPUs)",
                     "value": s["objs"] * xs / s["t_dev"], "unit": "object-updates/s", "ms_per_step": s["t_dev"] / xs * 1e3,
                     "candidates_per_s": s["n_cand"] * xs / s["t_dev"], "latency_ms": lat_stats(s["lat_all"]), "steps": xs,
                     "per_rank_ms": s["per_rank_ms"], "pairs_emitted": s["n_pairs"], "candidates": s["n_cand"],
-                    "pairs_stored_cap_per_gpu": int(args.max_pairs),
+                    "pairs_stored_cap_per_gpu": big,
                     "note": "counts are exact beyond the pair buffer; records past it are not stored"}
                 s["job"].close()
                 _FRAME_CACHE.clear()

@@ -506,7 +506,7 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->pair_tile_counter, 2));
     // the fp32 stages forward about 5 candidate entries per emitted pair on clustered frames; a full
     // queue is not an error (the pair is then finished in place) but it is slower
-    h->qcap = (u32)std::min<u64>(6 * h->max_pairs + 65536, 1ull << 28);
+    h->qcap = (u32)std::min<u64>(6 * h->max_pairs + 65536, (1ull << 31) - (1ull << 24));  // (32-bit entry indices)
     CREATE_TRY(dev_alloc(&h->q3, (size_t)h->qcap));
     // the S1 filter forwards ~60 (predict) / ~20 (detect) pairs per object at the density of the bench frame;
     // the pair queue is handed out in blocks of QA_BLOCK entries, one per warp at a time

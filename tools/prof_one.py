@@ -11,8 +11,11 @@ elif name == "1m":
     frame, bounds = W.uniform_frame(1_000_000, 5, map_size=31623.0), ((0, 0, 0), (31623, 31623, 0))
 elif name == "1mc":
     frame, bounds = W.make_workload("cfg4_1m_clustered3d"), ((0, 0, 0), (31623, 31623, 100))
+elif name == "cfg5":
+    side = 100000.0 * (1_250_000 / 10_000_000) ** 0.5
+    frame, bounds = W.hotspot_frame(1_250_000, 2003, side, 25, zipf_s=1.0), ((0, 0, 0), (side, side, 100))
 n = len(frame["px"])
-with FrameEngine(n, 40_000_000, world_bounds=bounds) as e:
+with FrameEngine(n, 256_000_000 if name == "cfg5" else 40_000_000, world_bounds=bounds) as e:
     e.upload(frame)
     e.set_patterns(np.full(n, 2, np.uint8))
     for r in range(reps):
