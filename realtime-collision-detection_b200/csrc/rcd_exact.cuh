@@ -29,6 +29,9 @@ __device__ __forceinline__ ObjD widen(const float4 &p0, const float4 &p1, const 
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+// x / 2 as the reference writes it: the same real number rounded once, so x * 0.5 gives the same bits without the
+// division sequence
+__device__ __forceinline__ double half_d(double x) { return __dmul_rn(x, 0.5); }
 
 // collision_detection.py:391-406 (and spatial_index.py:285-300)
 __device__ __forceinline__ double dist3_d(double x1, double y1, double z1, double x2, double y2, double z2) {
@@ -45,7 +48,7 @@ __device__ __forceinline__ double pos1_d(double p, double v, double a, double t)
 }
 // collision_detection.py:484-496
 __device__ __forceinline__ double safe_d(double s1, double s2) {
-    return dadd(__ddiv_rn(dadd(s1, s2), 2.0), SAFE_DISTANCE_DEFAULT);
+    return dadd(half_d(dadd(s1, s2)), SAFE_DISTANCE_DEFAULT);
 }
 
 // collision_detection.py:344-389 + :498-513
@@ -98,9 +101,9 @@ __device__ __noinline__ HitD precise_hit_d(double pix, double piy, double piz, d
         double d = dist3_d(xi, yi, zi, xj, yj, zj);
         if (d <= safe) {
             h.k = k; h.dist = d;
-            h.mx = __ddiv_rn(dadd(xi, xj), 2.0);
-            h.my = __ddiv_rn(dadd(yi, yj), 2.0);
-            h.mz = __ddiv_rn(dadd(zi, zj), 2.0);
+            h.mx = half_d(dadd(xi, xj));
+            h.my = half_d(dadd(yi, yj));
+            h.mz = half_d(dadd(zi, zj));
             return h;
         }
     }
@@ -223,9 +226,9 @@ __device__ __noinline__ ComputeNodeResultD compute_node_pair_d(const ObjD &a, co
     }
     r.hit = true;
     r.ttc = ttc; r.fut = fut; r.rs = rs; r.risk = risk;
-    r.mx = __ddiv_rn(dadd(fix, fjx), 2.0);
-    r.my = __ddiv_rn(dadd(fiy, fjy), 2.0);
-    r.mz = __ddiv_rn(dadd(fiz, fjz), 2.0);
+    r.mx = half_d(dadd(fix, fjx));
+    r.my = half_d(dadd(fiy, fjy));
+    r.mz = half_d(dadd(fiz, fjz));
     return r;
 }
 

@@ -3,12 +3,14 @@
 // Three kernels per frame, connected by compact queues in global memory, so that every stage runs
 // with full warps and each kernel's hot loop stays small:
 //
-//   k_pairs  : persistent, the S1 filter only.  A tile is 32 queries in *query order* (Morton order of
-//              the centres of the query volumes, rcd_index.cuh), handled by ONE warp with one lane per
-//              query; warps take tiles from an atomic counter.  Every query has a volume a neighbour
-//              must lie in to matter -- a ball of radius R, or (predict) the capsule of radius 100 m
-//              about the chord of the predicted centre path -- and the warp streams the cell rows under
-//              the bounding box of its queries' volumes through its own slice of shared memory
+//   k_tile_plan: one warp per tile of 32 queries in *query order* (Morton order of the centres of the query
+//              volumes, rcd_index.cuh).  Every query has a volume a neighbour must lie in to matter -- a ball
+//              of radius R, or (predict) the capsule of radius 100 m about the chord of the predicted centre
+//              path.  The plan stores the cell box of the tile's volumes, an x range for every cell row of the
+//              box (what some volume reaches inside the row's y band: the corners of the box are empty), and
+//              cuts the tile into work items of about equal numbers of 32-neighbour chunks.
+//   k_pairs  : persistent, the S1 filter only.  A warp takes work items from an atomic counter; lane = query.
+//              It streams the cell rows of its tile through its own slice of shared memory
 //              (cp.async one chunk of 32 neighbours ahead, re-laid two neighbours side by side).  For
 //              every (query, neighbour) the lane takes, in packed fp32 (FADD2 / FFMA2, two neighbours
 //              per instruction):
@@ -23,14 +25,15 @@
 //                  part of the 10 samples' motion that is not along g1 (the samples of an offset move with the
 //                  pair's CURRENT relative velocity rv = g1 + delta for tau <= 0.9 s: the part along g1 only
 //                  stretches the window by 0.9 s, |delta| <= |v_i - uv_i| + tm |ca| goes into the bound).
-//              Survivors (about 1 in 20) are appended to the pair queue QA, which warps fill in private
-//              2048-entry blocks (one global atomic per block, not per push).
+//              The outcome of a test is the sign bit of a packed subtraction, shifted into per-lane bit masks
+//              (one funnel shift per test; no compare, no store); the pass rule is applied once per chunk.
+//              Survivors (about 1 in 29) are appended to the pair queue QA, which warps fill in private
+//              256-entry blocks (one global atomic per block, not per push).
 //   k_narrow : QA -> Q3.  A warp takes 32 queued pairs (lane = pair): detect narrow phase (temporal
-//              filter + closest approach) and, for predict queries, the time window that can hold a hit
-//              (trajectory re-expanded about the middle of the window, twice) -> offsets m_lo..m_hi; then
-//              the per-offset work in three more phases with different lane assignments
-//              ((pair, offset) / surviving item / pair): reach and radius tests, the 10 samples, the
-//              max-risk merge.
+//              filter + closest approach) and, for predict queries, the offsets whose 10 samples can reach
+//              the safe distance at all (all 20 offsets in packed fp32) -> offset mask; then the per-offset
+//              work in three more phases with different lane assignments ((pair, offset) / surviving item /
+//              pair): radius test, the 10 samples, the max-risk merge.
 //   k_exact  : lane = pair; the decision is taken in fp64 in the reference's operation order
 //              (rcd_exact.cuh), merged over offsets, emitted through one 64-bit atomic cursor and
 //              classified (alert priority).
@@ -324,8 +327,8 @@ __device__ __noinline__ EmitRec exact_predict_resolved(const PairParams &P, u32 
     const double rs = mag3_d(dsub(A.vx, B.vx), dsub(A.vy, B.vy), dsub(A.vz, B.vz));
     const double risk = risk_level_d(A.heading, B.heading, A.type, B.type, tau, d, safe, rs);
     const double ttc = dadd(tau, t);
-    return make_rec(si, sj, ttc, d, rs, risk, __ddiv_rn(dadd(xi, xj), 2.0), __ddiv_rn(dadd(yi, yj), 2.0),
-                    __ddiv_rn(dadd(zi, zj), 2.0), t, 0.0, priority_d(risk, ttc), m, true);
+    return make_rec(si, sj, ttc, d, rs, risk, half_d(dadd(xi, xj)), half_d(dadd(yi, yj)),
+                    half_d(dadd(zi, zj)), t, 0.0, priority_d(risk, ttc), m, true);
 }
 
 __device__ __noinline__ EmitRec exact_compute_node(const PairParams &P, u32 si, u32 sj) {
