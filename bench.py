@@ -381,10 +381,13 @@ def time_resident(job: SlabJob, steps: int, warmup: int, flush):
     return lat, halo_ms, {k: v / steps for k, v in stage_acc.items()}, launches, counts, t_wall
 
 
-def time_e2e(job: SlabJob, steps: int, warmup: int, delivery: str, inflight: int, bufs):
+def time_e2e(job: SlabJob, steps: int, warmup: int, delivery: str, inflight: int, bufs, period: float = 0.0):
     """K frames through the host API from pinned memory: H2D -> (halo) -> frame -> delivery, wall clock.
     delivery 'summary': alert changes + per-object risk counts + totals; 'pairs': every rcd_pair record.
-    inflight 2: the delivery of frame k overlaps the kernels of frame k + 1 (twin buffers in the handle)."""
+    inflight 2: the delivery of frame k overlaps the kernels of frame k + 1 (twin buffers in the handle).
+    period > 0: frames ARRIVE every `period` seconds (the reference harness paces its frames at a target rate,
+    performance_test.py:760-830) instead of being submitted as fast as the host can; a frame's latency then runs from its
+    arrival time to the arrival of its results."""
     eng = job.eng
     now = [1000.0]
 
@@ -403,15 +406,26 @@ def time_e2e(job: SlabJob, steps: int, warmup: int, delivery: str, inflight: int
         got, _c = eng.download_finish()
         return got.nbytes + 96, int(got.shape[0])
 
-    def run(n_frames):
+    def run(n_frames, period=0.0):
         lat, nbytes, items, t_start = [], 0, 0, {}
+        t_origin = time.perf_counter()
+
+        def arrive(k):  # the moment frame k's data is there: now, or the k-th tick of the arrival clock
+            if period > 0.0:
+                tick = t_origin + k * period
+                while time.perf_counter() < tick:
+                    pass
+                t_start[k] = tick
+            else:
+                t_start[k] = time.perf_counter()
+
         if inflight >= 2:
-            t_start[0] = time.perf_counter()
+            arrive(0)
             job.frame(0, host=True)
             begin(0)
             for k in range(1, n_frames + 1):
                 if k < n_frames:
-                    t_start[k] = time.perf_counter()
+                    arrive(k)
                     job.frame(k, host=True)
                 b, m = finish(k - 1)
                 lat.append(time.perf_counter() - t_start[k - 1])
@@ -421,11 +435,11 @@ def time_e2e(job: SlabJob, steps: int, warmup: int, delivery: str, inflight: int
                     begin(k)
         else:
             for k in range(n_frames):
-                t0 = time.perf_counter()
+                arrive(k)
                 job.frame(k, host=True)
                 begin(k)
                 b, m = finish(k)
-                lat.append(time.perf_counter() - t0)
+                lat.append(time.perf_counter() - t_start[k])
                 nbytes += b
                 items += m
         return lat, nbytes, items
@@ -433,7 +447,7 @@ def time_e2e(job: SlabJob, steps: int, warmup: int, delivery: str, inflight: int
     run(max(2, min(warmup, 4)))  # allocates the twin buffers, fills the alert table: outside the timed region
     barrier(job.world)
     t0 = time.perf_counter()
-    lat, nbytes, items = run(steps)
+    lat, nbytes, items = run(steps, period)
     barrier(job.world)
     t = time.perf_counter() - t0
     return {"t": t, "lat_ms": np.array(lat) * 1e3, "d2h_per_step": nbytes / steps, "items_per_step": items / steps}
@@ -588,6 +602,16 @@ def measure(args, workload, per_gpu, world, rank, local_rank, flush, steps, warm
                "events_per_step": r["items_per_step"],
                "other": {k: {"ms_per_step": t_best[k] / steps * 1e3, "p99_ms": float(np.percentile(runs[k]["lat_ms"], 99))}
                          for k in runs if k != pick}}
+        if 2 in runs:  # frames arriving at a fixed rate just below saturation: the latency a periodic feed sees
+            period = 1.05 * t_best[2] / steps
+            rp = time_e2e(job, steps, warmup, "summary", 2, bufs, period=period)
+            lat_p = torch.from_numpy(rp["lat_ms"]).cuda()
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(lat_p, op=dist.ReduceOp.MAX)
+            lat_p = lat_p.cpu().numpy()
+            e2e["paced"] = {"period_ms": period * 1e3, "ms_per_step": reduce_max(world, [rp["t"]])[0] / steps * 1e3,
+                            "p50_ms": float(np.percentile(lat_p, 50)), "p99_ms": float(np.percentile(lat_p, 99))}
         # full pair records (every CollisionRisk), two frames in flight
         k_full = max(3, min(steps, 10))
         cap_pairs = min(job.max_pairs, int(args.host_pairs_cap))
@@ -745,6 +769,10 @@ def run_b200(args):
                     "alert_events_per_step": m["events"], "ms_per_step": e2e["t"] / steps * 1e3,
                     "p99_ms": float(np.percentile(e2e["lat_ms"], 99)), "frames_in_flight": e2e["inflight"],
                     "other_inflight": e2e["other"],
+                    "paced_arrivals": (dict(e2e["paced"], value=m["objs"] / (e2e["paced"]["ms_per_step"] * 1e-3),
+                                            note="frames arrive every period_ms (1.05 x the closed-loop step, like the reference "
+                                                 "harness's target rate); latency from arrival to delivered results, max over ranks")
+                                       if "paced" in e2e else None),
                     "full_pairs": {"value": m["objs"] * e2e["full"]["steps"] / e2e["full"]["t"], "unit": "object-updates/s",
                                    "delivery": "every emitted pair as a 48-byte rcd_pair (rcd_download_begin/_finish), 2 frames in flight",
                                    "d2h_bytes_per_step": int(m["d2h_full"]), "ms_per_step": e2e["full"]["t"] / e2e["full"]["steps"] * 1e3,
