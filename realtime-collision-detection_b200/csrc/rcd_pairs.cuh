@@ -412,6 +412,7 @@ struct PredictCoef {
     float cvx, cvy, cvz, cax, cay, caz;
     float rvx, rvy, rvz, inv_rv2, lim2;  // sample motion: relative velocity, 1/|rv|^2, (safe_b + 0.405 |ra|)^2
     float safe_b2, hr, hr2;
+    float safe, safe_b;                  // safe distance, and with its guard band
 };
 __device__ __forceinline__ PredictCoef predict_coef(const float4 &a0, const float4 &a1, const float4 &a2,
                                                     const float4 &b0, const float4 &b1, const float4 &b2,
@@ -431,6 +432,8 @@ __device__ __forceinline__ PredictCoef predict_coef(const float4 &a0, const floa
     float d2 = c.dx * c.dx + c.dy * c.dy + c.dz * c.dz;
     float safe = (a0.w + b0.w) * 0.5f + 5.0f;
     float safe_b = safe + 2.0e-3f + 1.0e-6f * sqrt_ub(d2);
+    c.safe = safe;
+    c.safe_b = safe_b;
     c.safe_b2 = safe_b * safe_b;
     // the 10 samples move the pair by at most |rv|*0.9 + |ra|*0.405 from the offset state
     c.hr = safe_b + rvn * 0.9f + ran * 0.405f;
@@ -1349,6 +1352,7 @@ struct SampleShared {
     unsigned short items[64];                  // pair | offset << 5
 };
 constexpr int QA_BATCHES_PER_BLOCK = QA_BLOCK / 32;
+constexpr u32 SAMPLE_ITEMS = 32u;  // items per pass of the sample phase (two lanes per item, 5 samples each, measured slower)
 
 __device__ __forceinline__ float sqrt_approx(float x) {
     float r;
@@ -1430,6 +1434,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                             // packed instruction
                             const float nir = -c.inv_rv2 * (1.0f / 0.9f);
                             const float r9x = 0.9f * c.rvx, r9y = 0.9f * c.rvy, r9z = 0.9f * c.rvz;
+                            u32 fmask = 0;
 #pragma unroll
                             for (int m = 0; m < PREDICT_OFFSETS; m += 2) {
                                 const float2 t2 = make_float2(0.5f * (float)m, 0.5f * (float)(m + 1));
@@ -1441,8 +1446,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                                 const float2 sc = make_float2(__saturatef(dot.x * nir), __saturatef(dot.y * nir));  // tau / 0.9
                                 const float2 ex = fma2(splat2(r9x), sc, gx), ey = fma2(splat2(r9y), sc, gy), ez = fma2(splat2(r9z), sc, gz);
                                 const float2 e2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
-                                mask |= (e2.x <= c.lim2 ? (1u << m) : 0u) | (e2.y <= c.lim2 ? (2u << m) : 0u);
+                                const float2 tf = fma2(e2, splat2(-1.0f), splat2(c.lim2));  // < 0 <=> out of reach
+                                fmask = shift_in_sign(shift_in_sign(fmask, tf.x), tf.y);
                             }
+                            // offset m failed <=> bit (PREDICT_OFFSETS - 1 - m) of fmask
+                            mask = (~__brev(fmask) >> (32 - PREDICT_OFFSETS)) & ((1u << PREDICT_OFFSETS) - 1u);
                         }
                         if (mask) {
                             float *o = sh.coef[lane];
@@ -1453,12 +1461,10 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                             o[SC_RA] = a2.x - b2.x; o[SC_RA + 1] = a2.y - b2.y; o[SC_RA + 2] = a2.z - b2.z;
                             o[SC_UV] = c.uvx; o[SC_UV + 1] = c.uvy; o[SC_UV + 2] = c.uvz;
                             o[SC_UA] = c.uax; o[SC_UA + 1] = c.uay; o[SC_UA + 2] = c.uaz;
-                            o[SC_HR2] = c.hr2; o[SC_INVRV2] = c.inv_rv2; o[SC_LIM2] = c.lim2; o[SC_SAFEB2] = c.safe_b2;
-                            const float safe = (a0.w + b0.w) * 0.5f + 5.0f;
-                            const float band = sqrtf(c.safe_b2) - safe;  // the guard band of predict_coef
-                            const float safe_in = fmaxf(safe - band, 0.0f);
+                            o[SC_SAFEB2] = c.safe_b2;  // (SC_HR2 / SC_INVRV2 / SC_LIM2 were phase 2's: taken in phase 1 now)
+                            const float safe_in = fmaxf(c.safe - (c.safe_b - c.safe), 0.0f);  // safe minus the guard band
                             o[SC_SAFEIN2] = safe_in * safe_in;
-                            o[SC_INVSAFE] = 1.0f / safe;
+                            o[SC_INVSAFE] = rcp_fast(c.safe);  // (feeds the fp32 merge key only: ~1e-7 relative)
                         }
                     }
                 }
@@ -1560,10 +1566,10 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
                 if (pass) sh.items[n_items + __popc(bal & lanemask_lt())] = (unsigned short)(pr | (m << 5));
                 n_items += __popc(bal);
                 __syncwarp();
-                if (n_items >= 32) run_samples(32);
+                while (n_items >= SAMPLE_ITEMS) run_samples(SAMPLE_ITEMS);
             }
         }
-        if (n_items) run_samples(n_items);
+        while (n_items) run_samples(min(n_items, SAMPLE_ITEMS));
         __syncwarp();
 
         // ---- 4. lane = pair: merge over the offsets ------------------------------------------------------
