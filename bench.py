@@ -562,8 +562,47 @@ def verify_frame(job: SlabJob, k: int, n_queries: int):
     return res
 
 
+def verify_counts(job: SlabJob, k: int, n_queries: int):
+    """Light form of verify_frame for frames whose pair lists are too large to bring back: the number of risks every
+    sampled query emits (detect + predict, `rcd_download_risk_counts`) against the CPU oracle's count for that query."""
+    import torch.distributed as dist
+    from oracle import oracle as O  # the checker, never the thing measured
+    from rcd_b200.host import workloads as W
+    world, rank = job.world, job.rank
+    frame = job.frames[k % len(job.frames)]
+    n = job.n_total
+    stride = max(1, n // max(1, n_queries))
+    job.frame(k)
+    job.eng.sync()
+    ids = job.own_ids[k % len(job.own_ids)]
+    rc = job.eng.risk_counts()[: len(ids)]
+    sel = ids % stride == 0
+    mine = np.stack([ids[sel].astype(np.int64), rc[sel].astype(np.int64)], 1)
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    if rank != 0:
+        return None
+    t0 = time.perf_counter()
+    got = np.concatenate(parts)
+    got = got[np.argsort(got[:, 0])]
+    f64 = W.frame_to_f64(frame)
+    threads = max(O.max_threads(), os.cpu_count() or 1)
+    pat = np.full(n, 2, np.uint8)
+    want = np.zeros(n, np.int64)
+    for mode in ("detect", "predict"):
+        ora = O.frame_A(f64, mode, pattern_codes=pat if mode == "predict" else None, want_potentials=False,
+                        query_stride=stride, risk_cap=1 << 26, threads=threads)["risks"]
+        want += np.bincount(ora["i"].astype(np.int64), minlength=n)
+    q = np.arange(0, n, stride)
+    ok = len(got) == len(q) and np.array_equal(got[:, 0], q) and np.array_equal(got[:, 1], want[q])
+    return {"kind": "risks per sampled query (detect + predict) against the oracle", "queries": int(len(q)), "stride": int(stride),
+            "risks_checked": int(want[q].sum()), "ok": bool(ok), "oracle_seconds": round(time.perf_counter() - t0, 2)}
+
+
 def measure(args, workload, per_gpu, world, rank, local_rank, flush, steps, warmup, rebalance_rounds, with_e2e=True,
-            with_verify=True, sampler=None, max_pairs=None):
+            with_verify=True, sampler=None, max_pairs=None, verify_kind="pairs", verify_queries=None):
     """Everything for one workload: (re-balanced) slabs, device-timed frames, end-to-end frames, verification."""
     import torch
     from rcd_b200.host import _native as N
@@ -620,7 +659,9 @@ def measure(args, workload, per_gpu, world, rank, local_rank, flush, steps, warm
         e2e["full"] = {"t": reduce_max(world, [rf["t"]])[0], "steps": k_full, "lat_ms": rf["lat_ms"], "d2h_per_step": rf["d2h_per_step"]}
         bufs.clear()
     out["e2e"] = e2e
-    out["verify"] = verify_frame(job, 0, args.verify_queries) if with_verify and args.verify_queries > 0 else None
+    nq = args.verify_queries if verify_queries is None else min(verify_queries, args.verify_queries)
+    out["verify"] = ((verify_frame if verify_kind == "pairs" else verify_counts)(job, 0, nq)
+                     if with_verify and nq > 0 else None)
     # ---- reduce over ranks (max time, summed counts) ---------------------------------------------------
     t_dev = float(lat.sum()) / 1e3
     out["t_dev"] = reduce_max(world, [t_dev])[0]
@@ -671,7 +712,7 @@ def run_b200(args):
         time.sleep(0.3)
     steps = args.steps
     m = measure(args, args.workload, args.objects_per_gpu, world, rank, local_rank, flush, steps, args.warmup,
-                args.rebalance if world > 1 else 0)
+                args.rebalance if world > 1 else 0, verify_kind=args.verify_kind)
     clocks = sampler.stop() if rank == 0 else None
     job = m["job"]
 
@@ -681,24 +722,26 @@ def run_b200(args):
         job.close()
         xs = max(5, min(steps, 10))
         s = measure(args, "cfg4_1m_clustered3d", PER_GPU_DEFAULT // world, world, rank, local_rank, flush, xs, 3,
-                    min(args.rebalance, 2), with_e2e=False, with_verify=False)
+                    min(args.rebalance, 2), with_e2e=False, verify_queries=1000)
         extras["strong_scaling"] = {
             "workload": f"configs[3] as written: {int(s['objs'])} objects in total over {world} x-slabs", "scaling": "strong",
             "value": s["objs"] * xs / s["t_dev"], "unit": "object-updates/s", "ms_per_step": s["t_dev"] / xs * 1e3,
             "latency_ms": lat_stats(s["lat_all"]), "steps": xs, "per_rank_ms": s["per_rank_ms"],
-            "per_rank_halo_ms": s["per_rank_halo_ms"], "pairs_emitted": s["n_pairs"], "halo_objects": s["n_halo"]}
+            "per_rank_halo_ms": s["per_rank_halo_ms"], "pairs_emitted": s["n_pairs"], "halo_objects": s["n_halo"],
+            "verify": s["verify"]}
         s["job"].close()
         _FRAME_CACHE.clear()
         if world == 8:
             # the north-star size: 10 M objects on the box, at the configs[3] density (1.25 M per GPU)
             xs = max(5, min(steps, 10))
             s = measure(args, "cfg4_1m_clustered3d", 1_250_000, world, rank, local_rank, flush, xs, 3, min(args.rebalance, 2),
-                        with_e2e=False, with_verify=False)
+                        with_e2e=False, verify_kind="counts", verify_queries=1000)
             extras["north_star_10m"] = {
                 "workload": f"cfg4_1m_clustered3d: {s['job'].desc}", "scaling": "weak (1.25 M objects per GPU)",
                 "value": s["objs"] * xs / s["t_dev"], "unit": "object-updates/s", "ms_per_step": s["t_dev"] / xs * 1e3,
                 "latency_ms": lat_stats(s["lat_all"]), "steps": xs, "per_rank_ms": s["per_rank_ms"],
-                "per_rank_halo_ms": s["per_rank_halo_ms"], "pairs_emitted": s["n_pairs"], "halo_objects": s["n_halo"]}
+                "per_rank_halo_ms": s["per_rank_halo_ms"], "pairs_emitted": s["n_pairs"], "halo_objects": s["n_halo"],
+                "verify": s["verify"]}
             s["job"].close()
             _FRAME_CACHE.clear()
             for name in ("cfg5_10m_skew3d_uniform_disc", "cfg5_10m_skew3d"):
@@ -706,15 +749,15 @@ def run_b200(args):
                 # (the queues between the kernels are sized from the pair buffer: 256 M pairs keep this frame out of the
                 # overflow pass -- 1.8e9 risks per frame on the box with the reference's radial law)
                 big = 256_000_000
-                s = measure(args, name, 1_250_000, world, rank, local_rank, flush, xs, 3, 1, with_e2e=False, with_verify=False,
-                            max_pairs=big)
+                s = measure(args, name, 1_250_000, world, rank, local_rank, flush, xs, 3, 1, with_e2e=False, max_pairs=big,
+                            verify_kind="counts", verify_queries=400)
                 extras["configs4_10m" + ("_uniform_disc" if name.endswith("disc") else "_reference_law")] = {
                     "workload": f"{name}: {s['job'].desc}", "scaling": "n/a (10M objects on 8 GPUs)",
                     "value": s["objs"] * xs / s["t_dev"], "unit": "object-updates/s", "ms_per_step": s["t_dev"] / xs * 1e3,
                     "candidates_per_s": s["n_cand"] * xs / s["t_dev"], "latency_ms": lat_stats(s["lat_all"]), "steps": xs,
                     "per_rank_ms": s["per_rank_ms"], "pairs_emitted": s["n_pairs"], "candidates": s["n_cand"],
                     "pairs_stored_cap_per_gpu": big,
-                    "note": "counts are exact beyond the pair buffer; records past it are not stored"}
+                    "note": "counts are exact beyond the pair buffer; records past it are not stored", "verify": s["verify"]}
                 s["job"].close()
                 _FRAME_CACHE.clear()
 
@@ -847,6 +890,8 @@ def main():
     ap.add_argument("--rebalance", type=int, default=3, help="re-balancing rounds of the slab cuts during warm-up (N > 1)")
     ap.add_argument("--verify-queries", type=int, default=2000,
                     help="queries of the headline frame re-computed by the CPU oracle after the timed regions (0 = off)")
+    ap.add_argument("--verify-kind", choices=["pairs", "counts"], default="pairs",
+                    help="headline check: emitted pair records, or only the per-query risk counts (frames too large to bring back)")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the strong-scaling / 10M lines that follow the headline at N > 1")
     args = ap.parse_args()

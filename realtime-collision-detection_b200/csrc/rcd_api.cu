@@ -308,7 +308,7 @@ int build_index(rcd_handle h, float cell_req) {
     {
         int blocks = (int)std::min<u64>(((u64)n + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
         k_pack_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(input_state(h), n, (u32)h->n_owned, g, passes, h->keys[0],
-                                                            h->vals[0], h->hist, h->U);
+                                                            h->hist, h->U);
         KERNEL_CHECK(h);
         k_scan_hist<<<1, RADIX, 0, h->stream>>>(h->hist, passes);
         KERNEL_CHECK(h);
@@ -316,20 +316,14 @@ int build_index(rcd_handle h, float cell_req) {
     stage_end(h, RCD_STAGE_KEYS);
 
     stage_begin(h, RCD_STAGE_SORT);
-    int cur = 0;
-    for (int p = 0; p < passes; ++p) {
-        k_onesweep_pass<<<tiles, SORT_THREADS, 0, h->stream>>>(
-            h->keys[cur], h->vals[cur], h->keys[cur ^ 1], h->vals[cur ^ 1], n, p * RADIX_BITS,
-            h->hist + p * RADIX, h->tile_status + (size_t)p * tiles * RADIX, h->tile_counter + p);
-        KERNEL_CHECK(h);
-        cur ^= 1;
-    }
+    const int cur = launch_onesweep(h->keys, h->vals, n, passes, h->hist, h->tile_status, h->tile_counter, h->stream);
+    KERNEL_CHECK(h);
     h->sorted_buf = cur;
     stage_end(h, RCD_STAGE_SORT);
 
     stage_begin(h, RCD_STAGE_REORDER);
     k_reorder<<<(n + REORDER_THREADS - 1) / REORDER_THREADS, REORDER_THREADS, 0, h->stream>>>(
-        h->vals[cur], n, h->U, h->in_id, h->P0, h->P1, h->P2, h->sorted_slot, h->sorted_id);
+        h->vals[cur], n, h->U, h->P0, h->P1, h->P2, h->sorted_slot, h->sorted_id);
     KERNEL_CHECK(h);
     {
         int rcr = release_inputs(h);
@@ -369,18 +363,12 @@ int build_query_order(rcd_handle h, int kind) {
     q.x_longer = bits_x > bits_y ? 1 : 0;
     q.capsule = kind == 2 ? 1 : 0;
     const int blocks = (int)std::min<u64>(((u64)n + KEYS_THREADS - 1) / KEYS_THREADS, 148 * 8);
-    k_query_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(h->P0, h->P1, h->P2, n, q, h->qkeys[0], h->qvals[0], h->hist);
+    k_query_keys<<<blocks, KEYS_THREADS, 0, h->stream>>>(h->P0, h->P1, h->P2, n, q, h->qkeys[0], h->hist);
     KERNEL_CHECK(h);
     k_scan_hist<<<1, RADIX, 0, h->stream>>>(h->hist, QKEY_PASSES);
     KERNEL_CHECK(h);
-    int cur = 0;
-    for (int p = 0; p < QKEY_PASSES; ++p) {
-        k_onesweep_pass<<<tiles, SORT_THREADS, 0, h->stream>>>(
-            h->qkeys[cur], h->qvals[cur], h->qkeys[cur ^ 1], h->qvals[cur ^ 1], n, p * RADIX_BITS,
-            h->hist + p * RADIX, h->tile_status + (size_t)p * tiles * RADIX, h->tile_counter + p);
-        KERNEL_CHECK(h);
-        cur ^= 1;
-    }
+    const int cur = launch_onesweep(h->qkeys, h->qvals, n, QKEY_PASSES, h->hist, h->tile_status, h->tile_counter, h->stream);
+    KERNEL_CHECK(h);
     stage_end(h, RCD_STAGE_QORDER);
     h->q_sorted_buf = cur;
     h->qorder_kind = kind;
@@ -484,7 +472,7 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
     CREATE_TRY(dev_alloc(&h->P0, cap));
     CREATE_TRY(dev_alloc(&h->P1, cap));
     CREATE_TRY(dev_alloc(&h->P2, cap));
-    CREATE_TRY(dev_alloc(&h->U, 3 * (cap + 4)));
+    CREATE_TRY(dev_alloc(&h->U, 4 * (cap + 4)));
     CREATE_TRY(dev_alloc(&h->sorted_slot, cap));
     CREATE_TRY(dev_alloc(&h->sorted_id, cap));
     CREATE_TRY(dev_alloc(&h->cell_begin, (size_t)h->cells_cap + 2));

@@ -21,11 +21,12 @@ struct InputState {
 };
 
 // -------------------------------------------------------------------------------------------------
-// K1: one pass over the SoA state: cell keys + identity permutation + digit histograms of every
-// sort pass, and the state packed into one dense 48-byte record per object in upload order
-// ({x,y,z,size | vx,vy,vz,heading | ax,ay,az,meta}), so that the gather after the sort reads two
-// adjacent 32-byte sectors per object instead of twelve scattered 4-byte fields.
-// Algorithmic bytes: 46 N read + 8 N + 48 N written = 102 N.
+// K1: one pass over the SoA state: cell keys + digit histograms of every sort pass, and the state
+// packed into one 64-byte-aligned record per object in upload order
+// ({x,y,z,size | vx,vy,vz,heading | ax,ay,az,meta | id,-,-,-}), so that the gather after the sort reads
+// ONE aligned 64-byte block per object (the DRAM access granule) instead of thirteen scattered 4-byte
+// fields.  The first sort pass needs no permutation array: its values are the positions themselves.
+// Algorithmic bytes: 50 N read + 4 N (keys) + 52 N (records; 64 N with the padding) written = 106 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int KEYS_THREADS = 256;
 
@@ -35,13 +36,13 @@ __device__ __forceinline__ u32 pack_meta(u32 type, u32 pattern, bool owned) {
 
 __global__ void __launch_bounds__(KEYS_THREADS)
 k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__restrict__ keys,
-            u32 *__restrict__ vals, u32 *__restrict__ hist /* [MAX_PASSES][RADIX] */,
-            float4 *__restrict__ U /* [n][3]: one dense 48-byte record per object */) {
+            u32 *__restrict__ hist /* [MAX_PASSES][RADIX] */,
+            float4 *__restrict__ U /* [n][4]: one 64-byte record per object */) {
     __shared__ u32 s_hist[MAX_PASSES][RADIX];
     for (int k = threadIdx.x; k < MAX_PASSES * RADIX; k += KEYS_THREADS) (&s_hist[0][0])[k] = 0;
     __syncthreads();
-    // one object per thread: every field load and the key / permutation stores are fully coalesced
-    // 128-byte warp requests, and the three 16-byte record stores of a warp tile a dense 1.5 KB span
+    // one object per thread: every field load and the key store are fully coalesced 128-byte warp
+    // requests, and the four 16-byte record stores of a warp tile a dense 2 KB span
     const u32 stride = gridDim.x * KEYS_THREADS;
     for (u32 i = blockIdx.x * KEYS_THREADS + threadIdx.x; i < n; i += stride) {
         const float x = __ldcs(in.px + i), y = __ldcs(in.py + i), z = __ldcs(in.pz + i);
@@ -53,11 +54,11 @@ k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__
         // their own behind the grid, which is under no query's box
         const u32 k = (x == x && y == y && z == z) ? cell_key(g, x, y, z) : g.ncells;
         keys[i] = k;
-        vals[i] = i;
-        float4 *rec = U + 3 * (size_t)i;
+        float4 *rec = U + 4 * (size_t)i;
         rec[0] = r0;
         rec[1] = r1;
         rec[2] = r2;
+        rec[3] = make_float4(__uint_as_float(__ldcs(in.id + i)), 0.0f, 0.0f, 0.0f);
         for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(k >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
     }
     __syncthreads();
@@ -92,11 +93,24 @@ __global__ void __launch_bounds__(RADIX) k_scan_hist(u32 *__restrict__ hist, int
 // per pass.  Tiles take tickets from an atomic counter, so a tile only ever waits on tiles that
 // are already running (decoupled look-back, forward progress guaranteed inside one launch).
 // Ranking is stable: warp-striped loads, per-warp digit counters updated with match.any.
-// Algorithmic bytes per pass: 8 N read + 8 N written.
+// IDENTITY (the first pass): the values are the positions, nothing is read for them.
+// Algorithmic bytes per pass: 8 N read (4 N on the first pass) + 8 N written.
 // -------------------------------------------------------------------------------------------------
+#ifndef RCD_SORT_ITEMS
+#define RCD_SORT_ITEMS 16
+#endif
+#ifndef RCD_SORT_CTAS
+#define RCD_SORT_CTAS 3
+#endif
+#ifndef RCD_SORT_LOOKBACK
+#define RCD_SORT_LOOKBACK 8
+#endif
+#ifndef RCD_SORT_VAL_LATE
+#define RCD_SORT_VAL_LATE 0
+#endif
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 16;
+constexpr int SORT_ITEMS = RCD_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 4096 keys
 constexpr u32 STATUS_AGGREGATE = 1u << 30;
 constexpr u32 STATUS_PREFIX = 2u << 30;
@@ -133,12 +147,13 @@ __device__ __forceinline__ u32 match_digit(u32 digit, u32 peers /* lanes that ta
 }
 
 // One tile of one pass.  FULL: the tile holds SORT_TILE keys (every tile but the last): no bound checks.
-template <bool FULL>
+template <bool FULL, bool IDENTITY>
 __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                                               u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 tile,
                                               u32 tile_count, int shift, const u32 *__restrict__ digit_base,
                                               u32 *tile_status, u32 (*s_warp_hist)[RADIX], u32 *s_digit_excl,
                                               u32 *s_global_base, u32 *s_scan, uint2 *s_kv) {
+    constexpr bool VAL_LATE = RCD_SORT_VAL_LATE && !IDENTITY;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 tile_base = tile * SORT_TILE;
     // ---- load (warp-striped: item k of lane l is element warp*ITEMS*32 + k*32 + l) and rank ----
@@ -150,7 +165,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     for (int k = 0; k < SORT_ITEMS; ++k) {
         const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
         key[k] = valid ? __ldcs(kin + k * 32) : 0xffffffffu;
-        val[k] = valid ? __ldcs(vin + k * 32) : 0u;
+        if (!IDENTITY && !VAL_LATE) val[k] = valid ? __ldcs(vin + k * 32) : 0u;
     }
     const u32 lt = lanemask_lt();
     u32 *my_hist = s_warp_hist[warp];
@@ -166,6 +181,13 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
         if ((group & lt) == 0 && valid) my_hist[digit] = before + __popc(group);
         rank[k] = before + __popc(group & lt);
         __syncwarp();
+    }
+    if (VAL_LATE) {  // the values are not needed before the scatter: their loads fly over the digit scans
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
+            val[k] = valid ? __ldcs(vin + k * 32) : 0u;
+        }
     }
     __syncthreads();
 
@@ -205,7 +227,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
         if (FULL || warp_base + k * 32 + lane < tile_count) {
             const u32 digit = (key[k] >> shift) & (RADIX - 1);
             const u32 pos = s_digit_excl[digit] + my_hist[digit] + rank[k];
-            s_kv[pos] = make_uint2(key[k], val[k]);
+            s_kv[pos] = make_uint2(key[k], IDENTITY ? tile_base + warp_base + k * 32 + lane : val[k]);
         }
     }
     // ---- decoupled look-back for digit `tid` ----------------------------------------------------
@@ -213,7 +235,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     // long run of AGGREGATE tiles costs one memory latency per batch instead of one per tile.
     u32 excl = 0;
     if (tile > 0) {
-        constexpr int LOOKBACK = 8;
+        constexpr int LOOKBACK = RCD_SORT_LOOKBACK;
         int t = (int)tile - 1;
         bool done = false;
         while (!done) {
@@ -249,7 +271,8 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     }
 }
 
-__global__ void __launch_bounds__(SORT_THREADS, 3)
+template <bool IDENTITY>
+__global__ void __launch_bounds__(SORT_THREADS, RCD_SORT_CTAS)
 k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in,
                 u32 *__restrict__ keys_out, u32 *__restrict__ vals_out, u32 n, int shift,
                 const u32 *__restrict__ digit_base /* [RADIX] exclusive, this pass */,
@@ -268,34 +291,53 @@ k_onesweep_pass(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in
     const u32 tile = s_tile;
     const u32 tile_count = min((u32)SORT_TILE, n - tile * SORT_TILE);
     if (tile_count == SORT_TILE)
-        onesweep_tile<true>(keys_in, vals_in, keys_out, vals_out, tile, tile_count, shift, digit_base, tile_status, s_warp_hist,
-                            s_digit_excl, s_global_base, s_scan, s_kv);
+        onesweep_tile<true, IDENTITY>(keys_in, vals_in, keys_out, vals_out, tile, tile_count, shift, digit_base, tile_status,
+                                      s_warp_hist, s_digit_excl, s_global_base, s_scan, s_kv);
     else
-        onesweep_tile<false>(keys_in, vals_in, keys_out, vals_out, tile, tile_count, shift, digit_base, tile_status, s_warp_hist,
-                             s_digit_excl, s_global_base, s_scan, s_kv);
+        onesweep_tile<false, IDENTITY>(keys_in, vals_in, keys_out, vals_out, tile, tile_count, shift, digit_base, tile_status,
+                                       s_warp_hist, s_digit_excl, s_global_base, s_scan, s_kv);
+}
+
+// all passes of one sort: (keys[0], identity) -> (keys[cur], vals[cur]); returns cur
+inline int launch_onesweep(u32 *const keys[2], u32 *const vals[2], u32 n, int passes, const u32 *hist, u32 *tile_status,
+                           u32 *tile_counter, cudaStream_t stream) {
+    const u32 tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    int cur = 0;
+    for (int p = 0; p < passes; ++p) {
+        if (p == 0)
+            k_onesweep_pass<true><<<tiles, SORT_THREADS, 0, stream>>>(keys[0], nullptr, keys[1], vals[1], n, 0, hist, tile_status,
+                                                                    tile_counter);
+        else
+            k_onesweep_pass<false><<<tiles, SORT_THREADS, 0, stream>>>(
+                keys[cur], vals[cur], keys[cur ^ 1], vals[cur ^ 1], n, p * RADIX_BITS, hist + p * RADIX,
+                tile_status + (size_t)p * tiles * RADIX, tile_counter + p);
+        cur ^= 1;
+    }
+    return cur;
 }
 
 // -------------------------------------------------------------------------------------------------
-// K4: gather the packed planes into cell order.
-// Algorithmic bytes: 4 N (perm) + 52 N gathered (record + caller id) + 56 N written = 112 N;
-// a 48-byte record spans exactly two 32-byte sectors, so DRAM traffic is about 124 N.
+// K4: gather the packed records into the three planes in cell order.
+// Algorithmic bytes: 4 N (perm) + 52 N gathered (record with the caller id) + 56 N written = 112 N;
+// a record is one aligned 64-byte block, so DRAM traffic is 124 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int REORDER_THREADS = 256;
 
 __global__ void __launch_bounds__(REORDER_THREADS)
-k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U, const u32 *__restrict__ in_id,
+k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
           float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2, u32 *__restrict__ sorted_slot,
           u32 *__restrict__ sorted_id) {
     u32 s = blockIdx.x * REORDER_THREADS + threadIdx.x;
     if (s >= n) return;
     const u32 src = __ldcs(perm + s);
-    sorted_id[s] = __ldg(in_id + src);
-    const float4 *rec = U + 3 * (size_t)src;
+    const float4 *rec = U + 4 * (size_t)src;
     const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
+    const u32 id = __float_as_uint(__ldg(reinterpret_cast<const float *>(rec + 3)));
     P0[s] = a;
     P1[s] = b;
     P2[s] = c;
     sorted_slot[s] = src;
+    sorted_id[s] = id;
 }
 
 // lower bound in the sorted key array
@@ -371,7 +413,7 @@ k_cell_table(const u32 *__restrict__ keys, u32 n, u32 ncells, u32 *__restrict__ 
 // code of the centre of their volume -- the object itself for radius queries, the middle of the chord
 // of the predicted centre path (collision_detection.py:728-741) for predict queries -- and sorted;
 // consecutive 32 objects are then a compact tile at any density.  Halo copies (not queried) get the
-// top key and end up behind the last tile.  Bytes: 48 N read + 8 N written, then the sort passes.
+// top key and end up behind the last tile.  Bytes: 48 N read + 4 N written, then the sort passes.
 // -------------------------------------------------------------------------------------------------
 constexpr int QKEY_BITS = 23;                       // both axes together, split so that the key lattice is (nearly) square
 constexpr u32 QKEY_NOT_QUERIED = 1u << QKEY_BITS;   // bit 23: sorts behind every query
@@ -397,7 +439,7 @@ struct QueryKeyParams {
 
 __global__ void __launch_bounds__(KEYS_THREADS)
 k_query_keys(const float4 *__restrict__ P0, const float4 *__restrict__ P1, const float4 *__restrict__ P2, u32 n,
-             QueryKeyParams q, u32 *__restrict__ keys, u32 *__restrict__ vals, u32 *__restrict__ hist) {
+             QueryKeyParams q, u32 *__restrict__ keys, u32 *__restrict__ hist) {
     __shared__ u32 s_hist[QKEY_PASSES][RADIX];
     for (int k = threadIdx.x; k < QKEY_PASSES * RADIX; k += KEYS_THREADS) (&s_hist[0][0])[k] = 0;
     __syncthreads();
@@ -424,7 +466,6 @@ k_query_keys(const float4 *__restrict__ P0, const float4 *__restrict__ P1, const
                   (((q.x_longer ? ix : iy) >> q.bits_lo) << (2 * q.bits_lo));
         }
         keys[s] = key;
-        vals[s] = s;
 #pragma unroll
         for (int p = 0; p < QKEY_PASSES; ++p) atomicAdd(&s_hist[p][(key >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
     }

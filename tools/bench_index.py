@@ -34,7 +34,8 @@ for n in sizes:
                 best = ms
         ncells = (int(side / 100.22) + 1) ** 2
         passes = max(1, -(-int(np.ceil(np.log2(ncells))) // 8))
-        model = {"keys": 102.0 * n, "sort": 16.0 * passes * n, "reorder": 108.0 * n}
+        # K1 50N + 4N + 52N; K2 16N per pass, 12N for the first (no permutation read); K3 4N + 52N + 56N
+        model = {"keys": 106.0 * n, "sort": (16.0 * passes - 4.0) * n, "reorder": 112.0 * n}
         out = {"n": n, "passes": passes, "peak_gbs": peak}
         for k, b in model.items():
             out[k] = {"ms": round(best[k], 4), "alg_bytes": b, "gbs": round(b / best[k] / 1e6, 1), "frac": round(b / best[k] / 1e6 / peak, 3)}
