@@ -34,32 +34,69 @@ __device__ __forceinline__ u32 pack_meta(u32 type, u32 pattern, bool owned) {
     return type | ((pattern & 3u) << 8) | (owned ? META_OWNED : 0u);
 }
 
+#ifndef RCD_PACK_STAGED
+#define RCD_PACK_STAGED 1
+#endif
 __global__ void __launch_bounds__(KEYS_THREADS)
 k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__restrict__ keys,
             u32 *__restrict__ hist /* [MAX_PASSES][RADIX] */,
             float4 *__restrict__ U /* [n][4]: one 64-byte record per object */) {
     __shared__ u32 s_hist[MAX_PASSES][RADIX];
+#if RCD_PACK_STAGED
+    __shared__ float4 s_rec[KEYS_THREADS / 32][128];  // a warp's 32 records on their way to four dense 512-byte stores
+#endif
     for (int k = threadIdx.x; k < MAX_PASSES * RADIX; k += KEYS_THREADS) (&s_hist[0][0])[k] = 0;
     __syncthreads();
-    // one object per thread: every field load and the key store are fully coalesced 128-byte warp
-    // requests, and the four 16-byte record stores of a warp tile a dense 2 KB span
+    // one object per thread: every field load and the key store are fully coalesced 128-byte warp requests; the
+    // records are turned through shared memory so that a warp stores its 2 KB span as four dense 512-byte requests
+    // (16 full sectors each) instead of 4 x 32 half sectors
     const u32 stride = gridDim.x * KEYS_THREADS;
-    for (u32 i = blockIdx.x * KEYS_THREADS + threadIdx.x; i < n; i += stride) {
-        const float x = __ldcs(in.px + i), y = __ldcs(in.py + i), z = __ldcs(in.pz + i);
-        const float4 r0 = make_float4(x, y, z, __ldcs(in.size + i));
-        const float4 r1 = make_float4(__ldcs(in.vx + i), __ldcs(in.vy + i), __ldcs(in.vz + i), __ldcs(in.heading + i));
-        const u32 meta = pack_meta(__ldcs(in.type + i), __ldcs(in.pattern + i), i < n_owned);
-        const float4 r2 = make_float4(__ldcs(in.ax + i), __ldcs(in.ay + i), __ldcs(in.az + i), __uint_as_float(meta));
+    const u32 lane = threadIdx.x & 31u;
+    const u32 n_round = (n + 31u) & ~31u;  // whole warps run the loop: the staged stores are warp-wide
+    for (u32 i = blockIdx.x * KEYS_THREADS + threadIdx.x; i < n_round; i += stride) {
+        const bool live = i < n;
+        const u32 il = live ? i : n - 1;
+        const float x = __ldcs(in.px + il), y = __ldcs(in.py + il), z = __ldcs(in.pz + il);
+        const float4 r0 = make_float4(x, y, z, __ldcs(in.size + il));
+        const float4 r1 = make_float4(__ldcs(in.vx + il), __ldcs(in.vy + il), __ldcs(in.vz + il), __ldcs(in.heading + il));
+        const u32 meta = pack_meta(__ldcs(in.type + il), __ldcs(in.pattern + il), il < n_owned);
+        const float4 r2 = make_float4(__ldcs(in.ax + il), __ldcs(in.ay + il), __ldcs(in.az + il), __uint_as_float(meta));
+        const float4 r3 = make_float4(__uint_as_float(__ldcs(in.id + il)), 0.0f, 0.0f, 0.0f);
         // objects without a position (NaN: ghost slots of the halo exchange, rcd_halo_pack_async) go to a cell of
         // their own behind the grid, which is under no query's box
         const u32 k = (x == x && y == y && z == z) ? cell_key(g, x, y, z) : g.ncells;
-        keys[i] = k;
-        float4 *rec = U + 4 * (size_t)i;
-        rec[0] = r0;
-        rec[1] = r1;
-        rec[2] = r2;
-        rec[3] = make_float4(__uint_as_float(__ldcs(in.id + i)), 0.0f, 0.0f, 0.0f);
-        for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(k >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
+        if (live) keys[i] = k;
+#if RCD_PACK_STAGED
+        {
+            float4 *w = s_rec[threadIdx.x >> 5];
+            // quarter q of record l sits at slot 4 l + (q ^ ((l >> 1) & 3)): both the per-object writes (64-byte stride)
+            // and the dense reads below touch eight different 16-byte bank groups per quarter-warp
+            const u32 sw = (lane >> 1) & 3u;
+            w[4 * lane + (0u ^ sw)] = r0;
+            w[4 * lane + (1u ^ sw)] = r1;
+            w[4 * lane + (2u ^ sw)] = r2;
+            w[4 * lane + (3u ^ sw)] = r3;
+            __syncwarp();
+            const u32 base = i - lane;  // first object of the warp
+            float4 *dst = U + 4 * (size_t)base;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const u32 e = j * 32 + lane, o = e >> 2, q = e & 3u;
+                if (base + o < n) dst[e] = w[4 * o + (q ^ ((o >> 1) & 3u))];
+            }
+            __syncwarp();
+        }
+#else
+        if (live) {
+            float4 *rec = U + 4 * (size_t)i;
+            rec[0] = r0;
+            rec[1] = r1;
+            rec[2] = r2;
+            rec[3] = r3;
+        }
+#endif
+        if (live)
+            for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(k >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < passes * RADIX; k += KEYS_THREADS) {
@@ -108,6 +145,9 @@ __global__ void __launch_bounds__(RADIX) k_scan_hist(u32 *__restrict__ hist, int
 #ifndef RCD_SORT_VAL_LATE
 #define RCD_SORT_VAL_LATE 0
 #endif
+#ifndef RCD_SORT_ABLATE  // timing experiments only (wrong results): 1 no stores, 2 no look-back, 4 no ranking, 8 dense scatter
+#define RCD_SORT_ABLATE 0
+#endif
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_ITEMS = RCD_SORT_ITEMS;
@@ -130,7 +170,13 @@ __device__ __forceinline__ void st_status(u32 *p, u32 v) {
 // than one MATCH.ANY (whose latency the ranking chain would pay once per item).  Written in PTX so that
 // every bit costs four instructions (test, vote, select, and-xor) instead of the seven nvcc makes of the
 // C++ form: peers &= vote ^ (bit ? 0 : ~0).
+#ifndef RCD_SORT_HWMATCH
+#define RCD_SORT_HWMATCH 0
+#endif
 __device__ __forceinline__ u32 match_digit(u32 digit, u32 peers /* lanes that take part */) {
+#if RCD_SORT_HWMATCH
+    return __match_any_sync(FULL_MASK, digit) & peers;
+#endif
 #pragma unroll
     for (int b = 0; b < RADIX_BITS; ++b) {
         u32 t;
@@ -174,6 +220,10 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
         const u32 digit = (key[k] >> shift) & (RADIX - 1);
         // invalid lanes are in nobody's group and do not touch the counters
         const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
+#if RCD_SORT_ABLATE & 4
+        rank[k] = digit & 1;
+        continue;
+#endif
         const u32 group = match_digit(digit, FULL ? FULL_MASK : __ballot_sync(FULL_MASK, valid));
         // every lane of a group reads the counter (one broadcast per digit), the lowest lane advances it
         const u32 before = my_hist[digit];
@@ -226,7 +276,12 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     for (int k = 0; k < SORT_ITEMS; ++k) {
         if (FULL || warp_base + k * 32 + lane < tile_count) {
             const u32 digit = (key[k] >> shift) & (RADIX - 1);
-            const u32 pos = s_digit_excl[digit] + my_hist[digit] + rank[k];
+#if RCD_SORT_ABLATE & 8
+            const u32 pos = (warp_base + k * 32 + lane + ((s_digit_excl[digit] + my_hist[digit] + rank[k]) & 0)) & (SORT_TILE - 1);
+#else
+            const u32 pos = (RCD_SORT_ABLATE & 4) ? (s_digit_excl[digit] + my_hist[digit] + rank[k]) & (SORT_TILE - 1)
+                                                  : s_digit_excl[digit] + my_hist[digit] + rank[k];
+#endif
             s_kv[pos] = make_uint2(key[k], IDENTITY ? tile_base + warp_base + k * 32 + lane : val[k]);
         }
     }
@@ -234,7 +289,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     // Up to LOOKBACK predecessors are fetched with independent loads and then consumed in order, so a
     // long run of AGGREGATE tiles costs one memory latency per batch instead of one per tile.
     u32 excl = 0;
-    if (tile > 0) {
+    if (tile > 0 && !(RCD_SORT_ABLATE & 2)) {
         constexpr int LOOKBACK = RCD_SORT_LOOKBACK;
         int t = (int)tile - 1;
         bool done = false;
@@ -265,8 +320,15 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
         if (FULL || idx < tile_count) {
             const uint2 kv = s_kv[idx];
             const u32 out = s_global_base[(kv.x >> shift) & (RADIX - 1)] + idx;
-            keys_out[out] = kv.x;
-            vals_out[out] = kv.y;
+#if RCD_SORT_ABLATE & 1
+            if (kv.x == 0xdeadbeefu && kv.y == 0x12345678u && out == 0x0badf00du)
+#elif RCD_SORT_ABLATE & 16
+            if (out < (gridDim.x - 1u) * SORT_TILE)
+#endif
+            {
+                keys_out[out] = kv.x;
+                vals_out[out] = kv.y;
+            }
         }
     }
 }
@@ -322,7 +384,45 @@ inline int launch_onesweep(u32 *const keys[2], u32 *const vals[2], u32 n, int pa
 // a record is one aligned 64-byte block, so DRAM traffic is 124 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int REORDER_THREADS = 256;
+#ifndef RCD_REORDER_QUAD
+#define RCD_REORDER_QUAD 1
+#endif
 
+#if RCD_REORDER_QUAD
+// four lanes per object: one 16-byte load each, so a warp request covers 8 whole records (16 full sectors) and every
+// store instruction writes whole 128-byte runs of the planes
+__global__ void __launch_bounds__(REORDER_THREADS)
+k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
+          float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2, u32 *__restrict__ sorted_slot,
+          u32 *__restrict__ sorted_id) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 base = (blockIdx.x * REORDER_THREADS + threadIdx.x) - lane;  // first position of the warp
+    if (base >= n) return;
+    const u32 s_own = base + lane;
+    u32 src_own = s_own < n ? __ldcs(perm + s_own) : 0u;
+#if RCD_SORT_ABLATE
+    src_own = min(src_own, n - 1);
+#endif
+    if (s_own < n) sorted_slot[s_own] = src_own;
+    const u32 q = lane & 3u;
+    float4 *const plane = q == 0 ? P0 : q == 1 ? P1 : P2;
+    float4 v[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const u32 o = r * 8 + (lane >> 2);
+        const u32 src = __shfl_sync(FULL_MASK, src_own, o);
+        v[r] = __ldg(U + 4 * (size_t)src + q);  // (positions past n read record 0: harmless, never stored)
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const u32 s = base + r * 8 + (lane >> 2);
+        if (s < n) {
+            if (q < 3) plane[s] = v[r];
+            else sorted_id[s] = __float_as_uint(v[r].x);
+        }
+    }
+}
+#else
 __global__ void __launch_bounds__(REORDER_THREADS)
 k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
           float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2, u32 *__restrict__ sorted_slot,
@@ -339,6 +439,7 @@ k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
     sorted_slot[s] = src;
     sorted_id[s] = id;
 }
+#endif
 
 // lower bound in the sorted key array
 __device__ __forceinline__ u32 lower_bound_keys(const u32 *__restrict__ keys, u32 n, u32 key) {
@@ -376,6 +477,9 @@ k_cell_table(const u32 *__restrict__ keys, u32 n, u32 ncells, u32 *__restrict__ 
     const u32 s0 = s_range[0], s1 = s_range[1];
     for (u32 s = s0 + threadIdx.x; s < s1; s += CT_THREADS) {
         const u32 key = keys[s];
+#if RCD_SORT_ABLATE
+        if (key - c0 >= (u32)CT_CELLS) continue;
+#endif
         if (s == s0 || keys[s - 1] != key) s_first[key - c0] = s;
     }
     __syncthreads();
