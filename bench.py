@@ -771,7 +771,7 @@ def run_b200(args):
         n_loc = m["n_own_mean"] + counts["n_objects"] - counts["n_owned"]  # rank 0: owned + halo
         # algorithmic bytes per launch (DESIGN.md "byte model"), rank 0's objects
         npass = max(1, -(-int(np.ceil(np.log2(max(2, eng_ncells(job.bounds, job.xlo, job.xhi))))) // 8))
-        model = {"keys": 102.0 * n_loc, "sort": (16.0 * npass) * n_loc, "reorder": 108.0 * n_loc,
+        model = {"keys": 106.0 * n_loc, "sort": (16.0 * npass - 4.0) * n_loc, "reorder": 112.0 * n_loc,
                  "pairs": 56.0 * n_loc, "narrow": 0.0, "exact": 0.0, "qorder": 0.0}
         kernels = {}
         for key, ms in m["stage_ms"].items():

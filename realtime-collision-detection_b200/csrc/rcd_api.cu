@@ -732,7 +732,7 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         P.q3 = h->q3; P.qcap = h->qcap;
         P.q3_split = mode == RCD_MODE_PREDICT ? h->qcap / 4 : h->qcap;
         CUDA_TRY(h, cudaMemsetAsync(h->pair_tile_counter, 0, 2 * sizeof(u32), h->stream));
-        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_qa_blocks, 0, 5 * sizeof(unsigned long long), h->stream));
+        CUDA_TRY(h, cudaMemsetAsync(&h->counters->n_qa_blocks, 0, 6 * sizeof(unsigned long long), h->stream));
         const bool count = (h->flags & RCD_FLAG_COUNT_PREDICT_CANDIDATES) != 0;
         // persistent launch: as many blocks as can be resident, warps pull tiles from a counter
         const int variant = fused ? 4 : mode == RCD_MODE_DETECT ? 0 : (mode == RCD_MODE_COMPUTE_NODE ? 3 : (count ? 2 : 1));
@@ -805,10 +805,15 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         stage_end(h, RCD_STAGE_NARROW);
         const unsigned sb = (unsigned)std::min<u64>((u64)h->stage_blocks, (h->n + STAGE_THREADS - 1) / STAGE_THREADS + 1);
         stage_begin(h, RCD_STAGE_EXACT);
-        if (variant == 0) k_exact<RCD_MODE_DETECT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-        else if (variant == 3) k_exact<RCD_MODE_COMPUTE_NODE><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-        else if (variant == 4) k_exact<MODE_PREDICT_WITH_DETECT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-        else k_exact<RCD_MODE_PREDICT><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        if (variant == 0) k_exact<RCD_MODE_DETECT, 0><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        else if (variant == 3) k_exact<RCD_MODE_COMPUTE_NODE, 0><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        else if (variant == 4) {
+            k_exact<MODE_PREDICT_WITH_DETECT, 2><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+            k_exact<MODE_PREDICT_WITH_DETECT, 1><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        } else {
+            k_exact<RCD_MODE_PREDICT, 2><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+            k_exact<RCD_MODE_PREDICT, 1><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        }
         KERNEL_CHECK(h);
         stage_end(h, RCD_STAGE_EXACT);
     } else {

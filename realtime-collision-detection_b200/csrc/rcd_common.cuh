@@ -70,7 +70,7 @@ struct Counters {
     unsigned long long n_query_hits;  // rcd_query_radius
     // blocks of the pair queue handed out by k_pairs / length of the queue between k_narrow and k_exact
     // (reset before every step)
-    unsigned long long n_qa_blocks, n_q3, n_q3p;
+    unsigned long long n_qa_blocks, n_q3, n_q3p, n_q3u;
     unsigned long long n_overflow;  // parts of tiles k_pairs left to its overflow pass (pair queue full)
     unsigned long long n_items;     // work items of k_pairs (k_tile_plan)
     unsigned long long n_fallback;  // resolved entries the exact stage had to redo in full (expected 0)

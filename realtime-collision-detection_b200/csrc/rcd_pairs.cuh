@@ -309,7 +309,7 @@ __device__ __noinline__ EmitRec exact_predict_all(const PairParams &P, u32 si, u
     return mask ? exact_predict(P, si, sj, pattern, mask) : no_rec();
 }
 
-__device__ __noinline__ EmitRec exact_predict_resolved(const PairParams &P, u32 si, u32 sj, u32 pattern, int m, int k) {
+__device__ __forceinline__ EmitRec exact_predict_resolved_body(const PairParams &P, u32 si, u32 sj, u32 pattern, int m, int k) {
     ObjD A = widen(P.P0[si], P.P1[si], P.P2[si]), B = widen(P.P0[sj], P.P1[sj], P.P2[sj]);
     const double t = dmul(0.5, (double)m);
     double cx, cy, cz;
@@ -329,6 +329,10 @@ __device__ __noinline__ EmitRec exact_predict_resolved(const PairParams &P, u32 
     const double ttc = dadd(tau, t);
     return make_rec(si, sj, ttc, d, rs, risk, half_d(dadd(xi, xj)), half_d(dadd(yi, yj)),
                     half_d(dadd(zi, zj)), t, 0.0, priority_d(risk, ttc), m, true);
+}
+
+__device__ __noinline__ EmitRec exact_predict_resolved(const PairParams &P, u32 si, u32 sj, u32 pattern, int m, int k) {
+    return exact_predict_resolved_body(P, si, sj, pattern, m, k);
 }
 
 __device__ __noinline__ EmitRec exact_compute_node(const PairParams &P, u32 si, u32 sj) {
@@ -1360,13 +1364,19 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
-// Q3 holds two kinds of entries, kept apart so that the warps of k_exact run one code path: detect entries grow
-// from the front, predict entries fill [q3_split, qcap) (the predict modes; other modes: q3_split = qcap).
+// Q3 holds three kinds of entries, kept apart so that the warps of k_exact run one code path: detect entries grow
+// from the front; predict entries fill [q3_split, qcap) (the predict modes; other modes: q3_split = qcap), the RESOLVED
+// ones (one fp64 evaluation each) from q3_split on, those whose offsets fp64 has to scan in the last quarter of the region.
+__device__ __forceinline__ u32 q3_unresolved_begin(const PairParams &P) { return P.qcap - (P.qcap - P.q3_split) / 4u; }
 __device__ __forceinline__ bool push_detect(const PairParams &P, bool flag, u32 si, u32 sj, u32 word) {
     return global_push(P.q3, P.q3_split, &P.counters->n_q3, flag, si, sj, word);
 }
 __device__ __forceinline__ bool push_predict(const PairParams &P, bool flag, u32 si, u32 sj, u32 word) {
-    return global_push(P.q3 + P.q3_split, P.qcap - P.q3_split, &P.counters->n_q3p, flag, si, sj, word);
+    const u32 ub = q3_unresolved_begin(P);
+    const bool res = (word & RESOLVED) != 0;
+    const bool ok_r = global_push(P.q3 + P.q3_split, ub - P.q3_split, &P.counters->n_q3p, flag && res, si, sj, word);
+    const bool ok_u = global_push(P.q3 + ub, P.qcap - ub, &P.counters->n_q3u, flag && !res, si, sj, word);
+    return ok_r && ok_u;
 }
 
 template <int MODE, bool COUNT_CAND>
@@ -1606,25 +1616,60 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
 
 // k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp.
 // Detect entries (front of Q3) and predict entries (from q3_split on) are mapped to different warps.
+// SEG 0: every entry (radius-query modes); the predict modes run two launches: SEG 2 takes the RESOLVED predict entries
+// (one inlined fp64 evaluation each, fewer registers, more warps per SM), SEG 1 the detect entries and the predict
+// entries whose offsets fp64 has to scan.
 #ifndef RCD_EXACT_MIN_BLOCKS
 #define RCD_EXACT_MIN_BLOCKS 4
 #endif
-template <int MODE>
-__global__ void __launch_bounds__(STAGE_THREADS, RCD_EXACT_MIN_BLOCKS) k_exact(PairParams P) {
-    const unsigned long long nd = min(P.counters->n_q3, (unsigned long long)P.q3_split);
-    const unsigned long long np = min(P.counters->n_q3p, (unsigned long long)(P.qcap - P.q3_split));
-    const unsigned long long nd_pad = (nd + 31ULL) & ~31ULL;
-    const unsigned long long n = nd_pad + np;
+#ifndef RCD_EXACT_RES_MIN_BLOCKS
+#define RCD_EXACT_RES_MIN_BLOCKS 4
+#endif
+#ifndef RCD_EXACT_PREFETCH
+#define RCD_EXACT_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int MODE, int SEG>
+__global__ void __launch_bounds__(STAGE_THREADS, SEG == 2 ? RCD_EXACT_RES_MIN_BLOCKS : RCD_EXACT_MIN_BLOCKS) k_exact(PairParams P) {
+    const u32 ub = q3_unresolved_begin(P);
+    const unsigned long long nd = SEG == 2 ? 0ULL : min(P.counters->n_q3, (unsigned long long)P.q3_split);
+    const unsigned long long np = SEG == 1 ? 0ULL : min(P.counters->n_q3p, (unsigned long long)(ub - P.q3_split));
+    const unsigned long long nu = SEG == 2 ? 0ULL : min(P.counters->n_q3u, (unsigned long long)(P.qcap - ub));
+    const unsigned long long nd_pad = (nd + 31ULL) & ~31ULL, np_end = nd_pad + np, np_pad = (np_end + 31ULL) & ~31ULL;
+    const unsigned long long n = np_pad + nu;
     const unsigned long long stride = (unsigned long long)gridDim.x * STAGE_THREADS;
     const unsigned long long rounds = (n + stride - 1) / stride;
     const u32 lane = threadIdx.x & 31u;
     u32 n_pot = 0, n_exact = 0, n_high = 0, n_prio[4] = {0, 0, 0, 0};
+    // SEG 2 is bound by the latency of its gathers (16 warps per SM, one dependent chain per entry): the entry of the round
+    // after the next is loaded and the objects of the next round's entry are prefetched into L1 while this round computes
+    QEntry q_nxt, q_nn;
+    q_nxt.si = q_nxt.sj = q_nxt.mask = q_nn.si = q_nn.sj = q_nn.mask = 0u;
+    if (SEG == 2 && RCD_EXACT_PREFETCH) {
+        const unsigned long long k0 = (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
+        if (k0 < n) q_nxt = P.q3[P.q3_split + k0];
+        if (k0 + stride < n) q_nn = P.q3[P.q3_split + k0 + stride];
+    }
     for (unsigned long long r = 0; r < rounds; ++r) {  // uniform trip count: the emission is warp-wide
         const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
         EmitRec e = no_rec();
-        if (k < nd || (k >= nd_pad && k < n)) {
-            const QEntry q = k < nd ? P.q3[k] : P.q3[P.q3_split + (k - nd_pad)];
-            e = exact_entry<MODE>(P, q.si, q.sj, q.mask);
+        QEntry q_pre = q_nxt;
+        if (SEG == 2 && RCD_EXACT_PREFETCH) {
+            q_nxt = q_nn;
+            if (k + stride < n) {
+                prefetch_l1(P.P0 + q_nxt.si); prefetch_l1(P.P1 + q_nxt.si); prefetch_l1(P.P2 + q_nxt.si);
+                prefetch_l1(P.P0 + q_nxt.sj); prefetch_l1(P.P1 + q_nxt.sj); prefetch_l1(P.P2 + q_nxt.sj);
+            }
+            if (k + 2 * stride < n) q_nn = P.q3[P.q3_split + k + 2 * stride];
+        }
+        if (k < nd || (k >= nd_pad && k < np_end) || (k >= np_pad && k < n)) {
+            const QEntry q = (SEG == 2 && RCD_EXACT_PREFETCH) ? q_pre
+                             : k < nd ? P.q3[k] : k < np_end ? P.q3[P.q3_split + (k - nd_pad)] : P.q3[ub + (k - np_pad)];
+            if (SEG == 2)
+                e = exact_predict_resolved_body(P, q.si, q.sj, meta_pattern(__float_as_uint(P.P2[q.si].w)), (int)(q.mask & 31u),
+                                                (int)((q.mask >> 8) & 15u));
+            else
+                e = exact_entry<MODE>(P, q.si, q.sj, q.mask);
             n_pot += e.potential;
             n_exact += (is_predict(MODE) && (q.mask & 0xfffffu) && !(q.mask & RESOLVED)) ? (u32)__popc(q.mask & 0xfffffu) : 1u;
         }
@@ -1640,7 +1685,7 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_EXACT_MIN_BLOCKS) k_exact(P
                 if (e.prio >= 0) n_prio[e.prio] += 1u;
             }
         }
-        if (MODE == MODE_PREDICT_WITH_DETECT) {  // second copy of the records that are owed twice
+        if (MODE == MODE_PREDICT_WITH_DETECT && SEG != 2) {  // second copy of the records that are owed twice
             const bool again = e.hit && e.twice;
             const u32 b2 = __ballot_sync(FULL_MASK, again);
             if (b2) {
