@@ -1615,20 +1615,16 @@ __global__ void __launch_bounds__(STAGE_THREADS, RCD_NARROW_MIN_BLOCKS) k_narrow
 }
 
 // k_exact: one queued pair per thread, decided in fp64; the output cursor is claimed once per warp.
-// Detect entries (front of Q3) and predict entries (from q3_split on) are mapped to different warps.
+// The three kinds of Q3 entries are mapped to different warps (a warp that mixes one offset scan into 31 single
+// evaluations runs at the pace of the scan: 17 of 32 threads active per instruction before the split, 30 after).
 // SEG 0: every entry (radius-query modes); the predict modes run two launches: SEG 2 takes the RESOLVED predict entries
-// (one inlined fp64 evaluation each, fewer registers, more warps per SM), SEG 1 the detect entries and the predict
-// entries whose offsets fp64 has to scan.
+// (one inlined fp64 evaluation each), SEG 1 the detect entries and the predict entries whose offsets fp64 has to scan.
 #ifndef RCD_EXACT_MIN_BLOCKS
 #define RCD_EXACT_MIN_BLOCKS 4
 #endif
 #ifndef RCD_EXACT_RES_MIN_BLOCKS
 #define RCD_EXACT_RES_MIN_BLOCKS 4
 #endif
-#ifndef RCD_EXACT_PREFETCH
-#define RCD_EXACT_PREFETCH 0
-#endif
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 template <int MODE, int SEG>
 __global__ void __launch_bounds__(STAGE_THREADS, SEG == 2 ? RCD_EXACT_RES_MIN_BLOCKS : RCD_EXACT_MIN_BLOCKS) k_exact(PairParams P) {
     const u32 ub = q3_unresolved_begin(P);
@@ -1641,30 +1637,11 @@ __global__ void __launch_bounds__(STAGE_THREADS, SEG == 2 ? RCD_EXACT_RES_MIN_BL
     const unsigned long long rounds = (n + stride - 1) / stride;
     const u32 lane = threadIdx.x & 31u;
     u32 n_pot = 0, n_exact = 0, n_high = 0, n_prio[4] = {0, 0, 0, 0};
-    // SEG 2 is bound by the latency of its gathers (16 warps per SM, one dependent chain per entry): the entry of the round
-    // after the next is loaded and the objects of the next round's entry are prefetched into L1 while this round computes
-    QEntry q_nxt, q_nn;
-    q_nxt.si = q_nxt.sj = q_nxt.mask = q_nn.si = q_nn.sj = q_nn.mask = 0u;
-    if (SEG == 2 && RCD_EXACT_PREFETCH) {
-        const unsigned long long k0 = (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
-        if (k0 < n) q_nxt = P.q3[P.q3_split + k0];
-        if (k0 + stride < n) q_nn = P.q3[P.q3_split + k0 + stride];
-    }
     for (unsigned long long r = 0; r < rounds; ++r) {  // uniform trip count: the emission is warp-wide
         const unsigned long long k = r * stride + (unsigned long long)blockIdx.x * STAGE_THREADS + threadIdx.x;
         EmitRec e = no_rec();
-        QEntry q_pre = q_nxt;
-        if (SEG == 2 && RCD_EXACT_PREFETCH) {
-            q_nxt = q_nn;
-            if (k + stride < n) {
-                prefetch_l1(P.P0 + q_nxt.si); prefetch_l1(P.P1 + q_nxt.si); prefetch_l1(P.P2 + q_nxt.si);
-                prefetch_l1(P.P0 + q_nxt.sj); prefetch_l1(P.P1 + q_nxt.sj); prefetch_l1(P.P2 + q_nxt.sj);
-            }
-            if (k + 2 * stride < n) q_nn = P.q3[P.q3_split + k + 2 * stride];
-        }
         if (k < nd || (k >= nd_pad && k < np_end) || (k >= np_pad && k < n)) {
-            const QEntry q = (SEG == 2 && RCD_EXACT_PREFETCH) ? q_pre
-                             : k < nd ? P.q3[k] : k < np_end ? P.q3[P.q3_split + (k - nd_pad)] : P.q3[ub + (k - np_pad)];
+            const QEntry q = k < nd ? P.q3[k] : k < np_end ? P.q3[P.q3_split + (k - nd_pad)] : P.q3[ub + (k - np_pad)];
             if (SEG == 2)
                 e = exact_predict_resolved_body(P, q.si, q.sj, meta_pattern(__float_as_uint(P.P2[q.si].w)), (int)(q.mask & 31u),
                                                 (int)((q.mask >> 8) & 15u));

@@ -1,1 +1,2 @@
-timeout 900 ncu --set full --import-source on --clock-control none -k regex:"k_exact|k_narrow" --launch-skip 3 -c 3 -o gpurun_out/r2s_exact_narrow -f python tools/prof_one.py 1mc fused 2 > gpurun_out/r2s_ncu.log 2>&1; echo ncu rc=$?; tail -3 gpurun_out/r2s_ncu.log
+python tools/ab_stage.py build/ab/lib_seg.so build/ab/lib_res.so build/ab/lib_res_r5.so build/ab/lib_res_r3.so build/ab/lib_seg.so build/ab/lib_res.so | tee gpurun_out/r2t_ab.txt
+RCD_B200_LIB=$PWD/build/ab/lib_res.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
