@@ -748,7 +748,7 @@ def run_b200(args):
                 "verify": s["verify"]}
             s["job"].close()
             _FRAME_CACHE.clear()
-            for name in ("cfg5_10m_skew3d_uniform_disc", "cfg5_10m_skew3d"):
+            for name in (() if args.skip_configs4 else ("cfg5_10m_skew3d_uniform_disc", "cfg5_10m_skew3d")):
                 xs = 3
                 # (the queues between the kernels are sized from the pair buffer: 256 M pairs keep this frame out of the
                 # overflow pass -- 1.8e9 risks per frame on the box with the reference's radial law)
@@ -896,6 +896,8 @@ def main():
                     help="queries of the headline frame re-computed by the CPU oracle after the timed regions (0 = off)")
     ap.add_argument("--verify-kind", choices=["pairs", "counts"], default="pairs",
                     help="headline check: emitted pair records, or only the per-query risk counts (frames too large to bring back)")
+    ap.add_argument("--skip-configs4", action="store_true",
+                    help="at N = 8: leave out the two configs[4] lines (10 M heavy-skew objects, 256 M-pair buffers) of the extras")
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="skip the strong-scaling / 10M lines that follow the headline at N > 1")
     args = ap.parse_args()
