@@ -480,10 +480,6 @@ int rcd_create(const rcd_config *cfg, rcd_handle *out) {
         CREATE_TRY(dev_alloc(&h->qkeys[k], cap + 4));
         CREATE_TRY(dev_alloc(&h->qvals[k], cap + 4));
     }
-    if (const char *e = getenv("RCD_L2_FETCH")) {  // kernel-tuning experiments only: L2 fetch granularity (32 / 64 / 128)
-        const int v = atoi(e);
-        if (v == 32 || v == 64 || v == 128) (void)cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
-    }
     if (const char *e = getenv("RCD_CELL_SCALE")) {  // kernel-tuning experiments only
         const double v = atof(e);
         if (v >= 0.05 && v <= 4.0) h->cell_scale = (float)v;

@@ -34,17 +34,12 @@ __device__ __forceinline__ u32 pack_meta(u32 type, u32 pattern, bool owned) {
     return type | ((pattern & 3u) << 8) | (owned ? META_OWNED : 0u);
 }
 
-#ifndef RCD_PACK_STAGED
-#define RCD_PACK_STAGED 1
-#endif
 __global__ void __launch_bounds__(KEYS_THREADS)
 k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__restrict__ keys,
             u32 *__restrict__ hist /* [MAX_PASSES][RADIX] */,
             float4 *__restrict__ U /* [n][4]: one 64-byte record per object */) {
     __shared__ u32 s_hist[MAX_PASSES][RADIX];
-#if RCD_PACK_STAGED
     __shared__ float4 s_rec[KEYS_THREADS / 32][128];  // a warp's 32 records on their way to four dense 512-byte stores
-#endif
     for (int k = threadIdx.x; k < MAX_PASSES * RADIX; k += KEYS_THREADS) (&s_hist[0][0])[k] = 0;
     __syncthreads();
     // one object per thread: every field load and the key store are fully coalesced 128-byte warp requests; the
@@ -66,7 +61,6 @@ k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__
         // their own behind the grid, which is under no query's box
         const u32 k = (x == x && y == y && z == z) ? cell_key(g, x, y, z) : g.ncells;
         if (live) keys[i] = k;
-#if RCD_PACK_STAGED
         {
             float4 *w = s_rec[threadIdx.x >> 5];
             // quarter q of record l sits at slot 4 l + (q ^ ((l >> 1) & 3)): both the per-object writes (64-byte stride)
@@ -86,15 +80,6 @@ k_pack_keys(InputState in, u32 n, u32 n_owned, GridParams g, int passes, u32 *__
             }
             __syncwarp();
         }
-#else
-        if (live) {
-            float4 *rec = U + 4 * (size_t)i;
-            rec[0] = r0;
-            rec[1] = r1;
-            rec[2] = r2;
-            rec[3] = r3;
-        }
-#endif
         if (live)
             for (int p = 0; p < passes; ++p) atomicAdd(&s_hist[p][(k >> (p * RADIX_BITS)) & (RADIX - 1)], 1u);
     }
@@ -142,10 +127,7 @@ __global__ void __launch_bounds__(RADIX) k_scan_hist(u32 *__restrict__ hist, int
 #ifndef RCD_SORT_LOOKBACK
 #define RCD_SORT_LOOKBACK 8
 #endif
-#ifndef RCD_SORT_VAL_LATE
-#define RCD_SORT_VAL_LATE 0
-#endif
-#ifndef RCD_SORT_ABLATE  // timing experiments only (wrong results): 1 no stores, 2 no look-back, 4 no ranking, 8 dense scatter
+#ifndef RCD_SORT_ABLATE  // timing experiments only (WRONG RESULTS): 1 no global stores, 2 | 16 no look-back (16: stores bound-checked)
 #define RCD_SORT_ABLATE 0
 #endif
 constexpr int SORT_THREADS = 256;
@@ -170,13 +152,7 @@ __device__ __forceinline__ void st_status(u32 *p, u32 v) {
 // than one MATCH.ANY (whose latency the ranking chain would pay once per item).  Written in PTX so that
 // every bit costs four instructions (test, vote, select, and-xor) instead of the seven nvcc makes of the
 // C++ form: peers &= vote ^ (bit ? 0 : ~0).
-#ifndef RCD_SORT_HWMATCH
-#define RCD_SORT_HWMATCH 0
-#endif
 __device__ __forceinline__ u32 match_digit(u32 digit, u32 peers /* lanes that take part */) {
-#if RCD_SORT_HWMATCH
-    return __match_any_sync(FULL_MASK, digit) & peers;
-#endif
 #pragma unroll
     for (int b = 0; b < RADIX_BITS; ++b) {
         u32 t;
@@ -199,7 +175,6 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
                                               u32 tile_count, int shift, const u32 *__restrict__ digit_base,
                                               u32 *tile_status, u32 (*s_warp_hist)[RADIX], u32 *s_digit_excl,
                                               u32 *s_global_base, u32 *s_scan, uint2 *s_kv) {
-    constexpr bool VAL_LATE = RCD_SORT_VAL_LATE && !IDENTITY;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 tile_base = tile * SORT_TILE;
     // ---- load (warp-striped: item k of lane l is element warp*ITEMS*32 + k*32 + l) and rank ----
@@ -211,7 +186,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     for (int k = 0; k < SORT_ITEMS; ++k) {
         const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
         key[k] = valid ? __ldcs(kin + k * 32) : 0xffffffffu;
-        if (!IDENTITY && !VAL_LATE) val[k] = valid ? __ldcs(vin + k * 32) : 0u;
+        if (!IDENTITY) val[k] = valid ? __ldcs(vin + k * 32) : 0u;
     }
     const u32 lt = lanemask_lt();
     u32 *my_hist = s_warp_hist[warp];
@@ -220,10 +195,6 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
         const u32 digit = (key[k] >> shift) & (RADIX - 1);
         // invalid lanes are in nobody's group and do not touch the counters
         const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
-#if RCD_SORT_ABLATE & 4
-        rank[k] = digit & 1;
-        continue;
-#endif
         const u32 group = match_digit(digit, FULL ? FULL_MASK : __ballot_sync(FULL_MASK, valid));
         // every lane of a group reads the counter (one broadcast per digit), the lowest lane advances it
         const u32 before = my_hist[digit];
@@ -231,13 +202,6 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
         if ((group & lt) == 0 && valid) my_hist[digit] = before + __popc(group);
         rank[k] = before + __popc(group & lt);
         __syncwarp();
-    }
-    if (VAL_LATE) {  // the values are not needed before the scatter: their loads fly over the digit scans
-#pragma unroll
-        for (int k = 0; k < SORT_ITEMS; ++k) {
-            const bool valid = FULL || warp_base + k * 32 + lane < tile_count;
-            val[k] = valid ? __ldcs(vin + k * 32) : 0u;
-        }
     }
     __syncthreads();
 
@@ -276,12 +240,7 @@ __device__ __forceinline__ void onesweep_tile(const u32 *__restrict__ keys_in, c
     for (int k = 0; k < SORT_ITEMS; ++k) {
         if (FULL || warp_base + k * 32 + lane < tile_count) {
             const u32 digit = (key[k] >> shift) & (RADIX - 1);
-#if RCD_SORT_ABLATE & 8
-            const u32 pos = (warp_base + k * 32 + lane + ((s_digit_excl[digit] + my_hist[digit] + rank[k]) & 0)) & (SORT_TILE - 1);
-#else
-            const u32 pos = (RCD_SORT_ABLATE & 4) ? (s_digit_excl[digit] + my_hist[digit] + rank[k]) & (SORT_TILE - 1)
-                                                  : s_digit_excl[digit] + my_hist[digit] + rank[k];
-#endif
+            const u32 pos = s_digit_excl[digit] + my_hist[digit] + rank[k];
             s_kv[pos] = make_uint2(key[k], IDENTITY ? tile_base + warp_base + k * 32 + lane : val[k]);
         }
     }
@@ -384,11 +343,6 @@ inline int launch_onesweep(u32 *const keys[2], u32 *const vals[2], u32 n, int pa
 // a record is one aligned 64-byte block, so DRAM traffic is 124 N.
 // -------------------------------------------------------------------------------------------------
 constexpr int REORDER_THREADS = 256;
-#ifndef RCD_REORDER_QUAD
-#define RCD_REORDER_QUAD 1
-#endif
-
-#if RCD_REORDER_QUAD
 // four lanes per object: one 16-byte load each, so a warp request covers 8 whole records (16 full sectors) and every
 // store instruction writes whole 128-byte runs of the planes
 __global__ void __launch_bounds__(REORDER_THREADS)
@@ -422,24 +376,6 @@ k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
         }
     }
 }
-#else
-__global__ void __launch_bounds__(REORDER_THREADS)
-k_reorder(const u32 *__restrict__ perm, u32 n, const float4 *__restrict__ U,
-          float4 *__restrict__ P0, float4 *__restrict__ P1, float4 *__restrict__ P2, u32 *__restrict__ sorted_slot,
-          u32 *__restrict__ sorted_id) {
-    u32 s = blockIdx.x * REORDER_THREADS + threadIdx.x;
-    if (s >= n) return;
-    const u32 src = __ldcs(perm + s);
-    const float4 *rec = U + 4 * (size_t)src;
-    const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
-    const u32 id = __float_as_uint(__ldg(reinterpret_cast<const float *>(rec + 3)));
-    P0[s] = a;
-    P1[s] = b;
-    P2[s] = c;
-    sorted_slot[s] = src;
-    sorted_id[s] = id;
-}
-#endif
 
 // lower bound in the sorted key array
 __device__ __forceinline__ u32 lower_bound_keys(const u32 *__restrict__ keys, u32 n, u32 key) {

@@ -1,3 +1,3 @@
-set -x
-timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29527 bench.py --gpus 8 --steps 10 --warmup 3 --skip-configs4 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; echo rc=$?
-tail -c 400 gpurun_out/r02_bench_n8.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2 | tee gpurun_out/r02_pytest_gpu_final.log
+python tools/ab_stage.py - | tee gpurun_out/r2x_ab.txt
+python tools/bench_index.py 32000000 | tee -a gpurun_out/r2x_ab.txt
