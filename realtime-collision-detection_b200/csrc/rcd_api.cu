@@ -803,13 +803,15 @@ static int step_impl(rcd_handle h, int32_t mode, float search_radius, float time
         stage_begin(h, RCD_STAGE_EXACT);
         if (variant == 0) k_exact<RCD_MODE_DETECT, 0><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         else if (variant == 3) k_exact<RCD_MODE_COMPUTE_NODE, 0><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-        else if (variant == 4) {
-            k_exact<MODE_PREDICT_WITH_DETECT, 2><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-            k_exact<MODE_PREDICT_WITH_DETECT, 1><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-        } else {
-            k_exact<RCD_MODE_PREDICT, 2><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-            k_exact<RCD_MODE_PREDICT, 1><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
-        }
+        else if (variant == 4) k_exact<MODE_PREDICT_WITH_DETECT, 1><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        else k_exact<RCD_MODE_PREDICT, 1><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        KERNEL_CHECK(h);
+        // every record with predicted = 0 has been emitted by now (overflow passes, in-place fall-backs, detect entries):
+        // the alert fold's detect pass stops here instead of walking the whole buffer
+        CUDA_TRY(h, cudaMemcpyAsync(&h->counters->n_detect_end, &h->counters->n_pairs, sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToDevice, h->stream));
+        if (variant == 4) k_exact<MODE_PREDICT_WITH_DETECT, 2><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
+        else if (variant == 1 || variant == 2) k_exact<RCD_MODE_PREDICT, 2><<<sb, STAGE_THREADS, 0, h->stream>>>(P);
         KERNEL_CHECK(h);
         stage_end(h, RCD_STAGE_EXACT);
     } else {
@@ -1533,7 +1535,8 @@ int rcd_alerts_configure(rcd_handle h, uint64_t max_alerts) {
 
 // fold pairs into the table (both passes), events -> h->alert_ev
 static int alerts_enqueue_update(rcd_handle h, const rcd_pair *dev_pairs, u64 n_max, const unsigned long long *n_dev, double now,
-                                 int32_t report_refreshed, cudaStream_t on = nullptr) {
+                                 int32_t report_refreshed, cudaStream_t on = nullptr,
+                                 const unsigned long long *n_dev_detect = nullptr /* bound of the detect pass (null: n_dev) */) {
     if (n_max == 0) return RCD_OK;
     int sms = 0;
     CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
@@ -1549,7 +1552,8 @@ static int alerts_enqueue_update(rcd_handle h, const rcd_pair *dev_pairs, u64 n_
         on = h->stream;
     }
     for (int pass = 0; pass < 2; ++pass) {
-        k_alert_update<<<(unsigned)blocks, ALERT_THREADS, 0, on>>>(dev_pairs, n_max, n_dev, pass, now, h->alert_tab[h->alert_cur],
+        k_alert_update<<<(unsigned)blocks, ALERT_THREADS, 0, on>>>(dev_pairs, n_max, (pass == 0 && n_dev_detect) ? n_dev_detect : n_dev,
+                                                        pass, now, h->alert_tab[h->alert_cur],
                                                         h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
                                                         h->alert_counters, report_refreshed);
         KERNEL_CHECK(h);
@@ -1576,7 +1580,7 @@ int rcd_summary_begin(rcd_handle h, double now, int32_t report_refreshed) {
     CUDA_TRY(h, cudaEventRecord(h->ev_frame_done, h->stream));
     CUDA_TRY(h, cudaStreamWaitEvent(as, h->ev_frame_done, 0));
     CUDA_TRY(h, cudaMemsetAsync(h->alert_counters, 0, offsetof(AlertCounters, n_live), as));
-    rc = alerts_enqueue_update(h, h->out, h->max_pairs, &h->counters->n_pairs, now, report_refreshed, as);
+    rc = alerts_enqueue_update(h, h->out, h->max_pairs, &h->counters->n_pairs, now, report_refreshed, as, &h->counters->n_detect_end);
     if (rc) return rc;
     CUDA_TRY(h, cudaMemcpyAsync(h->pend_alert_counters_host, h->alert_counters, sizeof(AlertCounters), cudaMemcpyDeviceToHost, as));
     h->pend_kind = 2;

@@ -75,6 +75,7 @@ struct Counters {
     unsigned long long n_items;     // work items of k_pairs (k_tile_plan)
     unsigned long long n_fallback;  // resolved entries the exact stage had to redo in full (expected 0)
     unsigned long long n_tests;     // (query, neighbour) tests of the S1 filter (k_pairs), padding of last chunks included
+    unsigned long long n_detect_end;  // every record with predicted = 0 lies in front of this position of the pair buffer
 };
 
 // ---- warp / block helpers -----------------------------------------------------------------------
