@@ -141,6 +141,7 @@ struct rcd_handle_s {
     cudaEvent_t ev_frame_done = nullptr, ev_alert_done = nullptr;
     bool alert_async = false;  // work on alert_stream the handle's stream has not been ordered after yet
     u64 last_n_pairs = 0;      // emitted pairs of the last frame whose totals reached the host (sizes the alert fold's grid)
+    u64 last_n_detect_end = 0; // ... and where its records with predicted = 0 ended (grid of the fold's detect pass)
     bool flip_pending = false, download_pending = false;
     rcd_pair *pend_dev = nullptr, *pend_out = nullptr;
     u64 pend_cap = 0, pend_n = 0, pend_n_owned = 0;
@@ -1001,6 +1002,7 @@ int rcd_counts(rcd_handle h, rcd_counts_t *out) {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     const Counters &c = *h->counters_host;
     h->last_n_pairs = c.n_pairs;
+    h->last_n_detect_end = c.n_detect_end;
     out->n_objects = h->n;
     out->n_owned = h->n_owned;
     out->n_candidates = c.n_candidates;
@@ -1080,6 +1082,7 @@ static int alerts_join(rcd_handle h) {
 }
 static void counts_out(rcd_handle h, const Counters &c, rcd_counts_t *counts) {
     h->last_n_pairs = c.n_pairs;
+    h->last_n_detect_end = c.n_detect_end;
     if (!counts) return;
     counts->n_objects = h->pend_n;
     counts->n_owned = h->pend_n_owned;
@@ -1552,7 +1555,12 @@ static int alerts_enqueue_update(rcd_handle h, const rcd_pair *dev_pairs, u64 n_
         on = h->stream;
     }
     for (int pass = 0; pass < 2; ++pass) {
-        k_alert_update<<<(unsigned)blocks, ALERT_THREADS, 0, on>>>(dev_pairs, n_max, (pass == 0 && n_dev_detect) ? n_dev_detect : n_dev,
+        u64 grid = blocks;
+        if (pass == 0 && n_dev_detect && h->last_n_detect_end) {  // the detect pass ends early: a grid to match
+            const u64 est_d = h->last_n_detect_end + h->last_n_detect_end / 4;
+            grid = std::min<u64>(blocks, std::max<u64>((est_d + ALERT_THREADS - 1) / ALERT_THREADS, (u64)sms));
+        }
+        k_alert_update<<<(unsigned)grid, ALERT_THREADS, 0, on>>>(dev_pairs, n_max, (pass == 0 && n_dev_detect) ? n_dev_detect : n_dev,
                                                         pass, now, h->alert_tab[h->alert_cur],
                                                         h->alert_cap - 1, h->alert_ev, h->alert_ev_cap,
                                                         h->alert_counters, report_refreshed);
