@@ -190,13 +190,20 @@ def test_summary_delivery_equals_the_synchronous_calls_frame_by_frame():
         ref.alerts_configure(1 << 18)
         e.alerts_configure(1 << 18)
         want, got = [], []
+        def step(eng, k):  # fused frames and detect + appended predict frames alternate (the fold's detect pass is bounded
+            if k % 2:      # by where the records with predicted = 0 end: both layouts of the pair buffer are exercised)
+                eng.step(N.MODE_DETECT)
+                eng.step(N.MODE_PREDICT, append=True)
+            else:
+                eng.step(N.MODE_PREDICT, with_detect=True)
+
         for k, f in enumerate(frames):
-            ref.upload(f); ref.set_patterns(pat); ref.step(N.MODE_PREDICT, with_detect=True)
+            ref.upload(f); ref.set_patterns(pat); step(ref, k)
             pairs = ref.download()
             ev, st = ref.alerts_update(100.0 + k)
             assert np.array_equal(ref.risk_counts(), np.bincount(pairs["i"], minlength=n))
             want.append((key(ev), st, np.bincount(pairs["i"], minlength=n).astype(np.uint32), ref.counts()))
-            e.upload(f); e.set_patterns(pat); e.step(N.MODE_PREDICT, with_detect=True)
+            e.upload(f); e.set_patterns(pat); step(e, k)
             if k:
                 got.append(e.summary_finish(risk_counts=np.zeros(n, np.uint32)))
             e.summary_begin(100.0 + k)
