@@ -7,8 +7,11 @@
 // Here the table is an open-addressing hash table in HBM keyed by (i << 32 | j); a frame's emitted
 // pairs are folded into it where they lie (the pair buffer never leaves the device) and only the
 // CHANGES -- created alerts, priority changes, expiries -- are handed to the host.
-//   entry = 40 bytes: key, timestamp (float64 like time.time()), risk, ttc, distance, and one 64-bit state word
-//   {alert number, priority, acknowledged} that is read and written whole (an update never needs a fence)
+//   entry = 48 bytes, 16-byte aligned: {key, state word} in the first 16 bytes, so ONE 16-byte load per probe answers
+//   "is this the key" and "what is its alert number / priority / acknowledged bit" (a dependent second access -- a
+//   second DRAM access for the quarter of the 40-byte entries of the first layout that straddled a line -- is gone);
+//   then timestamp (float64 like time.time()), risk, ttc, distance.  The state word is read and written whole (an
+//   update never needs a fence).
 // Expiry rebuilds the table into its twin (no tombstones).
 #pragma once
 #include <cstddef>
@@ -16,25 +19,34 @@
 
 namespace rcd {
 
-struct AlertEntry {
+struct alignas(16) AlertEntry {
     unsigned long long key;  // i << 32 | j; ALERT_EMPTY = free
-    double ts;
-    float risk, ttc, distance;
-    u32 pad2;
-    // the state word (offset 32, 8-byte aligned): everything an update has to READ.  The creator of an entry writes it
-    // LAST, whole; the table is initialised to 0xff.., so an unpublished entry reads alert_id = ALERT_ID_NONE
+    // the state word (offset 8): everything an update has to READ.  The creator of an entry writes it LAST, whole; the
+    // table is initialised to 0xff.., so an unpublished entry reads alert_id = ALERT_ID_NONE
     u32 alert_id;
     int8_t priority;
     uint8_t acked;
     uint16_t pad;
+    double ts;
+    float risk, ttc, distance;
+    u32 pad2;
 };
-static_assert(sizeof(AlertEntry) == 40 && offsetof(AlertEntry, alert_id) == 32, "AlertEntry: 40 bytes, state word at 32");
+static_assert(sizeof(AlertEntry) == 48 && offsetof(AlertEntry, alert_id) == 8 && offsetof(AlertEntry, ts) == 16,
+              "AlertEntry: 48 bytes, {key, state word} in the first 16");
 static_assert(sizeof(rcd_alert_event) == 40, "rcd_alert_event is 40 bytes");
 constexpr unsigned long long ALERT_EMPTY = ~0ull;
 constexpr u32 ALERT_ID_NONE = 0xffffffffu;  // an entry whose creator has not published it yet
 
 __device__ __forceinline__ unsigned long long alert_state(u32 id, int priority, u32 acked) {
     return (unsigned long long)id | ((unsigned long long)(uint8_t)priority << 32) | ((unsigned long long)(acked & 0xffu) << 40);
+}
+// timestamp, risk, ttc in one 16-byte store (offset 16 of a 16-byte-aligned entry), distance in a second one
+__device__ __forceinline__ void alert_store_values(AlertEntry *a, double now, float risk, float ttc, float distance) {
+    const unsigned long long tb = (unsigned long long)__double_as_longlong(now);
+    uint4 v;
+    v.x = (u32)tb; v.y = (u32)(tb >> 32); v.z = __float_as_uint(risk); v.w = __float_as_uint(ttc);
+    *reinterpret_cast<uint4 *>(&a->ts) = v;
+    a->distance = distance;
 }
 __device__ __forceinline__ volatile unsigned long long *alert_state_ptr(AlertEntry *a) {
     return reinterpret_cast<volatile unsigned long long *>(&a->alert_id);
@@ -55,13 +67,24 @@ __device__ __forceinline__ unsigned long long alert_hash(unsigned long long k) {
     return k;
 }
 
-// find the entry of `key`, or claim a free slot for it; nullptr when the table is full
+// {key, state word} of a slot in one 16-byte access that bypasses L1 (other SMs publish state words during the pass)
+__device__ __forceinline__ ulonglong2 alert_load_head(const AlertEntry *a) {
+    return __ldcg(reinterpret_cast<const ulonglong2 *>(a));
+}
+
+// find the entry of `key`, or claim a free slot for it; nullptr when the table is full.  `state` is the entry's state
+// word as the probe saw it (found entries), or the unpublished pattern (the caller re-reads it after a lost race)
 __device__ __forceinline__ AlertEntry *alert_find_or_insert(AlertEntry *tab, unsigned long long mask, unsigned long long key,
-                                                            bool &inserted) {
+                                                            bool &inserted, unsigned long long &state) {
     unsigned long long s = alert_hash(key) & mask;
     for (unsigned long long probes = 0; probes <= mask; ++probes, s = (s + 1) & mask) {
-        unsigned long long prev = tab[s].key;
-        if (prev == ALERT_EMPTY) prev = atomicCAS(&tab[s].key, ALERT_EMPTY, key);
+        const ulonglong2 head = alert_load_head(tab + s);
+        unsigned long long prev = head.x;
+        state = head.y;
+        if (prev == ALERT_EMPTY) {
+            prev = atomicCAS(&tab[s].key, ALERT_EMPTY, key);
+            if (prev == key) state = *alert_state_ptr(tab + s);  // lost the race to another copy of the same key
+        }
         if (prev == ALERT_EMPTY) { inserted = true; return tab + s; }
         if (prev == key) { inserted = false; return tab + s; }
     }
@@ -97,7 +120,10 @@ constexpr int ALERT_THREADS = 128;
 // `predicted` flag equals `pass` (a frame that ran detect AND predict can carry one risk of each kind for
 // the same (i, j); two launches keep "the later risk wins" of the reference's loop deterministic;
 // pass < 0 takes every pair).  n_dev (if not null) is the device-side pair count, clamped to n_max.
-__global__ void __launch_bounds__(ALERT_THREADS)
+#ifndef RCD_ALERT_MIN_BLOCKS
+#define RCD_ALERT_MIN_BLOCKS 12  // <= 40 registers: a block of the fold fits beside five resident blocks of k_pairs
+#endif
+__global__ void __launch_bounds__(ALERT_THREADS, RCD_ALERT_MIN_BLOCKS)
 k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, const unsigned long long *n_dev, int pass,
                double now, AlertEntry *tab, unsigned long long mask, rcd_alert_event *ev, unsigned long long ev_cap,
                AlertCounters *c, int emit_refreshed) {
@@ -126,7 +152,8 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
             if (p.priority >= 0 && (pass < 0 || (int)p.predicted == pass)) {
                 const unsigned long long key = ((unsigned long long)p.i << 32) | p.j;
                 bool inserted = false;
-                AlertEntry *a = alert_find_or_insert(tab, mask, key, inserted);
+                unsigned long long st = 0;
+                AlertEntry *a = alert_find_or_insert(tab, mask, key, inserted, st);
                 if (!a) {
                     ++dropped;
                 } else {
@@ -135,7 +162,7 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
                     volatile u32 *idp = &a->alert_id;
                     if (inserted) {  // create_alert (:120-160)
                         a->pad2 = 0;
-                        a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->ts = now;
+                        alert_store_values(a, now, p.risk, p.ttc, p.distance);
                         e.alert_id = atomicAdd(&c->next_id, 1u);
                         __threadfence();
                         *sp = alert_state(e.alert_id, p.priority, 0u);  // publishes the entry
@@ -144,7 +171,6 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
                         ++created;
                         emit = true;
                     } else {
-                        const unsigned long long st = *sp;
                         e.alert_id = (u32)st;
                         if (e.alert_id == ALERT_ID_NONE) {  // being created by another thread of this pass
                             e.kind = RCD_ALERT_REFRESHED;
@@ -159,7 +185,7 @@ k_alert_update(const rcd_pair *__restrict__ pairs, unsigned long long n_max, con
                             const u32 acked = (u32)((st >> 40) & 0xffu);
                             e.old_priority = (int8_t)old_priority;
                             e.acknowledged = (uint8_t)acked;
-                            a->risk = p.risk; a->ttc = p.ttc; a->distance = p.distance; a->ts = now;
+                            alert_store_values(a, now, p.risk, p.ttc, p.distance);
                             if (old_priority != (int)p.priority) {
                                 *sp = alert_state(e.alert_id, p.priority, acked);
                                 e.kind = RCD_ALERT_PRIORITY_CHANGED; ++changed; emit = true;
@@ -213,7 +239,8 @@ k_alert_expire(const AlertEntry *__restrict__ src, unsigned long long cap, doubl
                     ++expired;
                 } else {
                     bool inserted = false;
-                    AlertEntry *d = alert_find_or_insert(dst, cap - 1, a.key, inserted);  // same capacity: always fits
+                    unsigned long long st_unused = 0;
+                    AlertEntry *d = alert_find_or_insert(dst, cap - 1, a.key, inserted, st_unused);  // same capacity: always fits
                     d->ts = a.ts; d->risk = a.risk; d->ttc = a.ttc; d->distance = a.distance; d->alert_id = a.alert_id;
                     d->priority = a.priority; d->acked = a.acked; d->pad = 0; d->pad2 = 0;
                     ++live;
