@@ -1,4 +1,5 @@
-for v in al_old al8 al12; do echo "== $v"; RCD_B200_LIB=$PWD/build/ab/lib_$v.so timeout 300 python tools/bench_alerts.py 2>&1 | sed -n 2,4p | cut -c1-200
-RCD_B200_LIB=$PWD/build/ab/lib_$v.so timeout 300 python bench.py --steps 20 --warmup 3 --verify-queries 0 --cpu-budget 1 2>/dev/null | python -c "
-import sys,json; d=json.load(sys.stdin); e=d['e2e']; print(d['ms_per_step'], 'e2e', e['ms_per_step'], e['value'], e['other_inflight'])"; done | tee gpurun_out/r2y_alerts.txt
-RCD_B200_LIB=$PWD/build/ab/lib_al12.so timeout 600 python -m pytest tests/test_gpu_alerts.py tests/test_gpu_dropin.py -m gpu -x -q 2>&1 | tail -2
+set -x
+python __graft_entry__.py --smoke > gpurun_out/r02_smoke.log 2>&1; tail -1 gpurun_out/r02_smoke.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_gpu_1gpu_final.log 2>&1; tail -2 gpurun_out/r02_pytest_gpu_1gpu_final.log
+python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; echo rc=$?
+python tools/bench_alerts.py > gpurun_out/r02_alerts_microbench.jsonl 2>&1; head -4 gpurun_out/r02_alerts_microbench.jsonl | cut -c1-200
